@@ -1,0 +1,121 @@
+/*
+ * rdvc_corr.h -- C ABI of librdvc_corr.so: the B200 (sm_100a) implementation of
+ * the RAFT correlation hot path of RDVC's motion branch.
+ *
+ * Drop-in boundary.  RDVC (R: = the reference repo) has no correlation code of
+ * its own; its encoder calls torchvision's RAFT (R:codec_processing.py:1442,
+ * R:test_2frames.py:496), whose CorrBlock (TV: = torchvision 0.26.0
+ * models/optical_flow/raft.py) is the path replaced here:
+ *
+ *   rdvc_corr_build   replaces  CorrBlock.build_pyramid      TV:raft.py:360-392
+ *                               (+ _compute_corr_volume      TV:raft.py:424-431)
+ *   rdvc_corr_lookup  replaces  CorrBlock.index_pyramid      TV:raft.py:394-422
+ *                               (+ grid_sample helper        TV:_utils.py:8-19)
+ *   rdvc_corr_pair_host         one frame pair end to end from HOST buffers
+ *                               (build + `iters` lookups, copies included);
+ *                               the call a non-PyTorch host would bind.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, no C++/torch types.
+ *   - All DEVICE buffers are allocated and owned by the caller.  The library
+ *     never allocates or frees caller-visible device memory and keeps no
+ *     pointer after a call returns (rdvc_corr_pair_host uses a private,
+ *     per-thread scratch arena that it owns and that rdvc_corr_release frees).
+ *   - Calls are asynchronous on `stream` (a cudaStream_t passed as void*; NULL
+ *     = the legacy default stream) except rdvc_corr_pair_host, which
+ *     synchronises before returning.  The caller sets the current device.
+ *   - Return 0 on success, a negative RDVC_E_* for argument errors, a positive
+ *     cudaError_t for CUDA failures.  rdvc_corr_last_error() returns a
+ *     thread-local message for the last non-zero return on this thread.
+ *   - No CPU fallback exists: on a machine without an sm_100 GPU every compute
+ *     entry point fails with a CUDA error.
+ *
+ * Pyramid layout (one caller-owned buffer, `rdvc_corr_pyramid_bytes` long):
+ *   level l lives at byte offset rdvc_corr_level_offset_bytes(..., l) (256-byte
+ *   aligned) and is a dense row-major array [B*h*w][h_l][w_l] with
+ *   h_l = h >> l, w_l = w >> l (floor halving, TV:raft.py:390-392) -- the same
+ *   element order as torchvision's corr_pyramid[l] viewed (B*h*w, 1, h_l, w_l).
+ */
+#ifndef RDVC_CORR_H_
+#define RDVC_CORR_H_
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RDVC_CORR_VERSION 100 /* 0.1.0 */
+
+/* element types */
+#define RDVC_DT_BF16 0
+#define RDVC_DT_F32 1
+#define RDVC_DT_F16 2
+
+/* argument errors (negative); CUDA errors are returned as positive cudaError_t */
+#define RDVC_OK 0
+#define RDVC_E_NULL (-1)        /* a required pointer is NULL                        */
+#define RDVC_E_SHAPE (-2)       /* non-positive dimension                            */
+#define RDVC_E_TOO_SMALL (-3)   /* h or w < 2 * 2^(num_levels-1)   (TV:raft.py:376)  */
+#define RDVC_E_DTYPE (-4)       /* unsupported in_dtype / vol_dtype                  */
+#define RDVC_E_UNSUPPORTED (-5) /* D % 64 != 0, D > 256, num_levels > 4, radius > 4  */
+#define RDVC_E_WORKSPACE (-6)   /* workspace smaller than rdvc_corr_workspace_bytes  */
+#define RDVC_E_ALIGN (-7)       /* a device pointer is not 16-byte aligned           */
+#define RDVC_E_DRIVER (-8)      /* cuTensorMapEncodeTiled unavailable / failed       */
+
+int rdvc_corr_version(void);
+const char* rdvc_corr_last_error(void);
+
+/* ---- sizes ------------------------------------------------------------- */
+/* vol_dtype: RDVC_DT_F32 or RDVC_DT_BF16 (storage type of the pyramid). */
+size_t rdvc_corr_pyramid_bytes(int B, int h, int w, int num_levels, int vol_dtype);
+size_t rdvc_corr_level_offset_bytes(int B, int h, int w, int level, int vol_dtype);
+/* scratch for the two K-major bf16 copies of the feature maps */
+size_t rdvc_corr_workspace_bytes(int B, int D, int h, int w);
+
+/* ---- build: correlation volume + all pyramid levels, written once ------ *
+ * fmap1, fmap2 : device, (B, D, h, w) contiguous, in_dtype in {F32, BF16, F16}
+ * pyramid      : device, rdvc_corr_pyramid_bytes(...) bytes, 256-byte aligned
+ * workspace    : device, rdvc_corr_workspace_bytes(...) bytes, 256-byte aligned
+ * Computes  pyr[0][b*N+i][y][x] = sum_c fmap1[b,c,i] * fmap2[b,c,y*w+x] / sqrt(D)
+ * with bf16 operands and fp32 accumulation (tcgen05), and pyr[l+1] = 2x2 mean of
+ * pyr[l] over (y,x) with the odd trailing row/column dropped.                  */
+int rdvc_corr_build(const void* fmap1, const void* fmap2, int B, int D, int h, int w,
+                    int in_dtype, void* pyramid, int vol_dtype, int num_levels,
+                    void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- lookup: (2r+1)^2 bilinear taps x num_levels ----------------------- *
+ * coords : device, (B, 2, h, w) fp32, channel 0 = x, channel 1 = y, absolute
+ *          pixel units of the 1/8 grid (TV:_utils.py:22-26)
+ * out    : device, (B, num_levels*(2r+1)^2, h, w) fp32 contiguous
+ * out[b, l*S*S + i*S + j, y, x] = bilinear(pyr[l][b*N + y*w + x],
+ *          xs = coords[b,0,y,x]/2^l + (i-r), ys = coords[b,1,y,x]/2^l + (j-r)),
+ * zero outside the level, pixel centres at integers (align_corners=True).     */
+int rdvc_corr_lookup(const void* pyramid, int vol_dtype, const float* coords, int B, int h,
+                     int w, int num_levels, int radius, float* out, void* stream);
+
+/* ---- one frame pair from host memory (blocking) ------------------------ *
+ * fmap1_host, fmap2_host : host fp32 (B, D, h, w)
+ * coords_host            : host fp32 (iters, B, 2, h, w)
+ * out_host               : host fp32 (iters, B, L*S*S, h, w)
+ * Copies in, builds, runs `iters` lookups, copies every lookup result out and
+ * synchronises.  Pinned host buffers make the copies asynchronous.            */
+int rdvc_corr_pair_host(const float* fmap1_host, const float* fmap2_host,
+                        const float* coords_host, float* out_host, int B, int D, int h,
+                        int w, int num_levels, int radius, int iters, int vol_dtype);
+
+/* Frees the per-thread scratch arena of rdvc_corr_pair_host (optional). */
+void rdvc_corr_release(void);
+
+/* ---- introspection for tests / benches --------------------------------- */
+/* Number of kernels this library has launched on the calling thread.         */
+unsigned long long rdvc_corr_launch_count(void);
+/* Debug/tuning knobs; unknown keys return RDVC_E_UNSUPPORTED.
+ *   key 0: lookup variant   (0 = auto, 1 = scalar loads, 2 = 128-bit loads)
+ *   key 1: build tile shape (0 = auto, 1 = 16x16, 2 = 8x32 fmap2 pixels)      */
+int rdvc_corr_set_option(int key, int value);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RDVC_CORR_H_ */

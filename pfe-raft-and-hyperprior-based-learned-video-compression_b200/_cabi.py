@@ -1,0 +1,81 @@
+"""ctypes binding of ``librdvc_corr.so`` -- exactly the symbols ``include/rdvc_corr.h`` declares.
+
+There is no fallback: if the library has not been built (``_build.build()`` /
+``__graft_entry__.build()``), importing a compute entry point raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+from . import _build
+
+RDVC_DT_BF16, RDVC_DT_F32, RDVC_DT_F16 = 0, 1, 2
+
+RDVC_E = {
+    -1: "RDVC_E_NULL", -2: "RDVC_E_SHAPE", -3: "RDVC_E_TOO_SMALL", -4: "RDVC_E_DTYPE",
+    -5: "RDVC_E_UNSUPPORTED", -6: "RDVC_E_WORKSPACE", -7: "RDVC_E_ALIGN", -8: "RDVC_E_DRIVER",
+}
+
+# every symbol of include/rdvc_corr.h: name -> (restype, argtypes)
+_c = ctypes
+SYMBOLS = {
+    "rdvc_corr_version": (_c.c_int, []),
+    "rdvc_corr_last_error": (_c.c_char_p, []),
+    "rdvc_corr_pyramid_bytes": (_c.c_size_t, [_c.c_int] * 5),
+    "rdvc_corr_level_offset_bytes": (_c.c_size_t, [_c.c_int] * 5),
+    "rdvc_corr_workspace_bytes": (_c.c_size_t, [_c.c_int] * 4),
+    "rdvc_corr_build": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int, _c.c_int, _c.c_int,
+                                   _c.c_int, _c.c_void_p, _c.c_int, _c.c_int, _c.c_void_p,
+                                   _c.c_size_t, _c.c_void_p]),
+    "rdvc_corr_lookup": (_c.c_int, [_c.c_void_p, _c.c_int, _c.c_void_p, _c.c_int, _c.c_int, _c.c_int,
+                                    _c.c_int, _c.c_int, _c.c_void_p, _c.c_void_p]),
+    "rdvc_corr_pair_host": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p] +
+                            [_c.c_int] * 8),
+    "rdvc_corr_release": (None, []),
+    "rdvc_corr_launch_count": (_c.c_ulonglong, []),
+    "rdvc_corr_set_option": (_c.c_int, [_c.c_int, _c.c_int]),
+}
+
+_lib = None
+
+
+def lib_path() -> str:
+    return _build.LIB_PATH
+
+
+def load():
+    """Load the shared library (never builds it implicitly on a GPU box: a
+    missing library is an error, not a reason to fall back)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = lib_path()
+    if not os.path.exists(path):
+        raise RuntimeError(
+            f"{path} is missing: the CUDA library has not been built. Run "
+            "`python -c 'import __graft_entry__ as g; g.build()'` (needs nvcc). "
+            "There is no CPU or PyTorch fallback for this path."
+        )
+    L = ctypes.CDLL(path)
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(L, name)  # AttributeError if the .so does not export it
+        fn.restype = res
+        fn.argtypes = args
+    _lib = L
+    return L
+
+
+def last_error() -> str:
+    return load().rdvc_corr_last_error().decode("utf-8", "replace")
+
+
+def check(rc: int, what: str):
+    """0 -> ok; negative RDVC_E_* -> ValueError (argument problems, mirrors the
+    ValueErrors of TV:raft.py:368-383); positive cudaError_t -> RuntimeError."""
+    if rc == 0:
+        return
+    msg = last_error()
+    if rc < 0:
+        raise ValueError(f"{what}: {RDVC_E.get(rc, rc)}: {msg}")
+    raise RuntimeError(f"{what}: CUDA error {rc}: {msg}")

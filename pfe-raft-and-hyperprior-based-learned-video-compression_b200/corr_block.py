@@ -1,0 +1,207 @@
+"""Host-side mirror of the reference's correlation-block interface.
+
+Two surfaces over the same C ABI (``include/rdvc_corr.h``):
+
+* :class:`TVCorrBlock` -- an ``nn.Module`` with torchvision's ``CorrBlock``
+  surface (TV:raft.py:337-431): ``build_pyramid(fmap1, fmap2)``,
+  ``index_pyramid(centroids_coords)``, ``out_channels``, ``num_levels``,
+  ``radius``, ``corr_pyramid``.  Inject it where RDVC builds its RAFT
+  (R:codec_processing.py:1289-1291): ``raft_large(weights=..., corr_block=TVCorrBlock())``
+  -- ``_raft`` pops the ``corr_block`` kwarg at TV:raft.py:792.
+* :class:`CorrBlock` -- the princeton-vl ``core/corr.py`` style façade that the
+  reference's ``local`` RAFT backend expects (R:codec_processing.py:64-72):
+  ``CorrBlock(fmap1, fmap2, num_levels=4, radius=4)`` builds on construction,
+  ``__call__(coords)`` looks up.
+
+PyTorch only provides device memory and the current stream; the arithmetic is
+in ``librdvc_corr.so``.  There is no fallback path.
+"""
+from __future__ import annotations
+
+from typing import List, Optional
+
+import torch
+from torch import Tensor, nn
+
+from . import _cabi
+
+_IN_DTYPES = {torch.float32: _cabi.RDVC_DT_F32, torch.bfloat16: _cabi.RDVC_DT_BF16,
+              torch.float16: _cabi.RDVC_DT_F16}
+_VOL_DTYPES = {torch.float32: _cabi.RDVC_DT_F32, torch.bfloat16: _cabi.RDVC_DT_BF16}
+
+
+def _stream_ptr(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+class CorrPyramid:
+    """Device-resident correlation pyramid: one byte buffer + its geometry."""
+
+    def __init__(self, B: int, h: int, w: int, num_levels: int, volume_dtype: torch.dtype,
+                 buffer: Tensor):
+        self.B, self.h, self.w = B, h, w
+        self.num_levels = num_levels
+        self.volume_dtype = volume_dtype
+        self.buffer = buffer  # uint8, 256-byte aligned
+
+    def level(self, l: int) -> Tensor:
+        """View of level ``l`` shaped like torchvision's ``corr_pyramid[l]``:
+        (B*h*w, 1, h >> l, w >> l)."""
+        lib = _cabi.load()
+        vd = _VOL_DTYPES[self.volume_dtype]
+        off = lib.rdvc_corr_level_offset_bytes(self.B, self.h, self.w, l, vd)
+        hl, wl = self.h >> l, self.w >> l
+        n = self.B * self.h * self.w * hl * wl
+        es = torch.empty((), dtype=self.volume_dtype).element_size()
+        flat = self.buffer[off: off + n * es].view(self.volume_dtype)
+        return flat.view(self.B * self.h * self.w, 1, hl, wl)
+
+    def levels(self) -> List[Tensor]:
+        return [self.level(l) for l in range(self.num_levels)]
+
+
+def _check_fmaps(fmap1: Tensor, fmap2: Tensor, num_levels: int):
+    # same checks, same messages as TV:raft.py:368-383
+    if fmap1.shape != fmap2.shape:
+        raise ValueError(
+            f"Input feature maps should have the same shape, instead got {fmap1.shape} (fmap1.shape) != {fmap2.shape} (fmap2.shape)"
+        )
+    if fmap1.dim() != 4:
+        raise ValueError(f"Feature maps should be (B, C, H, W), got {tuple(fmap1.shape)}")
+    min_fmap_size = 2 * (2 ** (num_levels - 1))
+    if any(fmap_size < min_fmap_size for fmap_size in fmap1.shape[-2:]):
+        raise ValueError(
+            "Feature maps are too small to be down-sampled by the correlation pyramid. "
+            f"H and W of feature maps should be at least {min_fmap_size}; got: {fmap1.shape[-2:]}. "
+            "Remember that input images to the model are downsampled by 8, so that means their "
+            f"dimensions should be at least 8 * {min_fmap_size} = {8 * min_fmap_size}."
+        )
+    if not fmap1.is_cuda or not fmap2.is_cuda:
+        raise RuntimeError(
+            "rdvc_corr_b200 runs on an sm_100 GPU only; got CPU feature maps. There is no CPU fallback."
+        )
+    if fmap1.dtype != fmap2.dtype or fmap1.dtype not in _IN_DTYPES:
+        raise ValueError(f"unsupported feature-map dtypes {fmap1.dtype} / {fmap2.dtype}")
+
+
+def build_pyramid(fmap1: Tensor, fmap2: Tensor, num_levels: int = 4,
+                  volume_dtype: torch.dtype = torch.float32,
+                  out: Optional[CorrPyramid] = None,
+                  workspace: Optional[Tensor] = None) -> CorrPyramid:
+    """Correlation volume + pyramid through ``rdvc_corr_build`` on the current stream."""
+    _check_fmaps(fmap1, fmap2, num_levels)
+    if volume_dtype not in _VOL_DTYPES:
+        raise ValueError(f"volume_dtype must be float32 or bfloat16, got {volume_dtype}")
+    lib = _cabi.load()
+    B, D, h, w = fmap1.shape
+    dev = fmap1.device
+    f1 = fmap1.contiguous()
+    f2 = fmap2.contiguous()
+    vd = _VOL_DTYPES[volume_dtype]
+    pyr_bytes = lib.rdvc_corr_pyramid_bytes(B, h, w, num_levels, vd)
+    ws_bytes = lib.rdvc_corr_workspace_bytes(B, D, h, w)
+    with torch.cuda.device(dev):
+        if out is not None and out.buffer.numel() >= pyr_bytes and out.buffer.device == dev:
+            buf = out.buffer
+        else:
+            buf = torch.empty(pyr_bytes, dtype=torch.uint8, device=dev)
+        if workspace is None or workspace.numel() < ws_bytes or workspace.device != dev:
+            workspace = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        rc = lib.rdvc_corr_build(f1.data_ptr(), f2.data_ptr(), B, D, h, w, _IN_DTYPES[f1.dtype],
+                                 buf.data_ptr(), vd, num_levels, workspace.data_ptr(),
+                                 workspace.numel(), _stream_ptr(dev))
+    _cabi.check(rc, "rdvc_corr_build")
+    # the workspace is consumed by kernels already enqueued on this stream; torch's
+    # caching allocator keeps it stream-ordered when it is dropped here
+    pyr = CorrPyramid(B, h, w, num_levels, volume_dtype, buf)
+    pyr._workspace = workspace
+    return pyr
+
+
+def index_pyramid(pyr: CorrPyramid, coords: Tensor, radius: int = 4,
+                  out: Optional[Tensor] = None) -> Tensor:
+    """(B, 2, h, w) coords -> (B, L*(2r+1)^2, h, w) fp32 through ``rdvc_corr_lookup``."""
+    lib = _cabi.load()
+    if coords.dim() != 4 or coords.shape[1] != 2:
+        raise ValueError(f"coords should be (B, 2, h, w), got {tuple(coords.shape)}")
+    B, _, h, w = coords.shape
+    if (B, h, w) != (pyr.B, pyr.h, pyr.w):
+        raise ValueError(
+            f"coords {tuple(coords.shape)} do not match the pyramid built for (B, h, w) = {(pyr.B, pyr.h, pyr.w)}"
+        )
+    if not coords.is_cuda:
+        raise RuntimeError("rdvc_corr_b200 runs on an sm_100 GPU only; got CPU coords.")
+    dev = coords.device
+    c = coords.detach().to(torch.float32).contiguous()
+    S = 2 * radius + 1
+    C = pyr.num_levels * S * S
+    if out is None:
+        out = torch.empty((B, C, h, w), dtype=torch.float32, device=dev)
+    elif tuple(out.shape) != (B, C, h, w) or out.dtype != torch.float32 or not out.is_contiguous():
+        raise ValueError("out must be a contiguous fp32 tensor of shape (B, L*(2r+1)^2, h, w)")
+    with torch.cuda.device(dev):
+        rc = lib.rdvc_corr_lookup(pyr.buffer.data_ptr(), _VOL_DTYPES[pyr.volume_dtype], c.data_ptr(),
+                                  B, h, w, pyr.num_levels, radius, out.data_ptr(), _stream_ptr(dev))
+    _cabi.check(rc, "rdvc_corr_lookup")
+    return out
+
+
+class TVCorrBlock(nn.Module):
+    """torchvision-surface correlation block backed by librdvc_corr.so.
+
+    Stateful like the original (``self.corr_pyramid``, TV:raft.py:352,389): one
+    instance per concurrent RAFT call.
+    """
+
+    def __init__(self, *, num_levels: int = 4, radius: int = 4,
+                 volume_dtype: torch.dtype = torch.float32):
+        super().__init__()
+        self.num_levels = num_levels
+        self.radius = radius
+        self.volume_dtype = volume_dtype
+        self.out_channels = num_levels * (2 * radius + 1) ** 2  # TV:raft.py:358
+        self._pyr: Optional[CorrPyramid] = None
+        self._workspace: Optional[Tensor] = None
+        self.corr_pyramid: List[Tensor] = [torch.tensor(0)]
+
+    def build_pyramid(self, fmap1: Tensor, fmap2: Tensor) -> None:
+        self._pyr = build_pyramid(fmap1, fmap2, self.num_levels, self.volume_dtype,
+                                  out=self._pyr, workspace=self._workspace)
+        self._workspace = self._pyr._workspace
+        self.corr_pyramid = self._pyr.levels()
+
+    def index_pyramid(self, centroids_coords: Tensor) -> Tensor:
+        if self._pyr is None:
+            raise RuntimeError("index_pyramid called before build_pyramid")
+        corr_features = index_pyramid(self._pyr, centroids_coords, self.radius)
+        batch_size, _, h, w = centroids_coords.shape
+        expected_output_shape = (batch_size, self.out_channels, h, w)
+        if corr_features.shape != expected_output_shape:  # TV:raft.py:416-420
+            raise ValueError(
+                f"Output shape of index pyramid is incorrect. Should be {expected_output_shape}, got {corr_features.shape}"
+            )
+        return corr_features
+
+    def release(self) -> None:
+        """Drop the pyramid (5.7 GB at 1080p fp32) back to torch's allocator."""
+        self._pyr = None
+        self._workspace = None
+        self.corr_pyramid = [torch.tensor(0)]
+
+
+class CorrBlock:
+    """princeton-vl style façade: ``CorrBlock(fmap1, fmap2, num_levels, radius)(coords)``.
+
+    ``coords`` is (B, 2, h, w) with channel 0 = x, channel 1 = y, as produced by
+    ``coords_grid`` in that code base; the result is (B, L*(2r+1)^2, h, w) fp32.
+    """
+
+    def __init__(self, fmap1: Tensor, fmap2: Tensor, num_levels: int = 4, radius: int = 4,
+                 volume_dtype: torch.dtype = torch.float32):
+        self.num_levels = num_levels
+        self.radius = radius
+        self.pyramid = build_pyramid(fmap1, fmap2, num_levels, volume_dtype)
+        self.corr_pyramid = self.pyramid.levels()
+
+    def __call__(self, coords: Tensor) -> Tensor:
+        return index_pyramid(self.pyramid, coords, self.radius)

@@ -1,0 +1,389 @@
+// corr_build_sm100.cuh -- all-pairs correlation volume + 4-level pyramid in ONE
+// pass (replaces TV:raft.py:360-392 build_pyramid and :424-431
+// _compute_corr_volume).
+//
+//   pyr[0][b*N + i][y][x] = (1/sqrt(D)) * sum_c fmap1[b,c,i] * fmap2[b,c,y*w+x]
+//   pyr[l+1]              = 2x2 mean of pyr[l] over (y, x), floor-cropped
+//
+// Shape of the computation: a [N x D] x [D x N] GEMM per batch item with D = 256
+// (only 16 UMMA k-steps) whose fp32 output (4.26 GB at 1080p) dwarfs its inputs
+// (2 x 16.7 MB bf16).  It is HBM-WRITE bound (0.87 ms at 6.5 TB/s vs 0.32 ms of
+// tensor time), so the kernel is organised around the epilogue:
+//
+//  * Persistent, one CTA per SM, warp-specialised:
+//      warp 0      TMA producer   (elected lane)
+//      warp 1      tcgen05.mma issuer (elected lane)
+//      warp 2      TMEM allocator (512 columns = two 128x256 fp32 accumulators)
+//      warp 3      idle
+//      warps 4-11  epilogue: TMEM -> registers -> pooled in registers ->
+//                  swizzled smem staging -> 16-byte coalesced global stores
+//  * fmap2-STATIONARY: one N-tile (256 fmap2 pixels x full K = 128 KB of smem)
+//    stays resident while 128-row fmap1 tiles stream through a 4-stage 16 KB
+//    ring.  L2->SM operand traffic is half the output bytes instead of equal.
+//  * An N-tile is a SPATIAL block of fmap2 (TILE_Y x TILE_X pixels, 16x16 or
+//    8x32) fetched with one 4-D TMA box per 64-channel slab, so a TMEM column is
+//    a pixel (ty, tx) of the block and one TMEM lane (= one thread of the
+//    epilogue) holds a whole 2-D patch for its query pixel.  All three pooling
+//    levels are therefore plain register adds in that thread -- no shuffles, no
+//    re-read of level 0.  Every level is written to HBM exactly once.
+//  * Two accumulators ping-pong so the MMAs of tile t+1 run under the epilogue
+//    of tile t.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cstdint>
+
+#include "ptx_sm100.cuh"
+
+namespace rdvc {
+
+constexpr int BLD_BLOCK_M = 128;
+constexpr int BLD_BLOCK_N = 256;
+constexpr int BLD_BLOCK_K = 64;  // bf16 per 128-byte swizzle row
+constexpr int BLD_UMMA_K = 16;
+constexpr int BLD_A_STAGES = 4;
+constexpr int BLD_MAX_KC = 4;    // D <= 256
+constexpr int BLD_A_STAGE_BYTES = BLD_BLOCK_M * BLD_BLOCK_K * 2;  // 16 KB
+constexpr int BLD_B_SLAB_BYTES = BLD_BLOCK_N * BLD_BLOCK_K * 2;   // 32 KB
+constexpr int BLD_EPI_WARPS = 8;
+constexpr int BLD_STG_BYTES = 4096;  // per epilogue warp: 32 rows x 32 fp32
+constexpr int BLD_THREADS = 128 + BLD_EPI_WARPS * 32;
+constexpr int BLD_MAX_LEVELS = 4;
+
+constexpr int BLD_SMEM_B = 0;
+constexpr int BLD_SMEM_A = BLD_SMEM_B + BLD_MAX_KC * BLD_B_SLAB_BYTES;       // 131072
+constexpr int BLD_SMEM_STG = BLD_SMEM_A + BLD_A_STAGES * BLD_A_STAGE_BYTES;  // 196608
+constexpr int BLD_SMEM_BAR = BLD_SMEM_STG + BLD_EPI_WARPS * BLD_STG_BYTES;   // 229376
+constexpr int BLD_SMEM_TOTAL = BLD_SMEM_BAR + 128;
+constexpr int BLD_SMEM_LAUNCH = BLD_SMEM_TOTAL + 1024;  // slack for 1024-byte alignment
+
+struct BuildParams {
+    void* lvl[BLD_MAX_LEVELS];  // level base pointers (256-byte aligned)
+    int hl[BLD_MAX_LEVELS];
+    int wl[BLD_MAX_LEVELS];
+    int B, h, w, N;
+    int num_levels;
+    int kc;             // D / 64
+    int m_blks;         // ceil(N / 128)
+    int nty, ntx;       // fmap2 tiles along y / x
+    long long total_tiles;
+    float scale;        // 1 / sqrt(D)
+};
+
+// ---- output element traits -------------------------------------------------
+template <typename OutT> struct OutTraits;
+template <> struct OutTraits<float> {
+    static constexpr int EPC = 4;  // elements per 16-byte chunk
+    static constexpr int CH = 8;   // chunks per 32-element staging row
+    __device__ static __forceinline__ int swz(int c, int r) { return c ^ (r & 7); }
+    __device__ static __forceinline__ uint4 pack(const float* v) {
+        return make_uint4(__float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]),
+                          __float_as_uint(v[3]));
+    }
+    __device__ static __forceinline__ float cvt(float x) { return x; }
+};
+template <> struct OutTraits<__nv_bfloat16> {
+    static constexpr int EPC = 8;
+    static constexpr int CH = 4;
+    __device__ static __forceinline__ int swz(int c, int r) { return c ^ ((r >> 1) & 3); }
+    __device__ static __forceinline__ uint32_t pk(float a, float b) {
+        __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+        return *reinterpret_cast<uint32_t*>(&t);
+    }
+    __device__ static __forceinline__ uint4 pack(const float* v) {
+        return make_uint4(pk(v[0], v[1]), pk(v[2], v[3]), pk(v[4], v[5]), pk(v[6], v[7]));
+    }
+    __device__ static __forceinline__ __nv_bfloat16 cvt(float x) { return __float2bfloat16_rn(x); }
+};
+
+__device__ __forceinline__ void st_stream_16(void* p, uint4 v) {
+    asm volatile("st.global.cs.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y),
+                 "r"(v.z), "r"(v.w)
+                 : "memory");
+}
+
+// One warp writes a [32 rows][32 elements] register block (lane = row) to global
+// memory through its private swizzled staging buffer so that global stores are
+// 16-byte vectors over contiguous segments.  The 32 elements of a row are
+// 32/S segments of S elements: segment s goes to level row (yl0 + s), columns
+// [xl0, xl0 + S).  Rows >= rows_valid and pixels outside (hl, wl) are skipped.
+template <typename OutT, int S>
+__device__ __forceinline__ void staged_store(uint8_t* stg, const float* v, int lane, OutT* lvl,
+                                             size_t img_elems, size_t row0, int rows_valid,
+                                             int yl0, int xl0, int hl, int wl, bool vec) {
+    using TR = OutTraits<OutT>;
+    constexpr int EPC = TR::EPC, CH = TR::CH;
+    uint4* s4 = reinterpret_cast<uint4*>(stg);
+#pragma unroll
+    for (int c = 0; c < CH; ++c) s4[lane * CH + TR::swz(c, lane)] = TR::pack(v + c * EPC);
+    __syncwarp();
+    if (vec) {
+#pragma unroll
+        for (int it = 0; it < CH; ++it) {
+            const int g = it * 32 + lane;
+            const int r = g / CH, c = g % CH;
+            const uint4 val = s4[r * CH + TR::swz(c, r)];
+            const int e0 = c * EPC;
+            const int y = yl0 + e0 / S, x = xl0 + e0 % S;
+            if (r < rows_valid && y < hl && x < wl)
+                st_stream_16(lvl + (row0 + r) * img_elems + static_cast<size_t>(y) * wl + x, val);
+        }
+    } else {
+        const OutT* se = reinterpret_cast<const OutT*>(stg);
+        const int c = lane / EPC, e = lane % EPC;
+        const int y = yl0 + lane / S, x = xl0 + lane % S;
+        const bool ok = (y < hl) && (x < wl);
+        for (int r = 0; r < rows_valid; ++r) {
+            const OutT val = se[(r * CH + TR::swz(c, r)) * EPC + e];
+            if (ok) lvl[(row0 + r) * img_elems + static_cast<size_t>(y) * wl + x] = val;
+        }
+    }
+    __syncwarp();
+}
+
+template <int TILE_Y, int TILE_X, typename OutT>
+__global__ void __launch_bounds__(BLD_THREADS, 1)
+corr_build_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
+                  const BuildParams p) {
+    static_assert(TILE_Y * TILE_X == BLD_BLOCK_N, "tile must hold 256 fmap2 pixels");
+    static_assert(TILE_Y % 8 == 0 && TILE_X % 16 == 0, "sub-tiles are 8 x 16");
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>(
+        (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    const uint32_t s_b = ptx::smem_u32(smem + BLD_SMEM_B);
+    const uint32_t s_a = ptx::smem_u32(smem + BLD_SMEM_A);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + BLD_SMEM_BAR);
+    const uint32_t bar0 = ptx::smem_u32(bars);
+    // barrier indices
+    constexpr int A_FULL = 0, A_EMPTY = 4, B_FULL = 8, B_EMPTY = 9, T_FULL = 10, T_EMPTY = 12;
+    auto bar = [&](int i) { return bar0 + 8u * i; };
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(bars + 14);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tensormap(&tm_a);
+        ptx::prefetch_tensormap(&tm_b);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < BLD_A_STAGES; ++i) {
+            ptx::mbar_init(bar(A_FULL + i), 1);
+            ptx::mbar_init(bar(A_EMPTY + i), 1);
+        }
+        ptx::mbar_init(bar(B_FULL), 1);
+        ptx::mbar_init(bar(B_EMPTY), 1);
+        for (int i = 0; i < 2; ++i) {
+            ptx::mbar_init(bar(T_FULL + i), 1);
+            ptx::mbar_init(bar(T_EMPTY + i), BLD_EPI_WARPS);
+        }
+        ptx::fence_mbar_init();
+    }
+    if (warp == 2) {
+        ptx::tmem_alloc(ptx::smem_u32(const_cast<uint32_t*>(tmem_slot)), 512);
+        ptx::tmem_relinquish();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    // contiguous share of the flat tile index (batch, n-tile, m-block), m-block fastest
+    const long long t_begin = p.total_tiles * blockIdx.x / gridDim.x;
+    const long long t_end = p.total_tiles * (blockIdx.x + 1) / gridDim.x;
+    const int ntiles = p.nty * p.ntx;
+    const int kc_n = p.kc;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            uint32_t a_it = 0, b_it = 0;
+            for (long long t = t_begin; t < t_end; ++t) {
+                const int mb = static_cast<int>(t % p.m_blks);
+                const long long nb = t / p.m_blks;
+                const int nt = static_cast<int>(nb % ntiles);
+                const int b = static_cast<int>(nb / ntiles);
+                if (t == t_begin || mb == 0) {
+                    // new stationary fmap2 tile: wait until the MMAs reading the old one retired
+                    ptx::mbar_wait(bar(B_EMPTY), (b_it & 1) ^ 1);
+                    ptx::mbar_arrive_expect_tx(bar(B_FULL), kc_n * BLD_B_SLAB_BYTES);
+                    const int y0 = (nt / p.ntx) * TILE_Y, x0 = (nt % p.ntx) * TILE_X;
+                    for (int kc = 0; kc < kc_n; ++kc)
+                        ptx::tma_load_4d(s_b + kc * BLD_B_SLAB_BYTES, &tm_b, bar(B_FULL),
+                                         kc * BLD_BLOCK_K, x0, y0, b);
+                    ++b_it;
+                }
+                for (int kc = 0; kc < kc_n; ++kc, ++a_it) {
+                    const uint32_t st = a_it % BLD_A_STAGES, ph = (a_it / BLD_A_STAGES) & 1;
+                    ptx::mbar_wait(bar(A_EMPTY + st), ph ^ 1);
+                    ptx::mbar_arrive_expect_tx(bar(A_FULL + st), BLD_A_STAGE_BYTES);
+                    ptx::tma_load_3d(s_a + st * BLD_A_STAGE_BYTES, &tm_a, bar(A_FULL + st),
+                                     kc * BLD_BLOCK_K, mb * BLD_BLOCK_M, b);
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            constexpr uint32_t idesc = ptx::umma_idesc(BLD_BLOCK_M, BLD_BLOCK_N, 1 /*bf16*/);
+            uint32_t a_it = 0, b_it = 0, tile_it = 0;
+            for (long long t = t_begin; t < t_end; ++t, ++tile_it) {
+                const int mb = static_cast<int>(t % p.m_blks);
+                if (t == t_begin || mb == 0) {
+                    ptx::mbar_wait(bar(B_FULL), b_it & 1);
+                    ++b_it;
+                }
+                const uint32_t acc = tile_it & 1, acc_ph = (tile_it >> 1) & 1;
+                ptx::mbar_wait(bar(T_EMPTY + acc), acc_ph ^ 1);
+                ptx::tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * BLD_BLOCK_N;
+                for (int kc = 0; kc < kc_n; ++kc, ++a_it) {
+                    const uint32_t st = a_it % BLD_A_STAGES, ph = (a_it / BLD_A_STAGES) & 1;
+                    ptx::mbar_wait(bar(A_FULL + st), ph);
+                    ptx::tc_fence_after();
+                    const uint32_t a_addr = s_a + st * BLD_A_STAGE_BYTES;
+                    const uint32_t b_addr = s_b + kc * BLD_B_SLAB_BYTES;
+#pragma unroll
+                    for (int k = 0; k < BLD_BLOCK_K / BLD_UMMA_K; ++k) {
+                        ptx::umma_bf16(d_tmem, ptx::umma_desc_k_sw128(a_addr + k * BLD_UMMA_K * 2),
+                                       ptx::umma_desc_k_sw128(b_addr + k * BLD_UMMA_K * 2), idesc,
+                                       (kc | k) != 0 ? 1u : 0u);
+                    }
+                    ptx::umma_commit(bar(A_EMPTY + st));  // frees the ring slot when the MMAs retire
+                }
+                ptx::umma_commit(bar(T_FULL + acc));      // accumulator ready for the epilogue
+                const bool last_of_b = (t + 1 == t_end) || (mb + 1 == p.m_blks);
+                if (last_of_b) ptx::umma_commit(bar(B_EMPTY));
+            }
+        }
+        __syncwarp();
+    } else if (warp >= 4) {
+        // ===================== epilogue =====================
+        using TR = OutTraits<OutT>;
+        const int e = warp - 4;
+        const int q = e & 3;          // TMEM lane quarter this warp may read (warp_id % 4)
+        const int sub = e >> 2;       // which 8x16 half of the tile
+        constexpr int SUBS_X = TILE_X / 16;
+        const int sy = (sub / SUBS_X) * 8, sx = (sub % SUBS_X) * 16;
+        uint8_t* stg = smem + BLD_SMEM_STG + e * BLD_STG_BYTES;
+        const float scale = p.scale;
+        const int L = p.num_levels;
+        OutT* const l0 = static_cast<OutT*>(p.lvl[0]);
+        OutT* const l1 = static_cast<OutT*>(p.lvl[1]);
+        OutT* const l2 = static_cast<OutT*>(p.lvl[2]);
+        OutT* const l3 = static_cast<OutT*>(p.lvl[3]);
+        const bool vec0 = (p.wl[0] % TR::EPC) == 0;
+        const bool vec1 = (L > 1) && (p.wl[1] % TR::EPC) == 0;
+        const bool vec2 = (L > 2) && (p.wl[2] % 4) == 0;
+        const bool vec3 = (L > 3) && (p.wl[3] % 2) == 0;
+        const size_t img0 = static_cast<size_t>(p.hl[0]) * p.wl[0];
+        const size_t img1 = static_cast<size_t>(p.hl[1]) * p.wl[1];
+        const size_t img2 = static_cast<size_t>(p.hl[2]) * p.wl[2];
+        const size_t img3 = static_cast<size_t>(p.hl[3]) * p.wl[3];
+
+        uint32_t tile_it = 0;
+        for (long long t = t_begin; t < t_end; ++t, ++tile_it) {
+            const int mb = static_cast<int>(t % p.m_blks);
+            const long long nb = t / p.m_blks;
+            const int nt = static_cast<int>(nb % ntiles);
+            const int b = static_cast<int>(nb / ntiles);
+            const int Y0 = (nt / p.ntx) * TILE_Y + sy;  // level-0 origin of this warp's 8x16 patch
+            const int X0 = (nt % p.ntx) * TILE_X + sx;
+            const int m0 = mb * BLD_BLOCK_M + q * 32;   // first query pixel of this warp
+            int rows_valid = p.N - m0;
+            rows_valid = rows_valid < 0 ? 0 : (rows_valid > 32 ? 32 : rows_valid);
+            const size_t row0 = static_cast<size_t>(b) * p.N + m0;
+
+            const uint32_t acc = tile_it & 1, acc_ph = (tile_it >> 1) & 1;
+            ptx::mbar_wait(bar(T_FULL + acc), acc_ph);
+            ptx::tc_fence_after();
+            const uint32_t taddr =
+                tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BLD_BLOCK_N;
+
+            float p1[32];  // level 1 of this patch: 4 rows x 8
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float v[32];  // level-0 rows 2j, 2j+1 of the patch, 16 columns each
+                ptx::tmem_ld_x16(taddr + (sy + 2 * j) * TILE_X + sx, v);
+                ptx::tmem_ld_x16(taddr + (sy + 2 * j + 1) * TILE_X + sx, v + 16);
+                ptx::tmem_ld_wait();
+                if (j == 3) {
+                    // every TMEM read of this tile is done: hand the accumulator back early
+                    ptx::tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) ptx::mbar_arrive(bar(T_EMPTY + acc));
+                }
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] *= scale;
+#pragma unroll
+                for (int x = 0; x < 8; ++x)
+                    p1[j * 8 + x] =
+                        (v[2 * x] + v[2 * x + 1] + v[16 + 2 * x] + v[16 + 2 * x + 1]) * 0.25f;
+                staged_store<OutT, 16>(stg, v, lane, l0, img0, row0, rows_valid, Y0 + 2 * j, X0,
+                                       p.hl[0], p.wl[0], vec0);
+            }
+            if (L > 1)
+                staged_store<OutT, 8>(stg, p1, lane, l1, img1, row0, rows_valid, Y0 >> 1, X0 >> 1,
+                                      p.hl[1], p.wl[1], vec1);
+            if (L > 2) {
+                float p2[8];  // 2 rows x 4
+#pragma unroll
+                for (int y = 0; y < 2; ++y)
+#pragma unroll
+                    for (int x = 0; x < 4; ++x)
+                        p2[y * 4 + x] = (p1[(2 * y) * 8 + 2 * x] + p1[(2 * y) * 8 + 2 * x + 1] +
+                                         p1[(2 * y + 1) * 8 + 2 * x] + p1[(2 * y + 1) * 8 + 2 * x + 1]) *
+                                        0.25f;
+                const bool row_ok = lane < rows_valid;
+                const int y2 = Y0 >> 2, x2 = X0 >> 2;
+                if (row_ok) {
+                    OutT* img = l2 + (row0 + lane) * img2;
+#pragma unroll
+                    for (int y = 0; y < 2; ++y) {
+                        if (y2 + y >= p.hl[2]) continue;
+                        OutT* dst = img + static_cast<size_t>(y2 + y) * p.wl[2] + x2;
+                        if (vec2 && x2 + 3 < p.wl[2]) {
+                            if constexpr (sizeof(OutT) == 4) {
+                                *reinterpret_cast<float4*>(dst) = make_float4(
+                                    p2[y * 4], p2[y * 4 + 1], p2[y * 4 + 2], p2[y * 4 + 3]);
+                            } else {
+                                *reinterpret_cast<uint2*>(dst) =
+                                    make_uint2(OutTraits<__nv_bfloat16>::pk(p2[y * 4], p2[y * 4 + 1]),
+                                               OutTraits<__nv_bfloat16>::pk(p2[y * 4 + 2], p2[y * 4 + 3]));
+                            }
+                        } else {
+#pragma unroll
+                            for (int x = 0; x < 4; ++x)
+                                if (x2 + x < p.wl[2]) dst[x] = TR::cvt(p2[y * 4 + x]);
+                        }
+                    }
+                }
+                if (L > 3) {
+                    const float p3a = (p2[0] + p2[1] + p2[4] + p2[5]) * 0.25f;
+                    const float p3b = (p2[2] + p2[3] + p2[6] + p2[7]) * 0.25f;
+                    const int y3 = Y0 >> 3, x3 = X0 >> 3;
+                    if (row_ok && y3 < p.hl[3]) {
+                        OutT* dst = l3 + (row0 + lane) * img3 + static_cast<size_t>(y3) * p.wl[3] + x3;
+                        if (vec3 && x3 + 1 < p.wl[3]) {
+                            if constexpr (sizeof(OutT) == 4) {
+                                *reinterpret_cast<float2*>(dst) = make_float2(p3a, p3b);
+                            } else {
+                                *reinterpret_cast<uint32_t*>(dst) = OutTraits<__nv_bfloat16>::pk(p3a, p3b);
+                            }
+                        } else {
+                            if (x3 < p.wl[3]) dst[0] = TR::cvt(p3a);
+                            if (x3 + 1 < p.wl[3]) dst[1] = TR::cvt(p3b);
+                        }
+                    }
+                }
+            }
+        }
+    }
+
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 2) ptx::tmem_dealloc(tmem_base, 512);
+}
+
+}  // namespace rdvc

@@ -1,0 +1,400 @@
+// rdvc_corr_abi.cu -- the C ABI of librdvc_corr.so (see include/rdvc_corr.h).
+// Argument checking, pyramid layout arithmetic, TMA descriptor encoding and the
+// kernel launches.  No torch, no C++ types across the boundary, no CPU fallback.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+
+#include "../../include/rdvc_corr.h"
+#include "corr_build_sm100.cuh"
+#include "corr_lookup.cuh"
+#include "corr_pack.cuh"
+
+namespace {
+
+thread_local char g_err[512] = "";
+thread_local unsigned long long g_launches = 0;
+std::atomic<int> g_opt_lookup{0};
+std::atomic<int> g_opt_tile{0};
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+    snprintf(g_err, sizeof(g_err), "%s: %s (%s)", what, cudaGetErrorName(e), cudaGetErrorString(e));
+    return static_cast<int>(e);
+}
+
+size_t elem_size(int dt) {
+    switch (dt) {
+        case RDVC_DT_F32: return 4;
+        case RDVC_DT_BF16: return 2;
+        case RDVC_DT_F16: return 2;
+        default: return 0;
+    }
+}
+
+size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+size_t level_bytes(int B, int h, int w, int level, size_t es) {
+    const size_t N = static_cast<size_t>(h) * w;
+    return static_cast<size_t>(B) * N * (h >> level) * (w >> level) * es;
+}
+
+int check_geometry(int B, int h, int w, int num_levels) {
+    if (B <= 0 || h <= 0 || w <= 0) return fail(RDVC_E_SHAPE, "non-positive dimension B=%d h=%d w=%d", B, h, w);
+    if (num_levels < 1 || num_levels > rdvc::BLD_MAX_LEVELS)
+        return fail(RDVC_E_UNSUPPORTED, "num_levels=%d not in [1, %d]", num_levels, rdvc::BLD_MAX_LEVELS);
+    const int min_size = 2 * (1 << (num_levels - 1));  // TV:raft.py:376
+    if (h < min_size || w < min_size)
+        return fail(RDVC_E_TOO_SMALL,
+                    "Feature maps are too small to be down-sampled by the correlation pyramid. "
+                    "H and W of feature maps should be at least %d; got: (%d, %d)", min_size, h, w);
+    return RDVC_OK;
+}
+
+// ---- driver entry point for TMA descriptors (no -lcuda link dependency) ----
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled_fn() {
+    static std::once_flag once;
+    static EncodeTiledFn fn = nullptr;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) ==
+                cudaSuccess && qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    });
+    return fn;
+}
+
+// bf16 tensor, innermost dimension K (= D channels), 128-byte swizzle, zero OOB fill.
+int make_tmap(CUtensorMap* m, void* base, int rank, const cuuint64_t* dims,
+              const cuuint64_t* strides_bytes, const cuuint32_t* box) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn) return fail(RDVC_E_DRIVER, "cuTensorMapEncodeTiled not available from the driver");
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, base, dims, strides_bytes, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(RDVC_E_DRIVER, "cuTensorMapEncodeTiled failed: CUresult %d", (int)r);
+    return RDVC_OK;
+}
+
+int sm_count() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+
+template <int TY, int TX, typename OutT>
+int launch_build(const CUtensorMap& ta, const CUtensorMap& tb, const rdvc::BuildParams& p,
+                 cudaStream_t st) {
+    auto kern = rdvc::corr_build_kernel<TY, TX, OutT>;
+    static bool attr_set = false;  // per instantiation
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             rdvc::BLD_SMEM_LAUNCH);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(build, max dynamic smem)");
+        attr_set = true;
+    }
+    long long grid = sm_count();
+    if (grid > p.total_tiles) grid = p.total_tiles;
+    kern<<<static_cast<unsigned>(grid), rdvc::BLD_THREADS, rdvc::BLD_SMEM_LAUNCH, st>>>(ta, tb, p);
+    ++g_launches;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "corr_build_kernel launch");
+    return RDVC_OK;
+}
+
+template <typename T>
+int launch_pack(const void* f1, const void* f2, void* d1, void* d2, int B, int D, int N,
+                cudaStream_t st) {
+    auto kern = rdvc::corr_pack_kernel<T>;
+    const size_t smem = static_cast<size_t>(D) * 33 * sizeof(float);
+    dim3 grid((N + rdvc::PACK_TN - 1) / rdvc::PACK_TN, B, 2);
+    kern<<<grid, rdvc::PACK_THREADS, smem, st>>>(
+        static_cast<const T*>(f1), static_cast<const T*>(f2), static_cast<__nv_bfloat16*>(d1),
+        static_cast<__nv_bfloat16*>(d2), D, N);
+    ++g_launches;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "corr_pack_kernel launch");
+    return RDVC_OK;
+}
+
+template <int R, typename VolT, bool VEC>
+int launch_lookup(const rdvc::LookupParams& p, cudaStream_t st) {
+    const unsigned grid = static_cast<unsigned>((p.total + 31) / 32);
+    rdvc::corr_lookup_kernel<R, VolT, VEC><<<grid, 32 * p.num_levels, 0, st>>>(p);
+    ++g_launches;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "corr_lookup_kernel launch");
+    return RDVC_OK;
+}
+
+template <typename VolT, bool VEC>
+int dispatch_lookup_radius(int radius, const rdvc::LookupParams& p, cudaStream_t st) {
+    switch (radius) {
+        case 1: return launch_lookup<1, VolT, VEC>(p, st);
+        case 2: return launch_lookup<2, VolT, VEC>(p, st);
+        case 3: return launch_lookup<3, VolT, VEC>(p, st);
+        case 4: return launch_lookup<4, VolT, VEC>(p, st);
+        default: return fail(RDVC_E_UNSUPPORTED, "radius=%d not in [1, 4]", radius);
+    }
+}
+
+struct HostArena {  // scratch owned by rdvc_corr_pair_host, one per thread
+    void* dev = nullptr;
+    size_t bytes = 0;
+    cudaStream_t compute = nullptr, copy = nullptr;
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+};
+thread_local HostArena g_arena;
+
+}  // namespace
+
+extern "C" {
+
+int rdvc_corr_version(void) { return RDVC_CORR_VERSION; }
+const char* rdvc_corr_last_error(void) { return g_err; }
+unsigned long long rdvc_corr_launch_count(void) { return g_launches; }
+
+int rdvc_corr_set_option(int key, int value) {
+    if (key == 0 && value >= 0 && value <= 2) { g_opt_lookup = value; return RDVC_OK; }
+    if (key == 1 && value >= 0 && value <= 2) { g_opt_tile = value; return RDVC_OK; }
+    return fail(RDVC_E_UNSUPPORTED, "unknown option key=%d value=%d", key, value);
+}
+
+size_t rdvc_corr_level_offset_bytes(int B, int h, int w, int level, int vol_dtype) {
+    const size_t es = elem_size(vol_dtype);
+    size_t off = 0;
+    for (int l = 0; l < level; ++l) off += align_up(level_bytes(B, h, w, l, es), 256);
+    return off;
+}
+
+size_t rdvc_corr_pyramid_bytes(int B, int h, int w, int num_levels, int vol_dtype) {
+    // every level padded to 256 bytes, so 16-byte gathers at a level's tail stay inside
+    return rdvc_corr_level_offset_bytes(B, h, w, num_levels, vol_dtype);
+}
+
+size_t rdvc_corr_workspace_bytes(int B, int D, int h, int w) {
+    return 2 * align_up(static_cast<size_t>(B) * h * w * D * 2, 256);
+}
+
+int rdvc_corr_build(const void* fmap1, const void* fmap2, int B, int D, int h, int w, int in_dtype,
+                    void* pyramid, int vol_dtype, int num_levels, void* workspace,
+                    size_t workspace_bytes, void* stream) {
+    if (!fmap1 || !fmap2 || !pyramid || !workspace) return fail(RDVC_E_NULL, "null pointer argument");
+    int rc = check_geometry(B, h, w, num_levels);
+    if (rc) return rc;
+    if (D <= 0) return fail(RDVC_E_SHAPE, "non-positive channel count D=%d", D);
+    if (D % 64 != 0 || D > 64 * rdvc::BLD_MAX_KC)
+        return fail(RDVC_E_UNSUPPORTED, "D=%d must be a multiple of 64 and <= %d", D, 64 * rdvc::BLD_MAX_KC);
+    if (in_dtype != RDVC_DT_F32 && in_dtype != RDVC_DT_BF16 && in_dtype != RDVC_DT_F16)
+        return fail(RDVC_E_DTYPE, "unsupported in_dtype=%d", in_dtype);
+    if (vol_dtype != RDVC_DT_F32 && vol_dtype != RDVC_DT_BF16)
+        return fail(RDVC_E_DTYPE, "unsupported vol_dtype=%d", vol_dtype);
+    if (workspace_bytes < rdvc_corr_workspace_bytes(B, D, h, w))
+        return fail(RDVC_E_WORKSPACE, "workspace %zu < required %zu", workspace_bytes,
+                    rdvc_corr_workspace_bytes(B, D, h, w));
+    if ((reinterpret_cast<uintptr_t>(pyramid) & 255) || (reinterpret_cast<uintptr_t>(workspace) & 255))
+        return fail(RDVC_E_ALIGN, "pyramid and workspace must be 256-byte aligned");
+    if (static_cast<long long>(h) * w > (1LL << 30) / 4)
+        return fail(RDVC_E_UNSUPPORTED, "h*w too large for 32-bit pixel indices");
+
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int N = h * w;
+    uint8_t* ws = static_cast<uint8_t*>(workspace);
+    void* a_km = ws;  // fmap1 as (B, N, D) bf16
+    void* b_km = ws + align_up(static_cast<size_t>(B) * N * D * 2, 256);
+
+    // 1. repack to K-major bf16
+    if (in_dtype == RDVC_DT_F32) rc = launch_pack<float>(fmap1, fmap2, a_km, b_km, B, D, N, st);
+    else if (in_dtype == RDVC_DT_BF16) rc = launch_pack<__nv_bfloat16>(fmap1, fmap2, a_km, b_km, B, D, N, st);
+    else rc = launch_pack<__half>(fmap1, fmap2, a_km, b_km, B, D, N, st);
+    if (rc) return rc;
+
+    // 2. tile shape: 16x16 fmap2 pixels unless 8x32 wastes less padding
+    int tile = g_opt_tile.load();
+    auto padded = [&](int ty, int tx) {
+        return static_cast<long long>((h + ty - 1) / ty) * ty * ((w + tx - 1) / tx) * tx;
+    };
+    if (tile == 0) tile = (padded(8, 32) < padded(16, 16)) ? 2 : 1;
+    const int TY = (tile == 1) ? 16 : 8, TX = (tile == 1) ? 16 : 32;
+
+    // 3. TMA descriptors over the repacked maps
+    CUtensorMap ta, tb;
+    {
+        cuuint64_t dims[3] = {(cuuint64_t)D, (cuuint64_t)N, (cuuint64_t)B};
+        cuuint64_t str[2] = {(cuuint64_t)D * 2, (cuuint64_t)N * D * 2};
+        cuuint32_t box[3] = {rdvc::BLD_BLOCK_K, rdvc::BLD_BLOCK_M, 1};
+        rc = make_tmap(&ta, a_km, 3, dims, str, box);
+        if (rc) return rc;
+    }
+    {
+        cuuint64_t dims[4] = {(cuuint64_t)D, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)B};
+        cuuint64_t str[3] = {(cuuint64_t)D * 2, (cuuint64_t)w * D * 2, (cuuint64_t)N * D * 2};
+        cuuint32_t box[4] = {rdvc::BLD_BLOCK_K, (cuuint32_t)TX, (cuuint32_t)TY, 1};
+        rc = make_tmap(&tb, b_km, 4, dims, str, box);
+        if (rc) return rc;
+    }
+
+    rdvc::BuildParams p;
+    memset(&p, 0, sizeof(p));
+    for (int l = 0; l < num_levels; ++l) {
+        p.lvl[l] = static_cast<uint8_t*>(pyramid) + rdvc_corr_level_offset_bytes(B, h, w, l, vol_dtype);
+        p.hl[l] = h >> l;
+        p.wl[l] = w >> l;
+    }
+    p.B = B; p.h = h; p.w = w; p.N = N;
+    p.num_levels = num_levels;
+    p.kc = D / 64;
+    p.m_blks = (N + rdvc::BLD_BLOCK_M - 1) / rdvc::BLD_BLOCK_M;
+    p.nty = (h + TY - 1) / TY;
+    p.ntx = (w + TX - 1) / TX;
+    p.total_tiles = static_cast<long long>(B) * p.nty * p.ntx * p.m_blks;
+    p.scale = static_cast<float>(1.0 / std::sqrt(static_cast<double>(D)));
+
+    if (vol_dtype == RDVC_DT_F32) {
+        return (tile == 1) ? launch_build<16, 16, float>(ta, tb, p, st)
+                           : launch_build<8, 32, float>(ta, tb, p, st);
+    }
+    return (tile == 1) ? launch_build<16, 16, __nv_bfloat16>(ta, tb, p, st)
+                       : launch_build<8, 32, __nv_bfloat16>(ta, tb, p, st);
+}
+
+int rdvc_corr_lookup(const void* pyramid, int vol_dtype, const float* coords, int B, int h, int w,
+                     int num_levels, int radius, float* out, void* stream) {
+    if (!pyramid || !coords || !out) return fail(RDVC_E_NULL, "null pointer argument");
+    int rc = check_geometry(B, h, w, num_levels);
+    if (rc) return rc;
+    if (vol_dtype != RDVC_DT_F32 && vol_dtype != RDVC_DT_BF16)
+        return fail(RDVC_E_DTYPE, "unsupported vol_dtype=%d", vol_dtype);
+    if (reinterpret_cast<uintptr_t>(pyramid) & 15)
+        return fail(RDVC_E_ALIGN, "pyramid must be 16-byte aligned");
+    rdvc::LookupParams p;
+    memset(&p, 0, sizeof(p));
+    for (int l = 0; l < num_levels; ++l) {
+        p.lvl[l] = static_cast<const uint8_t*>(pyramid) + rdvc_corr_level_offset_bytes(B, h, w, l, vol_dtype);
+        p.hl[l] = h >> l;
+        p.wl[l] = w >> l;
+    }
+    p.coords = coords;
+    p.out = out;
+    p.B = B;
+    p.N = h * w;
+    p.num_levels = num_levels;
+    p.total = static_cast<long long>(B) * p.N;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int variant = g_opt_lookup.load();
+    if (vol_dtype == RDVC_DT_F32) {
+        if (variant == 1) return dispatch_lookup_radius<float, false>(radius, p, st);
+        return dispatch_lookup_radius<float, true>(radius, p, st);
+    }
+    return dispatch_lookup_radius<__nv_bfloat16, false>(radius, p, st);
+}
+
+void rdvc_corr_release(void) {
+    HostArena& a = g_arena;
+    if (a.dev) cudaFree(a.dev);
+    if (a.compute) cudaStreamDestroy(a.compute);
+    if (a.copy) cudaStreamDestroy(a.copy);
+    for (auto& e : a.ev) if (e) cudaEventDestroy(e);
+    a = HostArena();
+}
+
+int rdvc_corr_pair_host(const float* fmap1_host, const float* fmap2_host, const float* coords_host,
+                        float* out_host, int B, int D, int h, int w, int num_levels, int radius,
+                        int iters, int vol_dtype) {
+    if (!fmap1_host || !fmap2_host || !coords_host || !out_host) return fail(RDVC_E_NULL, "null pointer argument");
+    int rc = check_geometry(B, h, w, num_levels);
+    if (rc) return rc;
+    if (iters <= 0 || D <= 0) return fail(RDVC_E_SHAPE, "iters=%d D=%d must be positive", iters, D);
+    if (radius < 1 || radius > 4) return fail(RDVC_E_UNSUPPORTED, "radius=%d not in [1, 4]", radius);
+    const size_t N = static_cast<size_t>(h) * w;
+    const size_t S = 2 * radius + 1;
+    const size_t fmap_bytes = align_up(static_cast<size_t>(B) * D * N * 4, 256);
+    const size_t coords_bytes = align_up(static_cast<size_t>(B) * 2 * N * 4, 256);
+    const size_t out_elems = static_cast<size_t>(B) * num_levels * S * S * N;
+    const size_t out_bytes = align_up(out_elems * 4, 256);
+    const size_t pyr_bytes = rdvc_corr_pyramid_bytes(B, h, w, num_levels, vol_dtype);
+    const size_t ws_bytes = rdvc_corr_workspace_bytes(B, D, h, w);
+    const size_t need = 2 * fmap_bytes + iters * coords_bytes + 2 * out_bytes + pyr_bytes + ws_bytes;
+
+    HostArena& a = g_arena;
+    cudaError_t e;
+    if (!a.compute) {
+        if ((e = cudaStreamCreateWithFlags(&a.compute, cudaStreamNonBlocking)) != cudaSuccess) return cuda_fail(e, "stream create");
+        if ((e = cudaStreamCreateWithFlags(&a.copy, cudaStreamNonBlocking)) != cudaSuccess) return cuda_fail(e, "stream create");
+        for (auto& ev : a.ev)
+            if ((e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess) return cuda_fail(e, "event create");
+    }
+    if (a.bytes < need) {
+        if (a.dev) cudaFree(a.dev);
+        a.dev = nullptr; a.bytes = 0;
+        if ((e = cudaMalloc(&a.dev, need)) != cudaSuccess) return cuda_fail(e, "cudaMalloc(scratch arena)");
+        a.bytes = need;
+    }
+    uint8_t* base = static_cast<uint8_t*>(a.dev);
+    uint8_t* d_f1 = base;
+    uint8_t* d_f2 = d_f1 + fmap_bytes;
+    uint8_t* d_co = d_f2 + fmap_bytes;
+    uint8_t* d_out[2] = {d_co + iters * coords_bytes, d_co + iters * coords_bytes + out_bytes};
+    uint8_t* d_pyr = d_out[1] + out_bytes;
+    uint8_t* d_ws = d_pyr + pyr_bytes;
+
+    // inputs in (one copy each), then build
+    const size_t fmap_raw = static_cast<size_t>(B) * D * N * 4;
+    const size_t coords_raw = static_cast<size_t>(B) * 2 * N * 4;
+    if ((e = cudaMemcpyAsync(d_f1, fmap1_host, fmap_raw, cudaMemcpyHostToDevice, a.compute)) != cudaSuccess) return cuda_fail(e, "H2D fmap1");
+    if ((e = cudaMemcpyAsync(d_f2, fmap2_host, fmap_raw, cudaMemcpyHostToDevice, a.compute)) != cudaSuccess) return cuda_fail(e, "H2D fmap2");
+    for (int it = 0; it < iters; ++it)
+        if ((e = cudaMemcpyAsync(d_co + it * coords_bytes, coords_host + it * (coords_raw / 4), coords_raw,
+                                 cudaMemcpyHostToDevice, a.compute)) != cudaSuccess) return cuda_fail(e, "H2D coords");
+    rc = rdvc_corr_build(d_f1, d_f2, B, D, h, w, RDVC_DT_F32, d_pyr, vol_dtype, num_levels, d_ws, ws_bytes, a.compute);
+    if (rc) return rc;
+    // lookups ping-pong between two device buffers; the copy stream drains them
+    bool used[2] = {false, false};
+    for (int it = 0; it < iters; ++it) {
+        const int s = it & 1;
+        if (used[s]) {  // the D2H that last read this buffer must have finished
+            if ((e = cudaStreamWaitEvent(a.compute, a.ev[s], 0)) != cudaSuccess) return cuda_fail(e, "wait event");
+        }
+        rc = rdvc_corr_lookup(d_pyr, vol_dtype, reinterpret_cast<const float*>(d_co + it * coords_bytes), B, h, w,
+                              num_levels, radius, reinterpret_cast<float*>(d_out[s]), a.compute);
+        if (rc) return rc;
+        cudaEvent_t done;  // lookup finished -> copy stream may read
+        if ((e = cudaEventCreateWithFlags(&done, cudaEventDisableTiming)) != cudaSuccess) return cuda_fail(e, "event create");
+        cudaEventRecord(done, a.compute);
+        cudaStreamWaitEvent(a.copy, done, 0);
+        cudaEventDestroy(done);
+        if ((e = cudaMemcpyAsync(out_host + it * out_elems, d_out[s], out_elems * 4, cudaMemcpyDeviceToHost, a.copy)) != cudaSuccess) return cuda_fail(e, "D2H out");
+        cudaEventRecord(a.ev[s], a.copy);
+        used[s] = true;
+    }
+    if ((e = cudaStreamSynchronize(a.compute)) != cudaSuccess) return cuda_fail(e, "sync compute");
+    if ((e = cudaStreamSynchronize(a.copy)) != cudaSuccess) return cuda_fail(e, "sync copy");
+    return RDVC_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,32 @@
+"""Shared helpers for the parity tests (test infrastructure)."""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+
+def rel_max(a, b) -> float:
+    """max|a-b| / max|b|  -- the max-norm relative error SURVEY.md 8(c) states tolerances in."""
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    d = np.abs(a - b).max() if a.size else 0.0
+    m = np.abs(b).max() if b.size else 1.0
+    return float(d / (m if m > 0 else 1.0))
+
+
+def pyramid_from_levels(rc, levels, B, h, w, volume_dtype=torch.float32, device="cuda"):
+    """Pack oracle level tensors [(B*N, h_l, w_l)] into a CorrPyramid in the library's layout."""
+    lib = rc._cabi.load()
+    vd = {torch.float32: rc.RDVC_DT_F32, torch.bfloat16: rc.RDVC_DT_BF16}[volume_dtype]
+    L = len(levels)
+    nbytes = lib.rdvc_corr_pyramid_bytes(B, h, w, L, vd)
+    buf = torch.zeros(nbytes, dtype=torch.uint8, device=device)
+    pyr = rc.CorrPyramid(B, h, w, L, volume_dtype, buf)
+    for l, lv in enumerate(levels):
+        t = torch.as_tensor(np.asarray(lv), dtype=torch.float32).to(device).to(volume_dtype)
+        pyr.level(l).copy_(t.reshape(pyr.level(l).shape))
+    return pyr
+
+
+def bf16_round(x: np.ndarray) -> np.ndarray:
+    return torch.from_numpy(np.ascontiguousarray(x)).to(torch.bfloat16).to(torch.float32).numpy()
