@@ -70,7 +70,7 @@ const char* rdvc_corr_last_error(void);
 /* vol_dtype: RDVC_DT_F32 or RDVC_DT_BF16 (storage type of the pyramid). */
 size_t rdvc_corr_pyramid_bytes(int B, int h, int w, int num_levels, int vol_dtype);
 size_t rdvc_corr_level_offset_bytes(int B, int h, int w, int level, int vol_dtype);
-/* scratch for the two K-major bf16 copies of the feature maps */
+/* scratch for the K-major bf16 copies of fmap1 and of fmap2 at every pyramid level */
 size_t rdvc_corr_workspace_bytes(int B, int D, int h, int w);
 
 /* ---- build: correlation volume + all pyramid levels, written once ------ *
@@ -112,7 +112,10 @@ void rdvc_corr_release(void);
 unsigned long long rdvc_corr_launch_count(void);
 /* Debug/tuning knobs; unknown keys return RDVC_E_UNSUPPORTED.
  *   key 0: lookup variant   (0 = auto, 1 = scalar loads, 2 = 128-bit loads)
- *   key 1: build tile shape (0 = auto, 1 = 16x16, 2 = 8x32 fmap2 pixels)      */
+ *   key 1: build tile shape (0 = auto, 1 = 16x16, 2 = 8x32 fmap2 pixels)
+ *   key 2: build m-range slices per fmap2 tile (0 = auto)
+ *   key 3: debug: bit mask of pyramid levels the build writes (default 15)
+ *   key 4: build mode (0 = auto, 1 = fused pooling epilogue, 2 = pooled-fmap2 rows) */
 int rdvc_corr_set_option(int key, int value);
 
 #ifdef __cplusplus

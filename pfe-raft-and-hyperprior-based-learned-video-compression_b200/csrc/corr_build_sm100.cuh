@@ -65,9 +65,12 @@ struct BuildParams {
     int num_levels;
     int kc;             // D / 64
     int m_blks;         // ceil(N / 128)
-    int nty, ntx;       // fmap2 tiles along y / x
-    long long total_tiles;
+    int nty, ntx;       // MODE_FUSED: fmap2 tiles along y / x
+    int ntiles;         // N-tiles per batch item (fused: nty * ntx; linear: sum over levels)
+    int tile_start[BLD_MAX_LEVELS];  // MODE_LINEAR: first N-tile of each level
+    int msplit;         // m-range slices per fmap2 tile (work item = tile x slice)
     float scale;        // 1 / sqrt(D)
+    int dbg_store_mask; // debug: bit l set = write level l (default 15)
 };
 
 // ---- output element traits -------------------------------------------------
@@ -102,49 +105,96 @@ __device__ __forceinline__ void st_stream_16(void* p, uint4 v) {
                  : "memory");
 }
 
+__device__ __forceinline__ void sts_16(uint32_t addr, uint4 v) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z),
+                 "r"(v.w)
+                 : "memory");
+}
+__device__ __forceinline__ uint4 lds_16(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                 : "r"(addr)
+                 : "memory");
+    return v;
+}
+template <typename OutT> __device__ __forceinline__ OutT lds_elem(uint32_t addr);
+template <> __device__ __forceinline__ float lds_elem<float>(uint32_t addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+    return v;
+}
+template <> __device__ __forceinline__ __nv_bfloat16 lds_elem<__nv_bfloat16>(uint32_t addr) {
+    uint16_t v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr) : "memory");
+    return __ushort_as_bfloat16(v);
+}
+
 // One warp writes a [32 rows][32 elements] register block (lane = row) to global
-// memory through its private swizzled staging buffer so that global stores are
-// 16-byte vectors over contiguous segments.  The 32 elements of a row are
-// 32/S segments of S elements: segment s goes to level row (yl0 + s), columns
-// [xl0, xl0 + S).  Rows >= rows_valid and pixels outside (hl, wl) are skipped.
+// memory through its private swizzled staging buffer (`stg`: 32-bit shared
+// address) so that global stores are 16-byte vectors over contiguous segments.
+// The 32 elements of a row are 32/S segments of S elements: segment s goes to
+// level row (yl0 + s), columns [xl0, xl0 + S).  `img0` points at the image of the
+// warp's first row; rows >= rows_valid and pixels outside (hl, wl) are skipped.
 template <typename OutT, int S>
-__device__ __forceinline__ void staged_store(uint8_t* stg, const float* v, int lane, OutT* lvl,
-                                             size_t img_elems, size_t row0, int rows_valid,
-                                             int yl0, int xl0, int hl, int wl, bool vec) {
+__device__ __forceinline__ void staged_store(uint32_t stg, const float* v, int lane, OutT* img0,
+                                             size_t img_elems, int rows_valid, int yl0, int xl0,
+                                             int hl, int wl, bool vec) {
     using TR = OutTraits<OutT>;
     constexpr int EPC = TR::EPC, CH = TR::CH;
-    uint4* s4 = reinterpret_cast<uint4*>(stg);
+    constexpr int RPI = 32 / CH;  // rows covered per read-back iteration
 #pragma unroll
-    for (int c = 0; c < CH; ++c) s4[lane * CH + TR::swz(c, lane)] = TR::pack(v + c * EPC);
+    for (int c = 0; c < CH; ++c)
+        sts_16(stg + (lane * CH + TR::swz(c, lane)) * 16, TR::pack(v + c * EPC));
     __syncwarp();
     if (vec) {
+        const int c = lane % CH, r0 = lane / CH;
+        const int e0 = c * EPC;
+        const int y = yl0 + e0 / S, x = xl0 + e0 % S;
+        const bool ok = (y < hl) && (x < wl);
+        OutT* dst = img0 + static_cast<size_t>(r0) * img_elems + static_cast<size_t>(y) * wl + x;
+        uint4 val[CH];
 #pragma unroll
         for (int it = 0; it < CH; ++it) {
-            const int g = it * 32 + lane;
-            const int r = g / CH, c = g % CH;
-            const uint4 val = s4[r * CH + TR::swz(c, r)];
-            const int e0 = c * EPC;
-            const int y = yl0 + e0 / S, x = xl0 + e0 % S;
-            if (r < rows_valid && y < hl && x < wl)
-                st_stream_16(lvl + (row0 + r) * img_elems + static_cast<size_t>(y) * wl + x, val);
+            const int r = it * RPI + r0;
+            val[it] = lds_16(stg + (r * CH + TR::swz(c, r)) * 16);
+        }
+#pragma unroll
+        for (int it = 0; it < CH; ++it) {
+            const int r = it * RPI + r0;
+            if (ok && r < rows_valid) st_stream_16(dst + static_cast<size_t>(it * RPI) * img_elems, val[it]);
         }
     } else {
-        const OutT* se = reinterpret_cast<const OutT*>(stg);
         const int c = lane / EPC, e = lane % EPC;
         const int y = yl0 + lane / S, x = xl0 + lane % S;
         const bool ok = (y < hl) && (x < wl);
+        OutT* dst = img0 + static_cast<size_t>(y) * wl + x;
         for (int r = 0; r < rows_valid; ++r) {
-            const OutT val = se[(r * CH + TR::swz(c, r)) * EPC + e];
-            if (ok) lvl[(row0 + r) * img_elems + static_cast<size_t>(y) * wl + x] = val;
+            const OutT val = lds_elem<OutT>(stg + ((r * CH + TR::swz(c, r)) * EPC + e) * sizeof(OutT));
+            if (ok) dst[static_cast<size_t>(r) * img_elems] = val;
         }
     }
     __syncwarp();
 }
 
-template <int TILE_Y, int TILE_X, typename OutT>
+// MODE_FUSED : an N-tile is a TILE_Y x TILE_X spatial block of fmap2 (4-D TMA box); the
+//              epilogue pools levels 1..3 in registers (one thread = one query pixel = one
+//              2-D patch) and writes every level.  Elegant, exact pooling of the fp32
+//              accumulators -- but a CTA then owns only 64/32/16/8-byte pieces of each
+//              output line and HBM punishes sub-line writes (measured: +1.3 ms at 1080p).
+// MODE_LINEAR: pooling is linear, so level l = fmap1^T . avgpool_l(fmap2) / sqrt(D) exactly
+//              (SURVEY.md 7.3).  The pack pass emits the pooled fmap2 levels as extra K-major
+//              rows; an N-tile is 256 CONSECUTIVE pixels of one level, so every thread's
+//              output row is 1 KB contiguous and every store is a full, aligned line.
+//              +33 % tensor work (0.43 ms at peak, still under the 0.87 ms HBM bound).
+constexpr int MODE_FUSED = 0;
+constexpr int MODE_LINEAR = 1;
+
+template <int MODE, int TILE_Y, int TILE_X, typename OutT>
 __global__ void __launch_bounds__(BLD_THREADS, 1)
-corr_build_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
-                  const BuildParams p) {
+corr_build_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b0,
+                  const __grid_constant__ CUtensorMap tm_b1, const __grid_constant__ CUtensorMap tm_b2,
+                  const __grid_constant__ CUtensorMap tm_b3, const BuildParams p) {
     static_assert(TILE_Y * TILE_X == BLD_BLOCK_N, "tile must hold 256 fmap2 pixels");
     static_assert(TILE_Y % 8 == 0 && TILE_X % 16 == 0, "sub-tiles are 8 x 16");
     extern __shared__ uint8_t smem_raw[];
@@ -164,7 +214,7 @@ corr_build_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
 
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tensormap(&tm_a);
-        ptx::prefetch_tensormap(&tm_b);
+        ptx::prefetch_tensormap(&tm_b0);
     }
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < BLD_A_STAGES; ++i) {
@@ -188,37 +238,52 @@ corr_build_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    // contiguous share of the flat tile index (batch, n-tile, m-block), m-block fastest
-    const long long t_begin = p.total_tiles * blockIdx.x / gridDim.x;
-    const long long t_end = p.total_tiles * (blockIdx.x + 1) / gridDim.x;
-    const int ntiles = p.nty * p.ntx;
+    // Work decomposition.  A work item is one stationary fmap2 tile (batch b, tile nt)
+    // times one slice of the m-blocks; items are dealt round-robin, slice-major, so the
+    // CTAs running at the same time sweep the SAME query rows: their stores land in one
+    // moving window of the volume (a few 2 MB pages) instead of 148 scattered ones
+    // (measured 2x), and they share the streamed fmap1 tiles in L2.
+    const int ntiles = p.ntiles;       // N-tiles per batch item
+    const int units = p.B * ntiles;
+    const int n_items = units * p.msplit;
     const int kc_n = p.kc;
 
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (lane == 0) {
             uint32_t a_it = 0, b_it = 0;
-            for (long long t = t_begin; t < t_end; ++t) {
-                const int mb = static_cast<int>(t % p.m_blks);
-                const long long nb = t / p.m_blks;
-                const int nt = static_cast<int>(nb % ntiles);
-                const int b = static_cast<int>(nb / ntiles);
-                if (t == t_begin || mb == 0) {
-                    // new stationary fmap2 tile: wait until the MMAs reading the old one retired
-                    ptx::mbar_wait(bar(B_EMPTY), (b_it & 1) ^ 1);
-                    ptx::mbar_arrive_expect_tx(bar(B_FULL), kc_n * BLD_B_SLAB_BYTES);
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+                const int u = item % units, sl = item / units;
+                const int b = u / ntiles, nt = u % ntiles;
+                const int mb0 = static_cast<int>(static_cast<long long>(sl) * p.m_blks / p.msplit);
+                const int mb1 = static_cast<int>(static_cast<long long>(sl + 1) * p.m_blks / p.msplit);
+                if (mb0 == mb1) continue;
+                // new stationary fmap2 tile: wait until the MMAs reading the old one retired
+                ptx::mbar_wait(bar(B_EMPTY), (b_it & 1) ^ 1);
+                ptx::mbar_arrive_expect_tx(bar(B_FULL), kc_n * BLD_B_SLAB_BYTES);
+                if constexpr (MODE == MODE_FUSED) {
                     const int y0 = (nt / p.ntx) * TILE_Y, x0 = (nt % p.ntx) * TILE_X;
                     for (int kc = 0; kc < kc_n; ++kc)
-                        ptx::tma_load_4d(s_b + kc * BLD_B_SLAB_BYTES, &tm_b, bar(B_FULL),
+                        ptx::tma_load_4d(s_b + kc * BLD_B_SLAB_BYTES, &tm_b0, bar(B_FULL),
                                          kc * BLD_BLOCK_K, x0, y0, b);
-                    ++b_it;
+                } else {
+                    int l = 0;
+                    while (l + 1 < p.num_levels && nt >= p.tile_start[l + 1]) ++l;
+                    const CUtensorMap* tm = (l == 0) ? &tm_b0 : (l == 1) ? &tm_b1 : (l == 2) ? &tm_b2 : &tm_b3;
+                    const int c0 = (nt - p.tile_start[l]) * BLD_BLOCK_N;
+                    for (int kc = 0; kc < kc_n; ++kc)
+                        ptx::tma_load_3d(s_b + kc * BLD_B_SLAB_BYTES, tm, bar(B_FULL),
+                                         kc * BLD_BLOCK_K, c0, b);
                 }
-                for (int kc = 0; kc < kc_n; ++kc, ++a_it) {
-                    const uint32_t st = a_it % BLD_A_STAGES, ph = (a_it / BLD_A_STAGES) & 1;
-                    ptx::mbar_wait(bar(A_EMPTY + st), ph ^ 1);
-                    ptx::mbar_arrive_expect_tx(bar(A_FULL + st), BLD_A_STAGE_BYTES);
-                    ptx::tma_load_3d(s_a + st * BLD_A_STAGE_BYTES, &tm_a, bar(A_FULL + st),
-                                     kc * BLD_BLOCK_K, mb * BLD_BLOCK_M, b);
+                ++b_it;
+                for (int mb = mb0; mb < mb1; ++mb) {
+                    for (int kc = 0; kc < kc_n; ++kc, ++a_it) {
+                        const uint32_t st = a_it % BLD_A_STAGES, ph = (a_it / BLD_A_STAGES) & 1;
+                        ptx::mbar_wait(bar(A_EMPTY + st), ph ^ 1);
+                        ptx::mbar_arrive_expect_tx(bar(A_FULL + st), BLD_A_STAGE_BYTES);
+                        ptx::tma_load_3d(s_a + st * BLD_A_STAGE_BYTES, &tm_a, bar(A_FULL + st),
+                                         kc * BLD_BLOCK_K, mb * BLD_BLOCK_M, b);
+                    }
                 }
             }
         }
@@ -228,33 +293,35 @@ corr_build_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
         if (lane == 0) {
             constexpr uint32_t idesc = ptx::umma_idesc(BLD_BLOCK_M, BLD_BLOCK_N, 1 /*bf16*/);
             uint32_t a_it = 0, b_it = 0, tile_it = 0;
-            for (long long t = t_begin; t < t_end; ++t, ++tile_it) {
-                const int mb = static_cast<int>(t % p.m_blks);
-                if (t == t_begin || mb == 0) {
-                    ptx::mbar_wait(bar(B_FULL), b_it & 1);
-                    ++b_it;
-                }
-                const uint32_t acc = tile_it & 1, acc_ph = (tile_it >> 1) & 1;
-                ptx::mbar_wait(bar(T_EMPTY + acc), acc_ph ^ 1);
-                ptx::tc_fence_after();
-                const uint32_t d_tmem = tmem_base + acc * BLD_BLOCK_N;
-                for (int kc = 0; kc < kc_n; ++kc, ++a_it) {
-                    const uint32_t st = a_it % BLD_A_STAGES, ph = (a_it / BLD_A_STAGES) & 1;
-                    ptx::mbar_wait(bar(A_FULL + st), ph);
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+                const int sl = item / units;
+                const int mb0 = static_cast<int>(static_cast<long long>(sl) * p.m_blks / p.msplit);
+                const int mb1 = static_cast<int>(static_cast<long long>(sl + 1) * p.m_blks / p.msplit);
+                if (mb0 == mb1) continue;
+                ptx::mbar_wait(bar(B_FULL), b_it & 1);
+                ++b_it;
+                for (int mb = mb0; mb < mb1; ++mb, ++tile_it) {
+                    const uint32_t acc = tile_it & 1, acc_ph = (tile_it >> 1) & 1;
+                    ptx::mbar_wait(bar(T_EMPTY + acc), acc_ph ^ 1);
                     ptx::tc_fence_after();
-                    const uint32_t a_addr = s_a + st * BLD_A_STAGE_BYTES;
-                    const uint32_t b_addr = s_b + kc * BLD_B_SLAB_BYTES;
+                    const uint32_t d_tmem = tmem_base + acc * BLD_BLOCK_N;
+                    for (int kc = 0; kc < kc_n; ++kc, ++a_it) {
+                        const uint32_t st = a_it % BLD_A_STAGES, ph = (a_it / BLD_A_STAGES) & 1;
+                        ptx::mbar_wait(bar(A_FULL + st), ph);
+                        ptx::tc_fence_after();
+                        const uint32_t a_addr = s_a + st * BLD_A_STAGE_BYTES;
+                        const uint32_t b_addr = s_b + kc * BLD_B_SLAB_BYTES;
 #pragma unroll
-                    for (int k = 0; k < BLD_BLOCK_K / BLD_UMMA_K; ++k) {
-                        ptx::umma_bf16(d_tmem, ptx::umma_desc_k_sw128(a_addr + k * BLD_UMMA_K * 2),
-                                       ptx::umma_desc_k_sw128(b_addr + k * BLD_UMMA_K * 2), idesc,
-                                       (kc | k) != 0 ? 1u : 0u);
+                        for (int k = 0; k < BLD_BLOCK_K / BLD_UMMA_K; ++k) {
+                            ptx::umma_bf16(d_tmem, ptx::umma_desc_k_sw128(a_addr + k * BLD_UMMA_K * 2),
+                                           ptx::umma_desc_k_sw128(b_addr + k * BLD_UMMA_K * 2), idesc,
+                                           (kc | k) != 0 ? 1u : 0u);
+                        }
+                        ptx::umma_commit(bar(A_EMPTY + st));  // frees the ring slot when the MMAs retire
                     }
-                    ptx::umma_commit(bar(A_EMPTY + st));  // frees the ring slot when the MMAs retire
+                    ptx::umma_commit(bar(T_FULL + acc));      // accumulator ready for the epilogue
                 }
-                ptx::umma_commit(bar(T_FULL + acc));      // accumulator ready for the epilogue
-                const bool last_of_b = (t + 1 == t_end) || (mb + 1 == p.m_blks);
-                if (last_of_b) ptx::umma_commit(bar(B_EMPTY));
+                ptx::umma_commit(bar(B_EMPTY));  // every MMA that reads this fmap2 tile has been issued
             }
         }
         __syncwarp();
@@ -263,12 +330,58 @@ corr_build_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
         using TR = OutTraits<OutT>;
         const int e = warp - 4;
         const int q = e & 3;          // TMEM lane quarter this warp may read (warp_id % 4)
-        const int sub = e >> 2;       // which 8x16 half of the tile
-        constexpr int SUBS_X = TILE_X / 16;
-        const int sy = (sub / SUBS_X) * 8, sx = (sub % SUBS_X) * 16;
-        uint8_t* stg = smem + BLD_SMEM_STG + e * BLD_STG_BYTES;
+        const int sub = e >> 2;       // which half of the tile's 256 columns
+        const uint32_t stg = ptx::smem_u32(smem + BLD_SMEM_STG) + e * BLD_STG_BYTES;
         const float scale = p.scale;
         const int L = p.num_levels;
+        const int smask = p.dbg_store_mask;
+        uint32_t tile_it = 0;
+
+        if constexpr (MODE == MODE_LINEAR) {
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+                const int u = item % units, sl = item / units;
+                const int b = u / ntiles, nt = u % ntiles;
+                const int mb0 = static_cast<int>(static_cast<long long>(sl) * p.m_blks / p.msplit);
+                const int mb1 = static_cast<int>(static_cast<long long>(sl + 1) * p.m_blks / p.msplit);
+                int l = 0;
+                while (l + 1 < L && nt >= p.tile_start[l + 1]) ++l;
+                const int n_l = p.hl[l] * p.wl[l];                       // pixels of this level
+                const int col0 = (nt - p.tile_start[l]) * BLD_BLOCK_N + sub * (BLD_BLOCK_N / 2);
+                OutT* const lv = static_cast<OutT*>(p.lvl[l]);
+                const bool vec = (n_l % TR::EPC) == 0;
+                const bool wr = (smask >> l) & 1;
+                for (int mb = mb0; mb < mb1; ++mb, ++tile_it) {
+                    const int m0 = mb * BLD_BLOCK_M + q * 32;
+                    int rows_valid = p.N - m0;
+                    rows_valid = rows_valid < 0 ? 0 : (rows_valid > 32 ? 32 : rows_valid);
+                    OutT* const img0 = lv + (static_cast<size_t>(b) * p.N + m0) * n_l;
+                    const uint32_t acc = tile_it & 1, acc_ph = (tile_it >> 1) & 1;
+                    ptx::mbar_wait(bar(T_FULL + acc), acc_ph);
+                    ptx::tc_fence_after();
+                    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
+                                           acc * BLD_BLOCK_N + sub * (BLD_BLOCK_N / 2);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        float v[32];  // 32 consecutive pixels of this thread's query row
+                        ptx::tmem_ld_x16(taddr + j * 32, v);
+                        ptx::tmem_ld_x16(taddr + j * 32 + 16, v + 16);
+                        ptx::tmem_ld_wait();
+                        if (j == 3) {
+                            ptx::tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) ptx::mbar_arrive(bar(T_EMPTY + acc));
+                        }
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) v[i] *= scale;
+                        if (wr)
+                            staged_store<OutT, 32>(stg, v, lane, img0, n_l, rows_valid, 0, col0 + j * 32,
+                                                   1, n_l, vec);
+                    }
+                }
+            }
+        } else {
+        constexpr int SUBS_X = TILE_X / 16;
+        const int sy = (sub / SUBS_X) * 8, sx = (sub % SUBS_X) * 16;
         OutT* const l0 = static_cast<OutT*>(p.lvl[0]);
         OutT* const l1 = static_cast<OutT*>(p.lvl[1]);
         OutT* const l2 = static_cast<OutT*>(p.lvl[2]);
@@ -282,14 +395,14 @@ corr_build_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
         const size_t img2 = static_cast<size_t>(p.hl[2]) * p.wl[2];
         const size_t img3 = static_cast<size_t>(p.hl[3]) * p.wl[3];
 
-        uint32_t tile_it = 0;
-        for (long long t = t_begin; t < t_end; ++t, ++tile_it) {
-            const int mb = static_cast<int>(t % p.m_blks);
-            const long long nb = t / p.m_blks;
-            const int nt = static_cast<int>(nb % ntiles);
-            const int b = static_cast<int>(nb / ntiles);
-            const int Y0 = (nt / p.ntx) * TILE_Y + sy;  // level-0 origin of this warp's 8x16 patch
-            const int X0 = (nt % p.ntx) * TILE_X + sx;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+          const int u = item % units, sl = item / units;
+          const int b = u / ntiles, nt = u % ntiles;
+          const int mb0 = static_cast<int>(static_cast<long long>(sl) * p.m_blks / p.msplit);
+          const int mb1 = static_cast<int>(static_cast<long long>(sl + 1) * p.m_blks / p.msplit);
+          const int Y0 = (nt / p.ntx) * TILE_Y + sy;  // level-0 origin of this warp's 8x16 patch
+          const int X0 = (nt % p.ntx) * TILE_X + sx;
+          for (int mb = mb0; mb < mb1; ++mb, ++tile_it) {
             const int m0 = mb * BLD_BLOCK_M + q * 32;   // first query pixel of this warp
             int rows_valid = p.N - m0;
             rows_valid = rows_valid < 0 ? 0 : (rows_valid > 32 ? 32 : rows_valid);
@@ -320,12 +433,13 @@ corr_build_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
                 for (int x = 0; x < 8; ++x)
                     p1[j * 8 + x] =
                         (v[2 * x] + v[2 * x + 1] + v[16 + 2 * x] + v[16 + 2 * x + 1]) * 0.25f;
-                staged_store<OutT, 16>(stg, v, lane, l0, img0, row0, rows_valid, Y0 + 2 * j, X0,
-                                       p.hl[0], p.wl[0], vec0);
+                if (smask & 1)
+                    staged_store<OutT, 16>(stg, v, lane, l0 + row0 * img0, img0, rows_valid, Y0 + 2 * j,
+                                           X0, p.hl[0], p.wl[0], vec0);
             }
-            if (L > 1)
-                staged_store<OutT, 8>(stg, p1, lane, l1, img1, row0, rows_valid, Y0 >> 1, X0 >> 1,
-                                      p.hl[1], p.wl[1], vec1);
+            if (L > 1 && (smask & 2))
+                staged_store<OutT, 8>(stg, p1, lane, l1 + row0 * img1, img1, rows_valid, Y0 >> 1,
+                                      X0 >> 1, p.hl[1], p.wl[1], vec1);
             if (L > 2) {
                 float p2[8];  // 2 rows x 4
 #pragma unroll
@@ -337,7 +451,7 @@ corr_build_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
                                         0.25f;
                 const bool row_ok = lane < rows_valid;
                 const int y2 = Y0 >> 2, x2 = X0 >> 2;
-                if (row_ok) {
+                if (row_ok && (smask & 4)) {
                     OutT* img = l2 + (row0 + lane) * img2;
 #pragma unroll
                     for (int y = 0; y < 2; ++y) {
@@ -363,7 +477,7 @@ corr_build_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
                     const float p3a = (p2[0] + p2[1] + p2[4] + p2[5]) * 0.25f;
                     const float p3b = (p2[2] + p2[3] + p2[6] + p2[7]) * 0.25f;
                     const int y3 = Y0 >> 3, x3 = X0 >> 3;
-                    if (row_ok && y3 < p.hl[3]) {
+                    if (row_ok && y3 < p.hl[3] && (smask & 8)) {
                         OutT* dst = l3 + (row0 + lane) * img3 + static_cast<size_t>(y3) * p.wl[3] + x3;
                         if (vec3 && x3 + 1 < p.wl[3]) {
                             if constexpr (sizeof(OutT) == 4) {
@@ -378,7 +492,9 @@ corr_build_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
                     }
                 }
             }
-        }
+          }  // m-blocks of this item
+        }      // items
+        }      // MODE_FUSED
     }
 
     ptx::tc_fence_before();

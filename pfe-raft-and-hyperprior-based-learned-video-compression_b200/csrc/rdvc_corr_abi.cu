@@ -22,6 +22,9 @@ thread_local char g_err[512] = "";
 thread_local unsigned long long g_launches = 0;
 std::atomic<int> g_opt_lookup{0};
 std::atomic<int> g_opt_tile{0};
+std::atomic<int> g_opt_msplit{0};
+std::atomic<int> g_opt_store_mask{15};
+std::atomic<int> g_opt_mode{0};
 
 int fail(int code, const char* fmt, ...) {
     va_list ap;
@@ -107,10 +110,10 @@ int sm_count() {
     return n;
 }
 
-template <int TY, int TX, typename OutT>
-int launch_build(const CUtensorMap& ta, const CUtensorMap& tb, const rdvc::BuildParams& p,
+template <int MODE, int TY, int TX, typename OutT>
+int launch_build(const CUtensorMap& ta, const CUtensorMap* tb, const rdvc::BuildParams& p,
                  cudaStream_t st) {
-    auto kern = rdvc::corr_build_kernel<TY, TX, OutT>;
+    auto kern = rdvc::corr_build_kernel<MODE, TY, TX, OutT>;
     static bool attr_set = false;  // per instantiation
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -119,11 +122,27 @@ int launch_build(const CUtensorMap& ta, const CUtensorMap& tb, const rdvc::Build
         attr_set = true;
     }
     long long grid = sm_count();
-    if (grid > p.total_tiles) grid = p.total_tiles;
-    kern<<<static_cast<unsigned>(grid), rdvc::BLD_THREADS, rdvc::BLD_SMEM_LAUNCH, st>>>(ta, tb, p);
+    const long long n_items = static_cast<long long>(p.B) * p.ntiles * p.msplit;
+    if (grid > n_items) grid = n_items;
+    kern<<<static_cast<unsigned>(grid), rdvc::BLD_THREADS, rdvc::BLD_SMEM_LAUNCH, st>>>(
+        ta, tb[0], tb[1], tb[2], tb[3], p);
     ++g_launches;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "corr_build_kernel launch");
+    return RDVC_OK;
+}
+
+template <typename T>
+int launch_pool_pack(const void* f2, void* dst, int B, int D, int h, int w, int level, cudaStream_t st) {
+    auto kern = rdvc::corr_pool_pack_kernel<T>;
+    const size_t smem = static_cast<size_t>(D) * 33 * sizeof(float);
+    const int nl = (h >> level) * (w >> level);
+    dim3 grid((nl + rdvc::PACK_TN - 1) / rdvc::PACK_TN, B, 1);
+    kern<<<grid, rdvc::PACK_THREADS, smem, st>>>(static_cast<const T*>(f2),
+                                                 static_cast<__nv_bfloat16*>(dst), D, h, w, level);
+    ++g_launches;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "corr_pool_pack_kernel launch");
     return RDVC_OK;
 }
 
@@ -182,6 +201,9 @@ unsigned long long rdvc_corr_launch_count(void) { return g_launches; }
 int rdvc_corr_set_option(int key, int value) {
     if (key == 0 && value >= 0 && value <= 2) { g_opt_lookup = value; return RDVC_OK; }
     if (key == 1 && value >= 0 && value <= 2) { g_opt_tile = value; return RDVC_OK; }
+    if (key == 2 && value >= 0) { g_opt_msplit = value; return RDVC_OK; }
+    if (key == 3 && value >= 0 && value <= 15) { g_opt_store_mask = value; return RDVC_OK; }
+    if (key == 4 && value >= 0 && value <= 2) { g_opt_mode = value; return RDVC_OK; }
     return fail(RDVC_E_UNSUPPORTED, "unknown option key=%d value=%d", key, value);
 }
 
@@ -198,7 +220,12 @@ size_t rdvc_corr_pyramid_bytes(int B, int h, int w, int num_levels, int vol_dtyp
 }
 
 size_t rdvc_corr_workspace_bytes(int B, int D, int h, int w) {
-    return 2 * align_up(static_cast<size_t>(B) * h * w * D * 2, 256);
+    // fmap1 K-major + fmap2 K-major at every pyramid level (levels 1..3 are used by the
+    // linear build mode only), each 256-byte aligned
+    size_t total = align_up(static_cast<size_t>(B) * h * w * D * 2, 256);
+    for (int l = 0; l < rdvc::BLD_MAX_LEVELS; ++l)
+        total += align_up(static_cast<size_t>(B) * (h >> l) * (w >> l) * D * 2, 256);
+    return total;
 }
 
 int rdvc_corr_build(const void* fmap1, const void* fmap2, int B, int D, int h, int w, int in_dtype,
@@ -226,15 +253,33 @@ int rdvc_corr_build(const void* fmap1, const void* fmap2, int B, int D, int h, i
     const int N = h * w;
     uint8_t* ws = static_cast<uint8_t*>(workspace);
     void* a_km = ws;  // fmap1 as (B, N, D) bf16
-    void* b_km = ws + align_up(static_cast<size_t>(B) * N * D * 2, 256);
+    void* b_km[rdvc::BLD_MAX_LEVELS];  // fmap2 level l as (B, n_l, D) bf16
+    {
+        size_t off = align_up(static_cast<size_t>(B) * N * D * 2, 256);
+        for (int l = 0; l < rdvc::BLD_MAX_LEVELS; ++l) {
+            b_km[l] = ws + off;
+            off += align_up(static_cast<size_t>(B) * (h >> l) * (w >> l) * D * 2, 256);
+        }
+    }
+    int mode = g_opt_mode.load();
+    if (mode == 0) mode = 2;  // default: linear (pooled fmap2 rows), see corr_build_sm100.cuh
+    const bool linear = (mode == 2);
 
-    // 1. repack to K-major bf16
-    if (in_dtype == RDVC_DT_F32) rc = launch_pack<float>(fmap1, fmap2, a_km, b_km, B, D, N, st);
-    else if (in_dtype == RDVC_DT_BF16) rc = launch_pack<__nv_bfloat16>(fmap1, fmap2, a_km, b_km, B, D, N, st);
-    else rc = launch_pack<__half>(fmap1, fmap2, a_km, b_km, B, D, N, st);
+    // 1. repack to K-major bf16 (+ pooled fmap2 levels for the linear mode)
+    if (in_dtype == RDVC_DT_F32) rc = launch_pack<float>(fmap1, fmap2, a_km, b_km[0], B, D, N, st);
+    else if (in_dtype == RDVC_DT_BF16) rc = launch_pack<__nv_bfloat16>(fmap1, fmap2, a_km, b_km[0], B, D, N, st);
+    else rc = launch_pack<__half>(fmap1, fmap2, a_km, b_km[0], B, D, N, st);
     if (rc) return rc;
+    if (linear) {
+        for (int l = 1; l < num_levels; ++l) {
+            if (in_dtype == RDVC_DT_F32) rc = launch_pool_pack<float>(fmap2, b_km[l], B, D, h, w, l, st);
+            else if (in_dtype == RDVC_DT_BF16) rc = launch_pool_pack<__nv_bfloat16>(fmap2, b_km[l], B, D, h, w, l, st);
+            else rc = launch_pool_pack<__half>(fmap2, b_km[l], B, D, h, w, l, st);
+            if (rc) return rc;
+        }
+    }
 
-    // 2. tile shape: 16x16 fmap2 pixels unless 8x32 wastes less padding
+    // 2. fused mode tile shape: 16x16 fmap2 pixels unless 8x32 wastes less padding
     int tile = g_opt_tile.load();
     auto padded = [&](int ty, int tx) {
         return static_cast<long long>((h + ty - 1) / ty) * ty * ((w + tx - 1) / tx) * tx;
@@ -243,7 +288,7 @@ int rdvc_corr_build(const void* fmap1, const void* fmap2, int B, int D, int h, i
     const int TY = (tile == 1) ? 16 : 8, TX = (tile == 1) ? 16 : 32;
 
     // 3. TMA descriptors over the repacked maps
-    CUtensorMap ta, tb;
+    CUtensorMap ta, tb[rdvc::BLD_MAX_LEVELS];
     {
         cuuint64_t dims[3] = {(cuuint64_t)D, (cuuint64_t)N, (cuuint64_t)B};
         cuuint64_t str[2] = {(cuuint64_t)D * 2, (cuuint64_t)N * D * 2};
@@ -251,12 +296,23 @@ int rdvc_corr_build(const void* fmap1, const void* fmap2, int B, int D, int h, i
         rc = make_tmap(&ta, a_km, 3, dims, str, box);
         if (rc) return rc;
     }
-    {
+    if (linear) {
+        for (int l = 0; l < rdvc::BLD_MAX_LEVELS; ++l) {
+            const int ll = l < num_levels ? l : 0;  // unused slots alias level 0
+            const cuuint64_t nl = (cuuint64_t)(h >> ll) * (w >> ll);
+            cuuint64_t dims[3] = {(cuuint64_t)D, nl, (cuuint64_t)B};
+            cuuint64_t str[2] = {(cuuint64_t)D * 2, nl * D * 2};
+            cuuint32_t box[3] = {rdvc::BLD_BLOCK_K, rdvc::BLD_BLOCK_N, 1};
+            rc = make_tmap(&tb[l], b_km[ll], 3, dims, str, box);
+            if (rc) return rc;
+        }
+    } else {
         cuuint64_t dims[4] = {(cuuint64_t)D, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)B};
         cuuint64_t str[3] = {(cuuint64_t)D * 2, (cuuint64_t)w * D * 2, (cuuint64_t)N * D * 2};
         cuuint32_t box[4] = {rdvc::BLD_BLOCK_K, (cuuint32_t)TX, (cuuint32_t)TY, 1};
-        rc = make_tmap(&tb, b_km, 4, dims, str, box);
+        rc = make_tmap(&tb[0], b_km[0], 4, dims, str, box);
         if (rc) return rc;
+        tb[1] = tb[2] = tb[3] = tb[0];
     }
 
     rdvc::BuildParams p;
@@ -272,15 +328,48 @@ int rdvc_corr_build(const void* fmap1, const void* fmap2, int B, int D, int h, i
     p.m_blks = (N + rdvc::BLD_BLOCK_M - 1) / rdvc::BLD_BLOCK_M;
     p.nty = (h + TY - 1) / TY;
     p.ntx = (w + TX - 1) / TX;
-    p.total_tiles = static_cast<long long>(B) * p.nty * p.ntx * p.m_blks;
-    p.scale = static_cast<float>(1.0 / std::sqrt(static_cast<double>(D)));
-
-    if (vol_dtype == RDVC_DT_F32) {
-        return (tile == 1) ? launch_build<16, 16, float>(ta, tb, p, st)
-                           : launch_build<8, 32, float>(ta, tb, p, st);
+    if (linear) {
+        int t = 0;
+        for (int l = 0; l < rdvc::BLD_MAX_LEVELS; ++l) {
+            p.tile_start[l] = t;
+            if (l < num_levels) t += (p.hl[l] * p.wl[l] + rdvc::BLD_BLOCK_N - 1) / rdvc::BLD_BLOCK_N;
+        }
+        p.ntiles = t;
+    } else {
+        p.ntiles = p.nty * p.ntx;
     }
-    return (tile == 1) ? launch_build<16, 16, __nv_bfloat16>(ta, tb, p, st)
-                       : launch_build<8, 32, __nv_bfloat16>(ta, tb, p, st);
+    p.scale = static_cast<float>(1.0 / std::sqrt(static_cast<double>(D)));
+    p.dbg_store_mask = g_opt_store_mask.load();
+    {
+        // m-range slices per fmap2 tile: enough (tile, slice) items to fill the SMs in whole
+        // waves.  cost = waves x (m-blocks per slice + ~0.5 for the 128 KB tile reload); a mild
+        // bias toward few slices keeps concurrent CTAs on the same query rows (see kernel).
+        const long long units = static_cast<long long>(B) * p.ntiles;
+        const int G = sm_count();
+        int best = 1;
+        double best_cost = 1e300;
+        const int s_max = p.m_blks < 64 ? p.m_blks : 64;
+        for (int S = 1; S <= s_max; ++S) {
+            const long long waves = (units * S + G - 1) / G;
+            const double cost = waves * ((p.m_blks + S - 1) / S + 0.5) * (1.0 + 0.005 * S);
+            if (cost < best_cost) { best_cost = cost; best = S; }
+        }
+        const int forced = g_opt_msplit.load();
+        p.msplit = (forced > 0) ? (forced < p.m_blks ? forced : p.m_blks) : best;
+    }
+
+    using rdvc::MODE_FUSED;
+    using rdvc::MODE_LINEAR;
+    if (linear) {
+        return (vol_dtype == RDVC_DT_F32) ? launch_build<MODE_LINEAR, 16, 16, float>(ta, tb, p, st)
+                                          : launch_build<MODE_LINEAR, 16, 16, __nv_bfloat16>(ta, tb, p, st);
+    }
+    if (vol_dtype == RDVC_DT_F32) {
+        return (tile == 1) ? launch_build<MODE_FUSED, 16, 16, float>(ta, tb, p, st)
+                           : launch_build<MODE_FUSED, 8, 32, float>(ta, tb, p, st);
+    }
+    return (tile == 1) ? launch_build<MODE_FUSED, 16, 16, __nv_bfloat16>(ta, tb, p, st)
+                       : launch_build<MODE_FUSED, 8, 32, __nv_bfloat16>(ta, tb, p, st);
 }
 
 int rdvc_corr_lookup(const void* pyramid, int vol_dtype, const float* coords, int B, int h, int w,

@@ -30,3 +30,27 @@ def pyramid_from_levels(rc, levels, B, h, w, volume_dtype=torch.float32, device=
 
 def bf16_round(x: np.ndarray) -> np.ndarray:
     return torch.from_numpy(np.ascontiguousarray(x)).to(torch.bfloat16).to(torch.float32).numpy()
+
+
+def pool_fmap(f: np.ndarray, level: int) -> np.ndarray:
+    """(B,C,h,w) -> mean over 2^level x 2^level blocks, floor-cropped (fp64 math)."""
+    B, C, h, w = f.shape
+    k = 1 << level
+    hl, wl = h >> level, w >> level
+    x = f[:, :, : hl * k, : wl * k].astype(np.float64).reshape(B, C, hl, k, wl, k)
+    return x.mean(axis=(3, 5))
+
+
+def ref_pyramid_linear(f1: np.ndarray, f2: np.ndarray, num_levels: int):
+    """What the library's linear build mode computes, in fp64: level l =
+    bf16(fmap1)^T . bf16(avgpool_l(fmap2)) / sqrt(C)  (pooled in full precision, rounded once)."""
+    B, C, h, w = f1.shape
+    a = bf16_round(f1).reshape(B, C, h * w).astype(np.float64)
+    out = []
+    for l in range(num_levels):
+        pl = pool_fmap(f2, l)
+        b = bf16_round(pl.astype(np.float32)).astype(np.float64)
+        hl, wl = pl.shape[-2:]
+        v = np.einsum("bci,bcj->bij", a, b.reshape(B, C, hl * wl)) / np.sqrt(float(C))
+        out.append(v.reshape(B * h * w, hl, wl))
+    return out

@@ -46,17 +46,22 @@ def stage_lookup():
         lib.rdvc_corr_set_option(0, 0)
 
 
-def _build_case(B, D, h, w, tile, vol_dtype_name="float32", levels=4, verbose=True):
+def _build_case(B, D, h, w, tile, vol_dtype_name="float32", levels=4, verbose=True, mode=1):
     np, torch, rc, cn = _imports()
-    from helpers import bf16_round, rel_max
+    from helpers import bf16_round, rel_max, ref_pyramid_linear
     lib = rc._cabi.load()
     vol_dtype = getattr(torch, vol_dtype_name)
     f1, f2 = cn.synth_fmaps(B, D, h, w, seed=5)
     lib.rdvc_corr_set_option(1, tile)
+    lib.rdvc_corr_set_option(4, mode)
     pyr = rc.build_pyramid(torch.from_numpy(f1).cuda(), torch.from_numpy(f2).cuda(), levels, vol_dtype)
     torch.cuda.synchronize()
     lib.rdvc_corr_set_option(1, 0)
-    ref = cn.build_pyramid(bf16_round(f1), bf16_round(f2), levels)  # same rounded operands, fp64 math
+    lib.rdvc_corr_set_option(4, 0)
+    if mode == 1:
+        ref = cn.build_pyramid(bf16_round(f1), bf16_round(f2), levels)  # same rounded operands, fp64 math
+    else:
+        ref = ref_pyramid_linear(f1, f2, levels)
     ok = True
     for l in range(levels):
         got = pyr.level(l)[:, 0].float().cpu().numpy()
@@ -64,7 +69,7 @@ def _build_case(B, D, h, w, tile, vol_dtype_name="float32", levels=4, verbose=Tr
         tol = 1e-4 if vol_dtype == torch.float32 else 8e-3
         flag = "OK " if r < tol else "BAD"
         ok &= r < tol
-        print(f"build B{B} D{D} {h}x{w} tile={tile} {vol_dtype_name} level{l}: rel={r:.3e} {flag}")
+        print(f"build mode={mode} B{B} D{D} {h}x{w} tile={tile} {vol_dtype_name} level{l}: rel={r:.3e} {flag}")
         if r >= tol and verbose:
             bad = np.abs(got - ref[l]) > tol * np.abs(ref[l]).max()
             print("   bad fraction", bad.mean(), "nan", np.isnan(got).mean(), "zero", (got == 0).mean())
@@ -97,6 +102,15 @@ def stage_build_ref():
     _build_case(1, 256, 46, 80, 1, "bfloat16")
 
 
+def stage_build_linear():
+    _build_case(1, 64, 16, 16, 0, mode=2)
+    _build_case(2, 64, 18, 22, 0, mode=2)
+    _build_case(1, 128, 33, 47, 0, levels=3, mode=2)
+    _build_case(1, 256, 46, 80, 0, mode=2)
+    _build_case(1, 256, 46, 80, 0, "bfloat16", mode=2)
+    _build_case(2, 128, 24, 40, 0, "bfloat16", mode=2)
+
+
 def stage_perf():
     np, torch, rc, cn = _imports()
     lib = rc._cabi.load()
@@ -106,8 +120,10 @@ def stage_perf():
     f2 = torch.randn(B, D, h, w, device="cuda", generator=g)
     co = torch.from_numpy(cn.synth_coords(B, h, w, 2.0, seed=1)).cuda()
     for vol in (torch.float32, torch.bfloat16):
-        for tile in (1, 2):
+        for mode, tile, msplit in ((2, 0, 0), (2, 0, 1), (2, 0, 3), (1, 1, 0), (1, 2, 0)):
+            lib.rdvc_corr_set_option(4, mode)
             lib.rdvc_corr_set_option(1, tile)
+            lib.rdvc_corr_set_option(2, msplit)
             blk = rc.TVCorrBlock(volume_dtype=vol)
             for _ in range(2):
                 blk.build_pyramid(f1, f2)
@@ -119,7 +135,7 @@ def stage_perf():
             e1.record(); torch.cuda.synchronize()
             tb = e0.elapsed_time(e1) / 5
             nbytes = lib.rdvc_corr_pyramid_bytes(B, h, w, 4, rc.RDVC_DT_F32 if vol == torch.float32 else rc.RDVC_DT_BF16)
-            print(f"build 1080p {vol} tile={tile}: {tb:.3f} ms  ({nbytes / tb / 1e6:.0f} GB/s of pyramid bytes)")
+            print(f"build 1080p {vol} mode={mode} tile={tile} msplit={msplit}: {tb:.3f} ms  ({nbytes / tb / 1e6:.0f} GB/s of pyramid bytes)")
             for variant in (1, 2):
                 lib.rdvc_corr_set_option(0, variant)
                 for _ in range(2):
@@ -132,6 +148,8 @@ def stage_perf():
             lib.rdvc_corr_set_option(0, 0)
             blk.release()
     lib.rdvc_corr_set_option(1, 0)
+    lib.rdvc_corr_set_option(2, 0)
+    lib.rdvc_corr_set_option(4, 0)
     # stock torchvision on the same GPU for scale
     from oracle import tv_corr as tv
     blk = tv.tv_corr_block()
@@ -145,7 +163,7 @@ def stage_perf():
 
 
 STAGES = {"lookup": stage_lookup, "build_small": stage_build_small, "build_odd": stage_build_odd,
-          "build_ref": stage_build_ref, "perf": stage_perf}
+          "build_ref": stage_build_ref, "build_linear": stage_build_linear, "perf": stage_perf}
 
 if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
