@@ -115,7 +115,8 @@ unsigned long long rdvc_corr_launch_count(void);
  *   key 1: build tile shape (0 = auto, 1 = 16x16, 2 = 8x32 fmap2 pixels)
  *   key 2: build m-range slices per fmap2 tile (0 = auto)
  *   key 3: debug: bit mask of pyramid levels the build writes (default 15)
- *   key 4: build mode (0 = auto, 1 = fused pooling epilogue, 2 = pooled-fmap2 rows) */
+ *   key 4: build mode (0 = auto, 1 = fused pooling epilogue, 2 = pooled-fmap2 rows)
+ *   key 5: linear-mode output path (1 = TMA tiled stores [default], 0 = staged stores) */
 int rdvc_corr_set_option(int key, int value);
 
 #ifdef __cplusplus

@@ -71,6 +71,8 @@ struct BuildParams {
     int msplit;         // m-range slices per fmap2 tile (work item = tile x slice)
     float scale;        // 1 / sqrt(D)
     int dbg_store_mask; // debug: bit l set = write level l (default 15)
+    int dbg_policy;     // debug: TMA-store L2 policy (0 default, 1 evict_last, 2 evict_first)
+    int tma_out;        // MODE_LINEAR: bit l set = level l is written with TMA stores (tm_o<l>)
 };
 
 // ---- output element traits -------------------------------------------------
@@ -194,7 +196,9 @@ template <int MODE, int TILE_Y, int TILE_X, typename OutT>
 __global__ void __launch_bounds__(BLD_THREADS, 1)
 corr_build_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b0,
                   const __grid_constant__ CUtensorMap tm_b1, const __grid_constant__ CUtensorMap tm_b2,
-                  const __grid_constant__ CUtensorMap tm_b3, const BuildParams p) {
+                  const __grid_constant__ CUtensorMap tm_b3, const __grid_constant__ CUtensorMap tm_o0,
+                  const __grid_constant__ CUtensorMap tm_o1, const __grid_constant__ CUtensorMap tm_o2,
+                  const __grid_constant__ CUtensorMap tm_o3, const BuildParams p) {
     static_assert(TILE_Y * TILE_X == BLD_BLOCK_N, "tile must hold 256 fmap2 pixels");
     static_assert(TILE_Y % 8 == 0 && TILE_X % 16 == 0, "sub-tiles are 8 x 16");
     extern __shared__ uint8_t smem_raw[];
@@ -280,6 +284,10 @@ corr_build_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
                     for (int kc = 0; kc < kc_n; ++kc, ++a_it) {
                         const uint32_t st = a_it % BLD_A_STAGES, ph = (a_it / BLD_A_STAGES) & 1;
                         ptx::mbar_wait(bar(A_EMPTY + st), ph ^ 1);
+                        if ((p.dbg_store_mask & 16) && a_it >= BLD_A_STAGES) {  // debug: no A traffic
+                            ptx::mbar_arrive(bar(A_FULL + st));
+                            continue;
+                        }
                         ptx::mbar_arrive_expect_tx(bar(A_FULL + st), BLD_A_STAGE_BYTES);
                         ptx::tma_load_3d(s_a + st * BLD_A_STAGE_BYTES, &tm_a, bar(A_FULL + st),
                                          kc * BLD_BLOCK_K, mb * BLD_BLOCK_M, b);
@@ -350,6 +358,8 @@ corr_build_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
                 OutT* const lv = static_cast<OutT*>(p.lvl[l]);
                 const bool vec = (n_l % TR::EPC) == 0;
                 const bool wr = (smask >> l) & 1;
+                const bool use_tma = (p.tma_out >> l) & 1;
+                const CUtensorMap* tmo = (l == 0) ? &tm_o0 : (l == 1) ? &tm_o1 : (l == 2) ? &tm_o2 : &tm_o3;
                 for (int mb = mb0; mb < mb1; ++mb, ++tile_it) {
                     const int m0 = mb * BLD_BLOCK_M + q * 32;
                     int rows_valid = p.N - m0;
@@ -363,9 +373,14 @@ corr_build_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         float v[32];  // 32 consecutive pixels of this thread's query row
-                        ptx::tmem_ld_x16(taddr + j * 32, v);
-                        ptx::tmem_ld_x16(taddr + j * 32 + 16, v + 16);
-                        ptx::tmem_ld_wait();
+                        if (!(smask & 32)) {  // debug bit 5: skip the TMEM reads
+                            ptx::tmem_ld_x16(taddr + j * 32, v);
+                            ptx::tmem_ld_x16(taddr + j * 32 + 16, v + 16);
+                            ptx::tmem_ld_wait();
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) v[i] = 0.f;
+                        }
                         if (j == 3) {
                             ptx::tc_fence_before();
                             __syncwarp();
@@ -373,12 +388,34 @@ corr_build_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
                         }
 #pragma unroll
                         for (int i = 0; i < 32; ++i) v[i] *= scale;
-                        if (wr)
-                            staged_store<OutT, 32>(stg, v, lane, img0, n_l, rows_valid, 0, col0 + j * 32,
-                                                   1, n_l, vec);
+                        if (wr) {
+                            if (use_tma) {
+                                // the staging rows are 128 B with the chunk index XORed by (row & 7):
+                                // exactly TMA's SWIZZLE_128B, so the engine un-swizzles on the way out
+                                if (lane == 0) ptx::bulk_wait_read<0>();  // previous box left smem
+                                __syncwarp();
+#pragma unroll
+                                for (int c = 0; c < TR::CH; ++c)
+                                    sts_16(stg + (lane * TR::CH + TR::swz(c, lane)) * 16,
+                                           TR::pack(v + c * TR::EPC));
+                                ptx::fence_proxy_async_smem();
+                                __syncwarp();
+                                if (lane == 0) {
+                                    if (p.dbg_policy == 0) ptx::tma_store_3d(tmo, stg, col0 + j * 32, m0, b);
+                                    else ptx::tma_store_3d_hint(tmo, stg, col0 + j * 32, m0, b,
+                                                                p.dbg_policy == 1 ? ptx::policy_evict_last()
+                                                                                  : ptx::policy_evict_first());
+                                    ptx::bulk_commit();
+                                }
+                            } else {
+                                staged_store<OutT, 32>(stg, v, lane, img0, n_l, rows_valid, 0,
+                                                       col0 + j * 32, 1, n_l, vec);
+                            }
+                        }
                     }
                 }
             }
+            if (lane == 0) ptx::bulk_wait<0>();  // all TMA stores of this warp have landed
         } else {
         constexpr int SUBS_X = TILE_X / 16;
         const int sy = (sub / SUBS_X) * 8, sx = (sub % SUBS_X) * 16;

@@ -25,6 +25,8 @@ std::atomic<int> g_opt_tile{0};
 std::atomic<int> g_opt_msplit{0};
 std::atomic<int> g_opt_store_mask{15};
 std::atomic<int> g_opt_mode{0};
+std::atomic<int> g_opt_tma_out{1};
+std::atomic<int> g_opt_policy{0};
 
 int fail(int code, const char* fmt, ...) {
     va_list ap;
@@ -86,13 +88,13 @@ EncodeTiledFn encode_tiled_fn() {
     return fn;
 }
 
-// bf16 tensor, innermost dimension K (= D channels), 128-byte swizzle, zero OOB fill.
-int make_tmap(CUtensorMap* m, void* base, int rank, const cuuint64_t* dims,
+// Tiled TMA descriptor, 128-byte swizzle, zero OOB fill (loads) / clipped (stores).
+int make_tmap(CUtensorMap* m, CUtensorMapDataType dt, void* base, int rank, const cuuint64_t* dims,
               const cuuint64_t* strides_bytes, const cuuint32_t* box) {
     EncodeTiledFn fn = encode_tiled_fn();
     if (!fn) return fail(RDVC_E_DRIVER, "cuTensorMapEncodeTiled not available from the driver");
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, base, dims, strides_bytes, box, estr,
+    CUresult r = fn(m, dt, rank, base, dims, strides_bytes, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(RDVC_E_DRIVER, "cuTensorMapEncodeTiled failed: CUresult %d", (int)r);
@@ -111,7 +113,7 @@ int sm_count() {
 }
 
 template <int MODE, int TY, int TX, typename OutT>
-int launch_build(const CUtensorMap& ta, const CUtensorMap* tb, const rdvc::BuildParams& p,
+int launch_build(const CUtensorMap& ta, const CUtensorMap* tb, const CUtensorMap* to, const rdvc::BuildParams& p,
                  cudaStream_t st) {
     auto kern = rdvc::corr_build_kernel<MODE, TY, TX, OutT>;
     static bool attr_set = false;  // per instantiation
@@ -125,39 +127,50 @@ int launch_build(const CUtensorMap& ta, const CUtensorMap* tb, const rdvc::Build
     const long long n_items = static_cast<long long>(p.B) * p.ntiles * p.msplit;
     if (grid > n_items) grid = n_items;
     kern<<<static_cast<unsigned>(grid), rdvc::BLD_THREADS, rdvc::BLD_SMEM_LAUNCH, st>>>(
-        ta, tb[0], tb[1], tb[2], tb[3], p);
+        ta, tb[0], tb[1], tb[2], tb[3], to[0], to[1], to[2], to[3], p);
     ++g_launches;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "corr_build_kernel launch");
     return RDVC_OK;
 }
 
+// fmap1 only (maps == 1) or fmap1 + fmap2 (maps == 2) -> K-major bf16
 template <typename T>
-int launch_pool_pack(const void* f2, void* dst, int B, int D, int h, int w, int level, cudaStream_t st) {
-    auto kern = rdvc::corr_pool_pack_kernel<T>;
-    const size_t smem = static_cast<size_t>(D) * 33 * sizeof(float);
-    const int nl = (h >> level) * (w >> level);
-    dim3 grid((nl + rdvc::PACK_TN - 1) / rdvc::PACK_TN, B, 1);
-    kern<<<grid, rdvc::PACK_THREADS, smem, st>>>(static_cast<const T*>(f2),
-                                                 static_cast<__nv_bfloat16*>(dst), D, h, w, level);
-    ++g_launches;
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return cuda_fail(e, "corr_pool_pack_kernel launch");
-    return RDVC_OK;
-}
-
-template <typename T>
-int launch_pack(const void* f1, const void* f2, void* d1, void* d2, int B, int D, int N,
+int launch_pack(const void* f1, const void* f2, void* d1, void* d2, int B, int D, int N, int maps,
                 cudaStream_t st) {
     auto kern = rdvc::corr_pack_kernel<T>;
     const size_t smem = static_cast<size_t>(D) * 33 * sizeof(float);
-    dim3 grid((N + rdvc::PACK_TN - 1) / rdvc::PACK_TN, B, 2);
+    dim3 grid((N + rdvc::PACK_TN - 1) / rdvc::PACK_TN, B, maps);
     kern<<<grid, rdvc::PACK_THREADS, smem, st>>>(
         static_cast<const T*>(f1), static_cast<const T*>(f2), static_cast<__nv_bfloat16*>(d1),
         static_cast<__nv_bfloat16*>(d2), D, N);
     ++g_launches;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "corr_pack_kernel launch");
+    return RDVC_OK;
+}
+
+// fmap2 -> K-major bf16 rows of every pyramid level (linear build mode)
+template <typename T>
+int launch_pack_pool(const void* f2, void* const* dst, int B, int D, int h, int w, int num_levels,
+                     cudaStream_t st) {
+    auto kern = rdvc::corr_pack_pool_kernel<T>;
+    const size_t smem = static_cast<size_t>(D) * 65 * sizeof(float);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             256 * 65 * (int)sizeof(float));
+        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(pack_pool, max dynamic smem)");
+        attr_set = true;
+    }
+    rdvc::PoolPackParams pp;
+    for (int l = 0; l < 4; ++l) pp.dst[l] = static_cast<__nv_bfloat16*>(dst[l]);
+    pp.D = D; pp.h = h; pp.w = w; pp.num_levels = num_levels;
+    dim3 grid((w + rdvc::POOL_TS - 1) / rdvc::POOL_TS, (h + rdvc::POOL_TS - 1) / rdvc::POOL_TS, B);
+    kern<<<grid, rdvc::PACK_THREADS, smem, st>>>(static_cast<const T*>(f2), pp);
+    ++g_launches;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "corr_pack_pool_kernel launch");
     return RDVC_OK;
 }
 
@@ -202,8 +215,10 @@ int rdvc_corr_set_option(int key, int value) {
     if (key == 0 && value >= 0 && value <= 2) { g_opt_lookup = value; return RDVC_OK; }
     if (key == 1 && value >= 0 && value <= 2) { g_opt_tile = value; return RDVC_OK; }
     if (key == 2 && value >= 0) { g_opt_msplit = value; return RDVC_OK; }
-    if (key == 3 && value >= 0 && value <= 15) { g_opt_store_mask = value; return RDVC_OK; }
+    if (key == 3 && value >= 0 && value <= 63) { g_opt_store_mask = value; return RDVC_OK; }
     if (key == 4 && value >= 0 && value <= 2) { g_opt_mode = value; return RDVC_OK; }
+    if (key == 5 && value >= 0 && value <= 1) { g_opt_tma_out = value; return RDVC_OK; }
+    if (key == 6 && value >= 0 && value <= 2) { g_opt_policy = value; return RDVC_OK; }
     return fail(RDVC_E_UNSUPPORTED, "unknown option key=%d value=%d", key, value);
 }
 
@@ -265,16 +280,17 @@ int rdvc_corr_build(const void* fmap1, const void* fmap2, int B, int D, int h, i
     if (mode == 0) mode = 2;  // default: linear (pooled fmap2 rows), see corr_build_sm100.cuh
     const bool linear = (mode == 2);
 
-    // 1. repack to K-major bf16 (+ pooled fmap2 levels for the linear mode)
-    if (in_dtype == RDVC_DT_F32) rc = launch_pack<float>(fmap1, fmap2, a_km, b_km[0], B, D, N, st);
-    else if (in_dtype == RDVC_DT_BF16) rc = launch_pack<__nv_bfloat16>(fmap1, fmap2, a_km, b_km[0], B, D, N, st);
-    else rc = launch_pack<__half>(fmap1, fmap2, a_km, b_km[0], B, D, N, st);
-    if (rc) return rc;
-    if (linear) {
-        for (int l = 1; l < num_levels; ++l) {
-            if (in_dtype == RDVC_DT_F32) rc = launch_pool_pack<float>(fmap2, b_km[l], B, D, h, w, l, st);
-            else if (in_dtype == RDVC_DT_BF16) rc = launch_pool_pack<__nv_bfloat16>(fmap2, b_km[l], B, D, h, w, l, st);
-            else rc = launch_pool_pack<__half>(fmap2, b_km[l], B, D, h, w, l, st);
+    // 1. repack to K-major bf16; the linear mode also needs the pooled fmap2 levels
+    {
+        const int maps = linear ? 1 : 2;
+        if (in_dtype == RDVC_DT_F32) rc = launch_pack<float>(fmap1, fmap2, a_km, b_km[0], B, D, N, maps, st);
+        else if (in_dtype == RDVC_DT_BF16) rc = launch_pack<__nv_bfloat16>(fmap1, fmap2, a_km, b_km[0], B, D, N, maps, st);
+        else rc = launch_pack<__half>(fmap1, fmap2, a_km, b_km[0], B, D, N, maps, st);
+        if (rc) return rc;
+        if (linear) {
+            if (in_dtype == RDVC_DT_F32) rc = launch_pack_pool<float>(fmap2, b_km, B, D, h, w, num_levels, st);
+            else if (in_dtype == RDVC_DT_BF16) rc = launch_pack_pool<__nv_bfloat16>(fmap2, b_km, B, D, h, w, num_levels, st);
+            else rc = launch_pack_pool<__half>(fmap2, b_km, B, D, h, w, num_levels, st);
             if (rc) return rc;
         }
     }
@@ -293,7 +309,7 @@ int rdvc_corr_build(const void* fmap1, const void* fmap2, int B, int D, int h, i
         cuuint64_t dims[3] = {(cuuint64_t)D, (cuuint64_t)N, (cuuint64_t)B};
         cuuint64_t str[2] = {(cuuint64_t)D * 2, (cuuint64_t)N * D * 2};
         cuuint32_t box[3] = {rdvc::BLD_BLOCK_K, rdvc::BLD_BLOCK_M, 1};
-        rc = make_tmap(&ta, a_km, 3, dims, str, box);
+        rc = make_tmap(&ta, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, a_km, 3, dims, str, box);
         if (rc) return rc;
     }
     if (linear) {
@@ -303,14 +319,14 @@ int rdvc_corr_build(const void* fmap1, const void* fmap2, int B, int D, int h, i
             cuuint64_t dims[3] = {(cuuint64_t)D, nl, (cuuint64_t)B};
             cuuint64_t str[2] = {(cuuint64_t)D * 2, nl * D * 2};
             cuuint32_t box[3] = {rdvc::BLD_BLOCK_K, rdvc::BLD_BLOCK_N, 1};
-            rc = make_tmap(&tb[l], b_km[ll], 3, dims, str, box);
+            rc = make_tmap(&tb[l], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, b_km[ll], 3, dims, str, box);
             if (rc) return rc;
         }
     } else {
         cuuint64_t dims[4] = {(cuuint64_t)D, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)B};
         cuuint64_t str[3] = {(cuuint64_t)D * 2, (cuuint64_t)w * D * 2, (cuuint64_t)N * D * 2};
         cuuint32_t box[4] = {rdvc::BLD_BLOCK_K, (cuuint32_t)TX, (cuuint32_t)TY, 1};
-        rc = make_tmap(&tb[0], b_km[0], 4, dims, str, box);
+        rc = make_tmap(&tb[0], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, b_km[0], 4, dims, str, box);
         if (rc) return rc;
         tb[1] = tb[2] = tb[3] = tb[0];
     }
@@ -340,6 +356,7 @@ int rdvc_corr_build(const void* fmap1, const void* fmap2, int B, int D, int h, i
     }
     p.scale = static_cast<float>(1.0 / std::sqrt(static_cast<double>(D)));
     p.dbg_store_mask = g_opt_store_mask.load();
+    p.dbg_policy = g_opt_policy.load();
     {
         // m-range slices per fmap2 tile: enough (tile, slice) items to fill the SMs in whole
         // waves.  cost = waves x (m-blocks per slice + ~0.5 for the 128 KB tile reload); a mild
@@ -358,18 +375,35 @@ int rdvc_corr_build(const void* fmap1, const void* fmap2, int B, int D, int h, i
         p.msplit = (forced > 0) ? (forced < p.m_blks ? forced : p.m_blks) : best;
     }
 
+    // output descriptors: level l as a [B][N][n_l] fp32 tensor, 32 x 32 boxes (linear mode, fp32
+    // volume, rows 16-byte aligned); anything else takes the staged-store path
+    CUtensorMap to[rdvc::BLD_MAX_LEVELS];
+    for (int l = 0; l < rdvc::BLD_MAX_LEVELS; ++l) to[l] = ta;
+    if (linear && vol_dtype == RDVC_DT_F32 && g_opt_tma_out.load()) {
+        for (int l = 0; l < num_levels; ++l) {
+            const cuuint64_t nl = (cuuint64_t)p.hl[l] * p.wl[l];
+            if (nl % 4 != 0) continue;
+            cuuint64_t dims[3] = {nl, (cuuint64_t)N, (cuuint64_t)B};
+            cuuint64_t str[2] = {nl * 4, (cuuint64_t)N * nl * 4};
+            cuuint32_t box[3] = {32, 32, 1};
+            rc = make_tmap(&to[l], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, p.lvl[l], 3, dims, str, box);
+            if (rc) return rc;
+            p.tma_out |= 1 << l;
+        }
+    }
+
     using rdvc::MODE_FUSED;
     using rdvc::MODE_LINEAR;
     if (linear) {
-        return (vol_dtype == RDVC_DT_F32) ? launch_build<MODE_LINEAR, 16, 16, float>(ta, tb, p, st)
-                                          : launch_build<MODE_LINEAR, 16, 16, __nv_bfloat16>(ta, tb, p, st);
+        return (vol_dtype == RDVC_DT_F32) ? launch_build<MODE_LINEAR, 16, 16, float>(ta, tb, to, p, st)
+                                          : launch_build<MODE_LINEAR, 16, 16, __nv_bfloat16>(ta, tb, to, p, st);
     }
     if (vol_dtype == RDVC_DT_F32) {
-        return (tile == 1) ? launch_build<MODE_FUSED, 16, 16, float>(ta, tb, p, st)
-                           : launch_build<MODE_FUSED, 8, 32, float>(ta, tb, p, st);
+        return (tile == 1) ? launch_build<MODE_FUSED, 16, 16, float>(ta, tb, to, p, st)
+                           : launch_build<MODE_FUSED, 8, 32, float>(ta, tb, to, p, st);
     }
-    return (tile == 1) ? launch_build<MODE_FUSED, 16, 16, __nv_bfloat16>(ta, tb, p, st)
-                       : launch_build<MODE_FUSED, 8, 32, __nv_bfloat16>(ta, tb, p, st);
+    return (tile == 1) ? launch_build<MODE_FUSED, 16, 16, __nv_bfloat16>(ta, tb, to, p, st)
+                       : launch_build<MODE_FUSED, 8, 32, __nv_bfloat16>(ta, tb, to, p, st);
 }
 
 int rdvc_corr_lookup(const void* pyramid, int vol_dtype, const float* coords, int B, int h, int w,

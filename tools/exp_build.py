@@ -25,10 +25,13 @@ def timeit(vol, n=5):
     blk.release()
     return e0.elapsed_time(e1) / n
 
-# configs: (tile, msplit, store_mask)
-for vol in (torch.float32, torch.bfloat16):
-    for tile in (2,):
-        for mask in (15, 1, 3, 5, 9, 7, 13, 11):
-            lib.rdvc_corr_set_option(1, tile); lib.rdvc_corr_set_option(3, mask)
-            print(f"{str(vol):15s} tile={tile} store_mask={mask:2d}: {timeit(vol):.3f} ms", flush=True)
-lib.rdvc_corr_set_option(3, 15)
+cfgs = [tuple(int(x) for x in a.split(",")) for a in sys.argv[1:] if "=" not in a] or [(2, 0, 0, 15)]
+for a in sys.argv[1:]:
+    if "=" in a:
+        k, v = a.split("=")
+        assert lib.rdvc_corr_set_option(int(k), int(v)) == 0, a
+for vol in (torch.float32,):
+    for (mode, tile, msplit, mask) in cfgs:
+        lib.rdvc_corr_set_option(4, mode); lib.rdvc_corr_set_option(1, tile)
+        lib.rdvc_corr_set_option(2, msplit); lib.rdvc_corr_set_option(3, mask)
+        print(f"{str(vol):15s} mode={mode} tile={tile} msplit={msplit} mask={mask:2d}: {timeit(vol):.3f} ms", flush=True)

@@ -15,6 +15,10 @@ g = torch.Generator(device="cuda").manual_seed(0)
 f1 = torch.randn(B, D, h, w, device="cuda", generator=g)
 f2 = torch.randn(B, D, h, w, device="cuda", generator=g)
 rc._cabi.load().rdvc_corr_set_option(1, tile)
+for kv in os.environ.get("RDVC_OPTS", "").split(","):
+    if kv:
+        k, v = kv.split("=")
+        assert rc._cabi.load().rdvc_corr_set_option(int(k), int(v)) == 0, kv
 blk = rc.TVCorrBlock(volume_dtype=vol)
 for _ in range(nb):
     blk.build_pyramid(f1, f2)
