@@ -1,0 +1,363 @@
+"""GPU parity tests (-m gpu): the CUDA path, called through the C ABI, against the oracles.
+
+Tolerances (BASELINE.json north_star), all max-norm relative = max|a-b| / max|ref|:
+  * correlation volume / pyramid vs the fp32 reference ......... 2e-2  (bf16 operands, fp32 accumulate)
+  * same, vs an fp64 evaluation of the SAME rounded operands .... 1e-4  (fp32 out) / 8e-3 (bf16 out)
+  * lookup vs the oracle's lookup of the SAME pyramid ........... 1e-3  (observed ~1e-6)
+  * RAFT flow end-point error vs stock torchvision, 12 updates .. 0.05 px mean
+"""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import rdvc_corr_b200 as rc
+from helpers import bf16_round, pyramid_from_levels, ref_pyramid_linear, rel_max
+from oracle import corr_c as cc
+from oracle import corr_numpy as cn
+from oracle import tv_corr as tv
+
+pytestmark = pytest.mark.gpu
+
+TOL_VOLUME = 2e-2
+TOL_SAME_OPERANDS_F32 = 1e-4
+TOL_SAME_OPERANDS_BF16 = 8e-3
+TOL_LOOKUP = 1e-3
+TOL_EPE = 0.05
+SIGMAS = (0.0, 0.3, 4.0, 40.0)
+MODES = {"fused": 1, "linear": 2}
+
+
+@pytest.fixture(scope="module")
+def lib():
+    assert torch.cuda.is_available(), "GPU tests need a B200"
+    L = rc._cabi.load()
+    yield L
+    for k in range(7):
+        L.rdvc_corr_set_option(k, {3: 15, 5: 1}.get(k, 0))
+
+
+def set_opts(lib, **kw):
+    keys = {"lookup": 0, "tile": 1, "msplit": 2, "mode": 4, "tma": 5}
+    for k, v in kw.items():
+        assert lib.rdvc_corr_set_option(keys[k], v) == 0
+
+
+def gpu(x):
+    return torch.from_numpy(np.ascontiguousarray(x)).cuda()
+
+
+# ------------------------------------------------------------------ lookup
+@pytest.mark.parametrize("variant", [1, 2])
+@pytest.mark.parametrize("shape", [(2, 8, 18, 22), (1, 8, 46, 80), (1, 4, 16, 16)])
+def test_lookup_matches_oracle(lib, shape, variant):
+    B, C, h, w = shape
+    f1, f2 = cn.synth_fmaps(B, C, h, w, seed=3)
+    flat = cc.build_pyramid(f1, f2, 4)
+    pyr = pyramid_from_levels(rc, cc.split_levels(flat, B, h, w, 4), B, h, w)
+    set_opts(lib, lookup=variant)
+    for sigma in SIGMAS:
+        co = cn.synth_coords(B, h, w, sigma, seed=1)
+        got = rc.index_pyramid(pyr, gpu(co), 4).cpu().numpy()
+        assert got.shape == (B, 324, h, w)
+        assert rel_max(got, cc.index_pyramid(flat, co, 4, 4)) < TOL_LOOKUP
+    set_opts(lib, lookup=0)
+
+
+def test_lookup_golden_small_odd(lib, golden_dir):
+    """Pyramid and lookups straight from the torchvision-generated fixture."""
+    g = np.load(os.path.join(golden_dir, "corr_small_odd.npz"))
+    B, C, h, w = [int(x) for x in g["shape"]]
+    pyr = pyramid_from_levels(rc, [g[f"level{l}"] for l in range(4)], B, h, w)
+    for s in SIGMAS:
+        co = cn.synth_coords(B, h, w, s, seed=1)
+        got = rc.index_pyramid(pyr, gpu(co), 4).cpu().numpy()
+        assert rel_max(got, g[f"lookup_sigma{s:g}"]) < TOL_LOOKUP
+
+
+@pytest.mark.parametrize("radius,levels", [(3, 3), (1, 1), (2, 4)])
+def test_lookup_other_radius_and_levels(lib, radius, levels):
+    B, C, h, w = 2, 8, 18, 22
+    f1, f2 = cn.synth_fmaps(B, C, h, w, seed=4)
+    flat = cc.build_pyramid(f1, f2, levels)
+    pyr = pyramid_from_levels(rc, cc.split_levels(flat, B, h, w, levels), B, h, w)
+    co = cn.synth_coords(B, h, w, 2.5, seed=2)
+    got = rc.index_pyramid(pyr, gpu(co), radius).cpu().numpy()
+    assert got.shape == (B, levels * (2 * radius + 1) ** 2, h, w)
+    assert rel_max(got, cc.index_pyramid(flat, co, levels, radius)) < TOL_LOOKUP
+
+
+def test_lookup_bf16_volume(lib):
+    B, C, h, w = 1, 8, 24, 40
+    f1, f2 = cn.synth_fmaps(B, C, h, w, seed=6)
+    flat = bf16_round(cc.build_pyramid(f1, f2, 4))   # what a bf16 pyramid stores
+    pyr = pyramid_from_levels(rc, cc.split_levels(flat, B, h, w, 4), B, h, w, torch.bfloat16)
+    co = cn.synth_coords(B, h, w, 3.0, seed=3)
+    got = rc.index_pyramid(pyr, gpu(co), 4).cpu().numpy()
+    assert rel_max(got, cc.index_pyramid(flat, co, 4, 4)) < TOL_LOOKUP
+
+
+def test_lookup_integer_coords_are_exact_gathers(lib):
+    B, C, h, w = 1, 8, 16, 24
+    f1, f2 = cn.synth_fmaps(B, C, h, w, seed=9)
+    lv = cc.split_levels(cc.build_pyramid(f1, f2, 1), B, h, w, 1)
+    pyr = pyramid_from_levels(rc, lv, B, h, w)
+    got = rc.index_pyramid(pyr, gpu(cn.make_coords_grid(B, h, w)), 4).cpu().numpy()
+    q = 7 * w + 9
+    for (i, j) in [(4, 4), (6, 2), (0, 8), (8, 0)]:
+        assert got[0, i * 9 + j, 7, 9] == lv[0][q, 7 + j - 4, 9 + i - 4]
+    assert np.all(got[0, 0 * 9 + 4, :, 0:4] == 0)  # dx = -4 at the left border: zero padding
+
+
+# ------------------------------------------------------------------ build
+BUILD_SHAPES = [(1, 64, 16, 16), (2, 64, 18, 22), (1, 128, 33, 47), (1, 256, 46, 80), (3, 64, 24, 40),
+                (1, 192, 20, 28)]
+
+
+@pytest.mark.parametrize("mode", ["fused", "linear"])
+@pytest.mark.parametrize("shape", BUILD_SHAPES)
+def test_build_fp32_volume(lib, shape, mode):
+    B, D, h, w = shape
+    f1, f2 = cn.synth_fmaps(B, D, h, w, seed=5)
+    ref32 = cn.build_pyramid(f1, f2, 4)                       # fp64 math on the un-rounded inputs
+    same = (cn.build_pyramid(bf16_round(f1), bf16_round(f2), 4) if mode == "fused"
+            else ref_pyramid_linear(f1, f2, 4))               # fp64 math on what the kernel multiplies
+    for tile in ((1, 2) if mode == "fused" else (0,)):
+        set_opts(lib, mode=MODES[mode], tile=tile)
+        pyr = rc.build_pyramid(gpu(f1), gpu(f2), 4)
+        for l in range(4):
+            got = pyr.level(l)[:, 0].cpu().numpy()
+            assert got.shape == ref32[l].shape
+            assert rel_max(got, same[l]) < TOL_SAME_OPERANDS_F32, (mode, tile, l)
+            assert rel_max(got, ref32[l]) < TOL_VOLUME, (mode, tile, l)
+    set_opts(lib, mode=0, tile=0)
+
+
+@pytest.mark.parametrize("mode", ["fused", "linear"])
+def test_build_bf16_volume(lib, mode):
+    B, D, h, w = 1, 128, 46, 80
+    f1, f2 = cn.synth_fmaps(B, D, h, w, seed=5)
+    ref32 = cn.build_pyramid(f1, f2, 4)
+    set_opts(lib, mode=MODES[mode])
+    pyr = rc.build_pyramid(gpu(f1), gpu(f2), 4, torch.bfloat16)
+    for l in range(4):
+        got = pyr.level(l)[:, 0].float().cpu().numpy()
+        assert rel_max(got, ref32[l]) < TOL_VOLUME
+    set_opts(lib, mode=0)
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_build_half_inputs(lib, dtype):
+    """Under the reference's default AMP the fmaps arrive in half precision."""
+    B, D, h, w = 1, 64, 24, 40
+    f1, f2 = cn.synth_fmaps(B, D, h, w, seed=8)
+    ref32 = cn.build_pyramid(f1, f2, 4)
+    pyr = rc.build_pyramid(gpu(f1).to(dtype), gpu(f2).to(dtype), 4)
+    for l in range(4):
+        assert rel_max(pyr.level(l)[:, 0].cpu().numpy(), ref32[l]) < TOL_VOLUME
+
+
+@pytest.mark.parametrize("levels", [1, 2, 3])
+def test_build_fewer_levels(lib, levels):
+    B, D, h, w = 1, 64, 18, 22
+    f1, f2 = cn.synth_fmaps(B, D, h, w, seed=2)
+    ref = ref_pyramid_linear(f1, f2, levels)
+    pyr = rc.build_pyramid(gpu(f1), gpu(f2), levels)
+    assert len(pyr.levels()) == levels
+    for l in range(levels):
+        assert rel_max(pyr.level(l)[:, 0].cpu().numpy(), ref[l]) < TOL_SAME_OPERANDS_F32
+
+
+def test_build_staged_store_path(lib):
+    """Linear mode without TMA stores (the path odd-sized levels take)."""
+    B, D, h, w = 1, 64, 24, 40
+    f1, f2 = cn.synth_fmaps(B, D, h, w, seed=12)
+    ref = ref_pyramid_linear(f1, f2, 4)
+    set_opts(lib, mode=2, tma=0)
+    pyr = rc.build_pyramid(gpu(f1), gpu(f2), 4)
+    for l in range(4):
+        assert rel_max(pyr.level(l)[:, 0].cpu().numpy(), ref[l]) < TOL_SAME_OPERANDS_F32
+    set_opts(lib, mode=0, tma=1)
+
+
+def test_build_golden_ref_default(lib, golden_dir):
+    """D=256, 46x80: RDVC's default RAFT size; sampled entries from torchvision's fp32 CorrBlock."""
+    g = np.load(os.path.join(golden_dir, "corr_ref_default.npz"))
+    B, D, h, w = [int(x) for x in g["shape"]]
+    f1, f2 = cn.synth_fmaps(B, D, h, w, seed=int(g["seed"]))
+    blk = rc.TVCorrBlock()
+    blk.build_pyramid(gpu(f1), gpu(f2))
+    for l in range(4):
+        got = blk.corr_pyramid[l].reshape(-1)[torch.from_numpy(g[f"level{l}_idx"]).cuda()].cpu().numpy()
+        assert rel_max(got, g[f"level{l}_val"]) < TOL_VOLUME
+    own = [blk.corr_pyramid[l][:, 0].cpu().numpy() for l in range(4)]
+    flat = np.concatenate([x.reshape(-1) for x in own])
+    for s in SIGMAS:
+        co = cn.synth_coords(B, h, w, s, seed=1)
+        got = blk.index_pyramid(centroids_coords=gpu(co)).cpu().numpy()
+        # vs the oracle's lookup of OUR pyramid: isolates the lookup kernel (1e-3) ...
+        assert rel_max(got, cc.index_pyramid(flat, co, 4, 4)) < TOL_LOOKUP
+        # ... and end to end vs the fixture (bf16 operand error carried through): 2e-2
+        assert rel_max(got.reshape(-1)[::11], g[f"lookup_sigma{s:g}_stride11"]) < TOL_VOLUME
+
+
+def test_build_rejects_unsupported(lib):
+    f = torch.zeros(1, 32, 18, 22, device="cuda")
+    with pytest.raises(ValueError, match="RDVC_E_UNSUPPORTED"):
+        rc.build_pyramid(f, f, 4)
+    with pytest.raises(ValueError, match="too small"):
+        rc.build_pyramid(torch.zeros(1, 64, 8, 22, device="cuda"), torch.zeros(1, 64, 8, 22, device="cuda"), 4)
+
+
+def test_build_is_linear_and_deterministic(lib):
+    B, D, h, w = 1, 64, 24, 40
+    f1, f2 = cn.synth_fmaps(B, D, h, w, seed=13)
+    a = rc.build_pyramid(gpu(f1), gpu(f2), 4).buffer.clone()
+    b = rc.build_pyramid(gpu(f1), gpu(f2), 4).buffer.clone()
+    assert torch.equal(a, b)                                   # bit-identical reruns
+    p2 = rc.build_pyramid(gpu(f1), gpu(f2 * 2.0), 4)           # power-of-two scaling is exact in bf16
+    p1 = rc.build_pyramid(gpu(f1), gpu(f2), 4)
+    for l in range(4):
+        assert torch.equal(p2.level(l), p1.level(l) * 2.0)
+
+
+# ------------------------------------------------------------------ full size: 1920x1088
+def test_1080p_properties(lib):
+    """BASELINE.json config 2 shape: the oracle cannot hold the 5.7 GB pyramid in seconds, so
+    check size-independent properties + sampled rows against a torch fp32 matmul."""
+    B, D, h, w = 1, 256, 136, 240
+    N = h * w
+    g = torch.Generator(device="cuda").manual_seed(0)
+    f1 = torch.randn(B, D, h, w, device="cuda", generator=g)
+    f2 = torch.randn(B, D, h, w, device="cuda", generator=g)
+    blk = rc.TVCorrBlock()
+    blk.build_pyramid(f1, f2)
+    lv = blk.corr_pyramid
+    assert [tuple(x.shape) for x in lv] == [(N, 1, 136, 240), (N, 1, 68, 120), (N, 1, 34, 60), (N, 1, 17, 30)]
+    a = f1.to(torch.bfloat16).float().view(D, N)
+    f2p = [f2] + [torch.nn.functional.avg_pool2d(f2, 2 ** l) for l in (1, 2, 3)]
+    rows = torch.tensor([0, 1, 127, 128, 4097, 17000, N - 129, N - 1], device="cuda")
+    for l in range(4):
+        b = f2p[l].to(torch.bfloat16).float().view(D, -1)
+        ref = (a[:, rows].t().double() @ b.double() / 16.0).float()
+        got = lv[l][rows, 0].reshape(len(rows), -1)
+        err = (got - ref).abs().max().item() / ref.abs().max().item()
+        assert err < TOL_SAME_OPERANDS_F32, (l, err)
+    # pyramid consistency: level l+1 is the 2x2 mean of level l (to bf16-operand accuracy)
+    sl = slice(5000, 5256)
+    for l in range(3):
+        pooled = torch.nn.functional.avg_pool2d(lv[l][sl], 2)
+        err = (pooled - lv[l + 1][sl]).abs().max().item() / lv[l + 1][sl].abs().max().item()
+        assert err < TOL_VOLUME, (l, err)
+    # checksum of checksums: sum over fmap2 pixels == fmap1 . sum(fmap2)
+    tot = lv[0][rows, 0].double().sum(dim=(1, 2))
+    ref = (a[:, rows].t().double() @ f2.to(torch.bfloat16).double().view(D, N).sum(dim=1)) / 16.0
+    assert ((tot - ref).abs().max() / ref.abs().max()).item() < 1e-3
+    # lookup at the identity grid: centre tap of level 0 is the volume diagonal
+    co = gpu(cn.make_coords_grid(B, h, w))
+    out = blk.index_pyramid(centroids_coords=co)
+    assert out.shape == (B, 324, h, w) and out.is_contiguous() and out.dtype == torch.float32
+    diag = lv[0].view(N, N).diagonal()
+    assert torch.equal(out[0, 4 * 9 + 4].reshape(-1), diag)
+    # and a drifting lookup against torchvision's own index_pyramid ON OUR PYRAMID
+    co2 = gpu(cn.synth_coords(B, h, w, 3.0, seed=4))
+    got = blk.index_pyramid(centroids_coords=co2)
+    ref = tv.index_pyramid([x for x in lv], co2, 4)
+    err = (got - ref).abs().max().item() / ref.abs().max().item()
+    assert err < TOL_LOOKUP, err
+    blk.release()
+
+
+# ------------------------------------------------------------------ drop-in: torchvision RAFT
+def _preprocess(frame_u8, size_hw):
+    """R:codec_processing.py:751-759: to_tensor -> resize(antialias) -> [0,1], batch of 1."""
+    import torchvision.transforms.functional as TF
+    t = TF.resize(TF.to_tensor(frame_u8), list(size_hw), antialias=True)
+    return t.unsqueeze(0)
+
+
+def _seeded_raft(corr_block=None):
+    from torchvision.models.optical_flow import raft_large
+    torch.manual_seed(0)
+    kw = {} if corr_block is None else {"corr_block": corr_block}
+    return raft_large(weights=None, **kw).eval().cuda()
+
+
+@pytest.mark.parametrize("vol_dtype", [torch.float32, torch.bfloat16])
+def test_raft_flow_epe_vs_stock_torchvision(lib, golden_dir, vol_dtype):
+    """BASELINE.json config 1 shape: R:im1.png / R:im2.png at 368x640, 12 updates, seed-0
+    random-init raft_large (no weights offline), [0,1] inputs like the reference."""
+    g = np.load(os.path.join(golden_dir, "frames_im1_im2.npz"))
+    a = _preprocess(g["im1"], (368, 640)).cuda()
+    b = _preprocess(g["im2"], (368, 640)).cuda()
+    with torch.no_grad():
+        ref = _seeded_raft()(a, b, num_flow_updates=12)[-1]
+        blk = rc.TVCorrBlock(volume_dtype=vol_dtype)
+        n0 = lib.rdvc_corr_launch_count()
+        got = _seeded_raft(blk)(a, b, num_flow_updates=12)[-1]
+        launched = lib.rdvc_corr_launch_count() - n0
+    assert launched == 3 + 12, launched            # pack, pack+pool, build, 12 lookups
+    epe = (got - ref).pow(2).sum(dim=1).sqrt()
+    assert torch.isfinite(got).all()
+    assert epe.mean().item() < TOL_EPE, epe.mean().item()
+    # the CPU fixture (stock torchvision, CPU fp32) is a second, looser anchor
+    cpu_ref = torch.from_numpy(g["flow_stride2"]).cuda()
+    epe_cpu = (got[0, :, ::2, ::2] - cpu_ref).pow(2).sum(dim=0).sqrt()
+    assert epe_cpu.mean().item() < 2 * TOL_EPE, epe_cpu.mean().item()
+
+
+def test_raft_under_autocast(lib, golden_dir):
+    """The reference's default GPU setting wraps RAFT in autocast (R:codec_processing.py:1436)."""
+    g = np.load(os.path.join(golden_dir, "frames_im1_im2.npz"))
+    a = _preprocess(g["im1"], (256, 448)).cuda()
+    b = _preprocess(g["im2"], (256, 448)).cuda()
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):
+        ref = _seeded_raft()(a, b, num_flow_updates=12)[-1]
+        got = _seeded_raft(rc.TVCorrBlock())(a, b, num_flow_updates=12)[-1]
+    epe = (got.float() - ref.float()).pow(2).sum(dim=1).sqrt()
+    assert epe.mean().item() < TOL_EPE, epe.mean().item()
+
+
+def test_princeton_facade(lib):
+    B, D, h, w = 1, 64, 24, 40
+    f1, f2 = cn.synth_fmaps(B, D, h, w, seed=21)
+    corr = rc.CorrBlock(gpu(f1), gpu(f2), num_levels=4, radius=4)
+    co = cn.synth_coords(B, h, w, 1.5, seed=5)
+    got = corr(gpu(co)).cpu().numpy()
+    own = np.concatenate([x[:, 0].cpu().numpy().reshape(-1) for x in corr.corr_pyramid])
+    assert got.shape == (B, 324, h, w)
+    assert rel_max(got, cc.index_pyramid(own, co, 4, 4)) < TOL_LOOKUP
+
+
+# ------------------------------------------------------------------ ABI details
+def test_pair_host_entry_point(lib):
+    """rdvc_corr_pair_host: host buffers in, host buffers out, same numbers as the device calls."""
+    B, D, h, w, iters = 1, 64, 24, 40, 3
+    f1, f2 = cn.synth_fmaps(B, D, h, w, seed=31)
+    coords = np.stack([cn.synth_coords(B, h, w, 1.0 + i, seed=i) for i in range(iters)])
+    out = np.empty((iters, B, 324, h, w), np.float32)
+    fp = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    rc_ = lib.rdvc_corr_pair_host(fp(f1), fp(f2), fp(coords), fp(out), B, D, h, w, 4, 4, iters, rc.RDVC_DT_F32)
+    rc._cabi.check(rc_, "rdvc_corr_pair_host")
+    blk = rc.TVCorrBlock()
+    blk.build_pyramid(gpu(f1), gpu(f2))
+    for i in range(iters):
+        ref = blk.index_pyramid(centroids_coords=gpu(coords[i])).cpu().numpy()
+        assert np.array_equal(out[i], ref)
+    lib.rdvc_corr_release()
+
+
+def test_runs_on_callers_stream(lib):
+    B, D, h, w = 1, 64, 24, 40
+    f1, f2 = cn.synth_fmaps(B, D, h, w, seed=41)
+    a, b = gpu(f1), gpu(f2)
+    co = gpu(cn.synth_coords(B, h, w, 2.0, seed=1))
+    ref = rc.CorrBlock(a, b)(co)
+    torch.cuda.synchronize()
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        got = rc.CorrBlock(a, b)(co)
+    s.synchronize()
+    assert torch.equal(got, ref)
