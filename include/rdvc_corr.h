@@ -110,6 +110,10 @@ void rdvc_corr_release(void);
 /* ---- introspection for tests / benches --------------------------------- */
 /* Number of kernels this library has launched on the calling thread.         */
 unsigned long long rdvc_corr_launch_count(void);
+/* Caller-owned cudaEvent_t pair recorded on the build stream immediately before and after
+ * the main build kernel of the next rdvc_corr_build calls on this thread (NULL, NULL = off).
+ * Lets a bench time the dominant kernel alone, on the stream it runs on.             */
+void rdvc_corr_set_profile_events(void* start_event, void* stop_event);
 /* Debug/tuning knobs; unknown keys return RDVC_E_UNSUPPORTED.
  *   key 0: lookup variant   (0 = auto, 1 = scalar loads, 2 = 128-bit loads)
  *   key 1: build tile shape (0 = auto, 1 = 16x16, 2 = 8x32 fmap2 pixels)

@@ -35,6 +35,7 @@ SYMBOLS = {
     "rdvc_corr_release": (None, []),
     "rdvc_corr_launch_count": (_c.c_ulonglong, []),
     "rdvc_corr_set_option": (_c.c_int, [_c.c_int, _c.c_int]),
+    "rdvc_corr_set_profile_events": (None, [_c.c_void_p, _c.c_void_p]),
 }
 
 _lib = None

@@ -20,6 +20,7 @@ namespace {
 
 thread_local char g_err[512] = "";
 thread_local unsigned long long g_launches = 0;
+thread_local cudaEvent_t g_prof_start = nullptr, g_prof_stop = nullptr;
 std::atomic<int> g_opt_lookup{0};
 std::atomic<int> g_opt_tile{0};
 std::atomic<int> g_opt_msplit{0};
@@ -126,8 +127,10 @@ int launch_build(const CUtensorMap& ta, const CUtensorMap* tb, const CUtensorMap
     long long grid = sm_count();
     const long long n_items = static_cast<long long>(p.B) * p.ntiles * p.msplit;
     if (grid > n_items) grid = n_items;
+    if (g_prof_start) cudaEventRecord(g_prof_start, st);
     kern<<<static_cast<unsigned>(grid), rdvc::BLD_THREADS, rdvc::BLD_SMEM_LAUNCH, st>>>(
         ta, tb[0], tb[1], tb[2], tb[3], to[0], to[1], to[2], to[3], p);
+    if (g_prof_stop) cudaEventRecord(g_prof_stop, st);
     ++g_launches;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "corr_build_kernel launch");
@@ -210,6 +213,11 @@ extern "C" {
 int rdvc_corr_version(void) { return RDVC_CORR_VERSION; }
 const char* rdvc_corr_last_error(void) { return g_err; }
 unsigned long long rdvc_corr_launch_count(void) { return g_launches; }
+
+void rdvc_corr_set_profile_events(void* start, void* stop) {
+    g_prof_start = static_cast<cudaEvent_t>(start);
+    g_prof_stop = static_cast<cudaEvent_t>(stop);
+}
 
 int rdvc_corr_set_option(int key, int value) {
     if (key == 0 && value >= 0 && value <= 2) { g_opt_lookup = value; return RDVC_OK; }

@@ -1,0 +1,103 @@
+"""GOP sharding of RDVC's encoder over the GPUs of one box.
+
+The encoder is open loop -- the reference frame of a P-frame is the ORIGINAL previous frame
+(R:codec_processing.py:1498-1499) -- so a GOP (an I-frame plus the P-frames up to the next
+I-frame, `iframe_interval` frames, R:codec_processing.py:634,1392) depends on no other GOP.
+One process per GPU takes whole GOPs; the motion branch of every P-frame runs RAFT with the
+B200 correlation block.  There is NO collective on the data path: the only cross-rank step is
+a host-side gather of per-GOP byte strings into the `.rdvc` writer on rank 0.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Callable, Dict, List, Optional, Sequence, Tuple
+
+from . import rdvc_format as fmt
+
+
+@dataclass(frozen=True)
+class Gop:
+    index: int          # GOP number
+    start: int          # global index of its I-frame
+    stop: int           # one past its last frame
+
+    @property
+    def num_pframes(self) -> int:
+        return max(0, self.stop - self.start - 1)
+
+
+def split_gops(num_frames: int, iframe_interval: int) -> List[Gop]:
+    """Frame t is an I-frame iff t % iframe_interval == 0 (R:codec_processing.py:1392)."""
+    if num_frames < 0 or iframe_interval <= 0:
+        raise ValueError("num_frames must be >= 0 and iframe_interval > 0")
+    return [Gop(g, s, min(s + iframe_interval, num_frames))
+            for g, s in enumerate(range(0, num_frames, iframe_interval))]
+
+
+def assign_gops(gops: Sequence[Gop], world_size: int) -> List[List[Gop]]:
+    """Static longest-processing-time assignment by P-frame count: deterministic, identical on
+    every rank without communication, and balanced to within one GOP.  (60 GOPs on 8 GPUs
+    cannot beat 7.5x with whole GOPs; ragged tails are spread instead of piling on one rank.)"""
+    if world_size <= 0:
+        raise ValueError("world_size must be positive")
+    load = [0] * world_size
+    out: List[List[Gop]] = [[] for _ in range(world_size)]
+    for g in sorted(gops, key=lambda g: (-g.num_pframes, g.index)):
+        r = min(range(world_size), key=lambda r: (load[r], r))
+        out[r].append(g)
+        load[r] += max(1, g.num_pframes)
+    for lst in out:
+        lst.sort(key=lambda g: g.index)
+    return out
+
+
+def encode_gop(gop: Gop, frames: Callable[[int], object], encode_iframe: Callable[[object], bytes],
+               encode_pframe: Callable[[object, object], bytes]) -> bytes:
+    """Frame records of one GOP.  `frames(t)` returns frame t; `encode_iframe(frame)` returns the I
+    payload; `encode_pframe(prev_original, cur)` the P payload (motion branch + codec).  A failing
+    P-frame turns the NEXT frame into an I-frame, as the reference does
+    (R:codec_processing.py:1501-1506)."""
+    parts: List[bytes] = []
+    prev = None
+    force_i = True
+    for t in range(gop.start, gop.stop):
+        cur = frames(t)
+        if force_i or prev is None:
+            parts.append(fmt.FrameRecord(t, "I", encode_iframe(cur)).pack())
+            force_i = False
+        else:
+            try:
+                parts.append(fmt.FrameRecord(t, "P", encode_pframe(prev, cur)).pack())
+            except Exception:
+                parts.append(fmt.FrameRecord(t, "P", fmt.pframe_payload((0, 0), b"", (0, 0), b"")).pack())
+                force_i = True
+        prev = cur   # open loop: the ORIGINAL frame is the next reference
+    return b"".join(parts)
+
+
+def gather_stream(local: Dict[int, bytes], num_gops: int, metadata: dict, rank: int = 0,
+                  world_size: int = 1, group=None) -> Optional[bytes]:
+    """Host-side gather of {gop index: bytes} from every rank; rank 0 returns the `.rdvc` stream.
+    `total_frames_processed` / `total_pframe_payload_bytes` are plain host sums
+    (R:codec_processing.py:1528,1535)."""
+    if world_size > 1:
+        import torch.distributed as dist
+        gathered: List[Optional[Dict[int, bytes]]] = [None] * world_size if rank == 0 else None
+        dist.gather_object(local, gathered, dst=0, group=group)
+        if rank != 0:
+            return None
+        merged: Dict[int, bytes] = {}
+        for d in gathered:
+            merged.update(d)
+    else:
+        merged = dict(local)
+    missing = [g for g in range(num_gops) if g not in merged]
+    if missing:
+        raise RuntimeError(f"GOPs missing from the gather: {missing}")
+    ordered = [merged[g] for g in range(num_gops)]
+    import io
+    records = [r for b in ordered for r in fmt.iter_frames(io.BytesIO(b))]
+    meta = dict(metadata)
+    meta["total_frames_processed"] = len(records)
+    meta["total_pframe_payload_bytes"] = fmt.pframe_payload_bytes(records)
+    return fmt.write_stream(meta, ordered)

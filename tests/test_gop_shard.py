@@ -1,0 +1,152 @@
+"""CPU tests (-m "not gpu"): `.rdvc` container round trips and the GOP-sharded gather, including a
+real world_size=2 gloo run (the N>1 host path; there is no data-path collective to test)."""
+import io
+import os
+import socket
+import struct
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import rdvc_corr_b200 as rc
+
+fmt = rc.rdvc_format
+gs = rc.gop_shard
+
+
+# ------------------------------------------------------------------ container format
+def test_record_layout_is_the_references():
+    """Byte layout of R:codec_processing.py:1398-1418 / :1485-1495, spelled out by hand."""
+    i_payload = fmt.iframe_payload(b"\xff\xd8JPEG", ".jpg")
+    assert i_payload == b"\x04.jpg\xff\xd8JPEG"
+    rec = fmt.FrameRecord(7, "I", i_payload).pack()
+    assert rec == b"RDVCFRME" + struct.pack(">I", 7) + b"I" + struct.pack(">Q", len(i_payload)) + i_payload
+    p_payload = fmt.pframe_payload((17, 30), b"mm", (68, 120), b"rrr")
+    assert p_payload == (struct.pack(">i", 17) + struct.pack(">i", 30) + struct.pack(">I", 2) + b"mm" +
+                         struct.pack(">i", 68) + struct.pack(">i", 120) + struct.pack(">I", 3) + b"rrr")
+    assert fmt.parse_pframe_payload(p_payload) == ((17, 30), b"mm", (68, 120), b"rrr")
+    assert fmt.parse_iframe_payload(i_payload) == (".jpg", b"\xff\xd8JPEG")
+
+
+def test_stream_round_trip_and_errors():
+    recs = [fmt.FrameRecord(0, "I", fmt.iframe_payload(b"abc")),
+            fmt.FrameRecord(1, "P", fmt.pframe_payload((2, 3), b"m" * 5, (4, 6), b"r" * 9)),
+            fmt.FrameRecord(2, "P", fmt.pframe_payload((2, 3), b"", (4, 6), b""))]
+    data = fmt.write_stream({"rdvc_version": "1.0", "iframe_interval": 10}, [r.pack() for r in recs])
+    assert data.startswith(b"RDVCMETA") and data.endswith(b"RDVCEND_")
+    meta, out = fmt.read_stream(data)
+    assert meta["rdvc_version"] == "1.0" and out == recs
+    assert fmt.pframe_payload_bytes(out) == 14
+    with pytest.raises(ValueError, match="METADATA marker"):
+        fmt.read_stream(b"XXXXXXXX" + data[8:])
+    with pytest.raises(ValueError, match="FRAME marker"):
+        list(fmt.iter_frames(io.BytesIO(b"BADMARK_" + b"\0" * 20)))
+    with pytest.raises(EOFError):
+        list(fmt.iter_frames(io.BytesIO(recs[1].pack()[:-3])))
+    with pytest.raises(ValueError):
+        fmt.FrameRecord(0, "B", b"").pack()
+    empty_meta, empty = fmt.read_stream(fmt.write_stream({}, []))
+    assert empty == [] and empty_meta == {}
+
+
+# ------------------------------------------------------------------ GOP partition
+def test_split_gops():
+    g = gs.split_gops(600, 10)
+    assert len(g) == 60 and g[0] == gs.Gop(0, 0, 10) and g[-1] == gs.Gop(59, 590, 600)
+    r = gs.split_gops(25, 10)                       # ragged tail
+    assert [(x.start, x.stop, x.num_pframes) for x in r] == [(0, 10, 9), (10, 20, 9), (20, 25, 4)]
+    assert gs.split_gops(0, 10) == []
+    assert gs.split_gops(1, 5)[0].num_pframes == 0
+    with pytest.raises(ValueError):
+        gs.split_gops(10, 0)
+
+
+@pytest.mark.parametrize("world", [1, 2, 4, 8])
+def test_assign_gops_is_a_balanced_partition(world):
+    gops = gs.split_gops(600, 10)
+    parts = gs.assign_gops(gops, world)
+    flat = sorted(g.index for p in parts for g in p)
+    assert flat == list(range(60))                                  # partition: every GOP exactly once
+    loads = [sum(g.num_pframes for g in p) for p in parts]
+    assert max(loads) - min(loads) <= 9                             # within one GOP
+    assert gs.assign_gops(gops, world) == parts                     # deterministic on every rank
+    assert all(p == sorted(p, key=lambda g: g.index) for p in parts)
+    # more ranks than GOPs: the extras get nothing
+    few = gs.assign_gops(gs.split_gops(15, 10), 8)
+    assert sum(len(p) for p in few) == 2 and sum(1 for p in few if not p) == 6
+
+
+def _fake_encoders():
+    frames = lambda t: bytes([t % 251]) * 4
+    enc_i = lambda f: fmt.iframe_payload(b"J" + f)
+    enc_p = lambda prev, cur: fmt.pframe_payload((1, 2), prev, (3, 4), cur)
+    return frames, enc_i, enc_p
+
+
+def test_encode_gop_open_loop_and_failure_recovery():
+    frames, enc_i, enc_p = _fake_encoders()
+    recs = list(fmt.iter_frames(io.BytesIO(gs.encode_gop(gs.Gop(2, 20, 25), frames, enc_i, enc_p))))
+    assert [(r.index, r.kind) for r in recs] == [(20, "I"), (21, "P"), (22, "P"), (23, "P"), (24, "P")]
+    # open loop: the P-frame of t references the ORIGINAL frame t-1
+    assert fmt.parse_pframe_payload(recs[2].payload)[1] == frames(21)
+
+    def flaky(prev, cur):
+        if cur == frames(22):
+            raise RuntimeError("boom")
+        return enc_p(prev, cur)
+    recs = list(fmt.iter_frames(io.BytesIO(gs.encode_gop(gs.Gop(2, 20, 25), frames, enc_i, flaky))))
+    assert [(r.index, r.kind) for r in recs] == [(20, "I"), (21, "P"), (22, "P"), (23, "I"), (24, "P")]
+
+
+def _serial_stream(num_frames, interval, meta):
+    frames, enc_i, enc_p = _fake_encoders()
+    gops = gs.split_gops(num_frames, interval)
+    local = {g.index: gs.encode_gop(g, frames, enc_i, enc_p) for g in gops}
+    return gs.gather_stream(local, len(gops), meta)
+
+
+def test_single_rank_stream():
+    data = _serial_stream(25, 10, {"rdvc_version": "1.0"})
+    meta, recs = fmt.read_stream(data)
+    assert [r.index for r in recs] == list(range(25))
+    assert [r.kind for r in recs] == ["I" if t % 10 == 0 else "P" for t in range(25)]
+    assert meta["total_frames_processed"] == 25
+    assert meta["total_pframe_payload_bytes"] == 22 * 8
+    with pytest.raises(RuntimeError, match="missing"):
+        gs.gather_stream({0: b""}, 2, {})
+
+
+# ------------------------------------------------------------------ world_size = 2 over gloo
+def _worker(rank, world, port, num_frames, interval, out_path):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    frames, enc_i, enc_p = _fake_encoders()
+    gops = gs.split_gops(num_frames, interval)
+    mine = gs.assign_gops(gops, world)[rank]
+    local = {g.index: gs.encode_gop(g, frames, enc_i, enc_p) for g in mine}
+    data = gs.gather_stream(local, len(gops), {"rdvc_version": "1.0"}, rank, world)
+    if rank == 0:
+        with open(out_path, "wb") as f:
+            f.write(data)
+    else:
+        assert data is None
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+@pytest.mark.timeout(180)
+def test_two_rank_gather_equals_serial(tmp_path):
+    out = str(tmp_path / "two_rank.rdvc")
+    mp.spawn(_worker, args=(2, _free_port(), 47, 5, out), nprocs=2, join=True)
+    with open(out, "rb") as f:
+        sharded = f.read()
+    assert sharded == _serial_stream(47, 5, {"rdvc_version": "1.0"})   # byte-identical to 1-rank encode
