@@ -22,8 +22,9 @@ from .corr_block import (  # noqa: F401
     build_pyramid,
     index_pyramid,
 )
+from .raft_flow import raft_flow  # noqa: F401
 
 __all__ = [
-    "CorrBlock", "CorrPyramid", "TVCorrBlock", "build_pyramid", "index_pyramid",
+    "CorrBlock", "CorrPyramid", "TVCorrBlock", "build_pyramid", "index_pyramid", "raft_flow",
     "RDVC_DT_BF16", "RDVC_DT_F16", "RDVC_DT_F32",
 ]

@@ -1,0 +1,71 @@
+"""The motion branch's RAFT call, restated around the B200 correlation block ("next" row f-2).
+
+RDVC calls ``raft_model(img1, img2, num_flow_updates=12)`` and keeps only ``flow_preds[-1]``
+(R:codec_processing.py:1442-1444).  ``RAFT.forward`` (TV:raft.py:484-533) nevertheless runs the
+mask predictor and the 8x convex upsampling after EVERY update and keeps all 12 full-resolution
+flows.  :func:`raft_flow` executes the same modules in the same order but upsamples once, at the
+end -- bit-identical final flow, 11 mask-predictor + upsample passes fewer -- and uses the
+correlation block's preallocated output so the refinement loop allocates nothing.
+
+All convolutions stay stock PyTorch/cuDNN; only the correlation block is this library's.
+"""
+from __future__ import annotations
+
+from typing import List, Optional
+
+import torch
+import torch.nn.functional as F
+from torch import Tensor
+
+from .corr_block import TVCorrBlock, index_pyramid
+
+
+def _coords_grid(batch: int, h: int, w: int, device) -> Tensor:
+    """TV:_utils.py:22-26 -- channel 0 = x, channel 1 = y."""
+    ys, xs = torch.meshgrid(torch.arange(h, device=device), torch.arange(w, device=device), indexing="ij")
+    return torch.stack([xs, ys], dim=0).float()[None].repeat(batch, 1, 1, 1)
+
+
+@torch.no_grad()
+def raft_flow(model, image1: Tensor, image2: Tensor, num_flow_updates: int = 12,
+              corr_block: Optional[TVCorrBlock] = None, all_predictions: bool = False):
+    """Final optical flow (B, 2, H, W) of a torchvision RAFT ``model`` for one frame pair.
+
+    ``corr_block`` defaults to ``model.corr_block``, which must be a :class:`TVCorrBlock`
+    (inject it with ``raft_large(corr_block=TVCorrBlock())``).  With ``all_predictions=True`` the
+    list of all upsampled flows is returned, exactly like ``RAFT.forward``.
+    """
+    from torchvision.models.optical_flow._utils import upsample_flow
+
+    blk = corr_block if corr_block is not None else model.corr_block
+    if not isinstance(blk, TVCorrBlock):
+        raise TypeError("raft_flow needs a rdvc_corr_b200.TVCorrBlock as the model's corr_block")
+    batch, _, h, w = image1.shape
+    if (h, w) != image2.shape[-2:]:
+        raise ValueError(f"input images should have the same shape, instead got ({h}, {w}) != {image2.shape[-2:]}")
+    if not ((h % 8 == 0) and (w % 8 == 0)):
+        raise ValueError(f"input image H and W should be divisible by 8, instead got {h} (h) and {w} (w)")
+
+    fmaps = model.feature_encoder(torch.cat([image1, image2], dim=0))
+    fmap1, fmap2 = torch.chunk(fmaps, chunks=2, dim=0)
+    blk.build_pyramid(fmap1, fmap2)
+
+    context_out = model.context_encoder(image1)
+    hidden_size = model.update_block.hidden_state_size
+    hidden_state, context = torch.split(context_out, [hidden_size, context_out.shape[1] - hidden_size], dim=1)
+    hidden_state = torch.tanh(hidden_state)
+    context = F.relu(context)
+
+    coords0 = _coords_grid(batch, h // 8, w // 8, fmap1.device)
+    coords1 = coords0.clone()
+    corr_out = torch.empty((batch, blk.out_channels, h // 8, w // 8), dtype=torch.float32, device=fmap1.device)
+    preds: List[Tensor] = []
+    for it in range(num_flow_updates):
+        corr_features = index_pyramid(blk._pyr, coords1, blk.radius, out=corr_out)
+        flow = coords1 - coords0
+        hidden_state, delta_flow = model.update_block(hidden_state, context, corr_features, flow)
+        coords1 = coords1 + delta_flow
+        if all_predictions or it == num_flow_updates - 1:
+            up_mask = None if model.mask_predictor is None else model.mask_predictor(hidden_state)
+            preds.append(upsample_flow(flow=(coords1 - coords0), up_mask=up_mask))
+    return preds if all_predictions else preds[-1]

@@ -320,6 +320,25 @@ def test_raft_under_autocast(lib, golden_dir):
     assert epe.mean().item() < TOL_EPE, epe.mean().item()
 
 
+def test_raft_flow_runner_matches_forward(lib, golden_dir):
+    """rc.raft_flow == RAFT.forward(...)[-1] with the same block: same modules, same order, the 11
+    unused mask/upsample passes skipped (the caller keeps only flow_preds[-1], R:codec_processing.py:1444)."""
+    g = np.load(os.path.join(golden_dir, "frames_im1_im2.npz"))
+    a = _preprocess(g["im1"], (256, 448)).cuda()
+    b = _preprocess(g["im2"], (256, 448)).cuda()
+    model = _seeded_raft(rc.TVCorrBlock())
+    with torch.no_grad():
+        ref = model(a, b, num_flow_updates=12)
+        got = rc.raft_flow(model, a, b, num_flow_updates=12)
+        every = rc.raft_flow(model, a, b, num_flow_updates=12, all_predictions=True)
+    assert torch.allclose(got, ref[-1], rtol=0, atol=1e-5)
+    assert len(every) == 12 and all(torch.allclose(x, y, rtol=0, atol=1e-5) for x, y in zip(every, ref))
+    with pytest.raises(TypeError):
+        rc.raft_flow(_seeded_raft(), a, b)
+    with pytest.raises(ValueError, match="divisible by 8"):
+        rc.raft_flow(model, a[..., :250, :], b[..., :250, :])
+
+
 def test_princeton_facade(lib):
     B, D, h, w = 1, 64, 24, 40
     f1, f2 = cn.synth_fmaps(B, D, h, w, seed=21)
