@@ -368,6 +368,51 @@ def test_pair_host_entry_point(lib):
     lib.rdvc_corr_release()
 
 
+@pytest.mark.parametrize("mode", ["fused", "linear"])
+@pytest.mark.parametrize("vol", [torch.float32, torch.bfloat16])
+def test_no_out_of_bounds_writes(lib, mode, vol):
+    """compute-sanitizer is closed on this pool, so bounds are checked with canaries: every byte
+    outside the pyramid levels / lookup output / workspace (guard bands before and after, and the
+    256-byte padding between levels) must survive a build + lookups on odd shapes."""
+    CANARY, GUARD = 0xAB, 4096
+    vd = rc.RDVC_DT_F32 if vol == torch.float32 else rc.RDVC_DT_BF16
+    es = 4 if vol == torch.float32 else 2
+    set_opts(lib, mode=MODES[mode])
+    for (B, D, h, w) in [(2, 64, 18, 22), (1, 128, 33, 47), (1, 64, 17, 16)]:
+        N = h * w
+        f1, f2 = cn.synth_fmaps(B, D, h, w, seed=3)
+        a, b = gpu(f1), gpu(f2)
+        pb = lib.rdvc_corr_pyramid_bytes(B, h, w, 4, vd)
+        wb = lib.rdvc_corr_workspace_bytes(B, D, h, w)
+        ob = B * 324 * N * 4
+        bufs = {k: torch.full((n + 2 * GUARD,), CANARY, dtype=torch.uint8, device="cuda")
+                for k, n in (("pyr", pb), ("ws", wb), ("out", ob))}
+        ptr = {k: v.data_ptr() + GUARD for k, v in bufs.items()}
+        assert all(p % 256 == 0 for p in ptr.values())
+        st = torch.cuda.current_stream().cuda_stream
+        rc._cabi.check(lib.rdvc_corr_build(a.data_ptr(), b.data_ptr(), B, D, h, w, rc.RDVC_DT_F32, ptr["pyr"],
+                                           vd, 4, ptr["ws"], wb, st), "build")
+        co = gpu(cn.synth_coords(B, h, w, 5.0, seed=1))
+        for variant in (1, 2):
+            set_opts(lib, lookup=variant)
+            rc._cabi.check(lib.rdvc_corr_lookup(ptr["pyr"], vd, co.data_ptr(), B, h, w, 4, 4, ptr["out"], st),
+                           "lookup")
+        torch.cuda.synchronize()
+        for k, v in bufs.items():
+            assert bool((v[:GUARD] == CANARY).all()) and bool((v[-GUARD:] == CANARY).all()), (k, "guard band")
+        body = bufs["pyr"][GUARD:-GUARD]
+        for l in range(4):
+            off = lib.rdvc_corr_level_offset_bytes(B, h, w, l, vd)
+            end = off + B * N * (h >> l) * (w >> l) * es
+            nxt = lib.rdvc_corr_level_offset_bytes(B, h, w, l + 1, vd)
+            assert bool((body[end:nxt] == CANARY).all()), ("padding after level", l)
+            lvl = body[off:end].view(vol).float()
+            assert torch.isfinite(lvl).all()          # every element was written (0xABAB.. is finite but
+            assert not bool((body[off:end] == CANARY).all())   # ... the level is not all canary)
+        assert torch.isfinite(bufs["out"][GUARD:-GUARD].view(torch.float32)).all()
+    set_opts(lib, mode=0, lookup=0)
+
+
 def test_runs_on_callers_stream(lib):
     B, D, h, w = 1, 64, 24, 40
     f1, f2 = cn.synth_fmaps(B, D, h, w, seed=41)
