@@ -42,7 +42,8 @@ _lib = None
 
 
 def lib_path() -> str:
-    return _build.LIB_PATH
+    # RDVC_CORR_LIB: developer override to A/B-test an alternative build of the same ABI
+    return os.environ.get("RDVC_CORR_LIB") or _build.LIB_PATH
 
 
 def load():

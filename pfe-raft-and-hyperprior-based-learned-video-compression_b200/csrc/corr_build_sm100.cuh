@@ -18,8 +18,8 @@
 //      warps 4-11  epilogue: TMEM -> registers -> pooled in registers ->
 //                  swizzled smem staging -> 16-byte coalesced global stores
 //  * fmap2-STATIONARY: one N-tile (256 fmap2 pixels x full K = 128 KB of smem)
-//    stays resident while 128-row fmap1 tiles stream through a 4-stage 16 KB
-//    ring.  L2->SM operand traffic is half the output bytes instead of equal.
+//    stays resident while 128-row fmap1 tiles stream through a 3-stage 16 KB
+//    ring (measured: 3 stages 5 % faster than 4, 2 starve the MMA).  L2->SM operand traffic is half the output bytes instead of equal.
 //  * An N-tile is a SPATIAL block of fmap2 (TILE_Y x TILE_X pixels, 16x16 or
 //    8x32) fetched with one 4-D TMA box per 64-channel slab, so a TMEM column is
 //    a pixel (ty, tx) of the block and one TMEM lane (= one thread of the
@@ -41,7 +41,14 @@ constexpr int BLD_BLOCK_M = 128;
 constexpr int BLD_BLOCK_N = 256;
 constexpr int BLD_BLOCK_K = 64;  // bf16 per 128-byte swizzle row
 constexpr int BLD_UMMA_K = 16;
-constexpr int BLD_A_STAGES = 4;
+#ifndef RDVC_A_STAGES
+#define RDVC_A_STAGES 3
+#endif
+#ifndef RDVC_STG_BUFS
+#define RDVC_STG_BUFS 1
+#endif
+constexpr int BLD_A_STAGES = RDVC_A_STAGES;
+constexpr int BLD_STG_BUFS = RDVC_STG_BUFS;  // 4 KB TMA-store staging buffers per epilogue warp
 constexpr int BLD_MAX_KC = 4;    // D <= 256
 constexpr int BLD_A_STAGE_BYTES = BLD_BLOCK_M * BLD_BLOCK_K * 2;  // 16 KB
 constexpr int BLD_B_SLAB_BYTES = BLD_BLOCK_N * BLD_BLOCK_K * 2;   // 32 KB
@@ -53,7 +60,7 @@ constexpr int BLD_MAX_LEVELS = 4;
 constexpr int BLD_SMEM_B = 0;
 constexpr int BLD_SMEM_A = BLD_SMEM_B + BLD_MAX_KC * BLD_B_SLAB_BYTES;       // 131072
 constexpr int BLD_SMEM_STG = BLD_SMEM_A + BLD_A_STAGES * BLD_A_STAGE_BYTES;  // 196608
-constexpr int BLD_SMEM_BAR = BLD_SMEM_STG + BLD_EPI_WARPS * BLD_STG_BYTES;   // 229376
+constexpr int BLD_SMEM_BAR = BLD_SMEM_STG + BLD_EPI_WARPS * BLD_STG_BYTES * BLD_STG_BUFS;
 constexpr int BLD_SMEM_TOTAL = BLD_SMEM_BAR + 128;
 constexpr int BLD_SMEM_LAUNCH = BLD_SMEM_TOTAL + 1024;  // slack for 1024-byte alignment
 
@@ -210,6 +217,7 @@ corr_build_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
     const uint32_t bar0 = ptx::smem_u32(bars);
     // barrier indices
     constexpr int A_FULL = 0, A_EMPTY = 4, B_FULL = 8, B_EMPTY = 9, T_FULL = 10, T_EMPTY = 12;
+    static_assert(BLD_A_STAGES <= 4, "barrier slots");
     auto bar = [&](int i) { return bar0 + 8u * i; };
     volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(bars + 14);
 
@@ -339,7 +347,8 @@ corr_build_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
         const int e = warp - 4;
         const int q = e & 3;          // TMEM lane quarter this warp may read (warp_id % 4)
         const int sub = e >> 2;       // which half of the tile's 256 columns
-        const uint32_t stg = ptx::smem_u32(smem + BLD_SMEM_STG) + e * BLD_STG_BYTES;
+        const uint32_t stg = ptx::smem_u32(smem + BLD_SMEM_STG) + e * BLD_STG_BYTES * BLD_STG_BUFS;
+        uint32_t box_it = 0;  // TMA boxes issued by this warp (selects the staging buffer)
         const float scale = p.scale;
         const int L = p.num_levels;
         const int smask = p.dbg_store_mask;
@@ -370,46 +379,57 @@ corr_build_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
                     ptx::tc_fence_after();
                     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
                                            acc * BLD_BLOCK_N + sub * (BLD_BLOCK_N / 2);
+                    // CW columns per pass: a staged row is always 128 bytes (32 fp32 or 64 bf16)
+                    constexpr int CW = 128 / static_cast<int>(sizeof(OutT));
+                    constexpr int PASSES = (BLD_BLOCK_N / 2) / CW;
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        float v[32];  // 32 consecutive pixels of this thread's query row
+                    for (int j = 0; j < PASSES; ++j) {
+                        float v[CW];  // CW consecutive pixels of this thread's query row
                         if (!(smask & 32)) {  // debug bit 5: skip the TMEM reads
-                            ptx::tmem_ld_x16(taddr + j * 32, v);
-                            ptx::tmem_ld_x16(taddr + j * 32 + 16, v + 16);
+#pragma unroll
+                            for (int k = 0; k < CW / 16; ++k) ptx::tmem_ld_x16(taddr + j * CW + k * 16, v + k * 16);
                             ptx::tmem_ld_wait();
                         } else {
 #pragma unroll
-                            for (int i = 0; i < 32; ++i) v[i] = 0.f;
+                            for (int i = 0; i < CW; ++i) v[i] = 0.f;
                         }
-                        if (j == 3) {
+                        if (j == PASSES - 1) {
+                            // every TMEM read of this tile is done: hand the accumulator back early
                             ptx::tc_fence_before();
                             __syncwarp();
                             if (lane == 0) ptx::mbar_arrive(bar(T_EMPTY + acc));
                         }
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) v[i] *= scale;
+                        for (int i = 0; i < CW; ++i) v[i] *= scale;
                         if (wr) {
                             if (use_tma) {
-                                // the staging rows are 128 B with the chunk index XORed by (row & 7):
-                                // exactly TMA's SWIZZLE_128B, so the engine un-swizzles on the way out
-                                if (lane == 0) ptx::bulk_wait_read<0>();  // previous box left smem
+                                // staged rows are 128 B (8 x 16-byte chunks) with the chunk index XORed by
+                                // (row & 7): exactly TMA's SWIZZLE_128B, so the engine un-swizzles on the way out
+                                // the box that used this buffer BLD_STG_BUFS boxes ago has left smem
+                                if (lane == 0) ptx::bulk_wait_read<BLD_STG_BUFS - 1>();
                                 __syncwarp();
+                                const uint32_t sb = stg + (box_it % BLD_STG_BUFS) * BLD_STG_BYTES;
+                                ++box_it;
 #pragma unroll
-                                for (int c = 0; c < TR::CH; ++c)
-                                    sts_16(stg + (lane * TR::CH + TR::swz(c, lane)) * 16,
-                                           TR::pack(v + c * TR::EPC));
+                                for (int c = 0; c < 8; ++c)
+                                    sts_16(sb + (lane * 8 + (c ^ (lane & 7))) * 16, TR::pack(v + c * TR::EPC));
                                 ptx::fence_proxy_async_smem();
                                 __syncwarp();
                                 if (lane == 0) {
-                                    if (p.dbg_policy == 0) ptx::tma_store_3d(tmo, stg, col0 + j * 32, m0, b);
-                                    else ptx::tma_store_3d_hint(tmo, stg, col0 + j * 32, m0, b,
+                                    if (p.dbg_policy == 0) ptx::tma_store_3d(tmo, sb, col0 + j * CW, m0, b);
+                                    else ptx::tma_store_3d_hint(tmo, sb, col0 + j * CW, m0, b,
                                                                 p.dbg_policy == 1 ? ptx::policy_evict_last()
                                                                                   : ptx::policy_evict_first());
                                     ptx::bulk_commit();
                                 }
                             } else {
-                                staged_store<OutT, 32>(stg, v, lane, img0, n_l, rows_valid, 0,
-                                                       col0 + j * 32, 1, n_l, vec);
+                                // a TMA box of a previous (aligned) level may still be reading the buffer
+                                if (lane == 0) ptx::bulk_wait_read<0>();
+                                __syncwarp();
+#pragma unroll
+                                for (int k = 0; k < CW / 32; ++k)
+                                    staged_store<OutT, 32>(stg, v + 32 * k, lane, img0, n_l, rows_valid, 0,
+                                                           col0 + j * CW + 32 * k, 1, n_l, vec);
                             }
                         }
                     }

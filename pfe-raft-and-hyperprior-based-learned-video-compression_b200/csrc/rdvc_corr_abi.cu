@@ -137,43 +137,31 @@ int launch_build(const CUtensorMap& ta, const CUtensorMap* tb, const CUtensorMap
     return RDVC_OK;
 }
 
-// fmap1 only (maps == 1) or fmap1 + fmap2 (maps == 2) -> K-major bf16
+// both feature maps -> K-major bf16 rows (fmap2 at `levels2` pyramid levels), one launch
 template <typename T>
-int launch_pack(const void* f1, const void* f2, void* d1, void* d2, int B, int D, int N, int maps,
-                cudaStream_t st) {
+int launch_pack(const void* f1, const void* f2, void* a_km, void* const* b_km, int B, int D, int h, int w,
+                int levels2, cudaStream_t st) {
     auto kern = rdvc::corr_pack_kernel<T>;
-    const size_t smem = static_cast<size_t>(D) * 33 * sizeof(float);
-    dim3 grid((N + rdvc::PACK_TN - 1) / rdvc::PACK_TN, B, maps);
-    kern<<<grid, rdvc::PACK_THREADS, smem, st>>>(
-        static_cast<const T*>(f1), static_cast<const T*>(f2), static_cast<__nv_bfloat16*>(d1),
-        static_cast<__nv_bfloat16*>(d2), D, N);
-    ++g_launches;
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return cuda_fail(e, "corr_pack_kernel launch");
-    return RDVC_OK;
-}
-
-// fmap2 -> K-major bf16 rows of every pyramid level (linear build mode)
-template <typename T>
-int launch_pack_pool(const void* f2, void* const* dst, int B, int D, int h, int w, int num_levels,
-                     cudaStream_t st) {
-    auto kern = rdvc::corr_pack_pool_kernel<T>;
-    const size_t smem = static_cast<size_t>(D) * 65 * sizeof(float);
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             256 * 65 * (int)sizeof(float));
-        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(pack_pool, max dynamic smem)");
+                                             rdvc::PACK_SMEM_BYTES);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(pack, max dynamic smem)");
         attr_set = true;
     }
-    rdvc::PoolPackParams pp;
-    for (int l = 0; l < 4; ++l) pp.dst[l] = static_cast<__nv_bfloat16*>(dst[l]);
-    pp.D = D; pp.h = h; pp.w = w; pp.num_levels = num_levels;
-    dim3 grid((w + rdvc::POOL_TS - 1) / rdvc::POOL_TS, (h + rdvc::POOL_TS - 1) / rdvc::POOL_TS, B);
-    kern<<<grid, rdvc::PACK_THREADS, smem, st>>>(static_cast<const T*>(f2), pp);
+    rdvc::PackParams pp;
+    memset(&pp, 0, sizeof(pp));
+    pp.src[0] = f1; pp.src[1] = f2;
+    pp.dst[0][0] = static_cast<__nv_bfloat16*>(a_km);
+    for (int l = 0; l < 4; ++l) pp.dst[1][l] = static_cast<__nv_bfloat16*>(b_km[l]);
+    pp.levels[0] = 1; pp.levels[1] = levels2;
+    pp.B = B; pp.D = D; pp.h = h; pp.w = w;
+    dim3 grid((w + rdvc::PACK_TX - 1) / rdvc::PACK_TX, (h + rdvc::PACK_TY - 1) / rdvc::PACK_TY,
+              2 * B * (D / rdvc::PACK_CG));
+    kern<<<grid, rdvc::PACK_THREADS, rdvc::PACK_SMEM_BYTES, st>>>(pp);
     ++g_launches;
     cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return cuda_fail(e, "corr_pack_pool_kernel launch");
+    if (e != cudaSuccess) return cuda_fail(e, "corr_pack_kernel launch");
     return RDVC_OK;
 }
 
@@ -290,17 +278,11 @@ int rdvc_corr_build(const void* fmap1, const void* fmap2, int B, int D, int h, i
 
     // 1. repack to K-major bf16; the linear mode also needs the pooled fmap2 levels
     {
-        const int maps = linear ? 1 : 2;
-        if (in_dtype == RDVC_DT_F32) rc = launch_pack<float>(fmap1, fmap2, a_km, b_km[0], B, D, N, maps, st);
-        else if (in_dtype == RDVC_DT_BF16) rc = launch_pack<__nv_bfloat16>(fmap1, fmap2, a_km, b_km[0], B, D, N, maps, st);
-        else rc = launch_pack<__half>(fmap1, fmap2, a_km, b_km[0], B, D, N, maps, st);
+        const int levels2 = linear ? num_levels : 1;
+        if (in_dtype == RDVC_DT_F32) rc = launch_pack<float>(fmap1, fmap2, a_km, b_km, B, D, h, w, levels2, st);
+        else if (in_dtype == RDVC_DT_BF16) rc = launch_pack<__nv_bfloat16>(fmap1, fmap2, a_km, b_km, B, D, h, w, levels2, st);
+        else rc = launch_pack<__half>(fmap1, fmap2, a_km, b_km, B, D, h, w, levels2, st);
         if (rc) return rc;
-        if (linear) {
-            if (in_dtype == RDVC_DT_F32) rc = launch_pack_pool<float>(fmap2, b_km, B, D, h, w, num_levels, st);
-            else if (in_dtype == RDVC_DT_BF16) rc = launch_pack_pool<__nv_bfloat16>(fmap2, b_km, B, D, h, w, num_levels, st);
-            else rc = launch_pack_pool<__half>(fmap2, b_km, B, D, h, w, num_levels, st);
-            if (rc) return rc;
-        }
     }
 
     // 2. fused mode tile shape: 16x16 fmap2 pixels unless 8x32 wastes less padding
@@ -383,18 +365,21 @@ int rdvc_corr_build(const void* fmap1, const void* fmap2, int B, int D, int h, i
         p.msplit = (forced > 0) ? (forced < p.m_blks ? forced : p.m_blks) : best;
     }
 
-    // output descriptors: level l as a [B][N][n_l] fp32 tensor, 32 x 32 boxes (linear mode, fp32
-    // volume, rows 16-byte aligned); anything else takes the staged-store path
+    // output descriptors: level l as a [B][N][n_l] tensor, boxes of 32 query rows x 128 bytes (linear
+    // mode, row pitch 16-byte aligned); anything else takes the staged-store path
     CUtensorMap to[rdvc::BLD_MAX_LEVELS];
     for (int l = 0; l < rdvc::BLD_MAX_LEVELS; ++l) to[l] = ta;
-    if (linear && vol_dtype == RDVC_DT_F32 && g_opt_tma_out.load()) {
+    if (linear && g_opt_tma_out.load()) {
+        const bool f32 = (vol_dtype == RDVC_DT_F32);
+        const cuuint64_t es = f32 ? 4 : 2;
         for (int l = 0; l < num_levels; ++l) {
             const cuuint64_t nl = (cuuint64_t)p.hl[l] * p.wl[l];
-            if (nl % 4 != 0) continue;
+            if ((nl * es) % 16 != 0) continue;
             cuuint64_t dims[3] = {nl, (cuuint64_t)N, (cuuint64_t)B};
-            cuuint64_t str[2] = {nl * 4, (cuuint64_t)N * nl * 4};
-            cuuint32_t box[3] = {32, 32, 1};
-            rc = make_tmap(&to[l], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, p.lvl[l], 3, dims, str, box);
+            cuuint64_t str[2] = {nl * es, (cuuint64_t)N * nl * es};
+            cuuint32_t box[3] = {(cuuint32_t)(128 / es), 32, 1};   // 128-byte rows x 32 query pixels
+            rc = make_tmap(&to[l], f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
+                           p.lvl[l], 3, dims, str, box);
             if (rc) return rc;
             p.tma_out |= 1 << l;
         }
