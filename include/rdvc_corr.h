@@ -32,9 +32,18 @@
  *
  * Pyramid layout (one caller-owned buffer, `rdvc_corr_pyramid_bytes` long):
  *   level l lives at byte offset rdvc_corr_level_offset_bytes(..., l) (256-byte
- *   aligned) and is a dense row-major array [B*h*w][h_l][w_l] with
- *   h_l = h >> l, w_l = w >> l (floor halving, TV:raft.py:390-392) -- the same
- *   element order as torchvision's corr_pyramid[l] viewed (B*h*w, 1, h_l, w_l).
+ *   aligned); h_l = h >> l, w_l = w >> l (floor halving, TV:raft.py:390-392).
+ *   RDVC_LAYOUT_ROWMAJOR: dense [B*h*w][h_l][w_l] -- the element order of
+ *     torchvision's corr_pyramid[l] viewed (B*h*w, 1, h_l, w_l).
+ *   RDVC_LAYOUT_TILED (default of the Python mirror): each level image is padded to
+ *     whole tiles of tile_w x tile_h pixels (rdvc_corr_tile_shape: 16-byte rows x 4 rows =
+ *     one 64-byte DRAM atom; 4 x 4 for fp32, 8 x 4 for bf16) and stored tile by tile,
+ *     [B*h*w][ceil(h_l/tile_h)][ceil(w_l/tile_w)][tile_h][tile_w]; padding pixels hold 0.
+ *     The (2r+2)^2 footprint of a lookup then touches ~11 DRAM atoms per level instead of
+ *     ~20 (row-major: 10 rows x 40 bytes, each straddling 64-byte atoms): the gather is
+ *     DRAM-bound, so bytes fetched are what the layout is chosen for.  The build writes
+ *     either layout at the same cost (an image row of the volume is a permutation of the
+ *     GEMM's output columns, applied for free when fmap2 is packed).
  */
 #ifndef RDVC_CORR_H_
 #define RDVC_CORR_H_
@@ -45,12 +54,16 @@
 extern "C" {
 #endif
 
-#define RDVC_CORR_VERSION 100 /* 0.1.0 */
+#define RDVC_CORR_VERSION 102 /* 0.1.2 */
 
 /* element types */
 #define RDVC_DT_BF16 0
 #define RDVC_DT_F32 1
 #define RDVC_DT_F16 2
+
+/* pyramid layouts (see "Pyramid layout" above) */
+#define RDVC_LAYOUT_ROWMAJOR 0
+#define RDVC_LAYOUT_TILED 1
 
 /* argument errors (negative); CUDA errors are returned as positive cudaError_t */
 #define RDVC_OK 0
@@ -58,7 +71,7 @@ extern "C" {
 #define RDVC_E_SHAPE (-2)       /* non-positive dimension                            */
 #define RDVC_E_TOO_SMALL (-3)   /* h or w < 2 * 2^(num_levels-1)   (TV:raft.py:376)  */
 #define RDVC_E_DTYPE (-4)       /* unsupported in_dtype / vol_dtype                  */
-#define RDVC_E_UNSUPPORTED (-5) /* D % 64 != 0, D > 256, num_levels > 4, radius > 4  */
+#define RDVC_E_UNSUPPORTED (-5) /* D % 64 != 0, D > 256, num_levels > 4, radius > 4, layout */
 #define RDVC_E_WORKSPACE (-6)   /* workspace smaller than rdvc_corr_workspace_bytes  */
 #define RDVC_E_ALIGN (-7)       /* a device pointer is not 16-byte aligned           */
 #define RDVC_E_DRIVER (-8)      /* cuTensorMapEncodeTiled unavailable / failed       */
@@ -68,8 +81,10 @@ const char* rdvc_corr_last_error(void);
 
 /* ---- sizes ------------------------------------------------------------- */
 /* vol_dtype: RDVC_DT_F32 or RDVC_DT_BF16 (storage type of the pyramid). */
-size_t rdvc_corr_pyramid_bytes(int B, int h, int w, int num_levels, int vol_dtype);
-size_t rdvc_corr_level_offset_bytes(int B, int h, int w, int level, int vol_dtype);
+size_t rdvc_corr_pyramid_bytes(int B, int h, int w, int num_levels, int vol_dtype, int layout);
+size_t rdvc_corr_level_offset_bytes(int B, int h, int w, int level, int vol_dtype, int layout);
+/* tile shape (pixels) of RDVC_LAYOUT_TILED for a volume dtype */
+int rdvc_corr_tile_shape(int vol_dtype, int* tile_w, int* tile_h);
 /* scratch for the K-major bf16 copies of fmap1 and of fmap2 at every pyramid level */
 size_t rdvc_corr_workspace_bytes(int B, int D, int h, int w);
 
@@ -79,9 +94,10 @@ size_t rdvc_corr_workspace_bytes(int B, int D, int h, int w);
  * workspace    : device, rdvc_corr_workspace_bytes(...) bytes, 256-byte aligned
  * Computes  pyr[0][b*N+i][y][x] = sum_c fmap1[b,c,i] * fmap2[b,c,y*w+x] / sqrt(D)
  * with bf16 operands and fp32 accumulation (tcgen05), and pyr[l+1] = 2x2 mean of
- * pyr[l] over (y,x) with the odd trailing row/column dropped.                  */
+ * pyr[l] over (y,x) with the odd trailing row/column dropped.  The fused-epilogue build
+ * mode (option key 4 = 1) supports RDVC_LAYOUT_ROWMAJOR only.                       */
 int rdvc_corr_build(const void* fmap1, const void* fmap2, int B, int D, int h, int w,
-                    int in_dtype, void* pyramid, int vol_dtype, int num_levels,
+                    int in_dtype, void* pyramid, int vol_dtype, int layout, int num_levels,
                     void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- lookup: (2r+1)^2 bilinear taps x num_levels ----------------------- *
@@ -91,8 +107,8 @@ int rdvc_corr_build(const void* fmap1, const void* fmap2, int B, int D, int h, i
  * out[b, l*S*S + i*S + j, y, x] = bilinear(pyr[l][b*N + y*w + x],
  *          xs = coords[b,0,y,x]/2^l + (i-r), ys = coords[b,1,y,x]/2^l + (j-r)),
  * zero outside the level, pixel centres at integers (align_corners=True).     */
-int rdvc_corr_lookup(const void* pyramid, int vol_dtype, const float* coords, int B, int h,
-                     int w, int num_levels, int radius, float* out, void* stream);
+int rdvc_corr_lookup(const void* pyramid, int vol_dtype, int layout, const float* coords, int B,
+                     int h, int w, int num_levels, int radius, float* out, void* stream);
 
 /* ---- one frame pair from host memory (blocking) ------------------------ *
  * fmap1_host, fmap2_host : host fp32 (B, D, h, w)
@@ -115,12 +131,15 @@ unsigned long long rdvc_corr_launch_count(void);
  * Lets a bench time the dominant kernel alone, on the stream it runs on.             */
 void rdvc_corr_set_profile_events(void* start_event, void* stop_event);
 /* Debug/tuning knobs; unknown keys return RDVC_E_UNSUPPORTED.
- *   key 0: lookup variant   (0 = auto, 1 = scalar loads, 2 = 128-bit loads)
+ *   key 0: lookup variant   (0 = auto, 1 = scalar loads, 2 = 128-bit loads,
+ *                            3 / 4 = timing only: skip the volume loads / the output stores)
  *   key 1: build tile shape (0 = auto, 1 = 16x16, 2 = 8x32 fmap2 pixels)
  *   key 2: build m-range slices per fmap2 tile (0 = auto)
  *   key 3: debug: bit mask of pyramid levels the build writes (default 15)
  *   key 4: build mode (0 = auto, 1 = fused pooling epilogue, 2 = pooled-fmap2 rows)
- *   key 5: linear-mode output path (1 = TMA tiled stores [default], 0 = staged stores) */
+ *   key 5: linear-mode output path (1 = TMA tiled stores [default], 0 = staged stores)
+ *   key 6: debug: L2 policy of the TMA stores (0 default, 1 evict_last, 2 evict_first)
+ *   key 7 / 8: experiment: log2 tile width / height of RDVC_LAYOUT_TILED (0 = default)  */
 int rdvc_corr_set_option(int key, int value);
 
 #ifdef __cplusplus

@@ -14,7 +14,8 @@ Contents: ``csrc/`` (hand-written sm_100a kernels + the C ABI of
 ``corr_block`` (host-side mirror of the reference interface).
 """
 from . import _build, _cabi, gop_shard, rdvc_format  # noqa: F401
-from ._cabi import RDVC_DT_BF16, RDVC_DT_F16, RDVC_DT_F32  # noqa: F401
+from ._cabi import (RDVC_DT_BF16, RDVC_DT_F16, RDVC_DT_F32,  # noqa: F401
+                    RDVC_LAYOUT_ROWMAJOR, RDVC_LAYOUT_TILED)
 from .corr_block import (  # noqa: F401
     CorrBlock,
     CorrPyramid,
@@ -26,5 +27,5 @@ from .raft_flow import raft_flow  # noqa: F401
 
 __all__ = [
     "CorrBlock", "CorrPyramid", "TVCorrBlock", "build_pyramid", "index_pyramid", "raft_flow",
-    "RDVC_DT_BF16", "RDVC_DT_F16", "RDVC_DT_F32",
+    "RDVC_DT_BF16", "RDVC_DT_F16", "RDVC_DT_F32", "RDVC_LAYOUT_ROWMAJOR", "RDVC_LAYOUT_TILED",
 ]

@@ -11,6 +11,7 @@ import os
 from . import _build
 
 RDVC_DT_BF16, RDVC_DT_F32, RDVC_DT_F16 = 0, 1, 2
+RDVC_LAYOUT_ROWMAJOR, RDVC_LAYOUT_TILED = 0, 1
 
 RDVC_E = {
     -1: "RDVC_E_NULL", -2: "RDVC_E_SHAPE", -3: "RDVC_E_TOO_SMALL", -4: "RDVC_E_DTYPE",
@@ -22,14 +23,15 @@ _c = ctypes
 SYMBOLS = {
     "rdvc_corr_version": (_c.c_int, []),
     "rdvc_corr_last_error": (_c.c_char_p, []),
-    "rdvc_corr_pyramid_bytes": (_c.c_size_t, [_c.c_int] * 5),
-    "rdvc_corr_level_offset_bytes": (_c.c_size_t, [_c.c_int] * 5),
+    "rdvc_corr_pyramid_bytes": (_c.c_size_t, [_c.c_int] * 6),
+    "rdvc_corr_level_offset_bytes": (_c.c_size_t, [_c.c_int] * 6),
+    "rdvc_corr_tile_shape": (_c.c_int, [_c.c_int, _c.POINTER(_c.c_int), _c.POINTER(_c.c_int)]),
     "rdvc_corr_workspace_bytes": (_c.c_size_t, [_c.c_int] * 4),
     "rdvc_corr_build": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int, _c.c_int, _c.c_int,
-                                   _c.c_int, _c.c_void_p, _c.c_int, _c.c_int, _c.c_void_p,
+                                   _c.c_int, _c.c_void_p, _c.c_int, _c.c_int, _c.c_int, _c.c_void_p,
                                    _c.c_size_t, _c.c_void_p]),
-    "rdvc_corr_lookup": (_c.c_int, [_c.c_void_p, _c.c_int, _c.c_void_p, _c.c_int, _c.c_int, _c.c_int,
-                                    _c.c_int, _c.c_int, _c.c_void_p, _c.c_void_p]),
+    "rdvc_corr_lookup": (_c.c_int, [_c.c_void_p, _c.c_int, _c.c_int, _c.c_void_p, _c.c_int, _c.c_int,
+                                    _c.c_int, _c.c_int, _c.c_int, _c.c_void_p, _c.c_void_p]),
     "rdvc_corr_pair_host": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p] +
                             [_c.c_int] * 8),
     "rdvc_corr_release": (None, []),

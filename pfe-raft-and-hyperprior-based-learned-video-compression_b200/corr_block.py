@@ -34,27 +34,68 @@ def _stream_ptr(device) -> int:
     return torch.cuda.current_stream(device).cuda_stream
 
 
+ROWMAJOR, TILED = _cabi.RDVC_LAYOUT_ROWMAJOR, _cabi.RDVC_LAYOUT_TILED
+
+
+def tile_shape(volume_dtype: torch.dtype):
+    """(tile_w, tile_h) of the tiled pyramid layout for this storage type (include/rdvc_corr.h)."""
+    import ctypes
+    tw, th = ctypes.c_int(0), ctypes.c_int(0)
+    _cabi.check(_cabi.load().rdvc_corr_tile_shape(_VOL_DTYPES[volume_dtype], ctypes.byref(tw),
+                                                  ctypes.byref(th)), "rdvc_corr_tile_shape")
+    return tw.value, th.value
+
+
 class CorrPyramid:
-    """Device-resident correlation pyramid: one byte buffer + its geometry."""
+    """Device-resident correlation pyramid: one byte buffer + its geometry and layout
+    (``ROWMAJOR`` = torchvision's element order, ``TILED`` = the gather-friendly default)."""
 
     def __init__(self, B: int, h: int, w: int, num_levels: int, volume_dtype: torch.dtype,
-                 buffer: Tensor):
+                 buffer: Tensor, layout: int = TILED):
         self.B, self.h, self.w = B, h, w
         self.num_levels = num_levels
         self.volume_dtype = volume_dtype
         self.buffer = buffer  # uint8, 256-byte aligned
+        self.layout = layout
 
-    def level(self, l: int) -> Tensor:
-        """View of level ``l`` shaped like torchvision's ``corr_pyramid[l]``:
-        (B*h*w, 1, h >> l, w >> l)."""
+    def _tiles(self, l: int):
+        hl, wl = self.h >> l, self.w >> l
+        if self.layout == ROWMAJOR:
+            return hl, wl, 1, 1, hl, wl
+        tw, th = tile_shape(self.volume_dtype)
+        return hl, wl, tw, th, -(-hl // th) * th, -(-wl // tw) * tw
+
+    def storage(self, l: int) -> Tensor:
+        """Level ``l`` as stored: (B*h*w, padded_h * padded_w) in the pyramid's own layout."""
         lib = _cabi.load()
         vd = _VOL_DTYPES[self.volume_dtype]
-        off = lib.rdvc_corr_level_offset_bytes(self.B, self.h, self.w, l, vd)
-        hl, wl = self.h >> l, self.w >> l
-        n = self.B * self.h * self.w * hl * wl
+        off = lib.rdvc_corr_level_offset_bytes(self.B, self.h, self.w, l, vd, self.layout)
+        _, _, _, _, hp, wp = self._tiles(l)
+        n = self.B * self.h * self.w * hp * wp
         es = torch.empty((), dtype=self.volume_dtype).element_size()
-        flat = self.buffer[off: off + n * es].view(self.volume_dtype)
-        return flat.view(self.B * self.h * self.w, 1, hl, wl)
+        return self.buffer[off: off + n * es].view(self.volume_dtype).view(self.B * self.h * self.w, hp * wp)
+
+    def level(self, l: int) -> Tensor:
+        """Level ``l`` shaped like torchvision's ``corr_pyramid[l]``: (B*h*w, 1, h >> l, w >> l).
+        A view for ``ROWMAJOR``; an un-tiled copy for ``TILED``."""
+        hl, wl, tw, th, hp, wp = self._tiles(l)
+        st = self.storage(l)
+        if self.layout == ROWMAJOR:
+            return st.view(-1, 1, hl, wl)
+        img = st.view(-1, hp // th, wp // tw, th, tw).permute(0, 1, 3, 2, 4).reshape(-1, hp, wp)
+        return img[:, :hl, :wl].unsqueeze(1).contiguous()
+
+    def set_level(self, l: int, value: Tensor) -> None:
+        """Store a torchvision-ordered level tensor (B*h*w, [1,] h_l, w_l) in this pyramid's layout."""
+        hl, wl, tw, th, hp, wp = self._tiles(l)
+        value = value.reshape(-1, hl, wl).to(self.volume_dtype)
+        st = self.storage(l)
+        if self.layout == ROWMAJOR:
+            st.view(-1, hl, wl).copy_(value)
+            return
+        img = torch.zeros(value.shape[0], hp, wp, dtype=self.volume_dtype, device=st.device)
+        img[:, :hl, :wl] = value
+        st.copy_(img.view(-1, hp // th, th, wp // tw, tw).permute(0, 1, 3, 2, 4).reshape(st.shape))
 
     def levels(self) -> List[Tensor]:
         return [self.level(l) for l in range(self.num_levels)]
@@ -87,7 +128,7 @@ def _check_fmaps(fmap1: Tensor, fmap2: Tensor, num_levels: int):
 def build_pyramid(fmap1: Tensor, fmap2: Tensor, num_levels: int = 4,
                   volume_dtype: torch.dtype = torch.float32,
                   out: Optional[CorrPyramid] = None,
-                  workspace: Optional[Tensor] = None) -> CorrPyramid:
+                  workspace: Optional[Tensor] = None, layout: int = TILED) -> CorrPyramid:
     """Correlation volume + pyramid through ``rdvc_corr_build`` on the current stream."""
     _check_fmaps(fmap1, fmap2, num_levels)
     if volume_dtype not in _VOL_DTYPES:
@@ -98,7 +139,7 @@ def build_pyramid(fmap1: Tensor, fmap2: Tensor, num_levels: int = 4,
     f1 = fmap1.contiguous()
     f2 = fmap2.contiguous()
     vd = _VOL_DTYPES[volume_dtype]
-    pyr_bytes = lib.rdvc_corr_pyramid_bytes(B, h, w, num_levels, vd)
+    pyr_bytes = lib.rdvc_corr_pyramid_bytes(B, h, w, num_levels, vd, layout)
     ws_bytes = lib.rdvc_corr_workspace_bytes(B, D, h, w)
     with torch.cuda.device(dev):
         if out is not None and out.buffer.numel() >= pyr_bytes and out.buffer.device == dev:
@@ -108,12 +149,12 @@ def build_pyramid(fmap1: Tensor, fmap2: Tensor, num_levels: int = 4,
         if workspace is None or workspace.numel() < ws_bytes or workspace.device != dev:
             workspace = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         rc = lib.rdvc_corr_build(f1.data_ptr(), f2.data_ptr(), B, D, h, w, _IN_DTYPES[f1.dtype],
-                                 buf.data_ptr(), vd, num_levels, workspace.data_ptr(),
+                                 buf.data_ptr(), vd, layout, num_levels, workspace.data_ptr(),
                                  workspace.numel(), _stream_ptr(dev))
     _cabi.check(rc, "rdvc_corr_build")
     # the workspace is consumed by kernels already enqueued on this stream; torch's
     # caching allocator keeps it stream-ordered when it is dropped here
-    pyr = CorrPyramid(B, h, w, num_levels, volume_dtype, buf)
+    pyr = CorrPyramid(B, h, w, num_levels, volume_dtype, buf, layout)
     pyr._workspace = workspace
     return pyr
 
@@ -140,7 +181,7 @@ def index_pyramid(pyr: CorrPyramid, coords: Tensor, radius: int = 4,
     elif tuple(out.shape) != (B, C, h, w) or out.dtype != torch.float32 or not out.is_contiguous():
         raise ValueError("out must be a contiguous fp32 tensor of shape (B, L*(2r+1)^2, h, w)")
     with torch.cuda.device(dev):
-        rc = lib.rdvc_corr_lookup(pyr.buffer.data_ptr(), _VOL_DTYPES[pyr.volume_dtype], c.data_ptr(),
+        rc = lib.rdvc_corr_lookup(pyr.buffer.data_ptr(), _VOL_DTYPES[pyr.volume_dtype], pyr.layout, c.data_ptr(),
                                   B, h, w, pyr.num_levels, radius, out.data_ptr(), _stream_ptr(dev))
     _cabi.check(rc, "rdvc_corr_lookup")
     return out
@@ -154,21 +195,32 @@ class TVCorrBlock(nn.Module):
     """
 
     def __init__(self, *, num_levels: int = 4, radius: int = 4,
-                 volume_dtype: torch.dtype = torch.float32):
+                 volume_dtype: torch.dtype = torch.float32, layout: int = TILED):
         super().__init__()
         self.num_levels = num_levels
         self.radius = radius
         self.volume_dtype = volume_dtype
+        self.layout = layout
         self.out_channels = num_levels * (2 * radius + 1) ** 2  # TV:raft.py:358
         self._pyr: Optional[CorrPyramid] = None
         self._workspace: Optional[Tensor] = None
-        self.corr_pyramid: List[Tensor] = [torch.tensor(0)]
+        self._levels: Optional[List[Tensor]] = None
+
+    @property
+    def corr_pyramid(self) -> List[Tensor]:
+        """torchvision's attribute (TV:raft.py:352,389): the levels as (B*h*w, 1, h_l, w_l) tensors.
+        RAFT itself never reads it; with the tiled layout it is materialised on first access."""
+        if self._pyr is None:
+            return [torch.tensor(0)]
+        if self._levels is None:
+            self._levels = self._pyr.levels()
+        return self._levels
 
     def build_pyramid(self, fmap1: Tensor, fmap2: Tensor) -> None:
         self._pyr = build_pyramid(fmap1, fmap2, self.num_levels, self.volume_dtype,
-                                  out=self._pyr, workspace=self._workspace)
+                                  out=self._pyr, workspace=self._workspace, layout=self.layout)
         self._workspace = self._pyr._workspace
-        self.corr_pyramid = self._pyr.levels()
+        self._levels = None
 
     def index_pyramid(self, centroids_coords: Tensor) -> Tensor:
         if self._pyr is None:
@@ -186,7 +238,7 @@ class TVCorrBlock(nn.Module):
         """Drop the pyramid (5.7 GB at 1080p fp32) back to torch's allocator."""
         self._pyr = None
         self._workspace = None
-        self.corr_pyramid = [torch.tensor(0)]
+        self._levels = None
 
 
 class CorrBlock:
@@ -197,11 +249,14 @@ class CorrBlock:
     """
 
     def __init__(self, fmap1: Tensor, fmap2: Tensor, num_levels: int = 4, radius: int = 4,
-                 volume_dtype: torch.dtype = torch.float32):
+                 volume_dtype: torch.dtype = torch.float32, layout: int = TILED):
         self.num_levels = num_levels
         self.radius = radius
-        self.pyramid = build_pyramid(fmap1, fmap2, num_levels, volume_dtype)
-        self.corr_pyramid = self.pyramid.levels()
+        self.pyramid = build_pyramid(fmap1, fmap2, num_levels, volume_dtype, layout=layout)
+
+    @property
+    def corr_pyramid(self) -> List[Tensor]:
+        return self.pyramid.levels()
 
     def __call__(self, coords: Tensor) -> Tensor:
         return index_pyramid(self.pyramid, coords, self.radius)

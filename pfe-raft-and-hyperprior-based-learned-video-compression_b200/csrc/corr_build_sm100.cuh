@@ -68,6 +68,7 @@ struct BuildParams {
     void* lvl[BLD_MAX_LEVELS];  // level base pointers (256-byte aligned)
     int hl[BLD_MAX_LEVELS];
     int wl[BLD_MAX_LEVELS];
+    int nl[BLD_MAX_LEVELS];     // MODE_LINEAR: output columns (pixels incl. layout padding) of level l
     int B, h, w, N;
     int num_levels;
     int kc;             // D / 64
@@ -362,7 +363,7 @@ corr_build_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
                 const int mb1 = static_cast<int>(static_cast<long long>(sl + 1) * p.m_blks / p.msplit);
                 int l = 0;
                 while (l + 1 < L && nt >= p.tile_start[l + 1]) ++l;
-                const int n_l = p.hl[l] * p.wl[l];                       // pixels of this level
+                const int n_l = p.nl[l];                                 // pixels of this level
                 const int col0 = (nt - p.tile_start[l]) * BLD_BLOCK_N + sub * (BLD_BLOCK_N / 2);
                 OutT* const lv = static_cast<OutT*>(p.lvl[l]);
                 const bool vec = (n_l % TR::EPC) == 0;

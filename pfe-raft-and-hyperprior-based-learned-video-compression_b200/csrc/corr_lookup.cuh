@@ -15,9 +15,12 @@
 // emits one window row per footprint row.  Because lanes are consecutive
 // pixels, every output store is a fully coalesced 128-byte line of the
 // (B, L*S*S, h, w) tensor -- no staging, no transpose pass.
-// The gather side reads (S+1) floats from each of S+1 short rows; the `VEC`
-// variant fetches them as aligned 16-byte words (4 LDG.128 instead of 10
-// LDG.32 per row) and shifts in registers.
+// The gather side reads (S+1) elements from each of S+1 short rows as aligned
+// 16-byte words (LDG.128) and shifts in registers.  It is DRAM-bound (no reuse
+// between pixels: every query pixel owns its own image), so the pyramid layout
+// decides the cost: in RDVC_LAYOUT_TILED (16-byte x 4-row tiles = one 64-byte
+// DRAM atom) the footprint touches ~11 atoms per level instead of ~20 for
+// row-major rows; padding pixels are zeros, so no per-element masking either.
 #pragma once
 #include <cuda_bf16.h>
 #include <cstdint>
@@ -30,11 +33,15 @@ struct LookupParams {
     const void* lvl[LKP_MAX_LEVELS];
     int hl[LKP_MAX_LEVELS];
     int wl[LKP_MAX_LEVELS];
+    long long img[LKP_MAX_LEVELS];   // elements of one level image (incl. layout padding)
+    int tiles_w[LKP_MAX_LEVELS];     // RDVC_LAYOUT_TILED: tiles per image row
+    int twl, thl;                    // RDVC_LAYOUT_TILED: log2 tile width / height
     const float* coords;  // (B, 2, N)
     float* out;           // (B, L*S*S, N)
     int B, N;
     int num_levels;
     long long total;      // B * N
+    int dbg;              // debug: 1 = skip volume loads, 2 = skip output stores
 };
 
 template <typename VolT> __device__ __forceinline__ float vol_ld(const VolT* p);
@@ -56,26 +63,112 @@ __device__ __forceinline__ void load_row_scalar(const VolT* __restrict__ row, in
 }
 
 // Vector version (fp32 volume): the R2 floats starting at element `ge` of the level
-// buffer are covered by NV aligned 16-byte words; a word is fetched only if it
-// overlaps the valid part of the row, so no access leaves the (16-byte padded)
-// level buffer.  The sub-word shift s = ge & 3 is resolved with two rounds of
-// predicated register moves.
+// buffer are covered by NV aligned 16-byte words; a word is fetched only if it holds a
+// needed element inside the valid part of the row, so no access leaves the (16-byte
+// padded) level buffer.  Split in two so the fetch of row r+1 can be issued before row r
+// is consumed (software pipelining: the kernel is latency-bound, not issue-bound).
 template <int R2>
-__device__ __forceinline__ void load_row_vec_f32(const float* __restrict__ lvl, long long row_ge,
-                                                 int xa, int wl, float* t) {
-    constexpr int NV = (R2 + 3 + 3) / 4;  // words needed for any shift 0..3
-    constexpr int NC = NV * 4;
+struct RowWords {
+    static constexpr int NV = (R2 + 3 + 3) / 4;  // words needed for any shift 0..3
+    static constexpr int NC = NV * 4;
+    float c[NC];
+};
+
+template <int R2>
+__device__ __forceinline__ void fetch_row_vec_f32(const float* __restrict__ lvl, long long row_ge,
+                                                  int xa, int wl, bool live, RowWords<R2>& rw) {
+    constexpr int NV = RowWords<R2>::NV;
     const long long ge = row_ge + xa;
     const long long al = ge & ~3LL;
-    const int s = static_cast<int>(ge - al);
     const long long lo = row_ge, hi = row_ge + wl;  // valid global element range of this row
-    float c[NC];
 #pragma unroll
     for (int k = 0; k < NV; ++k) {
         const long long w0 = al + 4 * k;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (w0 + 3 >= lo && w0 < hi) v = __ldg(reinterpret_cast<const float4*>(lvl + w0));
-        c[4 * k] = v.x; c[4 * k + 1] = v.y; c[4 * k + 2] = v.z; c[4 * k + 3] = v.w;
+        if (live && w0 + 3 >= lo && w0 < hi && w0 < ge + R2)
+            v = __ldg(reinterpret_cast<const float4*>(lvl + w0));
+        rw.c[4 * k] = v.x; rw.c[4 * k + 1] = v.y; rw.c[4 * k + 2] = v.z; rw.c[4 * k + 3] = v.w;
+    }
+}
+
+// The sub-word shift s = ge & 3 is resolved with two rounds of predicated register moves.
+template <int R2>
+__device__ __forceinline__ void select_row_vec_f32(RowWords<R2>& rw, long long row_ge, int xa, int wl,
+                                                   float* t) {
+    constexpr int NC = RowWords<R2>::NC;
+    const int s = static_cast<int>((row_ge + xa) & 3LL);
+    if (s & 2) {
+#pragma unroll
+        for (int k = 0; k + 2 < NC; ++k) rw.c[k] = rw.c[k + 2];
+    }
+    if (s & 1) {
+#pragma unroll
+        for (int k = 0; k + 1 < NC; ++k) rw.c[k] = rw.c[k + 1];
+    }
+#pragma unroll
+    for (int k = 0; k < R2; ++k) {
+        const int x = xa + k;
+        t[k] = (x >= 0 && x < wl) ? rw.c[k] : 0.f;
+    }
+}
+
+// ---- RDVC_LAYOUT_TILED rows -------------------------------------------------
+// Footprint columns [xa, xa + R2) of image row y are covered by NV aligned 16-byte words;
+// word k starts at column x0 = (xa & ~(EPW-1)) + k * EPW, which never straddles a tile
+// (tile_w is a multiple of EPW).  A word is fetched iff it lies inside the padded image and
+// holds a needed column; everything else is zero -- and so are the padding pixels themselves.
+template <int R2, typename VolT>
+struct TileRow {
+    static constexpr int EPW = 16 / static_cast<int>(sizeof(VolT));  // elements per word
+    static constexpr int NV = (R2 + 2 * EPW - 2) / EPW;              // words for any shift
+    static constexpr int NC = NV * EPW;
+    uint4 wd[NV];
+};
+
+template <int R2, typename VolT>
+__device__ __forceinline__ void tile_row_fetch(const VolT* __restrict__ img, int y, bool live,
+                                               const long long* colpart, const bool* okx, int thl,
+                                               int twl, int tiles_w, TileRow<R2, VolT>& tr) {
+    constexpr int NV = TileRow<R2, VolT>::NV;
+    const long long rowpart = (static_cast<long long>((y >> thl) * tiles_w) << (twl + thl)) +
+                              ((y & ((1 << thl) - 1)) << twl);
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (live && okx[k]) v = __ldg(reinterpret_cast<const uint4*>(img + rowpart + colpart[k]));
+        tr.wd[k] = v;
+    }
+}
+
+template <int R2>
+__device__ __forceinline__ void tile_row_unpack(const TileRow<R2, float>& tr, float* c) {
+#pragma unroll
+    for (int k = 0; k < TileRow<R2, float>::NV; ++k) {
+        c[4 * k] = __uint_as_float(tr.wd[k].x); c[4 * k + 1] = __uint_as_float(tr.wd[k].y);
+        c[4 * k + 2] = __uint_as_float(tr.wd[k].z); c[4 * k + 3] = __uint_as_float(tr.wd[k].w);
+    }
+}
+template <int R2>
+__device__ __forceinline__ void tile_row_unpack(const TileRow<R2, __nv_bfloat16>& tr, float* c) {
+#pragma unroll
+    for (int k = 0; k < TileRow<R2, __nv_bfloat16>::NV; ++k) {
+        const uint32_t w[4] = {tr.wd[k].x, tr.wd[k].y, tr.wd[k].z, tr.wd[k].w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            c[8 * k + 2 * i] = __uint_as_float(w[i] << 16);
+            c[8 * k + 2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+        }
+    }
+}
+
+// c[0..NC) -> c[s..s+R2) moved to the front, s in [0, EPW): log2(EPW) rounds of predicated moves
+template <int NC, int EPW>
+__device__ __forceinline__ void shift_front(float* c, int s) {
+    if constexpr (EPW > 4) {
+        if (s & 4) {
+#pragma unroll
+            for (int k = 0; k + 4 < NC; ++k) c[k] = c[k + 4];
+        }
     }
     if (s & 2) {
 #pragma unroll
@@ -85,15 +178,14 @@ __device__ __forceinline__ void load_row_vec_f32(const float* __restrict__ lvl, 
 #pragma unroll
         for (int k = 0; k + 1 < NC; ++k) c[k] = c[k + 1];
     }
-#pragma unroll
-    for (int k = 0; k < R2; ++k) {
-        const int x = xa + k;
-        t[k] = (x >= 0 && x < wl) ? c[k] : 0.f;
-    }
 }
 
+// VARIANT: 0 = row-major, scalar loads; 1 = row-major, 128-bit loads (fp32 volume only);
+//          2 = RDVC_LAYOUT_TILED, 128-bit loads
+constexpr int LKP_ROW_SCALAR = 0, LKP_ROW_VEC = 1, LKP_TILED = 2;
+
 // grid: ceil(B*N / 32) blocks; block: 32 * num_levels threads.
-template <int R, typename VolT, bool VEC>
+template <int R, typename VolT, int VARIANT>
 __global__ void __launch_bounds__(32 * LKP_MAX_LEVELS)
 corr_lookup_kernel(const __grid_constant__ LookupParams p) {
     constexpr int S = 2 * R + 1;
@@ -119,14 +211,92 @@ corr_lookup_kernel(const __grid_constant__ LookupParams p) {
     const int ya = static_cast<int>(fy0) - R;  // first footprint row
 
     const VolT* lvl = static_cast<const VolT*>(p.lvl[l]);
-    const long long img_ge = pix * (static_cast<long long>(hl) * wl);  // element offset of this image
+    const long long img_ge = pix * p.img[l];  // element offset of this pixel's image
     const size_t C_out = static_cast<size_t>(p.num_levels) * S * S;
     float* outp = p.out + (static_cast<size_t>(b) * C_out + static_cast<size_t>(l) * S * S) * p.N + q;
 
     // whole window left/right of the level: every tap is zero
-    const bool x_dead = (xa + R2 <= 0) || (xa >= wl);
+    const bool x_dead = (xa + R2 <= 0) || (xa >= wl) || (p.dbg == 1);
 
     float prev[S];
+    if constexpr (VARIANT == LKP_TILED) {
+        using TRow = TileRow<R2, VolT>;
+        constexpr int EPW = TRow::EPW, NV = TRow::NV, NC = TRow::NC;
+        const int twl = p.twl, thl = p.thl, tiles_w = p.tiles_w[l];
+        const int wpad = tiles_w << twl;
+        const int x_al = xa & ~(EPW - 1), s = xa & (EPW - 1);
+        long long colpart[NV];
+        bool okx[NV];
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+            const int x0 = x_al + k * EPW;
+            okx[k] = (x0 >= 0) && (x0 < wpad) && (x0 < xa + R2) && (p.dbg != 1);
+            colpart[k] = (static_cast<long long>(x0 >> twl) << (twl + thl)) + (x0 & ((1 << twl) - 1));
+        }
+        const VolT* img = lvl + img_ge;
+        TRow buf[2];
+        tile_row_fetch<R2, VolT>(img, ya, ya >= 0 && ya < hl, colpart, okx, thl, twl, tiles_w, buf[0]);
+#pragma unroll
+        for (int rr = 0; rr < R2; ++rr) {
+            const int y = ya + rr;
+            if (rr + 1 < R2)  // issue the next row's loads before consuming this row
+                tile_row_fetch<R2, VolT>(img, y + 1, y + 1 >= 0 && y + 1 < hl, colpart, okx, thl, twl,
+                                         tiles_w, buf[(rr + 1) & 1]);
+            float c[NC];
+            tile_row_unpack<R2>(buf[rr & 1], c);
+            shift_front<NC, EPW>(c, s);
+            float hrow[S];
+#pragma unroll
+            for (int i = 0; i < S; ++i) hrow[i] = c[i] * (1.0f - fx) + c[i + 1] * fx;
+            if (rr > 0) {
+                const int j = rr - 1;  // window row: ys = cy + (j - R)
+#pragma unroll
+                for (int i = 0; i < S; ++i) {
+                    const float v = prev[i] * (1.0f - fy) + hrow[i] * fy;
+                    if (p.dbg != 2 || v == 12345.678f) __stcs(outp + static_cast<size_t>(i * S + j) * p.N, v);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < S; ++i) prev[i] = hrow[i];
+        }
+    } else if constexpr (VARIANT == LKP_ROW_VEC) {
+        const float* lv32 = reinterpret_cast<const float*>(lvl);
+        RowWords<R2> buf[2];
+        {
+            const int y = ya;
+            fetch_row_vec_f32<R2>(lv32, img_ge + static_cast<long long>(y) * wl, xa, wl,
+                                  y >= 0 && y < hl && !x_dead, buf[0]);
+        }
+#pragma unroll
+        for (int rr = 0; rr < R2; ++rr) {
+            const int y = ya + rr;
+            if (rr + 1 < R2) {  // issue the next row's loads before consuming this row
+                const int yn = y + 1;
+                fetch_row_vec_f32<R2>(lv32, img_ge + static_cast<long long>(yn) * wl, xa, wl,
+                                      yn >= 0 && yn < hl && !x_dead, buf[(rr + 1) & 1]);
+            }
+            float hrow[S];
+            if (y >= 0 && y < hl && !x_dead) {
+                float t[R2];
+                select_row_vec_f32<R2>(buf[rr & 1], img_ge + static_cast<long long>(y) * wl, xa, wl, t);
+#pragma unroll
+                for (int i = 0; i < S; ++i) hrow[i] = t[i] * (1.0f - fx) + t[i + 1] * fx;
+            } else {
+#pragma unroll
+                for (int i = 0; i < S; ++i) hrow[i] = 0.f;
+            }
+            if (rr > 0) {
+                const int j = rr - 1;  // window row: ys = cy + (j - R)
+#pragma unroll
+                for (int i = 0; i < S; ++i) {
+                    const float v = prev[i] * (1.0f - fy) + hrow[i] * fy;
+                    if (p.dbg != 2 || v == 12345.678f) __stcs(outp + static_cast<size_t>(i * S + j) * p.N, v);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < S; ++i) prev[i] = hrow[i];
+        }
+    } else {
 #pragma unroll
     for (int rr = 0; rr < R2; ++rr) {
         const int y = ya + rr;
@@ -134,11 +304,7 @@ corr_lookup_kernel(const __grid_constant__ LookupParams p) {
         if (y >= 0 && y < hl && !x_dead) {
             float t[R2];
             const long long row_ge = img_ge + static_cast<long long>(y) * wl;
-            if constexpr (VEC) {
-                load_row_vec_f32<R2>(reinterpret_cast<const float*>(lvl), row_ge, xa, wl, t);
-            } else {
-                load_row_scalar<R2, VolT>(lvl + row_ge, xa, wl, t);
-            }
+            load_row_scalar<R2, VolT>(lvl + row_ge, xa, wl, t);
 #pragma unroll
             for (int i = 0; i < S; ++i) hrow[i] = t[i] * (1.0f - fx) + t[i + 1] * fx;
         } else {
@@ -155,6 +321,7 @@ corr_lookup_kernel(const __grid_constant__ LookupParams p) {
         }
 #pragma unroll
         for (int i = 0; i < S; ++i) prev[i] = hrow[i];
+    }
     }
 }
 

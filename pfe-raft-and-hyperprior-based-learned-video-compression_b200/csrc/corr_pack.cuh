@@ -26,6 +26,8 @@ struct PackParams {
     const void* src[2];          // fmap1, fmap2
     __nv_bfloat16* dst[2][4];    // [map][level]
     int levels[2];               // levels to emit per map (fmap1: 1)
+    int tiled[2];                // per map: rows in RDVC_LAYOUT_TILED order instead of raster order
+    int twl, thl;                // log2 tile width / height of the tiled order
     int B, D, h, w;
 };
 
@@ -85,8 +87,19 @@ corr_pack_kernel(const __grid_constant__ PackParams p) {
                     a0 += t0[dy * PACK_TX + dx];
                     a1 += t0[PACK_PITCH + dy * PACK_TX + dx];
                 }
+            // operand row of pixel (Y, X): raster order, or tile by tile (see rdvc_corr.h); the
+            // build's output columns follow the operand rows, so this IS the volume's layout
+            size_t img = static_cast<size_t>(hl) * wl;
+            size_t pix = static_cast<size_t>(Y) * wl + X;
+            if (p.tiled[map]) {
+                const int twl = p.twl, thl = p.thl;
+                const int tiles_w = (wl + (1 << twl) - 1) >> twl, tiles_h = (hl + (1 << thl) - 1) >> thl;
+                img = static_cast<size_t>(tiles_w * tiles_h) << (twl + thl);
+                pix = (static_cast<size_t>((Y >> thl) * tiles_w + (X >> twl)) << (twl + thl)) +
+                      ((Y & ((1 << thl) - 1)) << twl) + (X & ((1 << twl) - 1));
+            }
             __nv_bfloat162* out = reinterpret_cast<__nv_bfloat162*>(
-                dst + ((static_cast<size_t>(b) * hl + Y) * wl + X) * D + cg * PACK_CG);
+                dst + (static_cast<size_t>(b) * img + pix) * D + cg * PACK_CG);
             out[lane] = __floats2bfloat162_rn(a0 * inv, a1 * inv);
         }
         row_base += nrows;

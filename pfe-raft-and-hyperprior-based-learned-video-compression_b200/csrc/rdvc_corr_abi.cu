@@ -28,6 +28,8 @@ std::atomic<int> g_opt_store_mask{15};
 std::atomic<int> g_opt_mode{0};
 std::atomic<int> g_opt_tma_out{1};
 std::atomic<int> g_opt_policy{0};
+std::atomic<int> g_opt_twl{0};
+std::atomic<int> g_opt_thl{0};
 
 int fail(int code, const char* fmt, ...) {
     va_list ap;
@@ -53,9 +55,33 @@ size_t elem_size(int dt) {
 
 size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-size_t level_bytes(int B, int h, int w, int level, size_t es) {
+// log2 tile shape of RDVC_LAYOUT_TILED: 16-byte rows x 4 rows (one 64-byte DRAM atom) unless
+// overridden by the experiment options (keys 7 / 8)
+void tile_log2(int vol_dtype, int* twl, int* thl) {
+    const int ow = g_opt_twl.load(), oh = g_opt_thl.load();
+    *twl = ow > 0 ? ow : (vol_dtype == RDVC_DT_F32 ? 2 : 3);
+    *thl = oh > 0 ? oh : 2;
+    if (vol_dtype != RDVC_DT_F32 && *twl < 3) *twl = 3;  // a 16-byte word must not straddle tiles
+}
+
+// elements of one level image in the given layout (TILED pads both sides to whole tiles)
+size_t level_image_elems(int h, int w, int level, int vol_dtype, int layout) {
+    const size_t hl = h >> level, wl = w >> level;
+    if (layout != RDVC_LAYOUT_TILED) return hl * wl;
+    int twl, thl;
+    tile_log2(vol_dtype, &twl, &thl);
+    return (((hl + (1u << thl) - 1) >> thl) << thl) * (((wl + (1u << twl) - 1) >> twl) << twl);
+}
+
+size_t level_bytes(int B, int h, int w, int level, int vol_dtype, int layout) {
     const size_t N = static_cast<size_t>(h) * w;
-    return static_cast<size_t>(B) * N * (h >> level) * (w >> level) * es;
+    return static_cast<size_t>(B) * N * level_image_elems(h, w, level, vol_dtype, layout) * elem_size(vol_dtype);
+}
+
+// upper bound of the K-major operand rows of fmap2 level l over every layout / tile option
+size_t operand_rows_max(int h, int w, int level) {
+    const size_t hl = h >> level, wl = w >> level;
+    return ((hl + 15) / 16 * 16) * ((wl + 15) / 16 * 16);
 }
 
 int check_geometry(int B, int h, int w, int num_levels) {
@@ -140,7 +166,7 @@ int launch_build(const CUtensorMap& ta, const CUtensorMap* tb, const CUtensorMap
 // both feature maps -> K-major bf16 rows (fmap2 at `levels2` pyramid levels), one launch
 template <typename T>
 int launch_pack(const void* f1, const void* f2, void* a_km, void* const* b_km, int B, int D, int h, int w,
-                int levels2, cudaStream_t st) {
+                int levels2, int layout, int twl, int thl, cudaStream_t st) {
     auto kern = rdvc::corr_pack_kernel<T>;
     static bool attr_set = false;
     if (!attr_set) {
@@ -156,6 +182,8 @@ int launch_pack(const void* f1, const void* f2, void* a_km, void* const* b_km, i
     for (int l = 0; l < 4; ++l) pp.dst[1][l] = static_cast<__nv_bfloat16*>(b_km[l]);
     pp.levels[0] = 1; pp.levels[1] = levels2;
     pp.B = B; pp.D = D; pp.h = h; pp.w = w;
+    pp.tiled[0] = 0; pp.tiled[1] = (layout == RDVC_LAYOUT_TILED);
+    pp.twl = twl; pp.thl = thl;
     dim3 grid((w + rdvc::PACK_TX - 1) / rdvc::PACK_TX, (h + rdvc::PACK_TY - 1) / rdvc::PACK_TY,
               2 * B * (D / rdvc::PACK_CG));
     kern<<<grid, rdvc::PACK_THREADS, rdvc::PACK_SMEM_BYTES, st>>>(pp);
@@ -165,23 +193,23 @@ int launch_pack(const void* f1, const void* f2, void* a_km, void* const* b_km, i
     return RDVC_OK;
 }
 
-template <int R, typename VolT, bool VEC>
+template <int R, typename VolT, int VARIANT>
 int launch_lookup(const rdvc::LookupParams& p, cudaStream_t st) {
     const unsigned grid = static_cast<unsigned>((p.total + 31) / 32);
-    rdvc::corr_lookup_kernel<R, VolT, VEC><<<grid, 32 * p.num_levels, 0, st>>>(p);
+    rdvc::corr_lookup_kernel<R, VolT, VARIANT><<<grid, 32 * p.num_levels, 0, st>>>(p);
     ++g_launches;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "corr_lookup_kernel launch");
     return RDVC_OK;
 }
 
-template <typename VolT, bool VEC>
+template <typename VolT, int VARIANT>
 int dispatch_lookup_radius(int radius, const rdvc::LookupParams& p, cudaStream_t st) {
     switch (radius) {
-        case 1: return launch_lookup<1, VolT, VEC>(p, st);
-        case 2: return launch_lookup<2, VolT, VEC>(p, st);
-        case 3: return launch_lookup<3, VolT, VEC>(p, st);
-        case 4: return launch_lookup<4, VolT, VEC>(p, st);
+        case 1: return launch_lookup<1, VolT, VARIANT>(p, st);
+        case 2: return launch_lookup<2, VolT, VARIANT>(p, st);
+        case 3: return launch_lookup<3, VolT, VARIANT>(p, st);
+        case 4: return launch_lookup<4, VolT, VARIANT>(p, st);
         default: return fail(RDVC_E_UNSUPPORTED, "radius=%d not in [1, 4]", radius);
     }
 }
@@ -208,26 +236,38 @@ void rdvc_corr_set_profile_events(void* start, void* stop) {
 }
 
 int rdvc_corr_set_option(int key, int value) {
-    if (key == 0 && value >= 0 && value <= 2) { g_opt_lookup = value; return RDVC_OK; }
+    if (key == 0 && value >= 0 && value <= 4) { g_opt_lookup = value; return RDVC_OK; }
     if (key == 1 && value >= 0 && value <= 2) { g_opt_tile = value; return RDVC_OK; }
     if (key == 2 && value >= 0) { g_opt_msplit = value; return RDVC_OK; }
     if (key == 3 && value >= 0 && value <= 63) { g_opt_store_mask = value; return RDVC_OK; }
     if (key == 4 && value >= 0 && value <= 2) { g_opt_mode = value; return RDVC_OK; }
     if (key == 5 && value >= 0 && value <= 1) { g_opt_tma_out = value; return RDVC_OK; }
     if (key == 6 && value >= 0 && value <= 2) { g_opt_policy = value; return RDVC_OK; }
+    if (key == 7 && value >= 0 && value <= 4) { g_opt_twl = value; return RDVC_OK; }
+    if (key == 8 && value >= 0 && value <= 4) { g_opt_thl = value; return RDVC_OK; }
     return fail(RDVC_E_UNSUPPORTED, "unknown option key=%d value=%d", key, value);
 }
 
-size_t rdvc_corr_level_offset_bytes(int B, int h, int w, int level, int vol_dtype) {
-    const size_t es = elem_size(vol_dtype);
+int rdvc_corr_tile_shape(int vol_dtype, int* tile_w, int* tile_h) {
+    if (vol_dtype != RDVC_DT_F32 && vol_dtype != RDVC_DT_BF16)
+        return fail(RDVC_E_DTYPE, "unsupported vol_dtype=%d", vol_dtype);
+    if (!tile_w || !tile_h) return fail(RDVC_E_NULL, "null pointer argument");
+    int twl, thl;
+    tile_log2(vol_dtype, &twl, &thl);
+    *tile_w = 1 << twl;
+    *tile_h = 1 << thl;
+    return RDVC_OK;
+}
+
+size_t rdvc_corr_level_offset_bytes(int B, int h, int w, int level, int vol_dtype, int layout) {
     size_t off = 0;
-    for (int l = 0; l < level; ++l) off += align_up(level_bytes(B, h, w, l, es), 256);
+    for (int l = 0; l < level; ++l) off += align_up(level_bytes(B, h, w, l, vol_dtype, layout), 256);
     return off;
 }
 
-size_t rdvc_corr_pyramid_bytes(int B, int h, int w, int num_levels, int vol_dtype) {
+size_t rdvc_corr_pyramid_bytes(int B, int h, int w, int num_levels, int vol_dtype, int layout) {
     // every level padded to 256 bytes, so 16-byte gathers at a level's tail stay inside
-    return rdvc_corr_level_offset_bytes(B, h, w, num_levels, vol_dtype);
+    return rdvc_corr_level_offset_bytes(B, h, w, num_levels, vol_dtype, layout);
 }
 
 size_t rdvc_corr_workspace_bytes(int B, int D, int h, int w) {
@@ -235,12 +275,12 @@ size_t rdvc_corr_workspace_bytes(int B, int D, int h, int w) {
     // linear build mode only), each 256-byte aligned
     size_t total = align_up(static_cast<size_t>(B) * h * w * D * 2, 256);
     for (int l = 0; l < rdvc::BLD_MAX_LEVELS; ++l)
-        total += align_up(static_cast<size_t>(B) * (h >> l) * (w >> l) * D * 2, 256);
+        total += align_up(static_cast<size_t>(B) * operand_rows_max(h, w, l) * D * 2, 256);
     return total;
 }
 
 int rdvc_corr_build(const void* fmap1, const void* fmap2, int B, int D, int h, int w, int in_dtype,
-                    void* pyramid, int vol_dtype, int num_levels, void* workspace,
+                    void* pyramid, int vol_dtype, int layout, int num_levels, void* workspace,
                     size_t workspace_bytes, void* stream) {
     if (!fmap1 || !fmap2 || !pyramid || !workspace) return fail(RDVC_E_NULL, "null pointer argument");
     int rc = check_geometry(B, h, w, num_levels);
@@ -252,6 +292,8 @@ int rdvc_corr_build(const void* fmap1, const void* fmap2, int B, int D, int h, i
         return fail(RDVC_E_DTYPE, "unsupported in_dtype=%d", in_dtype);
     if (vol_dtype != RDVC_DT_F32 && vol_dtype != RDVC_DT_BF16)
         return fail(RDVC_E_DTYPE, "unsupported vol_dtype=%d", vol_dtype);
+    if (layout != RDVC_LAYOUT_ROWMAJOR && layout != RDVC_LAYOUT_TILED)
+        return fail(RDVC_E_UNSUPPORTED, "unknown pyramid layout %d", layout);
     if (workspace_bytes < rdvc_corr_workspace_bytes(B, D, h, w))
         return fail(RDVC_E_WORKSPACE, "workspace %zu < required %zu", workspace_bytes,
                     rdvc_corr_workspace_bytes(B, D, h, w));
@@ -269,19 +311,35 @@ int rdvc_corr_build(const void* fmap1, const void* fmap2, int B, int D, int h, i
         size_t off = align_up(static_cast<size_t>(B) * N * D * 2, 256);
         for (int l = 0; l < rdvc::BLD_MAX_LEVELS; ++l) {
             b_km[l] = ws + off;
-            off += align_up(static_cast<size_t>(B) * (h >> l) * (w >> l) * D * 2, 256);
+            off += align_up(static_cast<size_t>(B) * operand_rows_max(h, w, l) * D * 2, 256);
         }
     }
     int mode = g_opt_mode.load();
     if (mode == 0) mode = 2;  // default: linear (pooled fmap2 rows), see corr_build_sm100.cuh
     const bool linear = (mode == 2);
+    if (!linear && layout != RDVC_LAYOUT_ROWMAJOR)
+        return fail(RDVC_E_UNSUPPORTED, "the fused-epilogue build mode writes RDVC_LAYOUT_ROWMAJOR only");
+    // pixels (K-major operand rows / output columns) of level l in this layout
+    size_t nl_of[rdvc::BLD_MAX_LEVELS];
+    for (int l = 0; l < rdvc::BLD_MAX_LEVELS; ++l) nl_of[l] = level_image_elems(h, w, l, vol_dtype, layout);
+    int twl = 0, thl = 0;
+    if (layout == RDVC_LAYOUT_TILED) {
+        tile_log2(vol_dtype, &twl, &thl);
+        // padding pixels of a level must come out of the GEMM as exact zeros: clear the operand
+        // rows of the levels that have any (the pack kernel writes only real pixels)
+        for (int l = 0; l < num_levels; ++l) {
+            if (nl_of[l] == static_cast<size_t>(h >> l) * (w >> l)) continue;
+            cudaError_t e = cudaMemsetAsync(b_km[l], 0, static_cast<size_t>(B) * nl_of[l] * D * 2, st);
+            if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(padded operand rows)");
+        }
+    }
 
     // 1. repack to K-major bf16; the linear mode also needs the pooled fmap2 levels
     {
         const int levels2 = linear ? num_levels : 1;
-        if (in_dtype == RDVC_DT_F32) rc = launch_pack<float>(fmap1, fmap2, a_km, b_km, B, D, h, w, levels2, st);
-        else if (in_dtype == RDVC_DT_BF16) rc = launch_pack<__nv_bfloat16>(fmap1, fmap2, a_km, b_km, B, D, h, w, levels2, st);
-        else rc = launch_pack<__half>(fmap1, fmap2, a_km, b_km, B, D, h, w, levels2, st);
+        if (in_dtype == RDVC_DT_F32) rc = launch_pack<float>(fmap1, fmap2, a_km, b_km, B, D, h, w, levels2, layout, twl, thl, st);
+        else if (in_dtype == RDVC_DT_BF16) rc = launch_pack<__nv_bfloat16>(fmap1, fmap2, a_km, b_km, B, D, h, w, levels2, layout, twl, thl, st);
+        else rc = launch_pack<__half>(fmap1, fmap2, a_km, b_km, B, D, h, w, levels2, layout, twl, thl, st);
         if (rc) return rc;
     }
 
@@ -305,7 +363,7 @@ int rdvc_corr_build(const void* fmap1, const void* fmap2, int B, int D, int h, i
     if (linear) {
         for (int l = 0; l < rdvc::BLD_MAX_LEVELS; ++l) {
             const int ll = l < num_levels ? l : 0;  // unused slots alias level 0
-            const cuuint64_t nl = (cuuint64_t)(h >> ll) * (w >> ll);
+            const cuuint64_t nl = (cuuint64_t)nl_of[ll];
             cuuint64_t dims[3] = {(cuuint64_t)D, nl, (cuuint64_t)B};
             cuuint64_t str[2] = {(cuuint64_t)D * 2, nl * D * 2};
             cuuint32_t box[3] = {rdvc::BLD_BLOCK_K, rdvc::BLD_BLOCK_N, 1};
@@ -324,9 +382,10 @@ int rdvc_corr_build(const void* fmap1, const void* fmap2, int B, int D, int h, i
     rdvc::BuildParams p;
     memset(&p, 0, sizeof(p));
     for (int l = 0; l < num_levels; ++l) {
-        p.lvl[l] = static_cast<uint8_t*>(pyramid) + rdvc_corr_level_offset_bytes(B, h, w, l, vol_dtype);
+        p.lvl[l] = static_cast<uint8_t*>(pyramid) + rdvc_corr_level_offset_bytes(B, h, w, l, vol_dtype, layout);
         p.hl[l] = h >> l;
         p.wl[l] = w >> l;
+        p.nl[l] = static_cast<int>(nl_of[l]);
     }
     p.B = B; p.h = h; p.w = w; p.N = N;
     p.num_levels = num_levels;
@@ -338,7 +397,7 @@ int rdvc_corr_build(const void* fmap1, const void* fmap2, int B, int D, int h, i
         int t = 0;
         for (int l = 0; l < rdvc::BLD_MAX_LEVELS; ++l) {
             p.tile_start[l] = t;
-            if (l < num_levels) t += (p.hl[l] * p.wl[l] + rdvc::BLD_BLOCK_N - 1) / rdvc::BLD_BLOCK_N;
+            if (l < num_levels) t += (p.nl[l] + rdvc::BLD_BLOCK_N - 1) / rdvc::BLD_BLOCK_N;
         }
         p.ntiles = t;
     } else {
@@ -373,7 +432,7 @@ int rdvc_corr_build(const void* fmap1, const void* fmap2, int B, int D, int h, i
         const bool f32 = (vol_dtype == RDVC_DT_F32);
         const cuuint64_t es = f32 ? 4 : 2;
         for (int l = 0; l < num_levels; ++l) {
-            const cuuint64_t nl = (cuuint64_t)p.hl[l] * p.wl[l];
+            const cuuint64_t nl = (cuuint64_t)p.nl[l];
             if ((nl * es) % 16 != 0) continue;
             cuuint64_t dims[3] = {nl, (cuuint64_t)N, (cuuint64_t)B};
             cuuint64_t str[2] = {nl * es, (cuuint64_t)N * nl * es};
@@ -399,21 +458,28 @@ int rdvc_corr_build(const void* fmap1, const void* fmap2, int B, int D, int h, i
                        : launch_build<MODE_FUSED, 8, 32, __nv_bfloat16>(ta, tb, to, p, st);
 }
 
-int rdvc_corr_lookup(const void* pyramid, int vol_dtype, const float* coords, int B, int h, int w,
-                     int num_levels, int radius, float* out, void* stream) {
+int rdvc_corr_lookup(const void* pyramid, int vol_dtype, int layout, const float* coords, int B, int h,
+                     int w, int num_levels, int radius, float* out, void* stream) {
     if (!pyramid || !coords || !out) return fail(RDVC_E_NULL, "null pointer argument");
     int rc = check_geometry(B, h, w, num_levels);
     if (rc) return rc;
     if (vol_dtype != RDVC_DT_F32 && vol_dtype != RDVC_DT_BF16)
         return fail(RDVC_E_DTYPE, "unsupported vol_dtype=%d", vol_dtype);
+    if (layout != RDVC_LAYOUT_ROWMAJOR && layout != RDVC_LAYOUT_TILED)
+        return fail(RDVC_E_UNSUPPORTED, "unknown pyramid layout %d", layout);
     if (reinterpret_cast<uintptr_t>(pyramid) & 15)
         return fail(RDVC_E_ALIGN, "pyramid must be 16-byte aligned");
     rdvc::LookupParams p;
     memset(&p, 0, sizeof(p));
     for (int l = 0; l < num_levels; ++l) {
-        p.lvl[l] = static_cast<const uint8_t*>(pyramid) + rdvc_corr_level_offset_bytes(B, h, w, l, vol_dtype);
+        p.lvl[l] = static_cast<const uint8_t*>(pyramid) + rdvc_corr_level_offset_bytes(B, h, w, l, vol_dtype, layout);
         p.hl[l] = h >> l;
         p.wl[l] = w >> l;
+        p.img[l] = static_cast<long long>(level_image_elems(h, w, l, vol_dtype, layout));
+    }
+    if (layout == RDVC_LAYOUT_TILED) {
+        tile_log2(vol_dtype, &p.twl, &p.thl);
+        for (int l = 0; l < num_levels; ++l) p.tiles_w[l] = ((w >> l) + (1 << p.twl) - 1) >> p.twl;
     }
     p.coords = coords;
     p.out = out;
@@ -423,11 +489,19 @@ int rdvc_corr_lookup(const void* pyramid, int vol_dtype, const float* coords, in
     p.total = static_cast<long long>(B) * p.N;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int variant = g_opt_lookup.load();
-    if (vol_dtype == RDVC_DT_F32) {
-        if (variant == 1) return dispatch_lookup_radius<float, false>(radius, p, st);
-        return dispatch_lookup_radius<float, true>(radius, p, st);
+    p.dbg = variant >= 3 ? variant - 2 : 0;
+    using rdvc::LKP_ROW_SCALAR;
+    using rdvc::LKP_ROW_VEC;
+    using rdvc::LKP_TILED;
+    if (layout == RDVC_LAYOUT_TILED) {
+        return (vol_dtype == RDVC_DT_F32) ? dispatch_lookup_radius<float, LKP_TILED>(radius, p, st)
+                                          : dispatch_lookup_radius<__nv_bfloat16, LKP_TILED>(radius, p, st);
     }
-    return dispatch_lookup_radius<__nv_bfloat16, false>(radius, p, st);
+    if (vol_dtype == RDVC_DT_F32) {
+        if (variant == 1) return dispatch_lookup_radius<float, LKP_ROW_SCALAR>(radius, p, st);
+        return dispatch_lookup_radius<float, LKP_ROW_VEC>(radius, p, st);
+    }
+    return dispatch_lookup_radius<__nv_bfloat16, LKP_ROW_SCALAR>(radius, p, st);
 }
 
 void rdvc_corr_release(void) {
@@ -453,7 +527,8 @@ int rdvc_corr_pair_host(const float* fmap1_host, const float* fmap2_host, const 
     const size_t coords_bytes = align_up(static_cast<size_t>(B) * 2 * N * 4, 256);
     const size_t out_elems = static_cast<size_t>(B) * num_levels * S * S * N;
     const size_t out_bytes = align_up(out_elems * 4, 256);
-    const size_t pyr_bytes = rdvc_corr_pyramid_bytes(B, h, w, num_levels, vol_dtype);
+    const int layout = (g_opt_mode.load() == 1) ? RDVC_LAYOUT_ROWMAJOR : RDVC_LAYOUT_TILED;
+    const size_t pyr_bytes = rdvc_corr_pyramid_bytes(B, h, w, num_levels, vol_dtype, layout);
     const size_t ws_bytes = rdvc_corr_workspace_bytes(B, D, h, w);
     const size_t need = 2 * fmap_bytes + iters * coords_bytes + 2 * out_bytes + pyr_bytes + ws_bytes;
 
@@ -487,7 +562,7 @@ int rdvc_corr_pair_host(const float* fmap1_host, const float* fmap2_host, const 
     for (int it = 0; it < iters; ++it)
         if ((e = cudaMemcpyAsync(d_co + it * coords_bytes, coords_host + it * (coords_raw / 4), coords_raw,
                                  cudaMemcpyHostToDevice, a.compute)) != cudaSuccess) return cuda_fail(e, "H2D coords");
-    rc = rdvc_corr_build(d_f1, d_f2, B, D, h, w, RDVC_DT_F32, d_pyr, vol_dtype, num_levels, d_ws, ws_bytes, a.compute);
+    rc = rdvc_corr_build(d_f1, d_f2, B, D, h, w, RDVC_DT_F32, d_pyr, vol_dtype, layout, num_levels, d_ws, ws_bytes, a.compute);
     if (rc) return rc;
     // lookups ping-pong between two device buffers; the copy stream drains them
     bool used[2] = {false, false};
@@ -496,7 +571,7 @@ int rdvc_corr_pair_host(const float* fmap1_host, const float* fmap2_host, const 
         if (used[s]) {  // the D2H that last read this buffer must have finished
             if ((e = cudaStreamWaitEvent(a.compute, a.ev[s], 0)) != cudaSuccess) return cuda_fail(e, "wait event");
         }
-        rc = rdvc_corr_lookup(d_pyr, vol_dtype, reinterpret_cast<const float*>(d_co + it * coords_bytes), B, h, w,
+        rc = rdvc_corr_lookup(d_pyr, vol_dtype, layout, reinterpret_cast<const float*>(d_co + it * coords_bytes), B, h, w,
                               num_levels, radius, reinterpret_cast<float*>(d_out[s]), a.compute);
         if (rc) return rc;
         cudaEvent_t done;  // lookup finished -> copy stream may read

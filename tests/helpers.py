@@ -14,17 +14,17 @@ def rel_max(a, b) -> float:
     return float(d / (m if m > 0 else 1.0))
 
 
-def pyramid_from_levels(rc, levels, B, h, w, volume_dtype=torch.float32, device="cuda"):
-    """Pack oracle level tensors [(B*N, h_l, w_l)] into a CorrPyramid in the library's layout."""
+def pyramid_from_levels(rc, levels, B, h, w, volume_dtype=torch.float32, device="cuda", layout=None):
+    """Pack oracle level tensors [(B*N, h_l, w_l)] into a CorrPyramid in one of the library's layouts."""
     lib = rc._cabi.load()
     vd = {torch.float32: rc.RDVC_DT_F32, torch.bfloat16: rc.RDVC_DT_BF16}[volume_dtype]
+    layout = rc.RDVC_LAYOUT_TILED if layout is None else layout
     L = len(levels)
-    nbytes = lib.rdvc_corr_pyramid_bytes(B, h, w, L, vd)
+    nbytes = lib.rdvc_corr_pyramid_bytes(B, h, w, L, vd, layout)
     buf = torch.zeros(nbytes, dtype=torch.uint8, device=device)
-    pyr = rc.CorrPyramid(B, h, w, L, volume_dtype, buf)
+    pyr = rc.CorrPyramid(B, h, w, L, volume_dtype, buf, layout)
     for l, lv in enumerate(levels):
-        t = torch.as_tensor(np.asarray(lv), dtype=torch.float32).to(device).to(volume_dtype)
-        pyr.level(l).copy_(t.reshape(pyr.level(l).shape))
+        pyr.set_level(l, torch.as_tensor(np.asarray(lv), dtype=torch.float32).to(device))
     return pyr
 
 

@@ -55,22 +55,32 @@ def test_library_is_sm100a_with_tcgen05_and_tma():
 
 
 def test_version_and_sizes(lib):
-    assert lib.rdvc_corr_version() == 100
+    assert lib.rdvc_corr_version() == 102
     F32, BF16 = rc.RDVC_DT_F32, rc.RDVC_DT_BF16
+    ROW, TILED = rc.RDVC_LAYOUT_ROWMAJOR, rc.RDVC_LAYOUT_TILED
     # 1080p: 136x240 -> 32640 query pixels, levels 136x240, 68x120, 34x60, 17x30
-    assert lib.rdvc_corr_pyramid_bytes(1, 136, 240, 4, F32) == 5_659_776_000
-    assert lib.rdvc_corr_pyramid_bytes(1, 136, 240, 4, BF16) == 2_829_888_000
-    assert lib.rdvc_corr_level_offset_bytes(1, 136, 240, 0, F32) == 0
-    assert lib.rdvc_corr_level_offset_bytes(1, 136, 240, 1, F32) == 32640 * 32640 * 4
+    assert lib.rdvc_corr_pyramid_bytes(1, 136, 240, 4, F32, ROW) == 5_659_776_000
+    assert lib.rdvc_corr_pyramid_bytes(1, 136, 240, 4, BF16, ROW) == 2_829_888_000
+    assert lib.rdvc_corr_level_offset_bytes(1, 136, 240, 0, F32, ROW) == 0
+    assert lib.rdvc_corr_level_offset_bytes(1, 136, 240, 1, F32, ROW) == 32640 * 32640 * 4
+    assert rc.corr_block.tile_shape(torch.float32) == (4, 4)      # 16-byte rows x 4 rows
+    assert rc.corr_block.tile_shape(torch.bfloat16) == (8, 4)
+    # tiled 1080p fp32: levels 2 and 3 are padded to 36x60 and 20x32 (+0.4 % bytes)
+    n = 32640
+    assert lib.rdvc_corr_pyramid_bytes(1, 136, 240, 4, F32, TILED) == 4 * n * (136 * 240 + 68 * 120 + 36 * 60 + 20 * 32)
     for (B, h, w) in [(2, 18, 22), (1, 46, 80), (3, 33, 47)]:
-        for vd, es in ((F32, 4), (BF16, 2)):
-            off = 0
-            for l in range(4):
-                assert lib.rdvc_corr_level_offset_bytes(B, h, w, l, vd) == off
-                assert off % 256 == 0
-                n = B * h * w * (h >> l) * (w >> l) * es
-                off += (n + 255) // 256 * 256
-            assert lib.rdvc_corr_pyramid_bytes(B, h, w, 4, vd) == off
+        for vd, es, tw in ((F32, 4, 4), (BF16, 2, 8)):
+            for layout in (ROW, TILED):
+                off = 0
+                for l in range(4):
+                    assert lib.rdvc_corr_level_offset_bytes(B, h, w, l, vd, layout) == off
+                    assert off % 256 == 0
+                    hl, wl = h >> l, w >> l
+                    if layout == TILED:
+                        hl, wl = -(-hl // 4) * 4, -(-wl // tw) * tw
+                    n = B * h * w * hl * wl * es
+                    off += (n + 255) // 256 * 256
+                assert lib.rdvc_corr_pyramid_bytes(B, h, w, 4, vd, layout) == off
     ws = lib.rdvc_corr_workspace_bytes(1, 256, 136, 240)
     assert ws >= 2 * 32640 * 256 * 2 and ws % 256 == 0
 
@@ -83,10 +93,10 @@ def test_argument_validation_returns_negative_codes(lib):
     big = 1 << 40
 
     def build(**kw):
-        a = dict(f1=p, f2=p, B=1, D=256, h=46, w=80, idt=F32, pyr=p, vdt=F32, L=4, ws=p, wsb=big, st=None)
+        a = dict(f1=p, f2=p, B=1, D=256, h=46, w=80, idt=F32, pyr=p, vdt=F32, lay=1, L=4, ws=p, wsb=big, st=None)
         a.update(kw)
         return lib.rdvc_corr_build(a["f1"], a["f2"], a["B"], a["D"], a["h"], a["w"], a["idt"], a["pyr"],
-                                   a["vdt"], a["L"], a["ws"], a["wsb"], a["st"])
+                                   a["vdt"], a["lay"], a["L"], a["ws"], a["wsb"], a["st"])
 
     assert build(f1=None) == -1 and "null" in rc._cabi.last_error()
     assert build(B=0) == -2
@@ -97,12 +107,15 @@ def test_argument_validation_returns_negative_codes(lib):
     assert build(D=100) == -5
     assert build(D=512) == -5
     assert build(L=5) == -5
+    assert build(lay=7) == -5
     assert build(wsb=16) == -6
     misaligned = ctypes.c_void_p(p.value + 8)
     assert build(pyr=misaligned) == -7
-    assert lib.rdvc_corr_lookup(None, F32, p, 1, 46, 80, 4, 4, p, None) == -1
-    assert lib.rdvc_corr_lookup(p, F32, p, 1, 46, 80, 4, 9, p, None) == -5
-    assert lib.rdvc_corr_lookup(p, F32, p, 1, 8, 80, 4, 4, p, None) == -3
+    assert lib.rdvc_corr_lookup(None, F32, 1, p, 1, 46, 80, 4, 4, p, None) == -1
+    assert lib.rdvc_corr_lookup(p, F32, 1, p, 1, 46, 80, 4, 9, p, None) == -5
+    assert lib.rdvc_corr_lookup(p, F32, 0, p, 1, 46, 80, 4, 9, p, None) == -5
+    assert lib.rdvc_corr_lookup(p, F32, 3, p, 1, 46, 80, 4, 4, p, None) == -5
+    assert lib.rdvc_corr_lookup(p, F32, 1, p, 1, 8, 80, 4, 4, p, None) == -3
     assert lib.rdvc_corr_set_option(99, 0) == -5
     assert lib.rdvc_corr_pair_host(None, p, p, p, 1, 256, 46, 80, 4, 4, 12, F32) == -1
     assert lib.rdvc_corr_pair_host(p, p, p, p, 1, 256, 46, 80, 4, 4, 0, F32) == -2

@@ -28,6 +28,10 @@ TOL_LOOKUP = 1e-3
 TOL_EPE = 0.05
 SIGMAS = (0.0, 0.3, 4.0, 40.0)
 MODES = {"fused": 1, "linear": 2}
+ROW, TILED = rc.RDVC_LAYOUT_ROWMAJOR, rc.RDVC_LAYOUT_TILED
+LAYOUTS = {"rowmajor": ROW, "tiled": TILED}
+# lookup code paths: (pyramid layout, lookup variant option)
+LOOKUP_PATHS = {"row_scalar": (ROW, 1), "row_vec": (ROW, 2), "tiled": (TILED, 0)}
 
 
 @pytest.fixture(scope="module")
@@ -35,7 +39,7 @@ def lib():
     assert torch.cuda.is_available(), "GPU tests need a B200"
     L = rc._cabi.load()
     yield L
-    for k in range(7):
+    for k in range(9):
         L.rdvc_corr_set_option(k, {3: 15, 5: 1}.get(k, 0))
 
 
@@ -50,13 +54,14 @@ def gpu(x):
 
 
 # ------------------------------------------------------------------ lookup
-@pytest.mark.parametrize("variant", [1, 2])
-@pytest.mark.parametrize("shape", [(2, 8, 18, 22), (1, 8, 46, 80), (1, 4, 16, 16)])
-def test_lookup_matches_oracle(lib, shape, variant):
+@pytest.mark.parametrize("path", list(LOOKUP_PATHS))
+@pytest.mark.parametrize("shape", [(2, 8, 18, 22), (1, 8, 46, 80), (1, 4, 16, 16), (1, 4, 17, 19)])
+def test_lookup_matches_oracle(lib, shape, path):
     B, C, h, w = shape
+    layout, variant = LOOKUP_PATHS[path]
     f1, f2 = cn.synth_fmaps(B, C, h, w, seed=3)
     flat = cc.build_pyramid(f1, f2, 4)
-    pyr = pyramid_from_levels(rc, cc.split_levels(flat, B, h, w, 4), B, h, w)
+    pyr = pyramid_from_levels(rc, cc.split_levels(flat, B, h, w, 4), B, h, w, layout=layout)
     set_opts(lib, lookup=variant)
     for sigma in SIGMAS:
         co = cn.synth_coords(B, h, w, sigma, seed=1)
@@ -66,37 +71,62 @@ def test_lookup_matches_oracle(lib, shape, variant):
     set_opts(lib, lookup=0)
 
 
-def test_lookup_golden_small_odd(lib, golden_dir):
+@pytest.mark.parametrize("layout", list(LAYOUTS))
+def test_lookup_golden_small_odd(lib, golden_dir, layout):
     """Pyramid and lookups straight from the torchvision-generated fixture."""
     g = np.load(os.path.join(golden_dir, "corr_small_odd.npz"))
     B, C, h, w = [int(x) for x in g["shape"]]
-    pyr = pyramid_from_levels(rc, [g[f"level{l}"] for l in range(4)], B, h, w)
+    pyr = pyramid_from_levels(rc, [g[f"level{l}"] for l in range(4)], B, h, w, layout=LAYOUTS[layout])
     for s in SIGMAS:
         co = cn.synth_coords(B, h, w, s, seed=1)
         got = rc.index_pyramid(pyr, gpu(co), 4).cpu().numpy()
         assert rel_max(got, g[f"lookup_sigma{s:g}"]) < TOL_LOOKUP
 
 
+@pytest.mark.parametrize("layout", list(LAYOUTS))
+@pytest.mark.parametrize("vol", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("radius,levels", [(3, 3), (1, 1), (2, 4)])
-def test_lookup_other_radius_and_levels(lib, radius, levels):
+def test_lookup_other_radius_and_levels(lib, radius, levels, vol, layout):
     B, C, h, w = 2, 8, 18, 22
     f1, f2 = cn.synth_fmaps(B, C, h, w, seed=4)
     flat = cc.build_pyramid(f1, f2, levels)
-    pyr = pyramid_from_levels(rc, cc.split_levels(flat, B, h, w, levels), B, h, w)
+    if vol == torch.bfloat16:
+        flat = bf16_round(flat)
+    pyr = pyramid_from_levels(rc, cc.split_levels(flat, B, h, w, levels), B, h, w, vol, layout=LAYOUTS[layout])
     co = cn.synth_coords(B, h, w, 2.5, seed=2)
     got = rc.index_pyramid(pyr, gpu(co), radius).cpu().numpy()
     assert got.shape == (B, levels * (2 * radius + 1) ** 2, h, w)
     assert rel_max(got, cc.index_pyramid(flat, co, levels, radius)) < TOL_LOOKUP
 
 
-def test_lookup_bf16_volume(lib):
-    B, C, h, w = 1, 8, 24, 40
+@pytest.mark.parametrize("layout", list(LAYOUTS))
+@pytest.mark.parametrize("shape", [(1, 8, 24, 40), (2, 8, 18, 22), (1, 4, 17, 19)])
+def test_lookup_bf16_volume(lib, shape, layout):
+    B, C, h, w = shape
     f1, f2 = cn.synth_fmaps(B, C, h, w, seed=6)
     flat = bf16_round(cc.build_pyramid(f1, f2, 4))   # what a bf16 pyramid stores
-    pyr = pyramid_from_levels(rc, cc.split_levels(flat, B, h, w, 4), B, h, w, torch.bfloat16)
-    co = cn.synth_coords(B, h, w, 3.0, seed=3)
-    got = rc.index_pyramid(pyr, gpu(co), 4).cpu().numpy()
-    assert rel_max(got, cc.index_pyramid(flat, co, 4, 4)) < TOL_LOOKUP
+    pyr = pyramid_from_levels(rc, cc.split_levels(flat, B, h, w, 4), B, h, w, torch.bfloat16,
+                              layout=LAYOUTS[layout])
+    for sigma in SIGMAS:
+        co = cn.synth_coords(B, h, w, sigma, seed=3)
+        got = rc.index_pyramid(pyr, gpu(co), 4).cpu().numpy()
+        assert rel_max(got, cc.index_pyramid(flat, co, 4, 4)) < TOL_LOOKUP
+
+
+def test_layouts_give_identical_lookups(lib):
+    """The layout is storage only: the same pyramid values in either layout -> bit-identical features."""
+    B, C, h, w = 2, 8, 18, 22
+    f1, f2 = cn.synth_fmaps(B, C, h, w, seed=14)
+    levels = cc.split_levels(cc.build_pyramid(f1, f2, 4), B, h, w, 4)
+    co = gpu(cn.synth_coords(B, h, w, 6.0, seed=2))
+    for vol in (torch.float32, torch.bfloat16):
+        a = rc.index_pyramid(pyramid_from_levels(rc, levels, B, h, w, vol, layout=ROW), co, 4)
+        b = rc.index_pyramid(pyramid_from_levels(rc, levels, B, h, w, vol, layout=TILED), co, 4)
+        assert torch.equal(a, b)
+    # and the tiled storage round-trips through level()/set_level()
+    pyr = pyramid_from_levels(rc, levels, B, h, w, layout=TILED)
+    for l in range(4):
+        assert np.array_equal(pyr.level(l)[:, 0].cpu().numpy(), levels[l])
 
 
 def test_lookup_integer_coords_are_exact_gathers(lib):
@@ -104,6 +134,7 @@ def test_lookup_integer_coords_are_exact_gathers(lib):
     f1, f2 = cn.synth_fmaps(B, C, h, w, seed=9)
     lv = cc.split_levels(cc.build_pyramid(f1, f2, 1), B, h, w, 1)
     pyr = pyramid_from_levels(rc, lv, B, h, w)
+    assert pyr.layout == TILED
     got = rc.index_pyramid(pyr, gpu(cn.make_coords_grid(B, h, w)), 4).cpu().numpy()
     q = 7 * w + 9
     for (i, j) in [(4, 4), (6, 2), (0, 8), (8, 0)]:
@@ -124,14 +155,20 @@ def test_build_fp32_volume(lib, shape, mode):
     ref32 = cn.build_pyramid(f1, f2, 4)                       # fp64 math on the un-rounded inputs
     same = (cn.build_pyramid(bf16_round(f1), bf16_round(f2), 4) if mode == "fused"
             else ref_pyramid_linear(f1, f2, 4))               # fp64 math on what the kernel multiplies
-    for tile in ((1, 2) if mode == "fused" else (0,)):
+    # fused mode: both tile shapes, row-major only; linear mode: both layouts
+    for tile, layout in (((1, ROW), (2, ROW)) if mode == "fused" else ((0, ROW), (0, TILED))):
         set_opts(lib, mode=MODES[mode], tile=tile)
-        pyr = rc.build_pyramid(gpu(f1), gpu(f2), 4)
+        pyr = rc.build_pyramid(gpu(f1), gpu(f2), 4, layout=layout)
         for l in range(4):
             got = pyr.level(l)[:, 0].cpu().numpy()
             assert got.shape == ref32[l].shape
-            assert rel_max(got, same[l]) < TOL_SAME_OPERANDS_F32, (mode, tile, l)
-            assert rel_max(got, ref32[l]) < TOL_VOLUME, (mode, tile, l)
+            assert rel_max(got, same[l]) < TOL_SAME_OPERANDS_F32, (mode, tile, layout, l)
+            assert rel_max(got, ref32[l]) < TOL_VOLUME, (mode, tile, layout, l)
+        if layout == TILED:  # padding pixels of the tiled storage are exact zeros
+            for l in range(4):
+                hl, wl, tw, th, hp, wp = pyr._tiles(l)
+                st = pyr.storage(l).view(-1, hp // th, wp // tw, th, tw).permute(0, 1, 3, 2, 4).reshape(-1, hp, wp)
+                assert not st[:, hl:, :].any() and not st[:, :, wl:].any()
     set_opts(lib, mode=0, tile=0)
 
 
@@ -141,10 +178,11 @@ def test_build_bf16_volume(lib, mode):
     f1, f2 = cn.synth_fmaps(B, D, h, w, seed=5)
     ref32 = cn.build_pyramid(f1, f2, 4)
     set_opts(lib, mode=MODES[mode])
-    pyr = rc.build_pyramid(gpu(f1), gpu(f2), 4, torch.bfloat16)
-    for l in range(4):
-        got = pyr.level(l)[:, 0].float().cpu().numpy()
-        assert rel_max(got, ref32[l]) < TOL_VOLUME
+    for layout in ((ROW,) if mode == "fused" else (ROW, TILED)):
+        pyr = rc.build_pyramid(gpu(f1), gpu(f2), 4, torch.bfloat16, layout=layout)
+        for l in range(4):
+            got = pyr.level(l)[:, 0].float().cpu().numpy()
+            assert rel_max(got, ref32[l]) < TOL_VOLUME
     set_opts(lib, mode=0)
 
 
@@ -176,9 +214,10 @@ def test_build_staged_store_path(lib):
     f1, f2 = cn.synth_fmaps(B, D, h, w, seed=12)
     ref = ref_pyramid_linear(f1, f2, 4)
     set_opts(lib, mode=2, tma=0)
-    pyr = rc.build_pyramid(gpu(f1), gpu(f2), 4)
-    for l in range(4):
-        assert rel_max(pyr.level(l)[:, 0].cpu().numpy(), ref[l]) < TOL_SAME_OPERANDS_F32
+    for layout in (ROW, TILED):
+        pyr = rc.build_pyramid(gpu(f1), gpu(f2), 4, layout=layout)
+        for l in range(4):
+            assert rel_max(pyr.level(l)[:, 0].cpu().numpy(), ref[l]) < TOL_SAME_OPERANDS_F32
     set_opts(lib, mode=0, tma=1)
 
 
@@ -221,6 +260,10 @@ def test_build_is_linear_and_deterministic(lib):
     p1 = rc.build_pyramid(gpu(f1), gpu(f2), 4)
     for l in range(4):
         assert torch.equal(p2.level(l), p1.level(l) * 2.0)
+    # the layout only permutes storage: row-major and tiled builds hold bit-identical values
+    pr = rc.build_pyramid(gpu(f1), gpu(f2), 4, layout=ROW)
+    for l in range(4):
+        assert torch.equal(pr.level(l), p1.level(l))
 
 
 # ------------------------------------------------------------------ full size: 1920x1088
@@ -368,9 +411,9 @@ def test_pair_host_entry_point(lib):
     lib.rdvc_corr_release()
 
 
-@pytest.mark.parametrize("mode", ["fused", "linear"])
+@pytest.mark.parametrize("mode,layout", [("fused", ROW), ("linear", ROW), ("linear", TILED)])
 @pytest.mark.parametrize("vol", [torch.float32, torch.bfloat16])
-def test_no_out_of_bounds_writes(lib, mode, vol):
+def test_no_out_of_bounds_writes(lib, mode, layout, vol):
     """compute-sanitizer is closed on this pool, so bounds are checked with canaries: every byte
     outside the pyramid levels / lookup output / workspace (guard bands before and after, and the
     256-byte padding between levels) must survive a build + lookups on odd shapes."""
@@ -382,7 +425,7 @@ def test_no_out_of_bounds_writes(lib, mode, vol):
         N = h * w
         f1, f2 = cn.synth_fmaps(B, D, h, w, seed=3)
         a, b = gpu(f1), gpu(f2)
-        pb = lib.rdvc_corr_pyramid_bytes(B, h, w, 4, vd)
+        pb = lib.rdvc_corr_pyramid_bytes(B, h, w, 4, vd, layout)
         wb = lib.rdvc_corr_workspace_bytes(B, D, h, w)
         ob = B * 324 * N * 4
         bufs = {k: torch.full((n + 2 * GUARD,), CANARY, dtype=torch.uint8, device="cuda")
@@ -391,20 +434,21 @@ def test_no_out_of_bounds_writes(lib, mode, vol):
         assert all(p % 256 == 0 for p in ptr.values())
         st = torch.cuda.current_stream().cuda_stream
         rc._cabi.check(lib.rdvc_corr_build(a.data_ptr(), b.data_ptr(), B, D, h, w, rc.RDVC_DT_F32, ptr["pyr"],
-                                           vd, 4, ptr["ws"], wb, st), "build")
+                                           vd, layout, 4, ptr["ws"], wb, st), "build")
         co = gpu(cn.synth_coords(B, h, w, 5.0, seed=1))
         for variant in (1, 2):
             set_opts(lib, lookup=variant)
-            rc._cabi.check(lib.rdvc_corr_lookup(ptr["pyr"], vd, co.data_ptr(), B, h, w, 4, 4, ptr["out"], st),
-                           "lookup")
+            rc._cabi.check(lib.rdvc_corr_lookup(ptr["pyr"], vd, layout, co.data_ptr(), B, h, w, 4, 4, ptr["out"],
+                                                st), "lookup")
         torch.cuda.synchronize()
         for k, v in bufs.items():
             assert bool((v[:GUARD] == CANARY).all()) and bool((v[-GUARD:] == CANARY).all()), (k, "guard band")
         body = bufs["pyr"][GUARD:-GUARD]
+        tw, th = rc.corr_block.tile_shape(vol) if layout == TILED else (1, 1)
         for l in range(4):
-            off = lib.rdvc_corr_level_offset_bytes(B, h, w, l, vd)
-            end = off + B * N * (h >> l) * (w >> l) * es
-            nxt = lib.rdvc_corr_level_offset_bytes(B, h, w, l + 1, vd)
+            off = lib.rdvc_corr_level_offset_bytes(B, h, w, l, vd, layout)
+            end = off + B * N * (-(-(h >> l) // th) * th) * (-(-(w >> l) // tw) * tw) * es
+            nxt = lib.rdvc_corr_level_offset_bytes(B, h, w, l + 1, vd, layout)
             assert bool((body[end:nxt] == CANARY).all()), ("padding after level", l)
             lvl = body[off:end].view(vol).float()
             assert torch.isfinite(lvl).all()          # every element was written (0xABAB.. is finite but

@@ -134,7 +134,7 @@ def stage_perf():
                 blk.build_pyramid(f1, f2)
             e1.record(); torch.cuda.synchronize()
             tb = e0.elapsed_time(e1) / 5
-            nbytes = lib.rdvc_corr_pyramid_bytes(B, h, w, 4, rc.RDVC_DT_F32 if vol == torch.float32 else rc.RDVC_DT_BF16)
+            nbytes = lib.rdvc_corr_pyramid_bytes(B, h, w, 4, rc.RDVC_DT_F32 if vol == torch.float32 else rc.RDVC_DT_BF16, rc.RDVC_LAYOUT_TILED)
             print(f"build 1080p {vol} mode={mode} tile={tile} msplit={msplit}: {tb:.3f} ms  ({nbytes / tb / 1e6:.0f} GB/s of pyramid bytes)")
             for variant in (1, 2):
                 lib.rdvc_corr_set_option(0, variant)
