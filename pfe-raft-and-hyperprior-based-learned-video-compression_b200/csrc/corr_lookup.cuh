@@ -41,7 +41,6 @@ struct LookupParams {
     int B, N;
     int num_levels;
     long long total;      // B * N
-    int dbg;              // debug: 1 = skip volume loads, 2 = skip output stores
 };
 
 template <typename VolT> __device__ __forceinline__ float vol_ld(const VolT* p);
@@ -125,21 +124,6 @@ struct TileRow {
     uint4 wd[NV];
 };
 
-template <int R2, typename VolT>
-__device__ __forceinline__ void tile_row_fetch(const VolT* __restrict__ img, int y, bool live,
-                                               const long long* colpart, const bool* okx, int thl,
-                                               int twl, int tiles_w, TileRow<R2, VolT>& tr) {
-    constexpr int NV = TileRow<R2, VolT>::NV;
-    const long long rowpart = (static_cast<long long>((y >> thl) * tiles_w) << (twl + thl)) +
-                              ((y & ((1 << thl) - 1)) << twl);
-#pragma unroll
-    for (int k = 0; k < NV; ++k) {
-        uint4 v = make_uint4(0u, 0u, 0u, 0u);
-        if (live && okx[k]) v = __ldg(reinterpret_cast<const uint4*>(img + rowpart + colpart[k]));
-        tr.wd[k] = v;
-    }
-}
-
 template <int R2>
 __device__ __forceinline__ void tile_row_unpack(const TileRow<R2, float>& tr, float* c) {
 #pragma unroll
@@ -180,12 +164,114 @@ __device__ __forceinline__ void shift_front(float* c, int s) {
     }
 }
 
-// VARIANT: 0 = row-major, scalar loads; 1 = row-major, 128-bit loads (fp32 volume only);
-//          2 = RDVC_LAYOUT_TILED, 128-bit loads
-constexpr int LKP_ROW_SCALAR = 0, LKP_ROW_VEC = 1, LKP_TILED = 2;
+// Per-thread setup shared by both kernels: the query pixel, its window origin and weights.
+template <int R>
+struct LookupSite {
+    int b, q;        // batch item, pixel index inside it
+    int xa, ya;      // first footprint column / row at this level
+    float fx, fy;    // fractional offset (shared by every tap of the window)
+    __device__ __forceinline__ void init(const LookupParams& p, long long pix, int l) {
+        b = static_cast<int>(pix / p.N);
+        q = static_cast<int>(pix - static_cast<long long>(b) * p.N);
+        const float inv = 1.0f / static_cast<float>(1 << l);
+        float cx = __ldg(p.coords + (static_cast<size_t>(b) * 2 + 0) * p.N + q) * inv;
+        float cy = __ldg(p.coords + (static_cast<size_t>(b) * 2 + 1) * p.N + q) * inv;
+        // keep float->int conversion defined for wild coordinates; anything this far
+        // outside samples only zeros anyway
+        cx = fminf(fmaxf(cx, -1.0e6f), 1.0e6f);
+        cy = fminf(fmaxf(cy, -1.0e6f), 1.0e6f);
+        const float fx0 = floorf(cx), fy0 = floorf(cy);
+        fx = cx - fx0;
+        fy = cy - fy0;
+        xa = static_cast<int>(fx0) - R;
+        ya = static_cast<int>(fy0) - R;
+    }
+};
 
-// grid: ceil(B*N / 32) blocks; block: 32 * num_levels threads.
-template <int R, typename VolT, int VARIANT>
+// ---- RDVC_LAYOUT_TILED kernel -------------------------------------------------------------
+// One CTA = 32 consecutive query pixels x all levels: warp = level, lane = pixel.
+// Measured at 1080p and rejected (tools/exp_lookup.py history): splitting a window's rows over
+// 2-3 warps (+20 % time: the shared boundary rows cost more than the extra parallelism gives),
+// 2-4 footprint rows in flight instead of 1 (no change), L2 evict_last hints on the volume loads
+// (no change: the per-iteration footprint exceeds what L2 keeps), plain instead of streaming
+// output stores (+15 %).  The kernel sits at the sum of a DRAM-bound gather (~5.5 TB/s over
+// the 64-byte atoms it touches) and an issue-bound filter/store phase that overlap only partly.
+// DBG (timing experiments only): 1 = no volume loads, 2 = no output stores.
+template <int R, typename VolT, int DBG>
+__global__ void __launch_bounds__(32 * LKP_MAX_LEVELS)
+corr_lookup_tiled_kernel(const __grid_constant__ LookupParams p) {
+    constexpr int S = 2 * R + 1;
+    constexpr int R2 = S + 1;                       // footprint side
+    using TRow = TileRow<R2, VolT>;
+    constexpr int EPW = TRow::EPW, NV = TRow::NV, NC = TRow::NC;
+    const int l = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const long long pix = static_cast<long long>(blockIdx.x) * 32 + lane;
+    if (pix >= p.total) return;
+    LookupSite<R> site;
+    site.init(p, pix, l);
+    const float fx = site.fx, fy = site.fy;
+    const int xa = site.xa, ya = site.ya;
+
+    const int hl = p.hl[l];
+    const int twl = p.twl, thl = p.thl, tiles_w = p.tiles_w[l];
+    const int wpad = tiles_w << twl;
+    const int x_al = xa & ~(EPW - 1), s = xa & (EPW - 1);
+    const VolT* img = static_cast<const VolT*>(p.lvl[l]) + pix * p.img[l];   // this pixel's image
+    // element offsets inside the image fit 32 bits: one IMAD.WIDE per address
+    int colpart[NV];
+    bool okx[NV];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        const int x0 = x_al + k * EPW;
+        okx[k] = (x0 >= 0) && (x0 < wpad) && (x0 < xa + R2) && (DBG != 1);
+        colpart[k] = ((x0 >> twl) << (twl + thl)) + (x0 & ((1 << twl) - 1));
+    }
+    auto fetch = [&](int y, TRow& tr) {
+        const bool live = (y >= 0) && (y < hl);
+        const int rowpart = (((y >> thl) * tiles_w) << (twl + thl)) + ((y & ((1 << thl) - 1)) << twl);
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+            uint4 v = make_uint4(0u, 0u, 0u, 0u);
+            if (live && okx[k]) v = __ldg(reinterpret_cast<const uint4*>(img + (rowpart + colpart[k])));
+            tr.wd[k] = v;
+        }
+    };
+
+    const size_t C_out = static_cast<size_t>(p.num_levels) * S * S;
+    float* outp = p.out + (static_cast<size_t>(site.b) * C_out + static_cast<size_t>(l) * S * S) * p.N + site.q;
+    const size_t chan_i = static_cast<size_t>(S) * p.N;   // stride of the window's x index
+
+    TRow buf[2];
+    fetch(ya, buf[0]);
+    float prev[S];
+#pragma unroll
+    for (int rr = 0; rr < R2; ++rr) {
+        if (rr + 1 < R2) fetch(ya + rr + 1, buf[(rr + 1) & 1]);   // next row in flight first
+        float c[NC];
+        tile_row_unpack<R2>(buf[rr & 1], c);
+        shift_front<NC, EPW>(c, s);
+        float hrow[S];
+#pragma unroll
+        for (int i = 0; i < S; ++i) hrow[i] = c[i] * (1.0f - fx) + c[i + 1] * fx;
+        if (rr > 0) {                               // window row j = rr - 1: ys = cy + (j - R)
+            float* o = outp + static_cast<size_t>(rr - 1) * p.N;
+#pragma unroll
+            for (int i = 0; i < S; ++i) {
+                const float v = prev[i] * (1.0f - fy) + hrow[i] * fy;
+                if (DBG != 2 || v == 12345.678f) __stcs(o, v);
+                o += chan_i;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < S; ++i) prev[i] = hrow[i];
+    }
+}
+
+// ---- RDVC_LAYOUT_ROWMAJOR kernel (torchvision's element order; kept for interchange) -------
+// VEC: 128-bit loads (fp32 volume only) instead of one predicated load per element.
+// grid: ceil(B*N / 32) blocks; block: 32 * num_levels threads (warp = level, lane = pixel).
+template <int R, typename VolT, bool VEC>
 __global__ void __launch_bounds__(32 * LKP_MAX_LEVELS)
 corr_lookup_kernel(const __grid_constant__ LookupParams p) {
     constexpr int S = 2 * R + 1;
@@ -194,79 +280,26 @@ corr_lookup_kernel(const __grid_constant__ LookupParams p) {
     const int lane = threadIdx.x & 31;
     const long long pix = static_cast<long long>(blockIdx.x) * 32 + lane;
     if (pix >= p.total) return;
-    const int b = static_cast<int>(pix / p.N);
-    const int q = static_cast<int>(pix - static_cast<long long>(b) * p.N);
-
+    LookupSite<R> site;
+    site.init(p, pix, l);
+    const float fx = site.fx, fy = site.fy;
+    const int xa = site.xa, ya = site.ya;
     const int hl = p.hl[l], wl = p.wl[l];
-    const float inv = 1.0f / static_cast<float>(1 << l);
-    float cx = __ldg(p.coords + (static_cast<size_t>(b) * 2 + 0) * p.N + q) * inv;
-    float cy = __ldg(p.coords + (static_cast<size_t>(b) * 2 + 1) * p.N + q) * inv;
-    // keep float->int conversion defined for wild coordinates; anything this far
-    // outside samples only zeros anyway
-    cx = fminf(fmaxf(cx, -1.0e6f), 1.0e6f);
-    cy = fminf(fmaxf(cy, -1.0e6f), 1.0e6f);
-    const float fx0 = floorf(cx), fy0 = floorf(cy);
-    const float fx = cx - fx0, fy = cy - fy0;
-    const int xa = static_cast<int>(fx0) - R;  // first footprint column
-    const int ya = static_cast<int>(fy0) - R;  // first footprint row
 
     const VolT* lvl = static_cast<const VolT*>(p.lvl[l]);
     const long long img_ge = pix * p.img[l];  // element offset of this pixel's image
     const size_t C_out = static_cast<size_t>(p.num_levels) * S * S;
-    float* outp = p.out + (static_cast<size_t>(b) * C_out + static_cast<size_t>(l) * S * S) * p.N + q;
+    float* outp = p.out + (static_cast<size_t>(site.b) * C_out + static_cast<size_t>(l) * S * S) * p.N + site.q;
 
     // whole window left/right of the level: every tap is zero
-    const bool x_dead = (xa + R2 <= 0) || (xa >= wl) || (p.dbg == 1);
+    const bool x_dead = (xa + R2 <= 0) || (xa >= wl);
 
     float prev[S];
-    if constexpr (VARIANT == LKP_TILED) {
-        using TRow = TileRow<R2, VolT>;
-        constexpr int EPW = TRow::EPW, NV = TRow::NV, NC = TRow::NC;
-        const int twl = p.twl, thl = p.thl, tiles_w = p.tiles_w[l];
-        const int wpad = tiles_w << twl;
-        const int x_al = xa & ~(EPW - 1), s = xa & (EPW - 1);
-        long long colpart[NV];
-        bool okx[NV];
-#pragma unroll
-        for (int k = 0; k < NV; ++k) {
-            const int x0 = x_al + k * EPW;
-            okx[k] = (x0 >= 0) && (x0 < wpad) && (x0 < xa + R2) && (p.dbg != 1);
-            colpart[k] = (static_cast<long long>(x0 >> twl) << (twl + thl)) + (x0 & ((1 << twl) - 1));
-        }
-        const VolT* img = lvl + img_ge;
-        TRow buf[2];
-        tile_row_fetch<R2, VolT>(img, ya, ya >= 0 && ya < hl, colpart, okx, thl, twl, tiles_w, buf[0]);
-#pragma unroll
-        for (int rr = 0; rr < R2; ++rr) {
-            const int y = ya + rr;
-            if (rr + 1 < R2)  // issue the next row's loads before consuming this row
-                tile_row_fetch<R2, VolT>(img, y + 1, y + 1 >= 0 && y + 1 < hl, colpart, okx, thl, twl,
-                                         tiles_w, buf[(rr + 1) & 1]);
-            float c[NC];
-            tile_row_unpack<R2>(buf[rr & 1], c);
-            shift_front<NC, EPW>(c, s);
-            float hrow[S];
-#pragma unroll
-            for (int i = 0; i < S; ++i) hrow[i] = c[i] * (1.0f - fx) + c[i + 1] * fx;
-            if (rr > 0) {
-                const int j = rr - 1;  // window row: ys = cy + (j - R)
-#pragma unroll
-                for (int i = 0; i < S; ++i) {
-                    const float v = prev[i] * (1.0f - fy) + hrow[i] * fy;
-                    if (p.dbg != 2 || v == 12345.678f) __stcs(outp + static_cast<size_t>(i * S + j) * p.N, v);
-                }
-            }
-#pragma unroll
-            for (int i = 0; i < S; ++i) prev[i] = hrow[i];
-        }
-    } else if constexpr (VARIANT == LKP_ROW_VEC) {
+    if constexpr (VEC) {
         const float* lv32 = reinterpret_cast<const float*>(lvl);
         RowWords<R2> buf[2];
-        {
-            const int y = ya;
-            fetch_row_vec_f32<R2>(lv32, img_ge + static_cast<long long>(y) * wl, xa, wl,
-                                  y >= 0 && y < hl && !x_dead, buf[0]);
-        }
+        fetch_row_vec_f32<R2>(lv32, img_ge + static_cast<long long>(ya) * wl, xa, wl,
+                              ya >= 0 && ya < hl && !x_dead, buf[0]);
 #pragma unroll
         for (int rr = 0; rr < R2; ++rr) {
             const int y = ya + rr;
@@ -288,40 +321,36 @@ corr_lookup_kernel(const __grid_constant__ LookupParams p) {
             if (rr > 0) {
                 const int j = rr - 1;  // window row: ys = cy + (j - R)
 #pragma unroll
-                for (int i = 0; i < S; ++i) {
-                    const float v = prev[i] * (1.0f - fy) + hrow[i] * fy;
-                    if (p.dbg != 2 || v == 12345.678f) __stcs(outp + static_cast<size_t>(i * S + j) * p.N, v);
-                }
+                for (int i = 0; i < S; ++i)
+                    __stcs(outp + static_cast<size_t>(i * S + j) * p.N, prev[i] * (1.0f - fy) + hrow[i] * fy);
             }
 #pragma unroll
             for (int i = 0; i < S; ++i) prev[i] = hrow[i];
         }
     } else {
 #pragma unroll
-    for (int rr = 0; rr < R2; ++rr) {
-        const int y = ya + rr;
-        float hrow[S];
-        if (y >= 0 && y < hl && !x_dead) {
-            float t[R2];
-            const long long row_ge = img_ge + static_cast<long long>(y) * wl;
-            load_row_scalar<R2, VolT>(lvl + row_ge, xa, wl, t);
+        for (int rr = 0; rr < R2; ++rr) {
+            const int y = ya + rr;
+            float hrow[S];
+            if (y >= 0 && y < hl && !x_dead) {
+                float t[R2];
+                const long long row_ge = img_ge + static_cast<long long>(y) * wl;
+                load_row_scalar<R2, VolT>(lvl + row_ge, xa, wl, t);
 #pragma unroll
-            for (int i = 0; i < S; ++i) hrow[i] = t[i] * (1.0f - fx) + t[i + 1] * fx;
-        } else {
+                for (int i = 0; i < S; ++i) hrow[i] = t[i] * (1.0f - fx) + t[i + 1] * fx;
+            } else {
 #pragma unroll
-            for (int i = 0; i < S; ++i) hrow[i] = 0.f;
-        }
-        if (rr > 0) {
-            const int j = rr - 1;  // window row: ys = cy + (j - R)
-#pragma unroll
-            for (int i = 0; i < S; ++i) {
-                const float v = prev[i] * (1.0f - fy) + hrow[i] * fy;
-                __stcs(outp + static_cast<size_t>(i * S + j) * p.N, v);
+                for (int i = 0; i < S; ++i) hrow[i] = 0.f;
             }
-        }
+            if (rr > 0) {
+                const int j = rr - 1;  // window row: ys = cy + (j - R)
 #pragma unroll
-        for (int i = 0; i < S; ++i) prev[i] = hrow[i];
-    }
+                for (int i = 0; i < S; ++i)
+                    __stcs(outp + static_cast<size_t>(i * S + j) * p.N, prev[i] * (1.0f - fy) + hrow[i] * fy);
+            }
+#pragma unroll
+            for (int i = 0; i < S; ++i) prev[i] = hrow[i];
+        }
     }
 }
 

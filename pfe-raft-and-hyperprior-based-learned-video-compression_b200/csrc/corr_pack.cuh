@@ -40,6 +40,24 @@ template <> __device__ __forceinline__ float pack_to_float<__half>(__half v) {
     return __half2float(v);
 }
 
+// 4 consecutive elements (16-byte / 8-byte aligned) -> 4 floats
+template <typename T> __device__ __forceinline__ void pack_ld4(const T* p, float* v);
+template <> __device__ __forceinline__ void pack_ld4<float>(const float* p, float* v) {
+    const float4 t = __ldg(reinterpret_cast<const float4*>(p));
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+}
+template <> __device__ __forceinline__ void pack_ld4<__nv_bfloat16>(const __nv_bfloat16* p, float* v) {
+    const uint2 t = __ldg(reinterpret_cast<const uint2*>(p));
+    v[0] = __uint_as_float(t.x << 16); v[1] = __uint_as_float(t.x & 0xffff0000u);
+    v[2] = __uint_as_float(t.y << 16); v[3] = __uint_as_float(t.y & 0xffff0000u);
+}
+template <> __device__ __forceinline__ void pack_ld4<__half>(const __half* p, float* v) {
+    const uint2 t = __ldg(reinterpret_cast<const uint2*>(p));
+    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&t.x));
+    const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&t.y));
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+}
+
 // grid: (ceil(w/32), ceil(h/8), 2 * B * D/64); block: 256 threads; dynamic smem: PACK_SMEM_BYTES.
 template <typename T>
 __global__ void __launch_bounds__(PACK_THREADS)
@@ -55,13 +73,49 @@ corr_pack_kernel(const __grid_constant__ PackParams p) {
     const T* src = static_cast<const T*>(p.src[map]) +
                    (static_cast<size_t>(b) * D + static_cast<size_t>(cg) * PACK_CG) * h * w;
 
-    // load: one 32-pixel source row (128 B of fp32) per warp instruction
-    for (int i = warp; i < PACK_CG * PACK_TY; i += PACK_THREADS / 32) {
-        const int c = i / PACK_TY, yy = i % PACK_TY;
-        const int y = y0 + yy, x = x0 + lane;
-        float v = 0.f;
-        if (y < h && x < w) v = pack_to_float<T>(src[(static_cast<size_t>(c) * h + y) * w + x]);
-        tile[c * PACK_PITCH + yy * PACK_TX + lane] = v;
+    // load.  Vector path (w % 4 == 0): one warp instruction fetches 4 pixels per lane for 4
+    // consecutive channels at one row (4 x 128 B of fp32), PACK_MLP of them in flight per
+    // thread before the first is consumed; the 4 channels land 257 floats apart, so the four
+    // scalar smem stores are conflict-free.  Scalar path: one 32-pixel row per instruction.
+    constexpr int NWARP = PACK_THREADS / 32, PACK_MLP = 8;
+    if ((w & 3) == 0) {
+        constexpr int ROWS4 = PACK_CG * PACK_TY / 4;   // 128 four-channel row groups
+        static_assert(ROWS4 % (NWARP * PACK_MLP) == 0, "load loop shape");
+        const int cl = lane >> 3, xq = (lane & 7) * 4;
+        const int x = x0 + xq;
+        for (int i0 = warp; i0 < ROWS4; i0 += NWARP * PACK_MLP) {
+            float v[PACK_MLP][4];
+#pragma unroll
+            for (int u = 0; u < PACK_MLP; ++u) {
+                const int i = i0 + u * NWARP;
+                const int c = (i / PACK_TY) * 4 + cl, y = y0 + i % PACK_TY;
+                v[u][0] = v[u][1] = v[u][2] = v[u][3] = 0.f;
+                if (y < h && x < w) pack_ld4<T>(src + (static_cast<size_t>(c) * h + y) * w + x, v[u]);
+            }
+#pragma unroll
+            for (int u = 0; u < PACK_MLP; ++u) {
+                const int i = i0 + u * NWARP;
+                float* t = tile + ((i / PACK_TY) * 4 + cl) * PACK_PITCH + (i % PACK_TY) * PACK_TX + xq;
+                t[0] = v[u][0]; t[1] = v[u][1]; t[2] = v[u][2]; t[3] = v[u][3];
+            }
+        }
+    } else {
+        static_assert((PACK_CG * PACK_TY) % (NWARP * PACK_MLP) == 0, "load loop shape");
+        const int x = x0 + lane;
+        for (int i0 = warp; i0 < PACK_CG * PACK_TY; i0 += NWARP * PACK_MLP) {
+            float v[PACK_MLP];
+#pragma unroll
+            for (int u = 0; u < PACK_MLP; ++u) {
+                const int i = i0 + u * NWARP;
+                const int c = i / PACK_TY, y = y0 + i % PACK_TY;
+                v[u] = (y < h && x < w) ? pack_to_float<T>(__ldg(src + (static_cast<size_t>(c) * h + y) * w + x)) : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < PACK_MLP; ++u) {
+                const int i = i0 + u * NWARP;
+                tile[(i / PACK_TY) * PACK_PITCH + (i % PACK_TY) * PACK_TX + lane] = v[u];
+            }
+        }
     }
     __syncthreads();
 

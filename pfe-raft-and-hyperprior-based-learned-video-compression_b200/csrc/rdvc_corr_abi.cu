@@ -193,24 +193,39 @@ int launch_pack(const void* f1, const void* f2, void* a_km, void* const* b_km, i
     return RDVC_OK;
 }
 
-template <int R, typename VolT, int VARIANT>
+// KIND: 0 / 1 = row-major layout, scalar / 128-bit loads; 2.. = tiled layout:
+//       2 + DBG (DBG in 0..2)
+template <int R, typename VolT, int KIND>
 int launch_lookup(const rdvc::LookupParams& p, cudaStream_t st) {
     const unsigned grid = static_cast<unsigned>((p.total + 31) / 32);
-    rdvc::corr_lookup_kernel<R, VolT, VARIANT><<<grid, 32 * p.num_levels, 0, st>>>(p);
+    if constexpr (KIND < 2) {
+        rdvc::corr_lookup_kernel<R, VolT, KIND == 1><<<grid, 32 * p.num_levels, 0, st>>>(p);
+    } else {
+        rdvc::corr_lookup_tiled_kernel<R, VolT, KIND - 2><<<grid, 32 * p.num_levels, 0, st>>>(p);
+    }
     ++g_launches;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "corr_lookup_kernel launch");
     return RDVC_OK;
 }
 
-template <typename VolT, int VARIANT>
+template <typename VolT, int KIND>
 int dispatch_lookup_radius(int radius, const rdvc::LookupParams& p, cudaStream_t st) {
     switch (radius) {
-        case 1: return launch_lookup<1, VolT, VARIANT>(p, st);
-        case 2: return launch_lookup<2, VolT, VARIANT>(p, st);
-        case 3: return launch_lookup<3, VolT, VARIANT>(p, st);
-        case 4: return launch_lookup<4, VolT, VARIANT>(p, st);
+        case 1: return launch_lookup<1, VolT, KIND>(p, st);
+        case 2: return launch_lookup<2, VolT, KIND>(p, st);
+        case 3: return launch_lookup<3, VolT, KIND>(p, st);
+        case 4: return launch_lookup<4, VolT, KIND>(p, st);
         default: return fail(RDVC_E_UNSUPPORTED, "radius=%d not in [1, 4]", radius);
+    }
+}
+
+template <typename VolT>
+int dispatch_lookup_tiled(int dbg, int radius, const rdvc::LookupParams& p, cudaStream_t st) {
+    switch (dbg) {
+        case 1: return dispatch_lookup_radius<VolT, 3>(radius, p, st);
+        case 2: return dispatch_lookup_radius<VolT, 4>(radius, p, st);
+        default: return dispatch_lookup_radius<VolT, 2>(radius, p, st);
     }
 }
 
@@ -489,19 +504,16 @@ int rdvc_corr_lookup(const void* pyramid, int vol_dtype, int layout, const float
     p.total = static_cast<long long>(B) * p.N;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int variant = g_opt_lookup.load();
-    p.dbg = variant >= 3 ? variant - 2 : 0;
-    using rdvc::LKP_ROW_SCALAR;
-    using rdvc::LKP_ROW_VEC;
-    using rdvc::LKP_TILED;
     if (layout == RDVC_LAYOUT_TILED) {
-        return (vol_dtype == RDVC_DT_F32) ? dispatch_lookup_radius<float, LKP_TILED>(radius, p, st)
-                                          : dispatch_lookup_radius<__nv_bfloat16, LKP_TILED>(radius, p, st);
+        const int dbg = variant >= 3 ? variant - 2 : 0;
+        return (vol_dtype == RDVC_DT_F32) ? dispatch_lookup_tiled<float>(dbg, radius, p, st)
+                                          : dispatch_lookup_tiled<__nv_bfloat16>(dbg, radius, p, st);
     }
     if (vol_dtype == RDVC_DT_F32) {
-        if (variant == 1) return dispatch_lookup_radius<float, LKP_ROW_SCALAR>(radius, p, st);
-        return dispatch_lookup_radius<float, LKP_ROW_VEC>(radius, p, st);
+        if (variant == 1) return dispatch_lookup_radius<float, 0>(radius, p, st);
+        return dispatch_lookup_radius<float, 1>(radius, p, st);
     }
-    return dispatch_lookup_radius<__nv_bfloat16, LKP_ROW_SCALAR>(radius, p, st);
+    return dispatch_lookup_radius<__nv_bfloat16, 0>(radius, p, st);
 }
 
 void rdvc_corr_release(void) {
