@@ -38,7 +38,8 @@
  *   RDVC_LAYOUT_TILED (default of the Python mirror): each level image is padded to
  *     whole tiles of tile_w x tile_h pixels (rdvc_corr_tile_shape: 16-byte rows x 4 rows =
  *     one 64-byte DRAM atom; 4 x 4 for fp32, 8 x 4 for bf16) and stored tile by tile,
- *     [B*h*w][ceil(h_l/tile_h)][ceil(w_l/tile_w)][tile_h][tile_w]; padding pixels hold 0.
+ *     [B*h*w][ceil(h_l/tile_h)][ceil(w_l/tile_w)][tile_h][tile_w], each image rounded up to a
+ *     multiple of 128 bytes (rdvc_corr_level_image_elems); padding holds 0.
  *     The (2r+2)^2 footprint of a lookup then touches ~11 DRAM atoms per level instead of
  *     ~20 (row-major: 10 rows x 40 bytes, each straddling 64-byte atoms): the gather is
  *     DRAM-bound, so bytes fetched are what the layout is chosen for.  The build writes
@@ -83,6 +84,9 @@ const char* rdvc_corr_last_error(void);
 /* vol_dtype: RDVC_DT_F32 or RDVC_DT_BF16 (storage type of the pyramid). */
 size_t rdvc_corr_pyramid_bytes(int B, int h, int w, int num_levels, int vol_dtype, int layout);
 size_t rdvc_corr_level_offset_bytes(int B, int h, int w, int level, int vol_dtype, int layout);
+/* elements one level image (one query pixel's h_l x w_l map) occupies, padding included:
+ * h_l * w_l for ROWMAJOR; whole tiles, rounded up to a multiple of 128 bytes, for TILED */
+size_t rdvc_corr_level_image_elems(int h, int w, int level, int vol_dtype, int layout);
 /* tile shape (pixels) of RDVC_LAYOUT_TILED for a volume dtype */
 int rdvc_corr_tile_shape(int vol_dtype, int* tile_w, int* tile_h);
 /* scratch for the K-major bf16 copies of fmap1 and of fmap2 at every pyramid level */
@@ -137,7 +141,8 @@ void rdvc_corr_set_profile_events(void* start_event, void* stop_event);
  *   key 2: build m-range slices per fmap2 tile (0 = auto)
  *   key 3: debug: bit mask of pyramid levels the build writes (default 15)
  *   key 4: build mode (0 = auto, 1 = fused pooling epilogue, 2 = pooled-fmap2 rows)
- *   key 5: linear-mode output path (1 = TMA tiled stores [default], 0 = staged stores)
+ *   key 5: linear-mode output path (1 = auto: TMA boxes 16 rows x 256 B where the row pitch allows,
+ *          else 32 rows x 128 B, else staged stores; 2 = never the wide boxes; 0 = staged only)
  *   key 6: debug: L2 policy of the TMA stores (0 default, 1 evict_last, 2 evict_first)
  *   key 7 / 8: experiment: log2 tile width / height of RDVC_LAYOUT_TILED (0 = default)  */
 int rdvc_corr_set_option(int key, int value);

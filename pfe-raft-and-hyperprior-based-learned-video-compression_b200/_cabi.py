@@ -25,6 +25,7 @@ SYMBOLS = {
     "rdvc_corr_last_error": (_c.c_char_p, []),
     "rdvc_corr_pyramid_bytes": (_c.c_size_t, [_c.c_int] * 6),
     "rdvc_corr_level_offset_bytes": (_c.c_size_t, [_c.c_int] * 6),
+    "rdvc_corr_level_image_elems": (_c.c_size_t, [_c.c_int] * 5),
     "rdvc_corr_tile_shape": (_c.c_int, [_c.c_int, _c.POINTER(_c.c_int), _c.POINTER(_c.c_int)]),
     "rdvc_corr_workspace_bytes": (_c.c_size_t, [_c.c_int] * 4),
     "rdvc_corr_build": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int, _c.c_int, _c.c_int,

@@ -66,14 +66,15 @@ class CorrPyramid:
         return hl, wl, tw, th, -(-hl // th) * th, -(-wl // tw) * tw
 
     def storage(self, l: int) -> Tensor:
-        """Level ``l`` as stored: (B*h*w, padded_h * padded_w) in the pyramid's own layout."""
+        """Level ``l`` as stored: (B*h*w, image_elems) in the pyramid's own layout; for ``TILED`` the
+        first padded_h * padded_w elements of a row are the tiles, the rest is 128-byte padding."""
         lib = _cabi.load()
         vd = _VOL_DTYPES[self.volume_dtype]
         off = lib.rdvc_corr_level_offset_bytes(self.B, self.h, self.w, l, vd, self.layout)
-        _, _, _, _, hp, wp = self._tiles(l)
-        n = self.B * self.h * self.w * hp * wp
+        img = lib.rdvc_corr_level_image_elems(self.h, self.w, l, vd, self.layout)
+        n = self.B * self.h * self.w * img
         es = torch.empty((), dtype=self.volume_dtype).element_size()
-        return self.buffer[off: off + n * es].view(self.volume_dtype).view(self.B * self.h * self.w, hp * wp)
+        return self.buffer[off: off + n * es].view(self.volume_dtype).view(self.B * self.h * self.w, img)
 
     def level(self, l: int) -> Tensor:
         """Level ``l`` shaped like torchvision's ``corr_pyramid[l]``: (B*h*w, 1, h >> l, w >> l).
@@ -82,7 +83,7 @@ class CorrPyramid:
         st = self.storage(l)
         if self.layout == ROWMAJOR:
             return st.view(-1, 1, hl, wl)
-        img = st.view(-1, hp // th, wp // tw, th, tw).permute(0, 1, 3, 2, 4).reshape(-1, hp, wp)
+        img = st[:, : hp * wp].reshape(-1, hp // th, wp // tw, th, tw).permute(0, 1, 3, 2, 4).reshape(-1, hp, wp)
         return img[:, :hl, :wl].unsqueeze(1).contiguous()
 
     def set_level(self, l: int, value: Tensor) -> None:
@@ -95,7 +96,8 @@ class CorrPyramid:
             return
         img = torch.zeros(value.shape[0], hp, wp, dtype=self.volume_dtype, device=st.device)
         img[:, :hl, :wl] = value
-        st.copy_(img.view(-1, hp // th, th, wp // tw, tw).permute(0, 1, 3, 2, 4).reshape(st.shape))
+        st.zero_()
+        st[:, : hp * wp] = img.view(-1, hp // th, th, wp // tw, tw).permute(0, 1, 3, 2, 4).reshape(-1, hp * wp)
 
     def levels(self) -> List[Tensor]:
         return [self.level(l) for l in range(self.num_levels)]

@@ -80,7 +80,9 @@ struct BuildParams {
     float scale;        // 1 / sqrt(D)
     int dbg_store_mask; // debug: bit l set = write level l (default 15)
     int dbg_policy;     // debug: TMA-store L2 policy (0 default, 1 evict_last, 2 evict_first)
-    int tma_out;        // MODE_LINEAR: bit l set = level l is written with TMA stores (tm_o<l>)
+    int tma_out;        // MODE_LINEAR: 2 bits per level: how level l is written --
+                        //   0 staged st.global, 1 = TMA boxes 32 rows x 128 B (3-D map {n_l, N, B}),
+                        //   2 = TMA boxes 16 rows x 256 B (4-D map {128 B, n_l*es/128, N, B})
 };
 
 // ---- output element traits -------------------------------------------------
@@ -368,7 +370,8 @@ corr_build_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
                 OutT* const lv = static_cast<OutT*>(p.lvl[l]);
                 const bool vec = (n_l % TR::EPC) == 0;
                 const bool wr = (smask >> l) & 1;
-                const bool use_tma = (p.tma_out >> l) & 1;
+                const int omode = (p.tma_out >> (2 * l)) & 3;
+                const bool use_tma = omode == 1;
                 const CUtensorMap* tmo = (l == 0) ? &tm_o0 : (l == 1) ? &tm_o1 : (l == 2) ? &tm_o2 : &tm_o3;
                 for (int mb = mb0; mb < mb1; ++mb, ++tile_it) {
                     const int m0 = mb * BLD_BLOCK_M + q * 32;
@@ -380,6 +383,78 @@ corr_build_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
                     ptx::tc_fence_after();
                     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
                                            acc * BLD_BLOCK_N + sub * (BLD_BLOCK_N / 2);
+                    if (omode == 2) {
+                        // ---- wide path: every row visit of a TMA box is 256 contiguous bytes (measured
+                        // 6.1 TB/s vs 5.5 TB/s for 128-byte visits, tools/micro/wbench3.cu).  A box is
+                        // 16 query rows x two 128-byte column blocks = 4 KB, smem order [row][block][128 B]
+                        // with TMA's SWIZZLE_128B; the warp's rows go out as two boxes (lanes 0-15, 16-31).
+                        constexpr int EPB = 128 / static_cast<int>(sizeof(OutT));   // elements per column block
+                        constexpr int GC = 2 * EPB;                                  // columns per 256-byte group
+                        constexpr int GROUPS = (BLD_BLOCK_N / 2) / GC;               // 2 (fp32) / 1 (bf16)
+#pragma unroll
+                        for (int g = 0; g < GROUPS; ++g) {
+                            uint32_t pk[64];  // this thread's 256 bytes: block 0 = pk[0..31], block 1 = pk[32..63]
+                            if constexpr (sizeof(OutT) == 4) {
+                                float v[64];
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) ptx::tmem_ld_x16(taddr + g * GC + k * 16, v + k * 16);
+                                ptx::tmem_ld_wait();
+#pragma unroll
+                                for (int i = 0; i < 64; ++i) pk[i] = __float_as_uint(v[i] * scale);
+                            } else {
+#pragma unroll
+                                for (int hb = 0; hb < 2; ++hb) {
+                                    float v[64];
+#pragma unroll
+                                    for (int k = 0; k < 4; ++k)
+                                        ptx::tmem_ld_x16(taddr + g * GC + hb * 64 + k * 16, v + k * 16);
+                                    ptx::tmem_ld_wait();
+#pragma unroll
+                                    for (int i = 0; i < 32; ++i)
+                                        pk[hb * 32 + i] = OutTraits<__nv_bfloat16>::pk(v[2 * i] * scale, v[2 * i + 1] * scale);
+                                }
+                            }
+                            if (g == GROUPS - 1) {
+                                // every TMEM read of this tile is done: hand the accumulator back early
+                                ptx::tc_fence_before();
+                                __syncwarp();
+                                if (lane == 0) ptx::mbar_arrive(bar(T_EMPTY + acc));
+                            }
+                            if (!wr) continue;
+                            const int r = lane & 15;
+                            const int flip = (r >> 2) & 1;   // lanes 4-7 / 12-15 write the other block first:
+                                                             // the 8 lanes of a store phase then hit 8 different
+                                                             // swizzled 16-byte columns (conflict-free)
+#pragma unroll
+                            for (int hh = 0; hh < 2; ++hh) {
+                                if (lane == 0) ptx::bulk_wait_read<0>();   // the previous box has left the buffer
+                                __syncwarp();
+                                if ((lane >> 4) == hh) {
+#pragma unroll
+                                    for (int ps = 0; ps < 2; ++ps) {
+                                        const int cb = ps ^ flip;
+                                        const int rr = r * 2 + cb;          // 128-byte row of the box in smem
+#pragma unroll
+                                        for (int c = 0; c < 8; ++c) {
+                                            uint4 w;
+                                            w.x = flip ? pk[(1 - ps) * 32 + c * 4 + 0] : pk[ps * 32 + c * 4 + 0];
+                                            w.y = flip ? pk[(1 - ps) * 32 + c * 4 + 1] : pk[ps * 32 + c * 4 + 1];
+                                            w.z = flip ? pk[(1 - ps) * 32 + c * 4 + 2] : pk[ps * 32 + c * 4 + 2];
+                                            w.w = flip ? pk[(1 - ps) * 32 + c * 4 + 3] : pk[ps * 32 + c * 4 + 3];
+                                            sts_16(stg + rr * 128 + ((c ^ (rr & 7)) << 4), w);
+                                        }
+                                    }
+                                }
+                                ptx::fence_proxy_async_smem();
+                                __syncwarp();
+                                if (lane == 0) {
+                                    ptx::tma_store_4d(tmo, stg, 0, (col0 + g * GC) / EPB, m0 + 16 * hh, b);
+                                    ptx::bulk_commit();
+                                }
+                            }
+                        }
+                        continue;
+                    }
                     // CW columns per pass: a staged row is always 128 bytes (32 fp32 or 64 bf16)
                     constexpr int CW = 128 / static_cast<int>(sizeof(OutT));
                     constexpr int PASSES = (BLD_BLOCK_N / 2) / CW;

@@ -194,7 +194,9 @@ struct LookupSite {
 // 2-3 warps (+20 % time: the shared boundary rows cost more than the extra parallelism gives),
 // 2-4 footprint rows in flight instead of 1 (no change), L2 evict_last hints on the volume loads
 // (no change: the per-iteration footprint exceeds what L2 keeps), plain instead of streaming
-// output stores (+15 %).  The kernel sits at the sum of a DRAM-bound gather (~5.5 TB/s over
+// output stores (+15 %), a cp.async (LDGSTS) ring of 3-4 rows per thread in shared memory
+// (3x SLOWER: the ring's shared memory takes the L1 capacity the gather lives on -- adjacent
+// footprint rows share 32-byte sectors).  The kernel sits at the sum of a DRAM-bound gather (~5.5 TB/s over
 // the 64-byte atoms it touches) and an issue-bound filter/store phase that overlap only partly.
 // DBG (timing experiments only): 1 = no volume loads, 2 = no output stores.
 template <int R, typename VolT, int DBG>

@@ -28,6 +28,7 @@ struct PackParams {
     int levels[2];               // levels to emit per map (fmap1: 1)
     int tiled[2];                // per map: rows in RDVC_LAYOUT_TILED order instead of raster order
     int twl, thl;                // log2 tile width / height of the tiled order
+    int img[2][4];               // [map][level]: operand rows per batch item (pixels incl. layout padding)
     int B, D, h, w;
 };
 
@@ -143,12 +144,11 @@ corr_pack_kernel(const __grid_constant__ PackParams p) {
                 }
             // operand row of pixel (Y, X): raster order, or tile by tile (see rdvc_corr.h); the
             // build's output columns follow the operand rows, so this IS the volume's layout
-            size_t img = static_cast<size_t>(hl) * wl;
+            const size_t img = static_cast<size_t>(p.img[map][l]);
             size_t pix = static_cast<size_t>(Y) * wl + X;
             if (p.tiled[map]) {
                 const int twl = p.twl, thl = p.thl;
-                const int tiles_w = (wl + (1 << twl) - 1) >> twl, tiles_h = (hl + (1 << thl) - 1) >> thl;
-                img = static_cast<size_t>(tiles_w * tiles_h) << (twl + thl);
+                const int tiles_w = (wl + (1 << twl) - 1) >> twl;
                 pix = (static_cast<size_t>((Y >> thl) * tiles_w + (X >> twl)) << (twl + thl)) +
                       ((Y & ((1 << thl) - 1)) << twl) + (X & ((1 << twl) - 1));
             }

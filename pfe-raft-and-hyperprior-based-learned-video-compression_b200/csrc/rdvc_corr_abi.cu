@@ -70,7 +70,11 @@ size_t level_image_elems(int h, int w, int level, int vol_dtype, int layout) {
     if (layout != RDVC_LAYOUT_TILED) return hl * wl;
     int twl, thl;
     tile_log2(vol_dtype, &twl, &thl);
-    return (((hl + (1u << thl) - 1) >> thl) << thl) * (((wl + (1u << twl) - 1) >> twl) << twl);
+    const size_t tiles = (((hl + (1u << thl) - 1) >> thl) << thl) * (((wl + (1u << twl) - 1) >> twl) << twl);
+    // whole 128-byte lines per image row of the volume (at most one extra all-zero tile at the end):
+    // the build's wide TMA boxes address an image as 128-byte column blocks
+    const size_t per_line = 128 / elem_size(vol_dtype);
+    return (tiles + per_line - 1) / per_line * per_line;
 }
 
 size_t level_bytes(int B, int h, int w, int level, int vol_dtype, int layout) {
@@ -166,7 +170,7 @@ int launch_build(const CUtensorMap& ta, const CUtensorMap* tb, const CUtensorMap
 // both feature maps -> K-major bf16 rows (fmap2 at `levels2` pyramid levels), one launch
 template <typename T>
 int launch_pack(const void* f1, const void* f2, void* a_km, void* const* b_km, int B, int D, int h, int w,
-                int levels2, int layout, int twl, int thl, cudaStream_t st) {
+                int levels2, int layout, int twl, int thl, const size_t* nl_of, cudaStream_t st) {
     auto kern = rdvc::corr_pack_kernel<T>;
     static bool attr_set = false;
     if (!attr_set) {
@@ -184,6 +188,8 @@ int launch_pack(const void* f1, const void* f2, void* a_km, void* const* b_km, i
     pp.B = B; pp.D = D; pp.h = h; pp.w = w;
     pp.tiled[0] = 0; pp.tiled[1] = (layout == RDVC_LAYOUT_TILED);
     pp.twl = twl; pp.thl = thl;
+    pp.img[0][0] = h * w;
+    for (int l = 0; l < 4; ++l) pp.img[1][l] = static_cast<int>(nl_of[l]);
     dim3 grid((w + rdvc::PACK_TX - 1) / rdvc::PACK_TX, (h + rdvc::PACK_TY - 1) / rdvc::PACK_TY,
               2 * B * (D / rdvc::PACK_CG));
     kern<<<grid, rdvc::PACK_THREADS, rdvc::PACK_SMEM_BYTES, st>>>(pp);
@@ -256,11 +262,16 @@ int rdvc_corr_set_option(int key, int value) {
     if (key == 2 && value >= 0) { g_opt_msplit = value; return RDVC_OK; }
     if (key == 3 && value >= 0 && value <= 63) { g_opt_store_mask = value; return RDVC_OK; }
     if (key == 4 && value >= 0 && value <= 2) { g_opt_mode = value; return RDVC_OK; }
-    if (key == 5 && value >= 0 && value <= 1) { g_opt_tma_out = value; return RDVC_OK; }
+    if (key == 5 && value >= 0 && value <= 2) { g_opt_tma_out = value; return RDVC_OK; }
     if (key == 6 && value >= 0 && value <= 2) { g_opt_policy = value; return RDVC_OK; }
     if (key == 7 && value >= 0 && value <= 4) { g_opt_twl = value; return RDVC_OK; }
     if (key == 8 && value >= 0 && value <= 4) { g_opt_thl = value; return RDVC_OK; }
     return fail(RDVC_E_UNSUPPORTED, "unknown option key=%d value=%d", key, value);
+}
+
+size_t rdvc_corr_level_image_elems(int h, int w, int level, int vol_dtype, int layout) {
+    if (elem_size(vol_dtype) == 0 || h <= 0 || w <= 0 || level < 0) return 0;
+    return level_image_elems(h, w, level, vol_dtype, layout);
 }
 
 int rdvc_corr_tile_shape(int vol_dtype, int* tile_w, int* tile_h) {
@@ -352,9 +363,9 @@ int rdvc_corr_build(const void* fmap1, const void* fmap2, int B, int D, int h, i
     // 1. repack to K-major bf16; the linear mode also needs the pooled fmap2 levels
     {
         const int levels2 = linear ? num_levels : 1;
-        if (in_dtype == RDVC_DT_F32) rc = launch_pack<float>(fmap1, fmap2, a_km, b_km, B, D, h, w, levels2, layout, twl, thl, st);
-        else if (in_dtype == RDVC_DT_BF16) rc = launch_pack<__nv_bfloat16>(fmap1, fmap2, a_km, b_km, B, D, h, w, levels2, layout, twl, thl, st);
-        else rc = launch_pack<__half>(fmap1, fmap2, a_km, b_km, B, D, h, w, levels2, layout, twl, thl, st);
+        if (in_dtype == RDVC_DT_F32) rc = launch_pack<float>(fmap1, fmap2, a_km, b_km, B, D, h, w, levels2, layout, twl, thl, nl_of, st);
+        else if (in_dtype == RDVC_DT_BF16) rc = launch_pack<__nv_bfloat16>(fmap1, fmap2, a_km, b_km, B, D, h, w, levels2, layout, twl, thl, nl_of, st);
+        else rc = launch_pack<__half>(fmap1, fmap2, a_km, b_km, B, D, h, w, levels2, layout, twl, thl, nl_of, st);
         if (rc) return rc;
     }
 
@@ -439,23 +450,35 @@ int rdvc_corr_build(const void* fmap1, const void* fmap2, int B, int D, int h, i
         p.msplit = (forced > 0) ? (forced < p.m_blks ? forced : p.m_blks) : best;
     }
 
-    // output descriptors: level l as a [B][N][n_l] tensor, boxes of 32 query rows x 128 bytes (linear
-    // mode, row pitch 16-byte aligned); anything else takes the staged-store path
+    // output descriptors (linear mode).  Row pitch a multiple of 128 bytes (always, in the tiled
+    // layout): level l as a {128 B, pitch/128, N, B} tensor written in boxes of 16 query rows x 256
+    // contiguous bytes.  Row pitch only 16-byte aligned: a {n_l, N, B} tensor, boxes of 32 rows x 128
+    // bytes.  Anything else takes the staged-store path.  (option key 5: 0 = staged only, 1 = auto,
+    // 2 = never the wide boxes)
     CUtensorMap to[rdvc::BLD_MAX_LEVELS];
     for (int l = 0; l < rdvc::BLD_MAX_LEVELS; ++l) to[l] = ta;
-    if (linear && g_opt_tma_out.load()) {
+    const int tma_opt = g_opt_tma_out.load();
+    if (linear && tma_opt) {
         const bool f32 = (vol_dtype == RDVC_DT_F32);
         const cuuint64_t es = f32 ? 4 : 2;
+        const CUtensorMapDataType dt = f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
         for (int l = 0; l < num_levels; ++l) {
             const cuuint64_t nl = (cuuint64_t)p.nl[l];
-            if ((nl * es) % 16 != 0) continue;
-            cuuint64_t dims[3] = {nl, (cuuint64_t)N, (cuuint64_t)B};
-            cuuint64_t str[2] = {nl * es, (cuuint64_t)N * nl * es};
-            cuuint32_t box[3] = {(cuuint32_t)(128 / es), 32, 1};   // 128-byte rows x 32 query pixels
-            rc = make_tmap(&to[l], f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
-                           p.lvl[l], 3, dims, str, box);
-            if (rc) return rc;
-            p.tma_out |= 1 << l;
+            if ((nl * es) % 128 == 0 && tma_opt == 1) {
+                cuuint64_t dims[4] = {128 / es, nl * es / 128, (cuuint64_t)N, (cuuint64_t)B};
+                cuuint64_t str[3] = {128, nl * es, (cuuint64_t)N * nl * es};
+                cuuint32_t box[4] = {(cuuint32_t)(128 / es), 2, 16, 1};
+                rc = make_tmap(&to[l], dt, p.lvl[l], 4, dims, str, box);
+                if (rc) return rc;
+                p.tma_out |= 2 << (2 * l);
+            } else if ((nl * es) % 16 == 0) {
+                cuuint64_t dims[3] = {nl, (cuuint64_t)N, (cuuint64_t)B};
+                cuuint64_t str[2] = {nl * es, (cuuint64_t)N * nl * es};
+                cuuint32_t box[3] = {(cuuint32_t)(128 / es), 32, 1};
+                rc = make_tmap(&to[l], dt, p.lvl[l], 3, dims, str, box);
+                if (rc) return rc;
+                p.tma_out |= 1 << (2 * l);
+            }
         }
     }
 

@@ -167,8 +167,9 @@ def test_build_fp32_volume(lib, shape, mode):
         if layout == TILED:  # padding pixels of the tiled storage are exact zeros
             for l in range(4):
                 hl, wl, tw, th, hp, wp = pyr._tiles(l)
-                st = pyr.storage(l).view(-1, hp // th, wp // tw, th, tw).permute(0, 1, 3, 2, 4).reshape(-1, hp, wp)
-                assert not st[:, hl:, :].any() and not st[:, :, wl:].any()
+                raw = pyr.storage(l)
+                st = raw[:, : hp * wp].reshape(-1, hp // th, wp // tw, th, tw).permute(0, 1, 3, 2, 4).reshape(-1, hp, wp)
+                assert not st[:, hl:, :].any() and not st[:, :, wl:].any() and not raw[:, hp * wp:].any()
     set_opts(lib, mode=0, tile=0)
 
 
@@ -208,16 +209,20 @@ def test_build_fewer_levels(lib, levels):
         assert rel_max(pyr.level(l)[:, 0].cpu().numpy(), ref[l]) < TOL_SAME_OPERANDS_F32
 
 
-def test_build_staged_store_path(lib):
-    """Linear mode without TMA stores (the path odd-sized levels take)."""
+@pytest.mark.parametrize("tma", [0, 2])
+@pytest.mark.parametrize("vol", [torch.float32, torch.bfloat16])
+def test_build_other_store_paths(lib, tma, vol):
+    """Linear mode without the wide TMA boxes: staged st.global (tma=0, the path odd-sized row-major
+    levels take) and 32-row x 128-byte boxes (tma=2, 16-byte-aligned row pitches)."""
     B, D, h, w = 1, 64, 24, 40
     f1, f2 = cn.synth_fmaps(B, D, h, w, seed=12)
     ref = ref_pyramid_linear(f1, f2, 4)
-    set_opts(lib, mode=2, tma=0)
+    tol = TOL_SAME_OPERANDS_F32 if vol == torch.float32 else TOL_SAME_OPERANDS_BF16
+    set_opts(lib, mode=2, tma=tma)
     for layout in (ROW, TILED):
-        pyr = rc.build_pyramid(gpu(f1), gpu(f2), 4, layout=layout)
+        pyr = rc.build_pyramid(gpu(f1), gpu(f2), 4, vol, layout=layout)
         for l in range(4):
-            assert rel_max(pyr.level(l)[:, 0].cpu().numpy(), ref[l]) < TOL_SAME_OPERANDS_F32
+            assert rel_max(pyr.level(l)[:, 0].float().cpu().numpy(), ref[l]) < tol
     set_opts(lib, mode=0, tma=1)
 
 
@@ -444,10 +449,9 @@ def test_no_out_of_bounds_writes(lib, mode, layout, vol):
         for k, v in bufs.items():
             assert bool((v[:GUARD] == CANARY).all()) and bool((v[-GUARD:] == CANARY).all()), (k, "guard band")
         body = bufs["pyr"][GUARD:-GUARD]
-        tw, th = rc.corr_block.tile_shape(vol) if layout == TILED else (1, 1)
         for l in range(4):
             off = lib.rdvc_corr_level_offset_bytes(B, h, w, l, vd, layout)
-            end = off + B * N * (-(-(h >> l) // th) * th) * (-(-(w >> l) // tw) * tw) * es
+            end = off + B * N * lib.rdvc_corr_level_image_elems(h, w, l, vd, layout) * es
             nxt = lib.rdvc_corr_level_offset_bytes(B, h, w, l + 1, vd, layout)
             assert bool((body[end:nxt] == CANARY).all()), ("padding after level", l)
             lvl = body[off:end].view(vol).float()
