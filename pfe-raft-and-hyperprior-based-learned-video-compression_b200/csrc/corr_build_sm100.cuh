@@ -44,25 +44,35 @@ constexpr int BLD_UMMA_K = 16;
 #ifndef RDVC_A_STAGES
 #define RDVC_A_STAGES 3
 #endif
-#ifndef RDVC_STG_BUFS
-#define RDVC_STG_BUFS 1
-#endif
 constexpr int BLD_A_STAGES = RDVC_A_STAGES;
-constexpr int BLD_STG_BUFS = RDVC_STG_BUFS;  // 4 KB TMA-store staging buffers per epilogue warp
 constexpr int BLD_MAX_KC = 4;    // D <= 256
 constexpr int BLD_A_STAGE_BYTES = BLD_BLOCK_M * BLD_BLOCK_K * 2;  // 16 KB
 constexpr int BLD_B_SLAB_BYTES = BLD_BLOCK_N * BLD_BLOCK_K * 2;   // 32 KB
-constexpr int BLD_EPI_WARPS = 8;
-constexpr int BLD_STG_BYTES = 4096;  // per epilogue warp: 32 rows x 32 fp32
-constexpr int BLD_THREADS = 128 + BLD_EPI_WARPS * 32;
+constexpr int BLD_STG_BYTES = 4096;  // one TMA-store staging buffer (a 4 KB box)
 constexpr int BLD_MAX_LEVELS = 4;
 
 constexpr int BLD_SMEM_B = 0;
 constexpr int BLD_SMEM_A = BLD_SMEM_B + BLD_MAX_KC * BLD_B_SLAB_BYTES;       // 131072
 constexpr int BLD_SMEM_STG = BLD_SMEM_A + BLD_A_STAGES * BLD_A_STAGE_BYTES;  // 196608
-constexpr int BLD_SMEM_BAR = BLD_SMEM_STG + BLD_EPI_WARPS * BLD_STG_BYTES * BLD_STG_BUFS;
-constexpr int BLD_SMEM_TOTAL = BLD_SMEM_BAR + 128;
-constexpr int BLD_SMEM_LAUNCH = BLD_SMEM_TOTAL + 1024;  // slack for 1024-byte alignment
+
+// Epilogue shape.  EW = 8 epilogue warps: two per TMEM lane quarter, each half a tile's width, one
+// 4 KB staging buffer per warp (32 KB in flight).  EW = 4: one warp per quarter, the whole tile
+// width, three buffers per warp (48 KB in flight).  The stationary fmap2 tile (128 KB) and the fmap1
+// ring (48 KB; 2 stages starve the MMA: 1.18 ms) leave ~49 KB for staging, so it is one or the other.
+// Measured at 1080p: fp32 volume 0.98 ms (EW 8) vs 1.03 ms (EW 4: one warp per quarter cannot issue
+// the boxes fast enough); bf16 volume 0.75 ms (EW 8: its two boxes per tile serialise on the single
+// buffer, ~0.8 us each) vs 0.68 ms (EW 4).
+template <int EW>
+struct BuildCfg {
+    static_assert(EW == 4 || EW == 8, "epilogue warps");
+    static constexpr int EPI_WARPS = EW;
+    static constexpr int SUBS = 8 / EW;                 // 128-column halves of a tile per epilogue warp
+    static constexpr int STG_BUFS = (EW == 4) ? 3 : 1;  // staging buffers per epilogue warp
+    static constexpr int THREADS = 128 + EW * 32;
+    static constexpr int SMEM_BAR = BLD_SMEM_STG + EW * BLD_STG_BYTES * STG_BUFS;
+    static constexpr int SMEM_TOTAL = SMEM_BAR + 128;
+    static constexpr int SMEM_LAUNCH = SMEM_TOTAL + 1024;  // slack for 1024-byte alignment
+};
 
 struct BuildParams {
     void* lvl[BLD_MAX_LEVELS];  // level base pointers (256-byte aligned)
@@ -202,13 +212,16 @@ __device__ __forceinline__ void staged_store(uint32_t stg, const float* v, int l
 constexpr int MODE_FUSED = 0;
 constexpr int MODE_LINEAR = 1;
 
-template <int MODE, int TILE_Y, int TILE_X, typename OutT>
-__global__ void __launch_bounds__(BLD_THREADS, 1)
+template <int MODE, int TILE_Y, int TILE_X, typename OutT, int EW>
+__global__ void __launch_bounds__(BuildCfg<EW>::THREADS, 1)
 corr_build_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b0,
                   const __grid_constant__ CUtensorMap tm_b1, const __grid_constant__ CUtensorMap tm_b2,
                   const __grid_constant__ CUtensorMap tm_b3, const __grid_constant__ CUtensorMap tm_o0,
                   const __grid_constant__ CUtensorMap tm_o1, const __grid_constant__ CUtensorMap tm_o2,
                   const __grid_constant__ CUtensorMap tm_o3, const BuildParams p) {
+    using Cfg = BuildCfg<EW>;
+    constexpr int BLD_EPI_WARPS = Cfg::EPI_WARPS, BLD_SUBS = Cfg::SUBS, BLD_STG_BUFS = Cfg::STG_BUFS;
+    constexpr int BLD_SMEM_BAR = Cfg::SMEM_BAR;
     static_assert(TILE_Y * TILE_X == BLD_BLOCK_N, "tile must hold 256 fmap2 pixels");
     static_assert(TILE_Y % 8 == 0 && TILE_X % 16 == 0, "sub-tiles are 8 x 16");
     extern __shared__ uint8_t smem_raw[];
@@ -349,7 +362,7 @@ corr_build_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
         using TR = OutTraits<OutT>;
         const int e = warp - 4;
         const int q = e & 3;          // TMEM lane quarter this warp may read (warp_id % 4)
-        const int sub = e >> 2;       // which half of the tile's 256 columns
+        const int sub0 = (e >> 2) * BLD_SUBS;   // first 128-column half of a tile this warp handles
         const uint32_t stg = ptx::smem_u32(smem + BLD_SMEM_STG) + e * BLD_STG_BYTES * BLD_STG_BUFS;
         uint32_t box_it = 0;  // TMA boxes issued by this warp (selects the staging buffer)
         const float scale = p.scale;
@@ -366,12 +379,11 @@ corr_build_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
                 int l = 0;
                 while (l + 1 < L && nt >= p.tile_start[l + 1]) ++l;
                 const int n_l = p.nl[l];                                 // pixels of this level
-                const int col0 = (nt - p.tile_start[l]) * BLD_BLOCK_N + sub * (BLD_BLOCK_N / 2);
+                const int tile_col0 = (nt - p.tile_start[l]) * BLD_BLOCK_N;
                 OutT* const lv = static_cast<OutT*>(p.lvl[l]);
                 const bool vec = (n_l % TR::EPC) == 0;
                 const bool wr = (smask >> l) & 1;
                 const int omode = (p.tma_out >> (2 * l)) & 3;
-                const bool use_tma = omode == 1;
                 const CUtensorMap* tmo = (l == 0) ? &tm_o0 : (l == 1) ? &tm_o1 : (l == 2) ? &tm_o2 : &tm_o3;
                 for (int mb = mb0; mb < mb1; ++mb, ++tile_it) {
                     const int m0 = mb * BLD_BLOCK_M + q * 32;
@@ -381,6 +393,11 @@ corr_build_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
                     const uint32_t acc = tile_it & 1, acc_ph = (tile_it >> 1) & 1;
                     ptx::mbar_wait(bar(T_FULL + acc), acc_ph);
                     ptx::tc_fence_after();
+#pragma unroll
+                    for (int sb_i = 0; sb_i < BLD_SUBS; ++sb_i) {
+                    const int sub = sub0 + sb_i;
+                    const bool last_sub = (sb_i == BLD_SUBS - 1);
+                    const int col0 = tile_col0 + sub * (BLD_BLOCK_N / 2);
                     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
                                            acc * BLD_BLOCK_N + sub * (BLD_BLOCK_N / 2);
                     if (omode == 2) {
@@ -388,6 +405,8 @@ corr_build_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
                         // 6.1 TB/s vs 5.5 TB/s for 128-byte visits, tools/micro/wbench3.cu).  A box is
                         // 16 query rows x two 128-byte column blocks = 4 KB, smem order [row][block][128 B]
                         // with TMA's SWIZZLE_128B; the warp's rows go out as two boxes (lanes 0-15, 16-31).
+                        // BLD_STG_BUFS boxes per warp are in flight: a store takes ~0.8 us to drain, so the
+                        // bytes in flight per SM (warps x buffers x 4 KB) bound the write rate.
                         constexpr int EPB = 128 / static_cast<int>(sizeof(OutT));   // elements per column block
                         constexpr int GC = 2 * EPB;                                  // columns per 256-byte group
                         constexpr int GROUPS = (BLD_BLOCK_N / 2) / GC;               // 2 (fp32) / 1 (bf16)
@@ -414,7 +433,7 @@ corr_build_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
                                         pk[hb * 32 + i] = OutTraits<__nv_bfloat16>::pk(v[2 * i] * scale, v[2 * i + 1] * scale);
                                 }
                             }
-                            if (g == GROUPS - 1) {
+                            if (last_sub && g == GROUPS - 1) {
                                 // every TMEM read of this tile is done: hand the accumulator back early
                                 ptx::tc_fence_before();
                                 __syncwarp();
@@ -427,8 +446,11 @@ corr_build_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
                                                              // swizzled 16-byte columns (conflict-free)
 #pragma unroll
                             for (int hh = 0; hh < 2; ++hh) {
-                                if (lane == 0) ptx::bulk_wait_read<0>();   // the previous box has left the buffer
+                                // the box that used this buffer BLD_STG_BUFS boxes ago has left smem
+                                if (lane == 0) ptx::bulk_wait_read<BLD_STG_BUFS - 1>();
                                 __syncwarp();
+                                const uint32_t sb = stg + (box_it % BLD_STG_BUFS) * BLD_STG_BYTES;
+                                ++box_it;
                                 if ((lane >> 4) == hh) {
 #pragma unroll
                                     for (int ps = 0; ps < 2; ++ps) {
@@ -441,14 +463,14 @@ corr_build_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
                                             w.y = flip ? pk[(1 - ps) * 32 + c * 4 + 1] : pk[ps * 32 + c * 4 + 1];
                                             w.z = flip ? pk[(1 - ps) * 32 + c * 4 + 2] : pk[ps * 32 + c * 4 + 2];
                                             w.w = flip ? pk[(1 - ps) * 32 + c * 4 + 3] : pk[ps * 32 + c * 4 + 3];
-                                            sts_16(stg + rr * 128 + ((c ^ (rr & 7)) << 4), w);
+                                            sts_16(sb + rr * 128 + ((c ^ (rr & 7)) << 4), w);
                                         }
                                     }
                                 }
                                 ptx::fence_proxy_async_smem();
                                 __syncwarp();
                                 if (lane == 0) {
-                                    ptx::tma_store_4d(tmo, stg, 0, (col0 + g * GC) / EPB, m0 + 16 * hh, b);
+                                    ptx::tma_store_4d(tmo, sb, 0, (col0 + g * GC) / EPB, m0 + 16 * hh, b);
                                     ptx::bulk_commit();
                                 }
                             }
@@ -469,7 +491,7 @@ corr_build_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
 #pragma unroll
                             for (int i = 0; i < CW; ++i) v[i] = 0.f;
                         }
-                        if (j == PASSES - 1) {
+                        if (last_sub && j == PASSES - 1) {
                             // every TMEM read of this tile is done: hand the accumulator back early
                             ptx::tc_fence_before();
                             __syncwarp();
@@ -478,10 +500,9 @@ corr_build_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
 #pragma unroll
                         for (int i = 0; i < CW; ++i) v[i] *= scale;
                         if (wr) {
-                            if (use_tma) {
+                            if (omode == 1) {
                                 // staged rows are 128 B (8 x 16-byte chunks) with the chunk index XORed by
                                 // (row & 7): exactly TMA's SWIZZLE_128B, so the engine un-swizzles on the way out
-                                // the box that used this buffer BLD_STG_BUFS boxes ago has left smem
                                 if (lane == 0) ptx::bulk_wait_read<BLD_STG_BUFS - 1>();
                                 __syncwarp();
                                 const uint32_t sb = stg + (box_it % BLD_STG_BUFS) * BLD_STG_BYTES;
@@ -499,7 +520,7 @@ corr_build_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
                                     ptx::bulk_commit();
                                 }
                             } else {
-                                // a TMA box of a previous (aligned) level may still be reading the buffer
+                                // TMA boxes of a previous (aligned) level may still be reading the buffers
                                 if (lane == 0) ptx::bulk_wait_read<0>();
                                 __syncwarp();
 #pragma unroll
@@ -509,12 +530,12 @@ corr_build_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
                             }
                         }
                     }
+                    }  // 128-column halves of this warp
                 }
             }
             if (lane == 0) ptx::bulk_wait<0>();  // all TMA stores of this warp have landed
         } else {
         constexpr int SUBS_X = TILE_X / 16;
-        const int sy = (sub / SUBS_X) * 8, sx = (sub % SUBS_X) * 16;
         OutT* const l0 = static_cast<OutT*>(p.lvl[0]);
         OutT* const l1 = static_cast<OutT*>(p.lvl[1]);
         OutT* const l2 = static_cast<OutT*>(p.lvl[2]);
@@ -533,8 +554,6 @@ corr_build_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
           const int b = u / ntiles, nt = u % ntiles;
           const int mb0 = static_cast<int>(static_cast<long long>(sl) * p.m_blks / p.msplit);
           const int mb1 = static_cast<int>(static_cast<long long>(sl + 1) * p.m_blks / p.msplit);
-          const int Y0 = (nt / p.ntx) * TILE_Y + sy;  // level-0 origin of this warp's 8x16 patch
-          const int X0 = (nt % p.ntx) * TILE_X + sx;
           for (int mb = mb0; mb < mb1; ++mb, ++tile_it) {
             const int m0 = mb * BLD_BLOCK_M + q * 32;   // first query pixel of this warp
             int rows_valid = p.N - m0;
@@ -546,6 +565,13 @@ corr_build_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
             ptx::tc_fence_after();
             const uint32_t taddr =
                 tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BLD_BLOCK_N;
+#pragma unroll
+            for (int sb_i = 0; sb_i < BLD_SUBS; ++sb_i) {
+            const int sub = sub0 + sb_i;
+            const bool last_sub = (sb_i == BLD_SUBS - 1);
+            const int sy = (sub / SUBS_X) * 8, sx = (sub % SUBS_X) * 16;
+            const int Y0 = (nt / p.ntx) * TILE_Y + sy;  // level-0 origin of this warp's 8x16 patch
+            const int X0 = (nt % p.ntx) * TILE_X + sx;
 
             float p1[32];  // level 1 of this patch: 4 rows x 8
 #pragma unroll
@@ -554,7 +580,7 @@ corr_build_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
                 ptx::tmem_ld_x16(taddr + (sy + 2 * j) * TILE_X + sx, v);
                 ptx::tmem_ld_x16(taddr + (sy + 2 * j + 1) * TILE_X + sx, v + 16);
                 ptx::tmem_ld_wait();
-                if (j == 3) {
+                if (last_sub && j == 3) {
                     // every TMEM read of this tile is done: hand the accumulator back early
                     ptx::tc_fence_before();
                     __syncwarp();
@@ -625,6 +651,7 @@ corr_build_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
                     }
                 }
             }
+            }  // 8x16 patches of this warp
           }  // m-blocks of this item
         }      // items
         }      // MODE_FUSED

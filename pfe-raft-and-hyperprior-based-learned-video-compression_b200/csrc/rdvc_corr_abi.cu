@@ -30,6 +30,7 @@ std::atomic<int> g_opt_tma_out{1};
 std::atomic<int> g_opt_policy{0};
 std::atomic<int> g_opt_twl{0};
 std::atomic<int> g_opt_thl{0};
+std::atomic<int> g_opt_epi_warps{0};
 
 int fail(int code, const char* fmt, ...) {
     va_list ap;
@@ -143,14 +144,15 @@ int sm_count() {
     return n;
 }
 
-template <int MODE, int TY, int TX, typename OutT>
+template <int MODE, int TY, int TX, typename OutT, int EW>
 int launch_build(const CUtensorMap& ta, const CUtensorMap* tb, const CUtensorMap* to, const rdvc::BuildParams& p,
                  cudaStream_t st) {
-    auto kern = rdvc::corr_build_kernel<MODE, TY, TX, OutT>;
+    auto kern = rdvc::corr_build_kernel<MODE, TY, TX, OutT, EW>;
+    using Cfg = rdvc::BuildCfg<EW>;
     static bool attr_set = false;  // per instantiation
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             rdvc::BLD_SMEM_LAUNCH);
+                                             Cfg::SMEM_LAUNCH);
         if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(build, max dynamic smem)");
         attr_set = true;
     }
@@ -158,7 +160,7 @@ int launch_build(const CUtensorMap& ta, const CUtensorMap* tb, const CUtensorMap
     const long long n_items = static_cast<long long>(p.B) * p.ntiles * p.msplit;
     if (grid > n_items) grid = n_items;
     if (g_prof_start) cudaEventRecord(g_prof_start, st);
-    kern<<<static_cast<unsigned>(grid), rdvc::BLD_THREADS, rdvc::BLD_SMEM_LAUNCH, st>>>(
+    kern<<<static_cast<unsigned>(grid), Cfg::THREADS, Cfg::SMEM_LAUNCH, st>>>(
         ta, tb[0], tb[1], tb[2], tb[3], to[0], to[1], to[2], to[3], p);
     if (g_prof_stop) cudaEventRecord(g_prof_stop, st);
     ++g_launches;
@@ -266,6 +268,7 @@ int rdvc_corr_set_option(int key, int value) {
     if (key == 6 && value >= 0 && value <= 2) { g_opt_policy = value; return RDVC_OK; }
     if (key == 7 && value >= 0 && value <= 4) { g_opt_twl = value; return RDVC_OK; }
     if (key == 8 && value >= 0 && value <= 4) { g_opt_thl = value; return RDVC_OK; }
+    if (key == 9 && (value == 0 || value == 4 || value == 8)) { g_opt_epi_warps = value; return RDVC_OK; }
     return fail(RDVC_E_UNSUPPORTED, "unknown option key=%d value=%d", key, value);
 }
 
@@ -485,15 +488,21 @@ int rdvc_corr_build(const void* fmap1, const void* fmap2, int B, int D, int h, i
     using rdvc::MODE_FUSED;
     using rdvc::MODE_LINEAR;
     if (linear) {
-        return (vol_dtype == RDVC_DT_F32) ? launch_build<MODE_LINEAR, 16, 16, float>(ta, tb, to, p, st)
-                                          : launch_build<MODE_LINEAR, 16, 16, __nv_bfloat16>(ta, tb, to, p, st);
+        // epilogue shape per storage type: see BuildCfg (option key 9: 0 = auto, 4 / 8 = force)
+        int ew = g_opt_epi_warps.load();
+        if (ew == 0) ew = (vol_dtype == RDVC_DT_F32) ? 8 : 4;
+        if (vol_dtype == RDVC_DT_F32)
+            return ew == 8 ? launch_build<MODE_LINEAR, 16, 16, float, 8>(ta, tb, to, p, st)
+                           : launch_build<MODE_LINEAR, 16, 16, float, 4>(ta, tb, to, p, st);
+        return ew == 8 ? launch_build<MODE_LINEAR, 16, 16, __nv_bfloat16, 8>(ta, tb, to, p, st)
+                       : launch_build<MODE_LINEAR, 16, 16, __nv_bfloat16, 4>(ta, tb, to, p, st);
     }
     if (vol_dtype == RDVC_DT_F32) {
-        return (tile == 1) ? launch_build<MODE_FUSED, 16, 16, float>(ta, tb, to, p, st)
-                           : launch_build<MODE_FUSED, 8, 32, float>(ta, tb, to, p, st);
+        return (tile == 1) ? launch_build<MODE_FUSED, 16, 16, float, 8>(ta, tb, to, p, st)
+                           : launch_build<MODE_FUSED, 8, 32, float, 8>(ta, tb, to, p, st);
     }
-    return (tile == 1) ? launch_build<MODE_FUSED, 16, 16, __nv_bfloat16>(ta, tb, to, p, st)
-                       : launch_build<MODE_FUSED, 8, 32, __nv_bfloat16>(ta, tb, to, p, st);
+    return (tile == 1) ? launch_build<MODE_FUSED, 16, 16, __nv_bfloat16, 8>(ta, tb, to, p, st)
+                       : launch_build<MODE_FUSED, 8, 32, __nv_bfloat16, 8>(ta, tb, to, p, st);
 }
 
 int rdvc_corr_lookup(const void* pyramid, int vol_dtype, int layout, const float* coords, int B, int h,

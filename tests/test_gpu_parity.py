@@ -39,12 +39,12 @@ def lib():
     assert torch.cuda.is_available(), "GPU tests need a B200"
     L = rc._cabi.load()
     yield L
-    for k in range(9):
+    for k in range(10):
         L.rdvc_corr_set_option(k, {3: 15, 5: 1}.get(k, 0))
 
 
 def set_opts(lib, **kw):
-    keys = {"lookup": 0, "tile": 1, "msplit": 2, "mode": 4, "tma": 5}
+    keys = {"lookup": 0, "tile": 1, "msplit": 2, "mode": 4, "tma": 5, "epi": 9}
     for k, v in kw.items():
         assert lib.rdvc_corr_set_option(keys[k], v) == 0
 
@@ -185,6 +185,23 @@ def test_build_bf16_volume(lib, mode):
             got = pyr.level(l)[:, 0].float().cpu().numpy()
             assert rel_max(got, ref32[l]) < TOL_VOLUME
     set_opts(lib, mode=0)
+
+
+@pytest.mark.parametrize("epi", [4, 8])
+@pytest.mark.parametrize("vol", [torch.float32, torch.bfloat16])
+def test_build_epilogue_shapes(lib, epi, vol):
+    """Both epilogue shapes of the linear build (4 warps x 3 staging buffers, 8 warps x 1) for both
+    storage types, on a shape with partial m-blocks, partial n-tiles and B > 1."""
+    B, D, h, w = 2, 64, 18, 22
+    f1, f2 = cn.synth_fmaps(B, D, h, w, seed=15)
+    ref = ref_pyramid_linear(f1, f2, 4)
+    tol = TOL_SAME_OPERANDS_F32 if vol == torch.float32 else TOL_SAME_OPERANDS_BF16
+    set_opts(lib, epi=epi)
+    for layout in (ROW, TILED):
+        pyr = rc.build_pyramid(gpu(f1), gpu(f2), 4, vol, layout=layout)
+        for l in range(4):
+            assert rel_max(pyr.level(l)[:, 0].float().cpu().numpy(), ref[l]) < tol, (layout, l)
+    set_opts(lib, epi=0)
 
 
 @pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
