@@ -8,8 +8,9 @@
 //
 // One CTA = an 8 x 32 spatial block x 64 channels, fp32 in shared memory: global reads are
 // 128-byte rows of the source, global writes are 128-byte pieces (64 channels) of the K-major
-// rows.  Each map is read exactly once.  HBM-bound and small next to the volume write
-// (67 MB in, 39 MB out at 1080p).
+// rows.  Each map is read exactly once and each staged value is read from shared memory once
+// (the pooled levels are register sums along a quad-ordered walk).  Small next to the volume
+// write (67 MB in, 39 MB out at 1080p).
 #pragma once
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
@@ -120,43 +121,67 @@ corr_pack_kernel(const __grid_constant__ PackParams p) {
     }
     __syncthreads();
 
-    // store: one K-major row piece (64 channels = 128 B of bf16) per warp instruction
+    // store: one K-major row piece (64 channels = 128 B of bf16) per warp instruction, lane = channel
+    // pair.  Warp wq owns the 4 x 8 pixel region (rows 4*(wq&1).., columns 8*(wq>>1)..) of the block and
+    // walks it quad by quad (2x2 inside 4x4), so every level-0 value is read from shared memory ONCE:
+    // the pooled levels are running sums in registers (level 1 = a quad, level 2 = four quads); the two
+    // warps of an 8 x 8 block combine their halves of the level-3 sum through shared memory.
     const int L = p.levels[map];
-    int row_base = 0;
-    for (int l = 0; l < L; ++l) {
-        const int sy = PACK_TY >> l, sx = PACK_TX >> l;   // pooled pixels in this block
-        const int f = 1 << l;
-        const int hl = h >> l, wl = w >> l;
-        const float inv = 1.0f / static_cast<float>(f * f);
-        __nv_bfloat16* dst = p.dst[map][l];
-        const int nrows = sy * sx;
-        // rows are dealt to warps continuing across levels so the heavy (pooled) rows spread out
-        for (int r = (warp - row_base % 8 + 8) % 8; r < nrows; r += PACK_THREADS / 32) {
-            const int oy = r / sx, ox = r % sx;
-            const int Y = (y0 >> l) + oy, X = (x0 >> l) + ox;
-            if (Y >= hl || X >= wl) continue;
-            const float* t0 = tile + (2 * lane) * PACK_PITCH + (oy * f) * PACK_TX + ox * f;
-            float a0 = 0.f, a1 = 0.f;
-            for (int dy = 0; dy < f; ++dy)
-                for (int dx = 0; dx < f; ++dx) {
-                    a0 += t0[dy * PACK_TX + dx];
-                    a1 += t0[PACK_PITCH + dy * PACK_TX + dx];
-                }
-            // operand row of pixel (Y, X): raster order, or tile by tile (see rdvc_corr.h); the
-            // build's output columns follow the operand rows, so this IS the volume's layout
-            const size_t img = static_cast<size_t>(p.img[map][l]);
-            size_t pix = static_cast<size_t>(Y) * wl + X;
-            if (p.tiled[map]) {
-                const int twl = p.twl, thl = p.thl;
-                const int tiles_w = (wl + (1 << twl) - 1) >> twl;
-                pix = (static_cast<size_t>((Y >> thl) * tiles_w + (X >> twl)) << (twl + thl)) +
-                      ((Y & ((1 << thl) - 1)) << twl) + (X & ((1 << twl) - 1));
-            }
-            __nv_bfloat162* out = reinterpret_cast<__nv_bfloat162*>(
-                dst + (static_cast<size_t>(b) * img + pix) * D + cg * PACK_CG);
-            out[lane] = __floats2bfloat162_rn(a0 * inv, a1 * inv);
+    const int ry0 = (warp & 1) * 4, cx0 = (warp >> 1) * 8;
+    auto row_ptr = [&](int l, int Y, int X) -> __nv_bfloat162* {
+        // operand row of pixel (Y, X) of level l: raster order, or tile by tile (see rdvc_corr.h); the
+        // build's output columns follow the operand rows, so this IS the volume's layout
+        const int wl = w >> l;
+        size_t pix = static_cast<size_t>(Y) * wl + X;
+        if (p.tiled[map]) {
+            const int twl = p.twl, thl = p.thl;
+            const int tiles_w = (wl + (1 << twl) - 1) >> twl;
+            pix = (static_cast<size_t>((Y >> thl) * tiles_w + (X >> twl)) << (twl + thl)) +
+                  ((Y & ((1 << thl) - 1)) << twl) + (X & ((1 << twl) - 1));
         }
-        row_base += nrows;
+        return reinterpret_cast<__nv_bfloat162*>(
+                   p.dst[map][l] + (static_cast<size_t>(b) * p.img[map][l] + pix) * D + cg * PACK_CG) + lane;
+    };
+    const float* t0 = tile + (2 * lane) * PACK_PITCH + ry0 * PACK_TX + cx0;
+    float s3a = 0.f, s3b = 0.f;                       // this warp's half of the level-3 sum (4 x 8 pixels)
+#pragma unroll
+    for (int b2 = 0; b2 < 2; ++b2) {                  // the two 4 x 4 blocks of the region
+        float s2a = 0.f, s2b = 0.f;
+#pragma unroll
+        for (int qd = 0; qd < 4; ++qd) {              // 2 x 2 quads of a 4 x 4 block
+            float s1a = 0.f, s1b = 0.f;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int yy = (qd >> 1) * 2 + (e >> 1), xx = b2 * 4 + (qd & 1) * 2 + (e & 1);
+                const float v0 = t0[yy * PACK_TX + xx], v1 = t0[PACK_PITCH + yy * PACK_TX + xx];
+                s1a += v0; s1b += v1;
+                const int Y = y0 + ry0 + yy, X = x0 + cx0 + xx;
+                if (Y < h && X < w) *row_ptr(0, Y, X) = __floats2bfloat162_rn(v0, v1);
+            }
+            s2a += s1a; s2b += s1b;
+            if (L > 1) {
+                const int Y = (y0 + ry0) / 2 + (qd >> 1), X = (x0 + cx0) / 2 + b2 * 2 + (qd & 1);
+                if (Y < (h >> 1) && X < (w >> 1)) *row_ptr(1, Y, X) = __floats2bfloat162_rn(s1a * 0.25f, s1b * 0.25f);
+            }
+        }
+        s3a += s2a; s3b += s2b;
+        if (L > 2) {
+            const int Y = (y0 + ry0) / 4, X = (x0 + cx0) / 4 + b2;
+            if (Y < (h >> 2) && X < (w >> 2))
+                *row_ptr(2, Y, X) = __floats2bfloat162_rn(s2a * (1.0f / 16.0f), s2b * (1.0f / 16.0f));
+        }
+    }
+    if (L > 3) {                                      // uniform over the block: all warps take it or none
+        __syncthreads();                              // the tile has been consumed: reuse its first floats
+        float2* part = reinterpret_cast<float2*>(tile);          // [4 blocks][32 lanes]
+        if (warp & 1) part[(warp >> 1) * 32 + lane] = make_float2(s3a, s3b);
+        __syncthreads();
+        if (!(warp & 1)) {
+            const float2 o = part[(warp >> 1) * 32 + lane];
+            const int Y = y0 / 8, X = (x0 + cx0) / 8;
+            if (Y < (h >> 3) && X < (w >> 3))
+                *row_ptr(3, Y, X) = __floats2bfloat162_rn((s3a + o.x) * (1.0f / 64.0f), (s3b + o.y) * (1.0f / 64.0f));
+        }
     }
 }
 
