@@ -267,6 +267,33 @@ def run_ours(args):
     launches = lib.rdvc_corr_launch_count() - launches0
     build_ms = [a.elapsed_time(b_) for a, b_ in kev]
 
+    # ---- the same timed loop with the other pyramid storage type (reported beside the headline: the
+    # reference's own GPU default is an fp16 volume under autocast, R:codec_processing.py:1436)
+    alt = None
+    if not args.no_alt:
+        alt_dtype = torch.bfloat16 if vol_dtype == torch.float32 else torch.float32
+        blk.release()
+        torch.cuda.empty_cache()
+        blk_alt = rc.TVCorrBlock(num_levels=LEVELS, radius=RADIUS, volume_dtype=alt_dtype)
+
+        def step_alt(i):
+            f1, f2 = fmaps[i % RING]
+            blk_alt.build_pyramid(f1, f2)
+            for k in range(ITERS):
+                rc.index_pyramid(blk_alt._pyr, coords[k], RADIUS, out=out)
+
+        for i in range(args.warmup):
+            step_alt(i)
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        a0.record()
+        for i in range(args.steps):
+            step_alt(args.warmup + i)
+        a1.record()
+        barrier()
+        alt = (alt_dtype, a0.elapsed_time(a1))
+        blk_alt.release()
+
     # ---- end to end through the C ABI with host buffers (pinned), copies inside the timed region
     h_f = [(f1.cpu().pin_memory(), f2.cpu().pin_memory()) for f1, f2 in fmaps[:2]]
     h_co = torch.stack([c_.cpu() for c_ in coords]).contiguous().pin_memory()
@@ -295,10 +322,11 @@ def run_ours(args):
     d2h = ITERS * B * LEVELS * (2 * RADIUS + 1) ** 2 * N * 4
 
     # ---- max over ranks
+    alt_ms = alt[1] if alt is not None else 0.0
     if dist is not None:
-        t = torch.tensor([ms_total, e2e_s], device=dev, dtype=torch.float64)
+        t = torch.tensor([ms_total, e2e_s, alt_ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total, e2e_s = t[0].item(), t[1].item()
+        ms_total, e2e_s, alt_ms = t[0].item(), t[1].item(), t[2].item()
     value = world * args.steps / (ms_total / 1e3)
     e2e_value = world * args.steps / e2e_s
 
@@ -330,6 +358,15 @@ def run_ours(args):
                 "whole_step_frac_of_roofline": (roof_pair_s * 1e3) / (ms_total / args.steps),
             },
         }
+        if alt is not None:
+            ab = 2 if alt[0] == torch.bfloat16 else 4
+            bb, bl = algorithmic_bytes(ab)
+            line["alt_volume_dtype"] = {
+                "volume_dtype": "bf16" if ab == 2 else "fp32", "value": world * args.steps / (alt_ms / 1e3), "unit": UNIT,
+                "ms_per_step": alt_ms / args.steps,
+                "whole_step_frac_of_roofline": ((bb + ITERS * bl) / (peak * 1e9) * 1e3) / (alt_ms / args.steps),
+                "note": "same timed loop, other pyramid storage type; not the headline",
+            }
         if world == 1 and not args.no_cpu_baseline:
             sec, sample, cores = reference_pair_seconds(steps=1, warmup=0)
             line["cpu_baseline"] = {"value": 1.0 / sec, "unit": UNIT, "cores": cores, "kind": "reference",
@@ -350,6 +387,7 @@ def main():
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--volume-dtype", choices=["fp32", "bf16"], default="fp32")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-alt", action="store_true", help="skip the extra timed loop with the other volume dtype")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3   # timing rule: at least 3 warm-up steps

@@ -1,6 +1,16 @@
 #!/usr/bin/env python
-"""bench_gop.py -- BASELINE.json config 3 ("next" row): P-frames/s of the motion branch's RAFT call
-on a synthetic 1080p GOP (I-frame every 10 -> 9 P-frames), 1 GPU.
+"""bench_gop.py -- BASELINE.json configs 3 and 4 ("next" rows): P-frames/s of the motion branch's RAFT
+call on synthetic 1080p GOPs (I-frame every 10 -> 9 P-frames).
+
+    python bench_gop.py                                  # config 3: one GOP, 1 GPU, vs stock torchvision
+    torchrun --nproc-per-node N bench_gop.py --frames 600   # config 4: GOP-sharded over N GPUs
+
+Config 4 shards whole GOPs over the ranks (gop_shard.assign_gops), every rank runs RAFT with the B200
+correlation block on its own P-frames, and rank 0 gathers the per-GOP frame records into one `.rdvc`
+stream on the host -- no collective on the data path.  The codec networks and the entropy coder are
+out of scope: the P payload carries a quantised 1/8-resolution flow as a stand-in for
+the motion bitstream, the I payload a small thumbnail, so the container, the frame indices and the
+gather are exercised for real while the byte counts mean nothing.
 
 Not the driver's bench (that is bench.py).  Compares, on the same B200 and the same seeded
 random-init raft_large (no weights offline):
@@ -44,14 +54,103 @@ def timed(fn, n_warm=1):
     return time.perf_counter() - t0, out
 
 
+def frame_at(big, t, h, w):
+    """Frame t of the synthetic sequence: the texture translated by (3, 2) px per frame, wrapped every 10."""
+    k = t % 10
+    dx, dy = 3 * k, 2 * k
+    return big[:, :, 32 - dy:32 - dy + h, 32 - dx:32 - dx + w].contiguous()
+
+
+def run_sharded(args):
+    """BASELINE.json config 4: `--frames` frames in GOPs of `--gop`, sharded over the ranks."""
+    import torch.distributed as dist
+    import rdvc_corr_b200 as rc
+    from torchvision.models.optical_flow import raft_large
+    gs, fmt = rc.gop_shard, rc.rdvc_format
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    host_group = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        host_group = dist.new_group(backend="gloo")      # byte strings travel over the host
+    torch.manual_seed(0)
+    model = raft_large(weights=None, corr_block=rc.TVCorrBlock()).eval().to(dev)
+    h, w = args.height, args.width
+    g = torch.Generator(device=dev).manual_seed(0)
+    base = torch.rand(1, 3, h // 16 + 8, w // 16 + 8, device=dev, generator=g)
+    big = F.interpolate(base, size=(h + 64, w + 64), mode="bicubic", align_corners=False).clamp(0, 1)
+    gops = gs.split_gops(args.frames, args.gop)
+    mine = gs.assign_gops(gops, world)[rank]
+    ctx = lambda: torch.autocast("cuda", dtype=torch.float16, enabled=args.amp)
+
+    def enc_i(frame):
+        thumb = (F.avg_pool2d(frame, 64) * 255).round().to(torch.uint8).cpu().numpy().tobytes()
+        return fmt.iframe_payload(thumb, ".raw")
+
+    def enc_p(prev, cur):
+        with torch.no_grad(), ctx():
+            flow = rc.raft_flow(model, prev, cur, 12)
+        small = F.avg_pool2d(flow.float(), 8)
+        q = (small * 4).round().clamp(-127, 127).to(torch.int8).cpu().numpy().tobytes()
+        return fmt.pframe_payload(tuple(small.shape[-2:]), q, (0, 0), b"")
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    with torch.no_grad(), ctx():                          # warm-up: cuDNN autotune + allocator
+        for _ in range(2):
+            rc.raft_flow(model, frame_at(big, 0, h, w), frame_at(big, 1, h, w), 12)
+    barrier()
+    t0 = time.perf_counter()
+    local = {gp.index: gs.encode_gop(gp, lambda t: frame_at(big, t, h, w), enc_i, enc_p) for gp in mine}
+    torch.cuda.synchronize()
+    t_local = time.perf_counter() - t0
+    stream = gs.gather_stream(local, len(gops), {"rdvc_version": "b200-bench", "iframe_interval": args.gop},
+                              rank, world, host_group)
+    barrier()
+    t_all = time.perf_counter() - t0
+    times = torch.tensor([t_all, t_local], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        meta, recs = fmt.read_stream(stream)
+        n_p = sum(1 for r in recs if r.kind == "P")
+        assert [r.index for r in recs] == list(range(args.frames)), "frame records out of order"
+        assert n_p == sum(gp.num_pframes for gp in gops)
+        assert all(len(fmt.parse_pframe_payload(r.payload)[1]) > 0 for r in recs if r.kind == "P"), "a P-frame failed"
+        line = {
+            "metric": "gop_sharded_raft_motion_branch_p_frames_per_s_1080p", "value": n_p / times[0].item(),
+            "unit": "P-frames/s", "n_gpus": world, "scaling": "strong",
+            "config": {"workload": f"{args.frames} synthetic frames {w}x{h}, GOP {args.gop}, 12 RAFT updates, "
+                                   "seed-0 random-init raft_large, B200 correlation block, final-only upsampling",
+                       "amp_fp16": args.amp, "gops": len(gops), "gops_per_rank_max": max(len(x) for x in gs.assign_gops(gops, world)),
+                       "payload": "placeholder (codec networks out of scope)", "collective": "none on the data path; "
+                       "host-side gather_object of per-GOP byte strings (gloo)"},
+            "seconds_total_max_over_ranks": times[0].item(), "seconds_encode_max_over_ranks": times[1].item(),
+            "p_frames": n_p, "stream_bytes": len(stream), "total_frames_processed": meta["total_frames_processed"],
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
+    ap.add_argument("--frames", type=int, default=0, help="> 0: GOP-sharded run over all ranks (config 4)")
     ap.add_argument("--height", type=int, default=1088)
     ap.add_argument("--width", type=int, default=1920)
     ap.add_argument("--gop", type=int, default=10)
     ap.add_argument("--stock-pframes", type=int, default=2, help="stock RAFT is slow at 1080p: time only this many")
     ap.add_argument("--amp", action="store_true", help="fp16 autocast like the reference's GPU default")
     args = ap.parse_args()
+    if args.frames > 0:
+        return run_sharded(args)
     import rdvc_corr_b200 as rc
     from torchvision.models.optical_flow import raft_large
     dev = torch.device("cuda", 0)

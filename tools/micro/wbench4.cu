@@ -1,0 +1,62 @@
+// wbench4.cu -- developer microbenchmark (round 1d): what separates torch.fill_ (7.5 TB/s) from the
+// tile-ordered writes of the build kernel (6.1 TB/s)?  Plain st.global.v4, 4.26 GB ([32640 x 32640] fp32).
+//   mode 0: grid-stride over CHUNK-byte chunks (global linear sweep, like an elementwise kernel)
+//   mode 1: m-block sweep: all CTAs work on the same 128-row block; a CTA owns a 1 KB column tile and writes
+//           its 128 rows (row pitch 130 KB) -- warp = 4 rows x 1 KB per pass  [the GEMM's natural order]
+//   mode 2: like 1 but the matrix is stored m-block-major: [mblk][ntile][128 rows][1 KB] -> each CTA tile is
+//           one contiguous 128 KB span and an m-block is one contiguous 16.7 MB span (what a blocked layout buys)
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o wbench4 wbench4.cu
+#include <cstdio>
+#include <cstdint>
+#include <cuda_runtime.h>
+__device__ __forceinline__ void st16(float* p) {
+    asm volatile("st.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(1.f), "f"(2.f), "f"(3.f), "f"(4.f) : "memory");
+}
+__global__ void __launch_bounds__(256) wk(float* out, long long rows, long long cols, int mode, long long chunk) {
+    const long long total = rows * cols * 4;
+    if (mode == 0) {
+        const long long nchunks = total / chunk;
+        for (long long c = blockIdx.x; c < nchunks; c += gridDim.x)
+            for (long long o = threadIdx.x * 16; o < chunk; o += blockDim.x * 16) st16(out + (c * chunk + o) / 4);
+        return;
+    }
+    const int ntiles = (int)(cols / 256), mblks = (int)(rows / 128);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (long long t = blockIdx.x; t < (long long)ntiles * mblks; t += gridDim.x) {
+        const int nt = (int)(t % ntiles), mb = (int)(t / ntiles);
+        for (int it = 0; it < 4; ++it) {                 // warp: 16 rows, 4 per pass (8 lanes x 16 B... x4 = 1 KB? no: 32 lanes x 16 B = 512 B)
+            for (int hf = 0; hf < 2; ++hf) {
+                const int r = warp * 16 + it * 4 + (hf * 2) + (lane >> 4) ;   // 2 rows per instruction, 256 B each
+                (void)r;
+            }
+        }
+        // simpler: each warp writes 16 rows; per row 1 KB = 2 instructions of 512 B
+        for (int rr = 0; rr < 16; ++rr) {
+            const long long r = (long long)mb * 128 + warp * 16 + rr;
+            for (int hf = 0; hf < 2; ++hf) {
+                float* p;
+                if (mode == 1) p = out + r * cols + (long long)nt * 256 + hf * 128 + lane * 4;
+                else p = out + (((long long)mb * ntiles + nt) * 128 + warp * 16 + rr) * 256 + hf * 128 + lane * 4;
+                st16(p);
+            }
+        }
+    }
+}
+int main() {
+    const long long rows = 32640, cols = 32640;
+    float* out; cudaMalloc(&out, rows * cols * 4);
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    struct Cfg { int mode; int grid; long long chunk; };
+    Cfg cfgs[] = {{0, 148, 4096}, {0, 148, 65536}, {0, 148 * 4, 8192}, {0, 148 * 8, 8192}, {0, 148 * 8, 131072}, {0, 148 * 32, 4096},
+                  {1, 148, 0}, {1, 148 * 2, 0}, {1, 148 * 4, 0}, {2, 148, 0}, {2, 148 * 2, 0}, {2, 148 * 4, 0}};
+    for (auto c : cfgs) {
+        for (int rep = 0; rep < 2; ++rep) wk<<<c.grid, 256>>>(out, rows, cols, c.mode, c.chunk);
+        cudaEventRecord(e0);
+        for (int rep = 0; rep < 5; ++rep) wk<<<c.grid, 256>>>(out, rows, cols, c.mode, c.chunk);
+        cudaEventRecord(e1); cudaEventSynchronize(e1);
+        float ms; cudaEventElapsedTime(&ms, e0, e1); ms /= 5;
+        printf("mode %d grid %5d chunk %7lld: %.3f ms  %.0f GB/s (%s)\n", c.mode, c.grid, c.chunk, ms, rows * cols * 4 / ms / 1e6,
+               cudaGetErrorString(cudaGetLastError()));
+    }
+    return 0;
+}
