@@ -76,11 +76,14 @@ class CorrPyramid:
         es = torch.empty((), dtype=self.volume_dtype).element_size()
         return self.buffer[off: off + n * es].view(self.volume_dtype).view(self.B * self.h * self.w, img)
 
-    def level(self, l: int) -> Tensor:
+    def level(self, l: int, rows: Optional[Tensor] = None) -> Tensor:
         """Level ``l`` shaped like torchvision's ``corr_pyramid[l]``: (B*h*w, 1, h >> l, w >> l).
-        A view for ``ROWMAJOR``; an un-tiled copy for ``TILED``."""
+        A view for ``ROWMAJOR``; an un-tiled copy for ``TILED``.  ``rows`` (an index tensor) restricts
+        it to those query pixels -- the only way to look at a 4K volume, whose levels do not fit twice."""
         hl, wl, tw, th, hp, wp = self._tiles(l)
         st = self.storage(l)
+        if rows is not None:
+            st = st[rows]
         if self.layout == ROWMAJOR:
             return st.view(-1, 1, hl, wl)
         img = st[:, : hp * wp].reshape(-1, hp // th, wp // tw, th, tw).permute(0, 1, 3, 2, 4).reshape(-1, hp, wp)

@@ -48,7 +48,7 @@ for (W, H) in SHAPES:
         for l in range(L):
             b = torch.nn.functional.avg_pool2d(f2, 2 ** l) if l else f2
             ref = (a @ b.to(torch.bfloat16).double().view(D, -1) / 16.0).float()
-            got = blk.corr_pyramid[l][rows, 0].reshape(len(rows), -1).float()
+            got = blk._pyr.level(l, rows)[:, 0].reshape(len(rows), -1).float()
             worst = max(worst, ((got - ref).abs().max() / ref.abs().max()).item())
         pyr_elems = sum((h >> l) * (w >> l) for l in range(L)) * N
         bytes_build = 2 * N * D * 2 + es * pyr_elems
