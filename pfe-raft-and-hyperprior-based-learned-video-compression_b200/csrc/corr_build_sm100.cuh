@@ -41,10 +41,12 @@ constexpr int BLD_BLOCK_M = 128;
 constexpr int BLD_BLOCK_N = 256;
 constexpr int BLD_BLOCK_K = 64;  // bf16 per 128-byte swizzle row
 constexpr int BLD_UMMA_K = 16;
-#ifndef RDVC_A_STAGES
-#define RDVC_A_STAGES 3
+#ifndef RDVC_EW4_A_STAGES      // experiment knobs for the 4-warp epilogue shape (see BuildCfg)
+#define RDVC_EW4_A_STAGES 4
 #endif
-constexpr int BLD_A_STAGES = RDVC_A_STAGES;
+#ifndef RDVC_EW4_STG_BUFS
+#define RDVC_EW4_STG_BUFS 2
+#endif
 constexpr int BLD_MAX_KC = 4;    // D <= 256
 constexpr int BLD_A_STAGE_BYTES = BLD_BLOCK_M * BLD_BLOCK_K * 2;  // 16 KB
 constexpr int BLD_B_SLAB_BYTES = BLD_BLOCK_N * BLD_BLOCK_K * 2;   // 32 KB
@@ -53,23 +55,26 @@ constexpr int BLD_MAX_LEVELS = 4;
 
 constexpr int BLD_SMEM_B = 0;
 constexpr int BLD_SMEM_A = BLD_SMEM_B + BLD_MAX_KC * BLD_B_SLAB_BYTES;       // 131072
-constexpr int BLD_SMEM_STG = BLD_SMEM_A + BLD_A_STAGES * BLD_A_STAGE_BYTES;  // 196608
 
 // Epilogue shape.  EW = 8 epilogue warps: two per TMEM lane quarter, each half a tile's width, one
-// 4 KB staging buffer per warp (32 KB in flight).  EW = 4: one warp per quarter, the whole tile
-// width, three buffers per warp (48 KB in flight).  The stationary fmap2 tile (128 KB) and the fmap1
-// ring (48 KB; 2 stages starve the MMA: 1.18 ms) leave ~49 KB for staging, so it is one or the other.
-// Measured at 1080p: fp32 volume 0.98 ms (EW 8) vs 1.03 ms (EW 4: one warp per quarter cannot issue
-// the boxes fast enough); bf16 volume 0.75 ms (EW 8: its two boxes per tile serialise on the single
-// buffer, ~0.8 us each) vs 0.68 ms (EW 4).
+// 4 KB staging buffer per warp (32 KB in flight) beside a 3-stage fmap1 ring.  EW = 4: one warp per
+// quarter, the whole tile width, two buffers per warp (32 KB in flight) beside a 4-stage ring.  The
+// stationary fmap2 tile takes 128 KB, so ring + staging share ~97 KB (2 ring stages starve the MMA:
+// 1.18 ms).  Measured at 1080p: fp32 volume 0.98 ms (EW 8) vs 1.02-1.05 ms (EW 4: one warp per
+// quarter cannot issue the boxes fast enough); bf16 volume 0.75 ms (EW 8: its two boxes per tile
+// serialise on the single buffer, ~0.8 us each) vs 0.66 ms (EW 4 with 4 + 2; 3 + 3 gives 0.68, 4 + 1
+// 0.675).  With the stores compiled out either shape runs in 0.50 ms (fmap1-load latency, not MMA
+// rate), so the bf16 volume (0.46 ms of writes) sits between its two bounds.
 template <int EW>
 struct BuildCfg {
     static_assert(EW == 4 || EW == 8, "epilogue warps");
     static constexpr int EPI_WARPS = EW;
     static constexpr int SUBS = 8 / EW;                 // 128-column halves of a tile per epilogue warp
-    static constexpr int STG_BUFS = (EW == 4) ? 3 : 1;  // staging buffers per epilogue warp
+    static constexpr int STG_BUFS = (EW == 4) ? RDVC_EW4_STG_BUFS : 1;   // staging buffers per epilogue warp
+    static constexpr int A_STAGES = (EW == 4) ? RDVC_EW4_A_STAGES : 3;   // fmap1 ring stages (16 KB each)
     static constexpr int THREADS = 128 + EW * 32;
-    static constexpr int SMEM_BAR = BLD_SMEM_STG + EW * BLD_STG_BYTES * STG_BUFS;
+    static constexpr int SMEM_STG = BLD_SMEM_A + A_STAGES * BLD_A_STAGE_BYTES;
+    static constexpr int SMEM_BAR = SMEM_STG + EW * BLD_STG_BYTES * STG_BUFS;
     static constexpr int SMEM_TOTAL = SMEM_BAR + 128;
     static constexpr int SMEM_LAUNCH = SMEM_TOTAL + 1024;  // slack for 1024-byte alignment
 };
@@ -221,7 +226,7 @@ corr_build_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
                   const __grid_constant__ CUtensorMap tm_o3, const BuildParams p) {
     using Cfg = BuildCfg<EW>;
     constexpr int BLD_EPI_WARPS = Cfg::EPI_WARPS, BLD_SUBS = Cfg::SUBS, BLD_STG_BUFS = Cfg::STG_BUFS;
-    constexpr int BLD_SMEM_BAR = Cfg::SMEM_BAR;
+    constexpr int BLD_SMEM_BAR = Cfg::SMEM_BAR, BLD_SMEM_STG = Cfg::SMEM_STG, BLD_A_STAGES = Cfg::A_STAGES;
     static_assert(TILE_Y * TILE_X == BLD_BLOCK_N, "tile must hold 256 fmap2 pixels");
     static_assert(TILE_Y % 8 == 0 && TILE_X % 16 == 0, "sub-tiles are 8 x 16");
     extern __shared__ uint8_t smem_raw[];
