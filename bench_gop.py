@@ -90,9 +90,14 @@ def run_sharded(args):
         thumb = (F.avg_pool2d(frame, 64) * 255).round().to(torch.uint8).cpu().numpy().tobytes()
         return fmt.iframe_payload(thumb, ".raw")
 
+    fh = args.height - 8 if args.height % 16 == 0 and args.height > 64 else args.height   # 1088 -> 1080 codec frame
+
     def enc_p(prev, cur):
         with torch.no_grad(), ctx():
             flow = rc.raft_flow(model, prev, cur, 12)
+        # steps 3 + 5a of the reference (R:codec_processing.py:1446,1456): flow to frame resolution and the
+        # warped previous frame, one fused launch; the MCN / residual / codecs that consume them are out of scope
+        warped, flow = rc.motion_warp(prev[:, :, :fh].contiguous(), flow, (fh, w))
         small = F.avg_pool2d(flow.float(), 8)
         q = (small * 4).round().clamp(-127, 127).to(torch.int8).cpu().numpy().tobytes()
         return fmt.pframe_payload(tuple(small.shape[-2:]), q, (0, 0), b"")

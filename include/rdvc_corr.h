@@ -124,6 +124,19 @@ int rdvc_corr_pair_host(const float* fmap1_host, const float* fmap2_host,
                         const float* coords_host, float* out_host, int B, int D, int h,
                         int w, int num_levels, int radius, int iters, int vol_dtype);
 
+/* ---- next row: flow resize + warp, fused (after RAFT, before the MCN) ---- *
+ * Replaces resize_flow (R:codec_processing.py:772-818, called at :1446) and WarpingLayer.forward
+ * (R:codec_processing.py:322-367, called at :1456) with one launch.
+ * flow     : device, (B, 2, h_in, w_in) fp32 -- RAFT's flow, channel 0 = dx, channel 1 = dy
+ * prev     : device, (B, C, H, W) fp32 previous frame, or NULL for a resize only
+ * warped   : device, (B, C, H, W) fp32, NULL iff prev is NULL
+ * flow_out : device, (B, 2, H, W) fp32 resized + rescaled flow, or NULL to skip materialising it
+ * flow_out = bilinear_resize(flow, align_corners=False) * (W/w_in, H/h_in) (the input itself when the
+ * sizes match); warped[b,c,i,j] = bilinear(prev[b,c]; i + dy, j + dx) with the sample point clamped
+ * to the frame (border padding), pixel centres at integers (align_corners=True).                  */
+int rdvc_motion_warp(const float* prev, const float* flow, int B, int C, int H, int W, int h_in,
+                     int w_in, float* warped, float* flow_out, void* stream);
+
 /* Frees the per-thread scratch arena of rdvc_corr_pair_host (optional). */
 void rdvc_corr_release(void);
 

@@ -15,6 +15,7 @@
 #include "corr_build_sm100.cuh"
 #include "corr_lookup.cuh"
 #include "corr_pack.cuh"
+#include "motion_warp.cuh"
 
 namespace {
 
@@ -546,6 +547,35 @@ int rdvc_corr_lookup(const void* pyramid, int vol_dtype, int layout, const float
         return dispatch_lookup_radius<float, 1>(radius, p, st);
     }
     return dispatch_lookup_radius<__nv_bfloat16, 0>(radius, p, st);
+}
+
+int rdvc_motion_warp(const float* prev, const float* flow, int B, int C, int H, int W, int h_in, int w_in,
+                     float* warped, float* flow_out, void* stream) {
+    if (!flow) return fail(RDVC_E_NULL, "null flow pointer");
+    if ((prev == nullptr) != (warped == nullptr))
+        return fail(RDVC_E_NULL, "prev and warped must both be given (warp) or both be NULL (resize only)");
+    if (!warped && !flow_out) return fail(RDVC_E_NULL, "nothing to compute: warped and flow_out are both NULL");
+    if (B <= 0 || H <= 0 || W <= 0 || h_in <= 0 || w_in <= 0 || (prev && C <= 0))
+        return fail(RDVC_E_SHAPE, "non-positive dimension B=%d C=%d H=%d W=%d h_in=%d w_in=%d", B, C, H, W, h_in, w_in);
+    if (H > 65535 || B > 65535) return fail(RDVC_E_UNSUPPORTED, "H and B must be <= 65535 (grid limits)");
+    if (static_cast<long long>(H) * W >= (1LL << 31))
+        return fail(RDVC_E_UNSUPPORTED, "H * W must fit 31 bits (in-plane offsets are 32-bit)");
+    rdvc::WarpParams p;
+    memset(&p, 0, sizeof(p));
+    p.prev = prev; p.flow = flow; p.warped = warped; p.flow_out = flow_out;
+    p.B = B; p.C = C; p.H = H; p.W = W; p.h_in = h_in; p.w_in = w_in;
+    p.ry = static_cast<float>(h_in) / static_cast<float>(H);
+    p.rx = static_cast<float>(w_in) / static_cast<float>(W);
+    p.sh = static_cast<float>(static_cast<double>(H) / h_in);
+    p.sw = static_cast<float>(static_cast<double>(W) / w_in);
+    p.same_size = (h_in == H && w_in == W);
+    const int per_block = rdvc::WARP_THREADS * rdvc::WARP_PIX;
+    dim3 grid((W + per_block - 1) / per_block, H, B);
+    rdvc::motion_warp_kernel<<<grid, rdvc::WARP_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(p);
+    ++g_launches;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "motion_warp_kernel launch");
+    return RDVC_OK;
 }
 
 void rdvc_corr_release(void) {

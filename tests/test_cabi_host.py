@@ -26,14 +26,14 @@ def lib():
 def header_functions():
     src = open(HEADER).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    return sorted(set(re.findall(r"\b(rdvc_corr_\w+)\s*\(", src)))
+    return sorted(set(re.findall(r"\b(rdvc_(?:corr|motion)_\w+)\s*\(", src)))
 
 
 def test_header_symbols_exported(lib):
     declared = header_functions()
     assert len(declared) >= 10
     out = subprocess.check_output(["nm", "-D", "--defined-only", rc._cabi.lib_path()], text=True)
-    exported = set(re.findall(r"\bT (rdvc_corr_\w+)", out))
+    exported = set(re.findall(r"\bT (rdvc_(?:corr|motion)_\w+)", out))
     missing = [f for f in declared if f not in exported]
     assert not missing, f"header declares symbols the library does not export: {missing}"
     # and the ctypes table binds exactly the header's functions
@@ -127,6 +127,12 @@ def test_argument_validation_returns_negative_codes(lib):
     assert lib.rdvc_corr_pair_host(p, p, p, p, 1, 256, 46, 80, 4, 4, 0, F32) == -2
     with pytest.raises(ValueError, match="RDVC_E_TOO_SMALL"):
         rc._cabi.check(build(h=15), "rdvc_corr_build")
+    # rdvc_motion_warp(prev, flow, B, C, H, W, h_in, w_in, warped, flow_out, stream)
+    assert lib.rdvc_motion_warp(p, None, 1, 3, 8, 8, 8, 8, p, p, None) == -1
+    assert lib.rdvc_motion_warp(p, p, 1, 3, 8, 8, 8, 8, None, p, None) == -1      # prev without warped
+    assert lib.rdvc_motion_warp(None, p, 1, 0, 8, 8, 8, 8, None, None, None) == -1  # nothing to do
+    assert lib.rdvc_motion_warp(p, p, 1, 3, 0, 8, 8, 8, p, p, None) == -2
+    assert lib.rdvc_motion_warp(p, p, 1, 3, 70000, 8, 8, 8, p, p, None) == -5
 
 
 # ------------------------------------------------------------------ Python host mirror
@@ -194,6 +200,29 @@ def test_injects_into_torchvision_raft():
     model = raft_large(weights=None, corr_block=blk)
     assert model.corr_block is blk
     assert model.update_block.motion_encoder.convcorr1[0].in_channels == 324
+
+
+def test_motion_warp_host_behaviour_matches_reference():
+    """resize_flow / WarpingLayer keep the reference's early-outs and messages
+    (R:codec_processing.py:782-797 and :336-340); compute needs the GPU and fails loudly without it."""
+    assert rc.resize_flow(None, (4, 4)) is None
+    f = torch.zeros(1, 2, 6, 8)
+    assert rc.resize_flow(f, (6, 8)) is f                                   # :788-789: no resize needed
+    with pytest.raises(ValueError, match="Flow tensor must have 2 channels, got 3"):
+        rc.resize_flow(torch.zeros(1, 3, 6, 8), (4, 4))
+    z = rc.resize_flow(torch.zeros(1, 2, 0, 8), (4, 5))
+    assert z.shape == (1, 2, 4, 5) and not z.any()
+    assert rc.resize_flow(f, (0, 5)).shape == (1, 2, 0, 5)
+    x = torch.zeros(2, 3, 6, 8)
+    with pytest.raises(ValueError) as e:
+        rc.WarpingLayer()(x, torch.zeros(2, 2, 6, 9))
+    assert str(e.value) == f"Input image (2,3,6,8) and flow ({torch.Size([2, 2, 6, 9])}) shape/channel mismatch."
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        rc.resize_flow(f, (12, 16))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        rc.WarpingLayer()(x, torch.zeros(2, 2, 6, 8))
+    with pytest.raises(ValueError, match="does not match"):
+        rc.motion_warp(x, torch.zeros(2, 2, 3, 4), (6, 9))
 
 
 def test_coords_validation_without_gpu():

@@ -494,3 +494,67 @@ def test_runs_on_callers_stream(lib):
         got = rc.CorrBlock(a, b)(co)
     s.synchronize()
     assert torch.equal(got, ref)
+
+
+# ------------------------------------------------------------------ next row: flow resize + warp
+TOL_FLOW_RESIZE = 1e-5    # relative to max(1, max|flow|): fp32 bilinear, same association as aten
+TOL_WARP = 1e-3           # absolute, images in [0,1]: the reference rounds its sampling grid through
+                          # linspace(-1,1,W) + flow/((W-1)/2) in fp32 (~1e-4 px at W = 1920); ours samples
+                          # at the absolute coordinate j + dx
+
+
+def test_motion_warp_matches_reference_fixtures(lib, golden_dir):
+    """rdvc_motion_warp vs the outputs of the reference's own resize_flow + WarpingLayer."""
+    from oracle import motion_warp as mw
+    g = np.load(os.path.join(golden_dir, "motion_warp.npz"))
+    names = sorted(k[: -len("_shape")] for k in g.files if k.endswith("_shape"))
+    for name in names:
+        B, C, H, W, h_in, w_in = [int(v) for v in g[f"{name}_shape"]]
+        img, flow = mw.synth_case(B, C, H, W, h_in, w_in, float(g[f"{name}_sigma"]), seed=len(name))
+        n0 = lib.rdvc_corr_launch_count()
+        warped, f = rc.motion_warp(gpu(img), gpu(flow), (H, W))
+        assert lib.rdvc_corr_launch_count() - n0 == 1                  # one launch for both steps
+        scale = max(1.0, float(np.abs(g[f"{name}_flow_frame"]).max()))
+        assert np.abs(f.cpu().numpy() - g[f"{name}_flow_frame"]).max() / scale < TOL_FLOW_RESIZE, name
+        assert np.abs(warped.cpu().numpy() - g[f"{name}_warped"]).max() < TOL_WARP, name
+        # the two reference-named entry points give the same numbers as the fused call
+        f2 = rc.resize_flow(gpu(flow), (H, W))
+        assert torch.equal(f2, f) if (h_in, w_in) != (H, W) else f2.data_ptr() != 0
+        assert torch.equal(rc.WarpingLayer()(gpu(img), f), warped)
+
+
+def test_motion_warp_vs_torch_ops_odd_shapes(lib):
+    """Against the same torch ops the reference composes (interpolate + grid_sample), on the GPU, for
+    shapes the fixtures do not cover (up- and down-scaling, C = 1..4, B = 3)."""
+    import torch.nn.functional as F
+    for (B, C, H, W, h_in, w_in) in [(3, 1, 31, 45, 17, 23), (1, 4, 64, 96, 72, 104), (2, 3, 50, 50, 25, 100)]:
+        gen = torch.Generator(device="cuda").manual_seed(H * W)
+        x = torch.rand(B, C, H, W, device="cuda", generator=gen)
+        fl = 3.0 * torch.randn(B, 2, h_in, w_in, device="cuda", generator=gen)
+        warped, f = rc.motion_warp(x, fl, (H, W))
+        ref_f = F.interpolate(fl, size=(H, W), mode="bilinear", align_corners=False, antialias=False)
+        ref_f = ref_f * torch.tensor([W / w_in, H / h_in], device="cuda").view(1, 2, 1, 1)
+        assert ((f - ref_f).abs().max() / ref_f.abs().max().clamp(min=1)).item() < TOL_FLOW_RESIZE
+        gy, gx = torch.meshgrid(torch.linspace(-1, 1, H, device="cuda"), torch.linspace(-1, 1, W, device="cuda"), indexing="ij")
+        grid = torch.stack((gx, gy), 2)[None] + torch.stack((ref_f[:, 0] / ((W - 1) / 2), ref_f[:, 1] / ((H - 1) / 2)), 3)
+        ref_w = F.grid_sample(x, grid, mode="bilinear", padding_mode="border", align_corners=True)
+        assert (warped - ref_w).abs().max().item() < TOL_WARP
+
+
+def test_motion_warp_1080p_properties(lib):
+    """Frame 1920x1080, RAFT flow at 1920x1088 (R:codec_processing.py:1446): size-independent properties."""
+    B, C, H, W, h_in, w_in = 1, 3, 1080, 1920, 1088, 1920
+    gen = torch.Generator(device="cuda").manual_seed(7)
+    x = torch.rand(B, C, H, W, device="cuda", generator=gen)
+    zero = torch.zeros(B, 2, h_in, w_in, device="cuda")
+    warped, f = rc.motion_warp(x, zero, (H, W))
+    assert torch.equal(warped, x) and not f.any()                       # zero flow: identity, bit exact
+    shift = zero.clone(); shift[:, 0] = 5.0; shift[:, 1] = -3.0 * h_in / H   # dy scales by H / h_in -> -3 px
+    warped, f = rc.motion_warp(x, shift, (H, W))
+    assert torch.allclose(f[:, 0], torch.full_like(f[:, 0], 5.0)) and torch.allclose(f[:, 1], torch.full_like(f[:, 1], -3.0), atol=1e-5)
+    assert torch.allclose(warped[:, :, 3:, : W - 5], x[:, :, : H - 3, 5:], atol=2e-5)   # integer shift = copy
+    assert torch.allclose(warped[:, :, 3:, W - 5:], x[:, :, : H - 3, W - 1:].expand(-1, -1, -1, 5), atol=2e-5)  # border
+    lin = torch.arange(w_in, device="cuda", dtype=torch.float32).view(1, 1, 1, w_in).expand(B, 1, h_in, w_in)
+    fl = torch.cat([lin * 0.001, lin * 0.0], 1).contiguous()             # resize is linear: exact on a ramp
+    f = rc.resize_flow(fl, (H, W))
+    assert torch.allclose(f[:, 0], (lin[:, 0, :H] * 0.001), atol=1e-5) and f.shape == (B, 2, H, W)
