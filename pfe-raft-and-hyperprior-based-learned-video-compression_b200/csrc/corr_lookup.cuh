@@ -196,8 +196,14 @@ struct LookupSite {
 // (no change: the per-iteration footprint exceeds what L2 keeps), plain instead of streaming
 // output stores (+15 %), a cp.async (LDGSTS) ring of 3-4 rows per thread in shared memory
 // (3x SLOWER: the ring's shared memory takes the L1 capacity the gather lives on -- adjacent
-// footprint rows share 32-byte sectors).  The kernel sits at the sum of a DRAM-bound gather (~5.5 TB/s over
-// the 64-byte atoms it touches) and an issue-bound filter/store phase that overlap only partly.
+// footprint rows share 32-byte sectors), L2 evict_first loads / evict_last stores in
+// any combination (no change), de-phasing the CTAs with __nanosleep (CTAs delayed by up to 7 us still
+// finish inside the same 28.8 us: the kernel is throughput-, not latency-bound).
+// What bounds it: DRAM transactions.  In steady state (12 lookups back to back) one launch moves
+// ~103 MB of 64-byte atoms in (10.6 atoms per window and level instead of the 6.25 its 400 bytes
+// need) and its 42 MB result out: 145 MB in 28.5 us = 5.1 TB/s of scattered traffic, 0.78 of the
+// measured copy peak.  (ncu's single cold launch shows only 13 MB written -- the rest is still
+// dirty in L2 when it ends -- which is why loads-only 18.7 us + stores-only 15 us looked additive.)
 // DBG (timing experiments only): 1 = no volume loads, 2 = no output stores.
 template <int R, typename VolT, int DBG>
 __global__ void __launch_bounds__(32 * LKP_MAX_LEVELS)
