@@ -39,7 +39,7 @@
  *     whole tiles of tile_w x tile_h pixels (rdvc_corr_tile_shape: 16-byte rows x 4 rows =
  *     one 64-byte DRAM atom; 4 x 4 for fp32, 8 x 4 for bf16) and stored tile by tile,
  *     [B*h*w][ceil(h_l/tile_h)][ceil(w_l/tile_w)][tile_h][tile_w], each image rounded up to a
- *     multiple of 128 bytes (rdvc_corr_level_image_elems); padding holds 0.
+ *     multiple of 256 bytes (rdvc_corr_level_image_elems); padding holds 0.
  *     The (2r+2)^2 footprint of a lookup then touches ~11 DRAM atoms per level instead of
  *     ~20 (row-major: 10 rows x 40 bytes, each straddling 64-byte atoms): the gather is
  *     DRAM-bound, so bytes fetched are what the layout is chosen for.  The build writes
@@ -85,7 +85,7 @@ const char* rdvc_corr_last_error(void);
 size_t rdvc_corr_pyramid_bytes(int B, int h, int w, int num_levels, int vol_dtype, int layout);
 size_t rdvc_corr_level_offset_bytes(int B, int h, int w, int level, int vol_dtype, int layout);
 /* elements one level image (one query pixel's h_l x w_l map) occupies, padding included:
- * h_l * w_l for ROWMAJOR; whole tiles, rounded up to a multiple of 128 bytes, for TILED */
+ * h_l * w_l for ROWMAJOR; whole tiles, rounded up to a multiple of 256 bytes, for TILED */
 size_t rdvc_corr_level_image_elems(int h, int w, int level, int vol_dtype, int layout);
 /* tile shape (pixels) of RDVC_LAYOUT_TILED for a volume dtype */
 int rdvc_corr_tile_shape(int vol_dtype, int* tile_w, int* tile_h);

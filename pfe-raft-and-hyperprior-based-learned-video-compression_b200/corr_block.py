@@ -67,7 +67,7 @@ class CorrPyramid:
 
     def storage(self, l: int) -> Tensor:
         """Level ``l`` as stored: (B*h*w, image_elems) in the pyramid's own layout; for ``TILED`` the
-        first padded_h * padded_w elements of a row are the tiles, the rest is 128-byte padding."""
+        first padded_h * padded_w elements of a row are the tiles, the rest is padding to 256 bytes."""
         lib = _cabi.load()
         vd = _VOL_DTYPES[self.volume_dtype]
         off = lib.rdvc_corr_level_offset_bytes(self.B, self.h, self.w, l, vd, self.layout)

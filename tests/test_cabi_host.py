@@ -65,10 +65,10 @@ def test_version_and_sizes(lib):
     assert lib.rdvc_corr_level_offset_bytes(1, 136, 240, 1, F32, ROW) == 32640 * 32640 * 4
     assert rc.corr_block.tile_shape(torch.float32) == (4, 4)      # 16-byte rows x 4 rows
     assert rc.corr_block.tile_shape(torch.bfloat16) == (8, 4)
-    # tiled 1080p fp32: levels 2 and 3 are padded to 36x60 (+16 elements to a 128-byte multiple) and
-    # 20x32 (+0.4 % bytes)
+    # tiled 1080p fp32: level images are whole tiles rounded up to 256 bytes: 68x120 -> +32 elements,
+    # 34x60 -> 36x60 + 16, 17x30 -> 20x32 (+0.6 % bytes)
     n = 32640
-    assert lib.rdvc_corr_pyramid_bytes(1, 136, 240, 4, F32, TILED) == 4 * n * (136 * 240 + 68 * 120 + 36 * 60 + 16 + 20 * 32)
+    assert lib.rdvc_corr_pyramid_bytes(1, 136, 240, 4, F32, TILED) == 4 * n * (136 * 240 + 68 * 120 + 32 + 36 * 60 + 16 + 20 * 32)
     assert lib.rdvc_corr_level_image_elems(136, 240, 2, F32, TILED) == 36 * 60 + 16
     assert lib.rdvc_corr_level_image_elems(136, 240, 2, F32, ROW) == 34 * 60
     for (B, h, w) in [(2, 18, 22), (1, 46, 80), (3, 33, 47)]:
@@ -82,7 +82,7 @@ def test_version_and_sizes(lib):
                     img = hl * wl
                     if layout == TILED:
                         img = (-(-hl // 4) * 4) * (-(-wl // tw) * tw)
-                        img = -(-img * es // 128) * 128 // es          # whole 128-byte lines
+                        img = -(-img * es // 256) * 256 // es          # whole 256-byte units
                     assert lib.rdvc_corr_level_image_elems(h, w, l, vd, layout) == img
                     n = B * h * w * img * es
                     off += (n + 255) // 256 * 256
