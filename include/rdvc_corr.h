@@ -158,7 +158,9 @@ void rdvc_corr_set_profile_events(void* start_event, void* stop_event);
  *          else 32 rows x 128 B, else staged stores; 2 = never the wide boxes; 0 = staged only)
  *   key 6: debug: L2 policy of the TMA stores (0 default, 1 evict_last, 2 evict_first)
  *   key 7 / 8: experiment: log2 tile width / height of RDVC_LAYOUT_TILED (0 = default)
- *   key 9: build epilogue warps (0 = auto: 8 for an fp32 volume, 4 for bf16; 4; 8)           */
+ *   key 9: build epilogue warps (0 = auto: 8 for an fp32 volume, 4 for bf16; 4; 8)
+ *   key 12: build kernel (0 = auto, 1 = one CTA per tile, 2 = CTA pairs / tcgen05 cta_group::2,
+ *           opt-in: bit-identical results, measured slower at 1080p)           */
 int rdvc_corr_set_option(int key, int value);
 
 #ifdef __cplusplus

@@ -13,9 +13,14 @@
 
 #include "../../include/rdvc_corr.h"
 #include "corr_build_sm100.cuh"
+#include "corr_build2_sm100.cuh"
 #include "corr_lookup.cuh"
 #include "corr_pack.cuh"
 #include "motion_warp.cuh"
+
+#ifndef RDVC_PAIR_DEFAULT
+#define RDVC_PAIR_DEFAULT 0   // the CTA-pair build kernel is opt-in (option key 12 = 2) until it wins
+#endif
 
 namespace {
 
@@ -32,6 +37,7 @@ std::atomic<int> g_opt_policy{0};
 std::atomic<int> g_opt_twl{0};
 std::atomic<int> g_opt_thl{0};
 std::atomic<int> g_opt_epi_warps{0};
+std::atomic<int> g_opt_pair{0};
 
 int fail(int code, const char* fmt, ...) {
     va_list ap;
@@ -171,6 +177,29 @@ int launch_build(const CUtensorMap& ta, const CUtensorMap* tb, const CUtensorMap
     return RDVC_OK;
 }
 
+template <typename OutT>
+int launch_build_pair(const CUtensorMap& ta, const CUtensorMap* tb, const CUtensorMap* to, const rdvc::BuildParams& p,
+                      cudaStream_t st) {
+    auto kern = rdvc::corr_build2_kernel<OutT>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, rdvc::B2_SMEM_LAUNCH);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(build pair, max dynamic smem)");
+        attr_set = true;
+    }
+    long long grid = sm_count() & ~1;     // whole CTA pairs
+    const long long n_items = static_cast<long long>(p.B) * p.ntiles * p.msplit;
+    if (grid > 2 * n_items) grid = 2 * n_items;
+    if (g_prof_start) cudaEventRecord(g_prof_start, st);
+    kern<<<static_cast<unsigned>(grid), rdvc::B2_THREADS, rdvc::B2_SMEM_LAUNCH, st>>>(
+        ta, tb[0], tb[1], tb[2], tb[3], to[0], to[1], to[2], to[3], p);
+    if (g_prof_stop) cudaEventRecord(g_prof_stop, st);
+    ++g_launches;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "corr_build2_kernel launch");
+    return RDVC_OK;
+}
+
 // both feature maps -> K-major bf16 rows (fmap2 at `levels2` pyramid levels), one launch
 template <typename T>
 int launch_pack(const void* f1, const void* f2, void* a_km, void* const* b_km, int B, int D, int h, int w,
@@ -271,6 +300,7 @@ int rdvc_corr_set_option(int key, int value) {
     if (key == 7 && value >= 0 && value <= 4) { g_opt_twl = value; return RDVC_OK; }
     if (key == 8 && value >= 0 && value <= 4) { g_opt_thl = value; return RDVC_OK; }
     if (key == 9 && (value == 0 || value == 4 || value == 8)) { g_opt_epi_warps = value; return RDVC_OK; }
+    if (key == 12 && value >= 0 && value <= 2) { g_opt_pair = value; return RDVC_OK; }
     return fail(RDVC_E_UNSUPPORTED, "unknown option key=%d value=%d", key, value);
 }
 
@@ -489,6 +519,41 @@ int rdvc_corr_build(const void* fmap1, const void* fmap2, int B, int D, int h, i
 
     using rdvc::MODE_FUSED;
     using rdvc::MODE_LINEAR;
+    // CTA-pair kernel (cta_group::2): linear mode with every level on the wide-box path (always true for
+    // the tiled layout).  Option key 12: 0 = auto, 1 = single-CTA kernel, 2 = pair kernel where possible.
+    bool pair_ok = linear && (sm_count() >= 2);
+    for (int l = 0; l < num_levels; ++l) pair_ok = pair_ok && (((p.tma_out >> (2 * l)) & 3) == 2);
+    const int pair_opt = g_opt_pair.load();
+    if (pair_ok && (pair_opt == 2 || (pair_opt == 0 && RDVC_PAIR_DEFAULT))) {
+        CUtensorMap tb2[rdvc::BLD_MAX_LEVELS];
+        for (int l = 0; l < rdvc::BLD_MAX_LEVELS; ++l) {
+            const int ll = l < num_levels ? l : 0;
+            const cuuint64_t nl = (cuuint64_t)nl_of[ll];
+            cuuint64_t dims[3] = {(cuuint64_t)D, nl, (cuuint64_t)B};
+            cuuint64_t str[2] = {(cuuint64_t)D * 2, nl * D * 2};
+            cuuint32_t box[3] = {rdvc::BLD_BLOCK_K, rdvc::BLD_BLOCK_N / 2, 1};   // each CTA loads half the tile
+            rc = make_tmap(&tb2[l], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, b_km[ll], 3, dims, str, box);
+            if (rc) return rc;
+        }
+        rdvc::BuildParams p2 = p;
+        p2.m_blks = (N + 2 * rdvc::BLD_BLOCK_M - 1) / (2 * rdvc::BLD_BLOCK_M);
+        {
+            const long long units = static_cast<long long>(B) * p2.ntiles;
+            const int G = sm_count() / 2;
+            int best = 1;
+            double best_cost = 1e300;
+            const int s_max = p2.m_blks < 64 ? p2.m_blks : 64;
+            for (int S = 1; S <= s_max; ++S) {
+                const long long waves = (units * S + G - 1) / G;
+                const double cost = waves * ((p2.m_blks + S - 1) / S + 0.5) * (1.0 + 0.005 * S);
+                if (cost < best_cost) { best_cost = cost; best = S; }
+            }
+            const int forced = g_opt_msplit.load();
+            p2.msplit = (forced > 0) ? (forced < p2.m_blks ? forced : p2.m_blks) : best;
+        }
+        return (vol_dtype == RDVC_DT_F32) ? launch_build_pair<float>(ta, tb2, to, p2, st)
+                                          : launch_build_pair<__nv_bfloat16>(ta, tb2, to, p2, st);
+    }
     if (linear) {
         // epilogue shape per storage type: see BuildCfg (option key 9: 0 = auto, 4 / 8 = force)
         int ew = g_opt_epi_warps.load();

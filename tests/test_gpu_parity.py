@@ -43,12 +43,12 @@ def lib():
     assert torch.cuda.is_available(), "GPU tests need a B200"
     L = rc._cabi.load()
     yield L
-    for k in range(10):
+    for k in list(range(10)) + [12]:
         L.rdvc_corr_set_option(k, {3: 15, 5: 1}.get(k, 0))
 
 
 def set_opts(lib, **kw):
-    keys = {"lookup": 0, "tile": 1, "msplit": 2, "mode": 4, "tma": 5, "epi": 9}
+    keys = {"lookup": 0, "tile": 1, "msplit": 2, "mode": 4, "tma": 5, "epi": 9, "pair": 12}
     for k, v in kw.items():
         assert lib.rdvc_corr_set_option(keys[k], v) == 0
 
@@ -206,6 +206,21 @@ def test_build_epilogue_shapes(lib, epi, vol):
         for l in range(4):
             assert rel_max(pyr.level(l)[:, 0].float().cpu().numpy(), ref[l]) < tol, (layout, l)
     set_opts(lib, epi=0)
+
+
+@pytest.mark.parametrize("vol", [torch.float32, torch.bfloat16])
+def test_build_cta_pair_kernel_is_bit_identical(lib, vol):
+    """The opt-in CTA-pair build (tcgen05 cta_group::2, M = 256 over two SMs; option key 12 = 2) performs the
+    same MMAs in the same K order as the single-CTA kernel: the pyramids must be bit-identical, including
+    partial 256-row blocks (N = 396: the peer CTA's rows fall off the end), partial tiles and B > 1."""
+    for (B, D, h, w) in [(2, 64, 18, 22), (1, 128, 33, 47), (1, 256, 46, 80)]:
+        f1, f2 = cn.synth_fmaps(B, D, h, w, seed=17)
+        set_opts(lib, pair=1)
+        a = rc.build_pyramid(gpu(f1), gpu(f2), 4, vol).buffer.clone()
+        set_opts(lib, pair=2)
+        b = rc.build_pyramid(gpu(f1), gpu(f2), 4, vol).buffer.clone()
+        assert torch.equal(a, b), (B, D, h, w)
+    set_opts(lib, pair=0)
 
 
 @pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
