@@ -141,15 +141,37 @@ int make_tmap(CUtensorMap* m, CUtensorMapDataType dt, void* base, int rank, cons
     return RDVC_OK;
 }
 
+// per-device facts, cached per device id (a process may drive several GPUs)
+constexpr int kMaxDevices = 64;
+
+int current_device() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return dev;
+}
+
 int sm_count() {
-    static int n = 0;
+    static std::atomic<int> cache[kMaxDevices];
+    const int dev = current_device();
+    int n = (dev >= 0 && dev < kMaxDevices) ? cache[dev].load() : 0;
     if (n == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
         if (n <= 0) n = 148;
+        if (dev >= 0 && dev < kMaxDevices) cache[dev].store(n);
     }
     return n;
+}
+
+// cudaFuncSetAttribute(max dynamic smem) is per device: do it once per (kernel instantiation, device)
+template <typename K>
+int ensure_dynamic_smem(K kern, int bytes, std::atomic<unsigned long long>& done_mask, const char* what) {
+    const int dev = current_device();
+    const unsigned long long bit = (dev >= 0 && dev < kMaxDevices) ? (1ull << dev) : 0ull;
+    if (bit && (done_mask.load() & bit)) return RDVC_OK;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e != cudaSuccess) return cuda_fail(e, what);
+    if (bit) done_mask.fetch_or(bit);
+    return RDVC_OK;
 }
 
 template <int MODE, int TY, int TX, typename OutT, int EW>
@@ -157,13 +179,9 @@ int launch_build(const CUtensorMap& ta, const CUtensorMap* tb, const CUtensorMap
                  cudaStream_t st) {
     auto kern = rdvc::corr_build_kernel<MODE, TY, TX, OutT, EW>;
     using Cfg = rdvc::BuildCfg<EW>;
-    static bool attr_set = false;  // per instantiation
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             Cfg::SMEM_LAUNCH);
-        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(build, max dynamic smem)");
-        attr_set = true;
-    }
+    static std::atomic<unsigned long long> attr_done{0};  // per instantiation, one bit per device
+    if (int rc = ensure_dynamic_smem(kern, Cfg::SMEM_LAUNCH, attr_done, "cudaFuncSetAttribute(build, max dynamic smem)"))
+        return rc;
     long long grid = sm_count();
     const long long n_items = static_cast<long long>(p.B) * p.ntiles * p.msplit;
     if (grid > n_items) grid = n_items;
@@ -181,12 +199,9 @@ template <typename OutT>
 int launch_build_pair(const CUtensorMap& ta, const CUtensorMap* tb, const CUtensorMap* to, const rdvc::BuildParams& p,
                       cudaStream_t st) {
     auto kern = rdvc::corr_build2_kernel<OutT>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, rdvc::B2_SMEM_LAUNCH);
-        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(build pair, max dynamic smem)");
-        attr_set = true;
-    }
+    static std::atomic<unsigned long long> attr_done{0};
+    if (int rc = ensure_dynamic_smem(kern, rdvc::B2_SMEM_LAUNCH, attr_done, "cudaFuncSetAttribute(build pair, max dynamic smem)"))
+        return rc;
     long long grid = sm_count() & ~1;     // whole CTA pairs
     const long long n_items = static_cast<long long>(p.B) * p.ntiles * p.msplit;
     if (grid > 2 * n_items) grid = 2 * n_items;
@@ -205,13 +220,9 @@ template <typename T>
 int launch_pack(const void* f1, const void* f2, void* a_km, void* const* b_km, int B, int D, int h, int w,
                 int levels2, int layout, int twl, int thl, const size_t* nl_of, cudaStream_t st) {
     auto kern = rdvc::corr_pack_kernel<T>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             rdvc::PACK_SMEM_BYTES);
-        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(pack, max dynamic smem)");
-        attr_set = true;
-    }
+    static std::atomic<unsigned long long> attr_done{0};
+    if (int rc = ensure_dynamic_smem(kern, rdvc::PACK_SMEM_BYTES, attr_done, "cudaFuncSetAttribute(pack, max dynamic smem)"))
+        return rc;
     rdvc::PackParams pp;
     memset(&pp, 0, sizeof(pp));
     pp.src[0] = f1; pp.src[1] = f2;
@@ -268,7 +279,8 @@ int dispatch_lookup_tiled(int dbg, int radius, const rdvc::LookupParams& p, cuda
     }
 }
 
-struct HostArena {  // scratch owned by rdvc_corr_pair_host, one per thread
+struct HostArena {  // scratch owned by rdvc_corr_pair_host, one per thread (and bound to one device)
+    int device = -1;
     void* dev = nullptr;
     size_t bytes = 0;
     cudaStream_t compute = nullptr, copy = nullptr;
@@ -674,6 +686,10 @@ int rdvc_corr_pair_host(const float* fmap1_host, const float* fmap2_host, const 
 
     HostArena& a = g_arena;
     cudaError_t e;
+    if (a.device != current_device()) {   // the caller switched GPUs: streams and scratch belong to the old one
+        rdvc_corr_release();
+        a.device = current_device();
+    }
     if (!a.compute) {
         if ((e = cudaStreamCreateWithFlags(&a.compute, cudaStreamNonBlocking)) != cudaSuccess) return cuda_fail(e, "stream create");
         if ((e = cudaStreamCreateWithFlags(&a.copy, cudaStreamNonBlocking)) != cudaSuccess) return cuda_fail(e, "stream create");
