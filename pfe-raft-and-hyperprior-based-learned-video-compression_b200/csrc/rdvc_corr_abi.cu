@@ -398,11 +398,16 @@ int rdvc_corr_build(const void* fmap1, const void* fmap2, int B, int D, int h, i
     int twl = 0, thl = 0;
     if (layout == RDVC_LAYOUT_TILED) {
         tile_log2(vol_dtype, &twl, &thl);
-        // padding pixels of a level must come out of the GEMM as exact zeros: clear the operand
-        // rows of the levels that have any (the pack kernel writes only real pixels)
-        for (int l = 0; l < num_levels; ++l) {
-            if (nl_of[l] == static_cast<size_t>(h >> l) * (w >> l)) continue;
-            cudaError_t e = cudaMemsetAsync(b_km[l], 0, static_cast<size_t>(B) * nl_of[l] * D * 2, st);
+        // padding pixels of a level must come out of the GEMM as exact zeros: clear the operand rows of
+        // the levels that have any (the pack kernel writes only real pixels) -- ONE memset from the first
+        // padded level to the end of the last level (the per-level buffers are contiguous)
+        int first = -1;
+        for (int l = 0; l < num_levels && first < 0; ++l)
+            if (nl_of[l] != static_cast<size_t>(h >> l) * (w >> l)) first = l;
+        if (first >= 0) {
+            uint8_t* lo = static_cast<uint8_t*>(b_km[first]);
+            uint8_t* hi = static_cast<uint8_t*>(b_km[num_levels - 1]) + static_cast<size_t>(B) * nl_of[num_levels - 1] * D * 2;
+            cudaError_t e = cudaMemsetAsync(lo, 0, static_cast<size_t>(hi - lo), st);
             if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(padded operand rows)");
         }
     }
