@@ -9,8 +9,17 @@
 #include <cstdio>
 #include <cstdint>
 #include <cuda_runtime.h>
+__device__ int g_random = 0;   // 1: write index-dependent (incompressible) values instead of a constant pattern
 __device__ __forceinline__ void st16(float* p) {
-    asm volatile("st.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(1.f), "f"(2.f), "f"(3.f), "f"(4.f) : "memory");
+    float a = 1.f, b = 2.f, c = 3.f, d = 4.f;
+    if (g_random) {
+        unsigned h = (unsigned)((unsigned long long)p >> 4) * 2654435761u;
+        a = __uint_as_float((h & 0x007fffffu) | 0x3f800000u); h = h * 1664525u + 1013904223u;
+        b = __uint_as_float((h & 0x007fffffu) | 0x3f800000u); h = h * 1664525u + 1013904223u;
+        c = __uint_as_float((h & 0x007fffffu) | 0x3f800000u); h = h * 1664525u + 1013904223u;
+        d = __uint_as_float((h & 0x007fffffu) | 0x3f800000u);
+    }
+    asm volatile("st.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 __global__ void __launch_bounds__(256) wk(float* out, long long rows, long long cols, int mode, long long chunk) {
     const long long total = rows * cols * 4;
@@ -49,6 +58,9 @@ int main() {
     struct Cfg { int mode; int grid; long long chunk; };
     Cfg cfgs[] = {{0, 148, 4096}, {0, 148, 65536}, {0, 148 * 4, 8192}, {0, 148 * 8, 8192}, {0, 148 * 8, 131072}, {0, 148 * 32, 4096},
                   {1, 148, 0}, {1, 148 * 2, 0}, {1, 148 * 4, 0}, {2, 148, 0}, {2, 148 * 2, 0}, {2, 148 * 4, 0}};
+    for (int rnd = 0; rnd < 2; ++rnd) {
+    cudaMemcpyToSymbol(g_random, &rnd, sizeof(int));
+    printf("---- %s data\n", rnd ? "index-dependent (incompressible)" : "constant pattern");
     for (auto c : cfgs) {
         for (int rep = 0; rep < 2; ++rep) wk<<<c.grid, 256>>>(out, rows, cols, c.mode, c.chunk);
         cudaEventRecord(e0);
@@ -57,6 +69,7 @@ int main() {
         float ms; cudaEventElapsedTime(&ms, e0, e1); ms /= 5;
         printf("mode %d grid %5d chunk %7lld: %.3f ms  %.0f GB/s (%s)\n", c.mode, c.grid, c.chunk, ms, rows * cols * 4 / ms / 1e6,
                cudaGetErrorString(cudaGetLastError()));
+    }
     }
     return 0;
 }
