@@ -475,7 +475,10 @@ corr_build_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
                                 ptx::fence_proxy_async_smem();
                                 __syncwarp();
                                 if (lane == 0) {
-                                    ptx::tma_store_4d(tmo, sb, 0, (col0 + g * GC) / EPB, m0 + 16 * hh, b);
+                                    if (p.dbg_policy == 0) ptx::tma_store_4d(tmo, sb, 0, (col0 + g * GC) / EPB, m0 + 16 * hh, b);
+                                    else ptx::tma_store_4d_hint(tmo, sb, 0, (col0 + g * GC) / EPB, m0 + 16 * hh, b,
+                                                                p.dbg_policy == 1 ? ptx::policy_evict_last()
+                                                                                  : ptx::policy_evict_first());
                                     ptx::bulk_commit();
                                 }
                             }
