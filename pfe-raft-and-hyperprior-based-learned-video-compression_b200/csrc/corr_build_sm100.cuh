@@ -5,29 +5,28 @@
 //   pyr[0][b*N + i][y][x] = (1/sqrt(D)) * sum_c fmap1[b,c,i] * fmap2[b,c,y*w+x]
 //   pyr[l+1]              = 2x2 mean of pyr[l] over (y, x), floor-cropped
 //
-// Shape of the computation: a [N x D] x [D x N] GEMM per batch item with D = 256
-// (only 16 UMMA k-steps) whose fp32 output (4.26 GB at 1080p) dwarfs its inputs
-// (2 x 16.7 MB bf16).  It is HBM-WRITE bound (0.87 ms at 6.5 TB/s vs 0.32 ms of
-// tensor time), so the kernel is organised around the epilogue:
+// Shape of the computation: a [N x D] x [D x n_l] GEMM per level and batch item with
+// D = 256 (only 16 UMMA k-steps) whose fp32 output (5.7 GB at 1080p) dwarfs its inputs
+// (2 x 16.7 MB bf16).  It is HBM-WRITE bound (0.87 ms at the measured 6.5 TB/s vs 0.43 ms
+// of tensor time), so the kernel is organised around the epilogue:
 //
 //  * Persistent, one CTA per SM, warp-specialised:
 //      warp 0      TMA producer   (elected lane)
-//      warp 1      tcgen05.mma issuer (elected lane)
+//      warp 1      tcgen05.mma issuer (elected lane), M128 x N256 x K16, bf16 -> fp32
 //      warp 2      TMEM allocator (512 columns = two 128x256 fp32 accumulators)
 //      warp 3      idle
-//      warps 4-11  epilogue: TMEM -> registers -> pooled in registers ->
-//                  swizzled smem staging -> 16-byte coalesced global stores
-//  * fmap2-STATIONARY: one N-tile (256 fmap2 pixels x full K = 128 KB of smem)
-//    stays resident while 128-row fmap1 tiles stream through a 3-stage 16 KB
-//    ring (measured: 3 stages 5 % faster than 4, 2 starve the MMA).  L2->SM operand traffic is half the output bytes instead of equal.
-//  * An N-tile is a SPATIAL block of fmap2 (TILE_Y x TILE_X pixels, 16x16 or
-//    8x32) fetched with one 4-D TMA box per 64-channel slab, so a TMEM column is
-//    a pixel (ty, tx) of the block and one TMEM lane (= one thread of the
-//    epilogue) holds a whole 2-D patch for its query pixel.  All three pooling
-//    levels are therefore plain register adds in that thread -- no shuffles, no
-//    re-read of level 0.  Every level is written to HBM exactly once.
-//  * Two accumulators ping-pong so the MMAs of tile t+1 run under the epilogue
-//    of tile t.
+//      warps 4+    epilogue (4 or 8 warps, BuildCfg): TMEM -> registers -> scale (-> bf16) ->
+//                  swizzled smem staging -> TMA tensor stores
+//  * fmap2-STATIONARY: one N-tile (256 fmap2 pixels x full K = 128 KB of smem) stays
+//    resident while 128-row fmap1 tiles stream through a 3- or 4-stage 16 KB ring, so
+//    L2->SM operand traffic is half the output bytes instead of equal.
+//  * Two accumulators ping-pong so the MMAs of tile t+1 run under the epilogue of tile t.
+//  * Two ways to get the pyramid (MODE below): LINEAR (default) computes every level as
+//    its own GEMM columns from pooled fmap2 rows, so all stores are full-width boxes;
+//    FUSED pools levels 1-3 in the epilogue's registers from spatial fmap2 tiles (exact
+//    pooling of the fp32 accumulators, but sub-line writes: 2.3x slower, kept for parity).
+//  * LINEAR-mode stores are 4 KB TMA boxes of 16 query rows x 256 contiguous bytes (wide
+//    path; 32 rows x 128 bytes or staged st.global for row pitches that do not allow it).
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
