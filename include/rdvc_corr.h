@@ -97,7 +97,8 @@ size_t rdvc_corr_workspace_bytes(int B, int D, int h, int w);
  * pyramid      : device, rdvc_corr_pyramid_bytes(...) bytes, 256-byte aligned
  * workspace    : device, rdvc_corr_workspace_bytes(...) bytes, 256-byte aligned
  * Computes  pyr[0][b*N+i][y][x] = sum_c fmap1[b,c,i] * fmap2[b,c,y*w+x] / sqrt(D)
- * with bf16 operands and fp32 accumulation (tcgen05), and pyr[l+1] = 2x2 mean of
+ * with bf16 operands (fp16 operands when in_dtype is F16: nothing of an fp16 input is lost) and fp32
+ * accumulation (tcgen05), and pyr[l+1] = 2x2 mean of
  * pyr[l] over (y,x) with the odd trailing row/column dropped.  The fused-epilogue build
  * mode (option key 4 = 1) supports RDVC_LAYOUT_ROWMAJOR only.                       */
 int rdvc_corr_build(const void* fmap1, const void* fmap2, int B, int D, int h, int w,

@@ -125,7 +125,7 @@ corr_build2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
     } else if (warp == 1) {
         // ===================== MMA issuer (leader CTA only) =====================
         if (leader && lane == 0) {
-            constexpr uint32_t idesc = ptx::umma_idesc(2 * BLD_BLOCK_M, BLD_BLOCK_N, 1 /*bf16*/);
+            const uint32_t idesc = ptx::umma_idesc(2 * BLD_BLOCK_M, BLD_BLOCK_N, p.ab_format);   // 1 = bf16, 0 = fp16 operands
             uint32_t a_it = 0, b_it = 0, tile_it = 0;
             for (int item = cluster_id; item < n_items; item += n_clusters) {
                 const int sl = item / units;

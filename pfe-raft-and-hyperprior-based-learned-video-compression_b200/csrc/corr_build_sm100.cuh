@@ -92,6 +92,7 @@ struct BuildParams {
     int tile_start[BLD_MAX_LEVELS];  // MODE_LINEAR: first N-tile of each level
     int msplit;         // m-range slices per fmap2 tile (work item = tile x slice)
     float scale;        // 1 / sqrt(D)
+    int ab_format;      // tcgen05 kind::f16 operand format: 1 = bf16, 0 = fp16
     int dbg_store_mask; // debug: bit l set = write level l (default 15)
     int dbg_policy;     // debug: TMA-store L2 policy (0 default, 1 evict_last, 2 evict_first)
     int tma_out;        // MODE_LINEAR: 2 bits per level: how level l is written --
@@ -327,7 +328,7 @@ corr_build_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
         if (lane == 0) {
-            constexpr uint32_t idesc = ptx::umma_idesc(BLD_BLOCK_M, BLD_BLOCK_N, 1 /*bf16*/);
+            const uint32_t idesc = ptx::umma_idesc(BLD_BLOCK_M, BLD_BLOCK_N, p.ab_format);   // 1 = bf16, 0 = fp16 operands
             uint32_t a_it = 0, b_it = 0, tile_it = 0;
             for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
                 const int sl = item / units;

@@ -1,6 +1,6 @@
 // corr_pack.cuh -- feature-map repack, one launch for both maps:
 //   (B, D, h, w) {fp32|bf16|fp16}, NCHW as torchvision's encoder emits them (TV:raft.py:492-493)
-//   -> K-major bf16 rows [B][n_l][D] (D contiguous), what the tcgen05 operand descriptors in
+//   -> K-major 16-bit rows [B][n_l][D] (D contiguous; bf16, or fp16 when the inputs are fp16), what the tcgen05 operand descriptors in
 //      corr_build_sm100.cuh expect: fmap1 at level 0; fmap2 at level 0 and, for the linear
 //      build mode, at the pooled levels 1..3.
 // Level l row (Y, X) is the mean over the 2^l x 2^l block of the source map (= l nested
@@ -30,6 +30,7 @@ struct PackParams {
     int tiled[2];                // per map: rows in RDVC_LAYOUT_TILED order instead of raster order
     int twl, thl;                // log2 tile width / height of the tiled order
     int img[2][4];               // [map][level]: operand rows per batch item (pixels incl. layout padding)
+    int f16;                     // operand format: 0 = bf16, 1 = fp16 (fp16 inputs keep their 11-bit mantissa)
     int B, D, h, w;
 };
 
@@ -58,6 +59,16 @@ template <> __device__ __forceinline__ void pack_ld4<__half>(const __half* p, fl
     const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&t.x));
     const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&t.y));
     v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+}
+
+// two floats -> one 32-bit operand pair (round to nearest even), bf16 or fp16
+__device__ __forceinline__ uint32_t pack_pair(float a, float b, int f16) {
+    if (f16) {
+        const __half2 t = __floats2half2_rn(a, b);
+        return *reinterpret_cast<const uint32_t*>(&t);
+    }
+    const __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<const uint32_t*>(&t);
 }
 
 // grid: (ceil(w/32), ceil(h/8), 2 * B * D/64); block: 256 threads; dynamic smem: PACK_SMEM_BYTES.
@@ -128,7 +139,8 @@ corr_pack_kernel(const __grid_constant__ PackParams p) {
     // warps of an 8 x 8 block combine their halves of the level-3 sum through shared memory.
     const int L = p.levels[map];
     const int ry0 = (warp & 1) * 4, cx0 = (warp >> 1) * 8;
-    auto row_ptr = [&](int l, int Y, int X) -> __nv_bfloat162* {
+    const int f16 = p.f16;
+    auto row_ptr = [&](int l, int Y, int X) -> uint32_t* {
         // operand row of pixel (Y, X) of level l: raster order, or tile by tile (see rdvc_corr.h); the
         // build's output columns follow the operand rows, so this IS the volume's layout
         const int wl = w >> l;
@@ -139,7 +151,7 @@ corr_pack_kernel(const __grid_constant__ PackParams p) {
             pix = (static_cast<size_t>((Y >> thl) * tiles_w + (X >> twl)) << (twl + thl)) +
                   ((Y & ((1 << thl) - 1)) << twl) + (X & ((1 << twl) - 1));
         }
-        return reinterpret_cast<__nv_bfloat162*>(
+        return reinterpret_cast<uint32_t*>(
                    p.dst[map][l] + (static_cast<size_t>(b) * p.img[map][l] + pix) * D + cg * PACK_CG) + lane;
     };
     const float* t0 = tile + (2 * lane) * PACK_PITCH + ry0 * PACK_TX + cx0;
@@ -156,19 +168,19 @@ corr_pack_kernel(const __grid_constant__ PackParams p) {
                 const float v0 = t0[yy * PACK_TX + xx], v1 = t0[PACK_PITCH + yy * PACK_TX + xx];
                 s1a += v0; s1b += v1;
                 const int Y = y0 + ry0 + yy, X = x0 + cx0 + xx;
-                if (Y < h && X < w) *row_ptr(0, Y, X) = __floats2bfloat162_rn(v0, v1);
+                if (Y < h && X < w) *row_ptr(0, Y, X) = pack_pair(v0, v1, f16);
             }
             s2a += s1a; s2b += s1b;
             if (L > 1) {
                 const int Y = (y0 + ry0) / 2 + (qd >> 1), X = (x0 + cx0) / 2 + b2 * 2 + (qd & 1);
-                if (Y < (h >> 1) && X < (w >> 1)) *row_ptr(1, Y, X) = __floats2bfloat162_rn(s1a * 0.25f, s1b * 0.25f);
+                if (Y < (h >> 1) && X < (w >> 1)) *row_ptr(1, Y, X) = pack_pair(s1a * 0.25f, s1b * 0.25f, f16);
             }
         }
         s3a += s2a; s3b += s2b;
         if (L > 2) {
             const int Y = (y0 + ry0) / 4, X = (x0 + cx0) / 4 + b2;
             if (Y < (h >> 2) && X < (w >> 2))
-                *row_ptr(2, Y, X) = __floats2bfloat162_rn(s2a * (1.0f / 16.0f), s2b * (1.0f / 16.0f));
+                *row_ptr(2, Y, X) = pack_pair(s2a * (1.0f / 16.0f), s2b * (1.0f / 16.0f), f16);
         }
     }
     if (L > 3) {                                      // uniform over the block: all warps take it or none
@@ -180,7 +192,7 @@ corr_pack_kernel(const __grid_constant__ PackParams p) {
             const float2 o = part[(warp >> 1) * 32 + lane];
             const int Y = y0 / 8, X = (x0 + cx0) / 8;
             if (Y < (h >> 3) && X < (w >> 3))
-                *row_ptr(3, Y, X) = __floats2bfloat162_rn((s3a + o.x) * (1.0f / 64.0f), (s3b + o.y) * (1.0f / 64.0f));
+                *row_ptr(3, Y, X) = pack_pair((s3a + o.x) * (1.0f / 64.0f), (s3b + o.y) * (1.0f / 64.0f), f16);
         }
     }
 }

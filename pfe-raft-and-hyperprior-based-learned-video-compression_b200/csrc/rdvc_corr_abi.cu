@@ -218,7 +218,7 @@ int launch_build_pair(const CUtensorMap& ta, const CUtensorMap* tb, const CUtens
 // both feature maps -> K-major bf16 rows (fmap2 at `levels2` pyramid levels), one launch
 template <typename T>
 int launch_pack(const void* f1, const void* f2, void* a_km, void* const* b_km, int B, int D, int h, int w,
-                int levels2, int layout, int twl, int thl, const size_t* nl_of, cudaStream_t st) {
+                int levels2, int layout, int twl, int thl, const size_t* nl_of, int f16, cudaStream_t st) {
     auto kern = rdvc::corr_pack_kernel<T>;
     static std::atomic<unsigned long long> attr_done{0};
     if (int rc = ensure_dynamic_smem(kern, rdvc::PACK_SMEM_BYTES, attr_done, "cudaFuncSetAttribute(pack, max dynamic smem)"))
@@ -232,6 +232,7 @@ int launch_pack(const void* f1, const void* f2, void* a_km, void* const* b_km, i
     pp.B = B; pp.D = D; pp.h = h; pp.w = w;
     pp.tiled[0] = 0; pp.tiled[1] = (layout == RDVC_LAYOUT_TILED);
     pp.twl = twl; pp.thl = thl;
+    pp.f16 = f16;
     pp.img[0][0] = h * w;
     for (int l = 0; l < 4; ++l) pp.img[1][l] = static_cast<int>(nl_of[l]);
     dim3 grid((w + rdvc::PACK_TX - 1) / rdvc::PACK_TX, (h + rdvc::PACK_TY - 1) / rdvc::PACK_TY,
@@ -412,12 +413,17 @@ int rdvc_corr_build(const void* fmap1, const void* fmap2, int B, int D, int h, i
         }
     }
 
-    // 1. repack to K-major bf16; the linear mode also needs the pooled fmap2 levels
+    // operand format: fp16 inputs (the reference's default autocast, R:codec_processing.py:1436) stay fp16
+    // -- same tensor-core rate, 11 instead of 8 mantissa bits; everything else is multiplied as bf16
+    const int f16_ops = (in_dtype == RDVC_DT_F16) ? 1 : 0;
+    const CUtensorMapDataType op_dt = f16_ops ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+
+    // 1. repack to K-major 16-bit rows; the linear mode also needs the pooled fmap2 levels
     {
         const int levels2 = linear ? num_levels : 1;
-        if (in_dtype == RDVC_DT_F32) rc = launch_pack<float>(fmap1, fmap2, a_km, b_km, B, D, h, w, levels2, layout, twl, thl, nl_of, st);
-        else if (in_dtype == RDVC_DT_BF16) rc = launch_pack<__nv_bfloat16>(fmap1, fmap2, a_km, b_km, B, D, h, w, levels2, layout, twl, thl, nl_of, st);
-        else rc = launch_pack<__half>(fmap1, fmap2, a_km, b_km, B, D, h, w, levels2, layout, twl, thl, nl_of, st);
+        if (in_dtype == RDVC_DT_F32) rc = launch_pack<float>(fmap1, fmap2, a_km, b_km, B, D, h, w, levels2, layout, twl, thl, nl_of, f16_ops, st);
+        else if (in_dtype == RDVC_DT_BF16) rc = launch_pack<__nv_bfloat16>(fmap1, fmap2, a_km, b_km, B, D, h, w, levels2, layout, twl, thl, nl_of, f16_ops, st);
+        else rc = launch_pack<__half>(fmap1, fmap2, a_km, b_km, B, D, h, w, levels2, layout, twl, thl, nl_of, f16_ops, st);
         if (rc) return rc;
     }
 
@@ -435,7 +441,7 @@ int rdvc_corr_build(const void* fmap1, const void* fmap2, int B, int D, int h, i
         cuuint64_t dims[3] = {(cuuint64_t)D, (cuuint64_t)N, (cuuint64_t)B};
         cuuint64_t str[2] = {(cuuint64_t)D * 2, (cuuint64_t)N * D * 2};
         cuuint32_t box[3] = {rdvc::BLD_BLOCK_K, rdvc::BLD_BLOCK_M, 1};
-        rc = make_tmap(&ta, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, a_km, 3, dims, str, box);
+        rc = make_tmap(&ta, op_dt, a_km, 3, dims, str, box);
         if (rc) return rc;
     }
     if (linear) {
@@ -445,14 +451,14 @@ int rdvc_corr_build(const void* fmap1, const void* fmap2, int B, int D, int h, i
             cuuint64_t dims[3] = {(cuuint64_t)D, nl, (cuuint64_t)B};
             cuuint64_t str[2] = {(cuuint64_t)D * 2, nl * D * 2};
             cuuint32_t box[3] = {rdvc::BLD_BLOCK_K, rdvc::BLD_BLOCK_N, 1};
-            rc = make_tmap(&tb[l], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, b_km[ll], 3, dims, str, box);
+            rc = make_tmap(&tb[l], op_dt, b_km[ll], 3, dims, str, box);
             if (rc) return rc;
         }
     } else {
         cuuint64_t dims[4] = {(cuuint64_t)D, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)B};
         cuuint64_t str[3] = {(cuuint64_t)D * 2, (cuuint64_t)w * D * 2, (cuuint64_t)N * D * 2};
         cuuint32_t box[4] = {rdvc::BLD_BLOCK_K, (cuuint32_t)TX, (cuuint32_t)TY, 1};
-        rc = make_tmap(&tb[0], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, b_km[0], 4, dims, str, box);
+        rc = make_tmap(&tb[0], op_dt, b_km[0], 4, dims, str, box);
         if (rc) return rc;
         tb[1] = tb[2] = tb[3] = tb[0];
     }
@@ -482,6 +488,7 @@ int rdvc_corr_build(const void* fmap1, const void* fmap2, int B, int D, int h, i
         p.ntiles = p.nty * p.ntx;
     }
     p.scale = static_cast<float>(1.0 / std::sqrt(static_cast<double>(D)));
+    p.ab_format = f16_ops ? 0 : 1;
     p.dbg_store_mask = g_opt_store_mask.load();
     p.dbg_policy = g_opt_policy.load();
     {
@@ -549,7 +556,7 @@ int rdvc_corr_build(const void* fmap1, const void* fmap2, int B, int D, int h, i
             cuuint64_t dims[3] = {(cuuint64_t)D, nl, (cuuint64_t)B};
             cuuint64_t str[2] = {(cuuint64_t)D * 2, nl * D * 2};
             cuuint32_t box[3] = {rdvc::BLD_BLOCK_K, rdvc::BLD_BLOCK_N / 2, 1};   // each CTA loads half the tile
-            rc = make_tmap(&tb2[l], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, b_km[ll], 3, dims, str, box);
+            rc = make_tmap(&tb2[l], op_dt, b_km[ll], 3, dims, str, box);
             if (rc) return rc;
         }
         rdvc::BuildParams p2 = p;

@@ -41,15 +41,21 @@ def pool_fmap(f: np.ndarray, level: int) -> np.ndarray:
     return x.mean(axis=(3, 5))
 
 
-def ref_pyramid_linear(f1: np.ndarray, f2: np.ndarray, num_levels: int):
+def fp16_round(x: np.ndarray) -> np.ndarray:
+    return np.asarray(x, np.float32).astype(np.float16).astype(np.float32)
+
+
+def ref_pyramid_linear(f1: np.ndarray, f2: np.ndarray, num_levels: int, round_fn=None):
     """What the library's linear build mode computes, in fp64: level l =
-    bf16(fmap1)^T . bf16(avgpool_l(fmap2)) / sqrt(C)  (pooled in full precision, rounded once)."""
+    r(fmap1)^T . r(avgpool_l(fmap2)) / sqrt(C)  (pooled in full precision, rounded once); r = bf16
+    rounding, or fp16 rounding (`round_fn=fp16_round`) for fp16 inputs."""
+    round_fn = round_fn or bf16_round
     B, C, h, w = f1.shape
-    a = bf16_round(f1).reshape(B, C, h * w).astype(np.float64)
+    a = round_fn(f1).reshape(B, C, h * w).astype(np.float64)
     out = []
     for l in range(num_levels):
         pl = pool_fmap(f2, l)
-        b = bf16_round(pl.astype(np.float32)).astype(np.float64)
+        b = round_fn(pl.astype(np.float32)).astype(np.float64)
         hl, wl = pl.shape[-2:]
         v = np.einsum("bci,bcj->bij", a, b.reshape(B, C, hl * wl)) / np.sqrt(float(C))
         out.append(v.reshape(B * h * w, hl, wl))
