@@ -3,6 +3,7 @@
 //   mode 0: grid-stride over CHUNK-byte chunks (global linear sweep, like an elementwise kernel)
 //   mode 1: m-block sweep: all CTAs work on the same 128-row block; a CTA owns a 1 KB column tile and writes
 //           its 128 rows (row pitch 130 KB) -- warp = 4 rows x 1 KB per pass  [the GEMM's natural order]
+//   mode 3: one 128-thread CTA per 8 KB chunk, non-persistent (what torch's elementwise kernels do)
 //   mode 2: like 1 but the matrix is stored m-block-major: [mblk][ntile][128 rows][1 KB] -> each CTA tile is
 //           one contiguous 128 KB span and an m-block is one contiguous 16.7 MB span (what a blocked layout buys)
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o wbench4 wbench4.cu
@@ -27,6 +28,11 @@ __global__ void __launch_bounds__(256) wk(float* out, long long rows, long long 
         const long long nchunks = total / chunk;
         for (long long c = blockIdx.x; c < nchunks; c += gridDim.x)
             for (long long o = threadIdx.x * 16; o < chunk; o += blockDim.x * 16) st16(out + (c * chunk + o) / 4);
+        return;
+    }
+    if (mode == 3) {   // elementwise-kernel style: one small CTA per 8 KB chunk, launched in address order
+        float* base = out + (long long)blockIdx.x * 2048;
+        for (int k = 0; k < 4; ++k) st16(base + (k * blockDim.x + threadIdx.x) * 4);
         return;
     }
     const int ntiles = (int)(cols / 256), mblks = (int)(rows / 128);
@@ -57,14 +63,16 @@ int main() {
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     struct Cfg { int mode; int grid; long long chunk; };
     Cfg cfgs[] = {{0, 148, 4096}, {0, 148, 65536}, {0, 148 * 4, 8192}, {0, 148 * 8, 8192}, {0, 148 * 8, 131072}, {0, 148 * 32, 4096},
+                  {3, (int)(rows * cols / 2048), 0},
                   {1, 148, 0}, {1, 148 * 2, 0}, {1, 148 * 4, 0}, {2, 148, 0}, {2, 148 * 2, 0}, {2, 148 * 4, 0}};
     for (int rnd = 0; rnd < 2; ++rnd) {
     cudaMemcpyToSymbol(g_random, &rnd, sizeof(int));
     printf("---- %s data\n", rnd ? "index-dependent (incompressible)" : "constant pattern");
     for (auto c : cfgs) {
-        for (int rep = 0; rep < 2; ++rep) wk<<<c.grid, 256>>>(out, rows, cols, c.mode, c.chunk);
+        const int bs = c.mode == 3 ? 128 : 256;
+        for (int rep = 0; rep < 2; ++rep) wk<<<c.grid, bs>>>(out, rows, cols, c.mode, c.chunk);
         cudaEventRecord(e0);
-        for (int rep = 0; rep < 5; ++rep) wk<<<c.grid, 256>>>(out, rows, cols, c.mode, c.chunk);
+        for (int rep = 0; rep < 5; ++rep) wk<<<c.grid, bs>>>(out, rows, cols, c.mode, c.chunk);
         cudaEventRecord(e1); cudaEventSynchronize(e1);
         float ms; cudaEventElapsedTime(&ms, e0, e1); ms /= 5;
         printf("mode %d grid %5d chunk %7lld: %.3f ms  %.0f GB/s (%s)\n", c.mode, c.grid, c.chunk, ms, rows * cols * 4 / ms / 1e6,
