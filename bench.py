@@ -238,6 +238,8 @@ def run_ours(args):
         blk.build_pyramid(f1, f2)
         for k in range(ITERS):
             rc.index_pyramid(blk._pyr, coords[k], RADIUS, out=out)
+        if ev is not None:
+            ev[2].record()          # end of the 12 lookups (same stream)
 
     def barrier():
         if dist is not None:
@@ -247,9 +249,10 @@ def run_ours(args):
     for i in range(args.warmup):
         step(i)
     # kernel-level events for the roofline: one pair per timed step around the build kernel
-    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    for a, b_ in kev:   # force creation of the underlying cudaEvent_t handles
-        a.record(); b_.record()
+    kev = [tuple(torch.cuda.Event(enable_timing=True) for _ in range(3)) for _ in range(args.steps)]
+    for evs in kev:   # force creation of the underlying cudaEvent_t handles
+        for e_ in evs:
+            e_.record()
     barrier()
 
     sampler = ClockSampler(local_rank)
@@ -265,7 +268,8 @@ def run_ours(args):
     lib.rdvc_corr_set_profile_events(None, None)
     ms_total = e0.elapsed_time(e1)
     launches = lib.rdvc_corr_launch_count() - launches0
-    build_ms = [a.elapsed_time(b_) for a, b_ in kev]
+    build_ms = [a.elapsed_time(b_) for a, b_, _ in kev]
+    lookup_ms = [b_.elapsed_time(c_) for _, b_, c_ in kev]
 
     # ---- the same timed loop with the other pyramid storage type (reported beside the headline: the
     # reference's own GPU default is an fp16 volume under autocast, R:codec_processing.py:1436)
@@ -356,6 +360,13 @@ def run_ours(args):
                 "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(args.volume_dtype),
                 "algorithmic_bytes_per_launch": bytes_build, "kernel_ms": kms, "peak_source": peak_src,
                 "whole_step_frac_of_roofline": (roof_pair_s * 1e3) / (ms_total / args.steps),
+                "secondary": {
+                    "kernel": "corr_lookup_tiled_kernel x %d" % ITERS, "us_per_launch": 1e3 * statistics.mean(lookup_ms) / ITERS,
+                    "algorithmic_bytes_per_launch": bytes_lookup,
+                    "achieved": bytes_lookup / (statistics.mean(lookup_ms) / ITERS * 1e-3) / 1e9,
+                    "frac": bytes_lookup / (statistics.mean(lookup_ms) / ITERS * 1e-3) / 1e9 / peak,
+                    "note": "steady-state DRAM traffic per launch is ~145 MB (64-byte atoms + the 42 MB result), see DESIGN.md 3.3",
+                },
             },
         }
         if alt is not None:
