@@ -92,9 +92,14 @@ def run_sharded(args):
 
     fh = args.height - 8 if args.height % 16 == 0 and args.height > 64 else args.height   # 1088 -> 1080 codec frame
 
+    runner = rc.GraphedRaftFlow(model, 12, amp_dtype=torch.float16 if args.amp else None) if args.graph else None
+
     def enc_p(prev, cur):
-        with torch.no_grad(), ctx():
-            flow = rc.raft_flow(model, prev, cur, 12)
+        if runner is not None:
+            flow = runner(prev, cur)
+        else:
+            with torch.no_grad(), ctx():
+                flow = rc.raft_flow(model, prev, cur, 12)
         # steps 3 + 5a of the reference (R:codec_processing.py:1446,1456): flow to frame resolution and the
         # warped previous frame, one fused launch; the MCN / residual / codecs that consume them are out of scope
         warped, flow = rc.motion_warp(prev[:, :, :fh].contiguous(), flow, (fh, w))
@@ -133,7 +138,7 @@ def run_sharded(args):
             "unit": "P-frames/s", "n_gpus": world, "scaling": "strong",
             "config": {"workload": f"{args.frames} synthetic frames {w}x{h}, GOP {args.gop}, 12 RAFT updates, "
                                    "seed-0 random-init raft_large, B200 correlation block, final-only upsampling",
-                       "amp_fp16": args.amp, "gops": len(gops), "gops_per_rank_max": max(len(x) for x in gs.assign_gops(gops, world)),
+                       "amp_fp16": args.amp, "cuda_graph": args.graph, "gops": len(gops), "gops_per_rank_max": max(len(x) for x in gs.assign_gops(gops, world)),
                        "payload": "placeholder (codec networks out of scope)", "collective": "none on the data path; "
                        "host-side gather_object of per-GOP byte strings (gloo)"},
             "seconds_total_max_over_ranks": times[0].item(), "seconds_encode_max_over_ranks": times[1].item(),
@@ -153,6 +158,7 @@ def main():
     ap.add_argument("--gop", type=int, default=10)
     ap.add_argument("--stock-pframes", type=int, default=2, help="stock RAFT is slow at 1080p: time only this many")
     ap.add_argument("--amp", action="store_true", help="fp16 autocast like the reference's GPU default")
+    ap.add_argument("--graph", action="store_true", help="replay rc.raft_flow as one CUDA graph (rc.GraphedRaftFlow)")
     args = ap.parse_args()
     if args.frames > 0:
         return run_sharded(args)
@@ -168,7 +174,11 @@ def main():
 
     ctx = lambda: torch.autocast("cuda", dtype=torch.float16, enabled=args.amp)
 
+    runner = rc.GraphedRaftFlow(ours, 12, amp_dtype=torch.float16 if args.amp else None) if args.graph else None
+
     def run_ours():
+        if runner is not None:
+            return [runner(a, b) for a, b in pairs]
         with torch.no_grad(), ctx():
             return [rc.raft_flow(ours, a, b, 12) for a, b in pairs]
 
@@ -182,7 +192,7 @@ def main():
     line = {
         "metric": "raft_motion_branch_p_frames_per_s_1080p", "unit": "P-frames/s", "n_gpus": 1,
         "config": {"workload": f"synthetic GOP of {args.gop} frames {args.width}x{args.height}, 12 RAFT updates, "
-                               "seed-0 random-init raft_large", "amp_fp16": args.amp},
+                               "seed-0 random-init raft_large", "amp_fp16": args.amp, "cuda_graph": args.graph},
         "ours": {"value": len(pairs) / t_ours, "ms_per_pframe": 1e3 * t_ours / len(pairs), "pframes": len(pairs)},
         "stock_torchvision_same_gpu": {"value": args.stock_pframes / t_stock,
                                        "ms_per_pframe": 1e3 * t_stock / args.stock_pframes,

@@ -8,6 +8,11 @@ end -- bit-identical final flow, 11 mask-predictor + upsample passes fewer -- an
 correlation block's preallocated output so the refinement loop allocates nothing.
 
 All convolutions stay stock PyTorch/cuDNN; only the correlation block is this library's.
+
+:class:`GraphedRaftFlow` replays the whole call as ONE CUDA graph per input shape.  At the reference's
+default RAFT size (368x640, R:codec_processing.py:649-650) a P-frame's ~700 kernel launches cost more
+CPU time than their GPU time (9.9 ms per P-frame eager, launch-bound); replayed as a graph the same
+kernels run back to back.  Same kernels, same order, same numbers (the test requires bit identity).
 """
 from __future__ import annotations
 
@@ -69,3 +74,60 @@ def raft_flow(model, image1: Tensor, image2: Tensor, num_flow_updates: int = 12,
             up_mask = None if model.mask_predictor is None else model.mask_predictor(hidden_state)
             preds.append(upsample_flow(flow=(coords1 - coords0), up_mask=up_mask))
     return preds if all_predictions else preds[-1]
+
+
+
+class GraphedRaftFlow:
+    """``raft_flow`` captured into a CUDA graph (one per input shape / dtype / autocast setting).
+
+    ``runner = GraphedRaftFlow(model); flow = runner(image1, image2)`` -- the first call for a shape
+    warms up, captures and replays; later calls copy the frames into the graph's static inputs and
+    replay.  Every captured shape owns its own :class:`TVCorrBlock` (the graph bakes in the pyramid's
+    address), so the model's own block stays free for eager use.  Inference only.
+    """
+
+    def __init__(self, model, num_flow_updates: int = 12, amp_dtype: Optional[torch.dtype] = None,
+                 volume_dtype: torch.dtype = torch.float32):
+        if not isinstance(model.corr_block, TVCorrBlock):
+            raise TypeError("GraphedRaftFlow needs a model built with corr_block=rdvc_corr_b200.TVCorrBlock()")
+        self.model = model
+        self.num_flow_updates = num_flow_updates
+        self.amp_dtype = amp_dtype
+        self.volume_dtype = volume_dtype
+        self._entries = {}
+
+    def _run(self, blk, a, b):
+        with torch.autocast("cuda", dtype=self.amp_dtype or torch.float16, enabled=self.amp_dtype is not None):
+            return raft_flow(self.model, a, b, self.num_flow_updates, corr_block=blk)
+
+    def _capture(self, image1: Tensor, image2: Tensor):
+        dev = image1.device
+        blk = TVCorrBlock(num_levels=self.model.corr_block.num_levels, radius=self.model.corr_block.radius,
+                          volume_dtype=self.volume_dtype, layout=self.model.corr_block.layout)
+        in1, in2 = image1.clone(), image2.clone()
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side), torch.no_grad():
+            for _ in range(3):                      # cuDNN algorithm choice, workspaces, the pyramid buffer
+                self._run(blk, in1, in2)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        graph = torch.cuda.CUDAGraph()
+        with torch.no_grad(), torch.cuda.graph(graph):
+            out = self._run(blk, in1, in2)
+        return {"graph": graph, "in1": in1, "in2": in2, "out": out, "blk": blk}
+
+    @torch.no_grad()
+    def __call__(self, image1: Tensor, image2: Tensor) -> Tensor:
+        if not image1.is_cuda:
+            raise RuntimeError("rdvc_corr_b200 runs on an sm_100 GPU only; got CPU frames.")
+        if image1.shape != image2.shape or image1.dtype != image2.dtype:
+            raise ValueError(f"input images should have the same shape and dtype, got {image1.shape} / {image2.shape}")
+        key = (tuple(image1.shape), image1.dtype, image1.device)
+        e = self._entries.get(key)
+        if e is None:
+            e = self._entries[key] = self._capture(image1, image2)
+        e["in1"].copy_(image1)
+        e["in2"].copy_(image2)
+        e["graph"].replay()
+        return e["out"].clone()

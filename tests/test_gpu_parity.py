@@ -429,6 +429,28 @@ def test_raft_flow_runner_matches_forward(lib, golden_dir):
         rc.raft_flow(model, a[..., :250, :], b[..., :250, :])
 
 
+def test_graphed_raft_flow_is_bit_identical(lib, golden_dir):
+    """GraphedRaftFlow replays rc.raft_flow as one CUDA graph: same kernels, same order -> the same bits,
+    for the captured pair and for new frames copied into the graph's static inputs."""
+    g = np.load(os.path.join(golden_dir, "frames_im1_im2.npz"))
+    a = _preprocess(g["im1"], (256, 448)).cuda()
+    b = _preprocess(g["im2"], (256, 448)).cuda()
+    model = _seeded_raft(rc.TVCorrBlock())
+    runner = rc.GraphedRaftFlow(model, 12)
+    with torch.no_grad():
+        eager_ab = rc.raft_flow(model, a, b, 12)
+        eager_ba = rc.raft_flow(model, b, a, 12)
+    n0 = lib.rdvc_corr_launch_count()
+    got_ab = runner(a, b)                 # warm-up + capture + replay
+    captured = lib.rdvc_corr_launch_count() - n0
+    got_ba = runner(b, a)                 # replay only: no launch goes through the C ABI again
+    assert lib.rdvc_corr_launch_count() - n0 == captured
+    assert torch.equal(got_ab, eager_ab) and torch.equal(got_ba, eager_ba)
+    assert torch.equal(runner(a, b), eager_ab)
+    with pytest.raises(TypeError):
+        rc.GraphedRaftFlow(_seeded_raft())
+
+
 def test_princeton_facade(lib):
     B, D, h, w = 1, 64, 24, 40
     f1, f2 = cn.synth_fmaps(B, D, h, w, seed=21)
