@@ -75,6 +75,32 @@ def encode_gop(gop: Gop, frames: Callable[[int], object], encode_iframe: Callabl
     return b"".join(parts)
 
 
+def encode_gop_batched(gop: Gop, frames: Callable[[int], object], encode_iframe: Callable[[object], bytes],
+                       encode_pframes: Callable[[Sequence[object], Sequence[object]], Sequence[bytes]],
+                       encode_pframe: Optional[Callable[[object, object], bytes]] = None) -> bytes:
+    """Like :func:`encode_gop`, but all P-frames of the GOP go through ONE call
+    `encode_pframes([prev originals], [current frames]) -> [payloads]`: the encoder is open loop, so every
+    (previous original, current) pair of a GOP is known up front and RAFT can run them as one batch.  If the
+    batched call fails and a per-frame `encode_pframe` is given, the GOP is redone frame by frame with the
+    reference's failure rule (:func:`encode_gop`)."""
+    ts = list(range(gop.start, gop.stop))
+    if not ts:
+        return b""
+    fr = [frames(t) for t in ts]
+    parts: List[bytes] = [fmt.FrameRecord(ts[0], "I", encode_iframe(fr[0])).pack()]
+    if len(ts) > 1:
+        try:
+            payloads = list(encode_pframes(fr[:-1], fr[1:]))
+            if len(payloads) != len(ts) - 1:
+                raise RuntimeError("encode_pframes returned the wrong number of payloads")
+        except Exception:
+            if encode_pframe is None:
+                raise
+            return encode_gop(gop, lambda t: fr[t - gop.start], encode_iframe, encode_pframe)
+        parts += [fmt.FrameRecord(t, "P", pl).pack() for t, pl in zip(ts[1:], payloads)]
+    return b"".join(parts)
+
+
 def gather_stream(local: Dict[int, bytes], num_gops: int, metadata: dict, rank: int = 0,
                   world_size: int = 1, group=None) -> Optional[bytes]:
     """Host-side gather of {gop index: bytes} from every rank; rank 0 returns the `.rdvc` stream.

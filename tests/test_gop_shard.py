@@ -150,3 +150,29 @@ def test_two_rank_gather_equals_serial(tmp_path):
     with open(out, "rb") as f:
         sharded = f.read()
     assert sharded == _serial_stream(47, 5, {"rdvc_version": "1.0"})   # byte-identical to 1-rank encode
+
+
+def test_encode_gop_batched_matches_per_frame_and_falls_back():
+    """encode_gop_batched: one call for all P-frames of a GOP gives the same records as the per-frame walk;
+    a failing batch falls back to the per-frame path (with the reference's failure rule)."""
+    gop = gs.Gop(3, 30, 36)
+    frames = lambda t: t
+    enc_i = lambda f: fmt.iframe_payload(b"I%d" % f)
+    enc_p = lambda prev, cur: fmt.pframe_payload((1, 2), b"m%d-%d" % (prev, cur), (3, 4), b"r")
+    want = gs.encode_gop(gop, frames, enc_i, enc_p)
+    calls = []
+
+    def enc_batch(prevs, curs):
+        calls.append((list(prevs), list(curs)))
+        return [enc_p(a, b) for a, b in zip(prevs, curs)]
+
+    assert gs.encode_gop_batched(gop, frames, enc_i, enc_batch) == want
+    assert calls == [([30, 31, 32, 33, 34], [31, 32, 33, 34, 35])]
+    def broken(prevs, curs):
+        raise RuntimeError("batch failed")
+    assert gs.encode_gop_batched(gop, frames, enc_i, broken, enc_p) == want
+    with pytest.raises(RuntimeError, match="batch failed"):
+        gs.encode_gop_batched(gop, frames, enc_i, broken)
+    assert gs.encode_gop_batched(gs.Gop(0, 5, 5), frames, enc_i, enc_batch) == b""
+    lone = gs.encode_gop_batched(gs.Gop(0, 7, 8), frames, enc_i, enc_batch)
+    assert [r.kind for r in fmt.iter_frames(io.BytesIO(lone))] == ["I"]
