@@ -77,7 +77,8 @@ def run_sharded(args):
         dist.init_process_group("nccl", device_id=dev)
         host_group = dist.new_group(backend="gloo")      # byte strings travel over the host
     torch.manual_seed(0)
-    model = raft_large(weights=None, corr_block=rc.TVCorrBlock()).eval().to(dev)
+    vol = torch.float32 if args.volume == "fp32" else torch.bfloat16
+    model = raft_large(weights=None, corr_block=rc.TVCorrBlock(volume_dtype=vol)).eval().to(dev)
     h, w = args.height, args.width
     g = torch.Generator(device=dev).manual_seed(0)
     base = torch.rand(1, 3, h // 16 + 8, w // 16 + 8, device=dev, generator=g)
@@ -92,7 +93,8 @@ def run_sharded(args):
 
     fh = args.height - 8 if args.height % 16 == 0 and args.height > 64 else args.height   # 1088 -> 1080 codec frame
 
-    runner = rc.GraphedRaftFlow(model, 12, amp_dtype=torch.float16 if args.amp else None) if args.graph else None
+    runner = (rc.GraphedRaftFlow(model, 12, amp_dtype=torch.float16 if args.amp else None, volume_dtype=vol)
+              if args.graph else None)
 
     def enc_p(prev, cur):
         if runner is not None:
@@ -161,7 +163,7 @@ def run_sharded(args):
             "unit": "P-frames/s", "n_gpus": world, "scaling": "strong",
             "config": {"workload": f"{args.frames} synthetic frames {w}x{h}, GOP {args.gop}, 12 RAFT updates, "
                                    "seed-0 random-init raft_large, B200 correlation block, final-only upsampling",
-                       "amp_fp16": args.amp, "cuda_graph": args.graph, "batched_gop": args.batch_gop, "gops": len(gops), "gops_per_rank_max": max(len(x) for x in gs.assign_gops(gops, world)),
+                       "amp_fp16": args.amp, "cuda_graph": args.graph, "batched_gop": args.batch_gop, "volume_dtype": args.volume, "gops": len(gops), "gops_per_rank_max": max(len(x) for x in gs.assign_gops(gops, world)),
                        "payload": "placeholder (codec networks out of scope)", "collective": "none on the data path; "
                        "host-side gather_object of per-GOP byte strings (gloo)"},
             "seconds_total_max_over_ranks": times[0].item(), "seconds_encode_max_over_ranks": times[1].item(),
@@ -182,6 +184,7 @@ def main():
     ap.add_argument("--stock-pframes", type=int, default=2, help="stock RAFT is slow at 1080p: time only this many")
     ap.add_argument("--amp", action="store_true", help="fp16 autocast like the reference's GPU default")
     ap.add_argument("--graph", action="store_true", help="replay rc.raft_flow as one CUDA graph (rc.GraphedRaftFlow)")
+    ap.add_argument("--volume", choices=["fp32", "bf16"], default="fp32", help="storage type of the correlation pyramid")
     ap.add_argument("--batch-gop", action="store_true",
                     help="run all P-frames of a GOP through RAFT as one batch (the encoder is open loop)")
     args = ap.parse_args()
