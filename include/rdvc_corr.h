@@ -138,7 +138,17 @@ int rdvc_corr_pair_host(const float* fmap1_host, const float* fmap2_host,
 int rdvc_motion_warp(const float* prev, const float* flow, int B, int C, int H, int W, int h_in,
                      int w_in, float* warped, float* flow_out, void* stream);
 
-/* Frees the per-thread scratch arena of rdvc_corr_pair_host (optional). */
+/* The same call split in two, for a host that has the next pair ready while the previous result is still
+ * crossing PCIe: _submit enqueues everything for one pair on private streams of `slot` (0 or 1) and returns;
+ * _wait blocks until that slot's output has landed in out_host.  Two slots overlap one pair's device->host
+ * copies (the bottleneck: 508 MB per 1080p pair) with the next pair's host->device copies and kernels.  The
+ * host buffers of a slot must stay valid and untouched until its _wait returns.                             */
+int rdvc_corr_pair_host_submit(const float* fmap1_host, const float* fmap2_host,
+                               const float* coords_host, float* out_host, int B, int D, int h,
+                               int w, int num_levels, int radius, int iters, int vol_dtype, int slot);
+int rdvc_corr_pair_host_wait(int slot);
+
+/* Frees the per-thread scratch arenas of rdvc_corr_pair_host* (optional). */
 void rdvc_corr_release(void);
 
 /* ---- introspection for tests / benches --------------------------------- */

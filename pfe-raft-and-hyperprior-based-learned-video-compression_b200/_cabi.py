@@ -36,6 +36,9 @@ SYMBOLS = {
     "rdvc_corr_pair_host": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p] +
                             [_c.c_int] * 8),
     "rdvc_motion_warp": (_c.c_int, [_c.c_void_p, _c.c_void_p] + [_c.c_int] * 6 + [_c.c_void_p, _c.c_void_p, _c.c_void_p]),
+    "rdvc_corr_pair_host_submit": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p] +
+                                   [_c.c_int] * 9),
+    "rdvc_corr_pair_host_wait": (_c.c_int, [_c.c_int]),
     "rdvc_corr_release": (None, []),
     "rdvc_corr_launch_count": (_c.c_ulonglong, []),
     "rdvc_corr_set_option": (_c.c_int, [_c.c_int, _c.c_int]),

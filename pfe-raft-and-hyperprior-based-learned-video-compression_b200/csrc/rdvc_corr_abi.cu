@@ -280,14 +280,26 @@ int dispatch_lookup_tiled(int dbg, int radius, const rdvc::LookupParams& p, cuda
     }
 }
 
-struct HostArena {  // scratch owned by rdvc_corr_pair_host, one per thread (and bound to one device)
+struct HostArena {  // scratch owned by rdvc_corr_pair_host*, one per (thread, slot), bound to one device
     int device = -1;
     void* dev = nullptr;
     size_t bytes = 0;
     cudaStream_t compute = nullptr, copy = nullptr;
     cudaEvent_t ev[2] = {nullptr, nullptr};
+    bool pending = false;   // a submitted pair has not been waited for yet
 };
-thread_local HostArena g_arena;
+constexpr int kHostSlots = 2;
+thread_local HostArena g_arena[kHostSlots];
+
+void release_arena(HostArena& a) {
+    if (a.compute) cudaStreamSynchronize(a.compute);
+    if (a.copy) cudaStreamSynchronize(a.copy);
+    if (a.dev) cudaFree(a.dev);
+    if (a.compute) cudaStreamDestroy(a.compute);
+    if (a.copy) cudaStreamDestroy(a.copy);
+    for (auto& e : a.ev) if (e) cudaEventDestroy(e);
+    a = HostArena();
+}
 
 }  // namespace
 
@@ -669,18 +681,14 @@ int rdvc_motion_warp(const float* prev, const float* flow, int B, int C, int H, 
 }
 
 void rdvc_corr_release(void) {
-    HostArena& a = g_arena;
-    if (a.dev) cudaFree(a.dev);
-    if (a.compute) cudaStreamDestroy(a.compute);
-    if (a.copy) cudaStreamDestroy(a.copy);
-    for (auto& e : a.ev) if (e) cudaEventDestroy(e);
-    a = HostArena();
+    for (auto& a : g_arena) release_arena(a);
 }
 
-int rdvc_corr_pair_host(const float* fmap1_host, const float* fmap2_host, const float* coords_host,
-                        float* out_host, int B, int D, int h, int w, int num_levels, int radius,
-                        int iters, int vol_dtype) {
+int rdvc_corr_pair_host_submit(const float* fmap1_host, const float* fmap2_host, const float* coords_host,
+                               float* out_host, int B, int D, int h, int w, int num_levels, int radius,
+                               int iters, int vol_dtype, int slot) {
     if (!fmap1_host || !fmap2_host || !coords_host || !out_host) return fail(RDVC_E_NULL, "null pointer argument");
+    if (slot < 0 || slot >= kHostSlots) return fail(RDVC_E_UNSUPPORTED, "slot=%d not in [0, %d)", slot, kHostSlots);
     int rc = check_geometry(B, h, w, num_levels);
     if (rc) return rc;
     if (iters <= 0 || D <= 0) return fail(RDVC_E_SHAPE, "iters=%d D=%d must be positive", iters, D);
@@ -696,10 +704,11 @@ int rdvc_corr_pair_host(const float* fmap1_host, const float* fmap2_host, const 
     const size_t ws_bytes = rdvc_corr_workspace_bytes(B, D, h, w);
     const size_t need = 2 * fmap_bytes + iters * coords_bytes + 2 * out_bytes + pyr_bytes + ws_bytes;
 
-    HostArena& a = g_arena;
+    HostArena& a = g_arena[slot];
     cudaError_t e;
+    if (a.pending) return fail(RDVC_E_UNSUPPORTED, "slot %d still has a submitted pair: call rdvc_corr_pair_host_wait first", slot);
     if (a.device != current_device()) {   // the caller switched GPUs: streams and scratch belong to the old one
-        rdvc_corr_release();
+        release_arena(a);
         a.device = current_device();
     }
     if (!a.compute) {
@@ -730,6 +739,7 @@ int rdvc_corr_pair_host(const float* fmap1_host, const float* fmap2_host, const 
     for (int it = 0; it < iters; ++it)
         if ((e = cudaMemcpyAsync(d_co + it * coords_bytes, coords_host + it * (coords_raw / 4), coords_raw,
                                  cudaMemcpyHostToDevice, a.compute)) != cudaSuccess) return cuda_fail(e, "H2D coords");
+    a.pending = true;
     rc = rdvc_corr_build(d_f1, d_f2, B, D, h, w, RDVC_DT_F32, d_pyr, vol_dtype, layout, num_levels, d_ws, ws_bytes, a.compute);
     if (rc) return rc;
     // lookups ping-pong between two device buffers; the copy stream drains them
@@ -751,9 +761,29 @@ int rdvc_corr_pair_host(const float* fmap1_host, const float* fmap2_host, const 
         cudaEventRecord(a.ev[s], a.copy);
         used[s] = true;
     }
+    return RDVC_OK;
+}
+
+int rdvc_corr_pair_host_wait(int slot) {
+    if (slot < 0 || slot >= kHostSlots) return fail(RDVC_E_UNSUPPORTED, "slot=%d not in [0, %d)", slot, kHostSlots);
+    HostArena& a = g_arena[slot];
+    if (!a.pending) return RDVC_OK;
+    a.pending = false;
+    cudaError_t e;
     if ((e = cudaStreamSynchronize(a.compute)) != cudaSuccess) return cuda_fail(e, "sync compute");
     if ((e = cudaStreamSynchronize(a.copy)) != cudaSuccess) return cuda_fail(e, "sync copy");
     return RDVC_OK;
+}
+
+int rdvc_corr_pair_host(const float* fmap1_host, const float* fmap2_host, const float* coords_host,
+                        float* out_host, int B, int D, int h, int w, int num_levels, int radius,
+                        int iters, int vol_dtype) {
+    int rc = rdvc_corr_pair_host_wait(0);
+    if (rc) return rc;
+    rc = rdvc_corr_pair_host_submit(fmap1_host, fmap2_host, coords_host, out_host, B, D, h, w, num_levels, radius,
+                                    iters, vol_dtype, 0);
+    const int rw = rdvc_corr_pair_host_wait(0);
+    return rc ? rc : rw;
 }
 
 }  // extern "C"

@@ -125,6 +125,9 @@ def test_argument_validation_returns_negative_codes(lib):
     assert lib.rdvc_corr_set_option(99, 0) == -5
     assert lib.rdvc_corr_pair_host(None, p, p, p, 1, 256, 46, 80, 4, 4, 12, F32) == -1
     assert lib.rdvc_corr_pair_host(p, p, p, p, 1, 256, 46, 80, 4, 4, 0, F32) == -2
+    assert lib.rdvc_corr_pair_host_submit(p, p, p, None, 1, 256, 46, 80, 4, 4, 12, F32, 0) == -1
+    assert lib.rdvc_corr_pair_host_submit(p, p, p, p, 1, 256, 46, 80, 4, 4, 12, F32, 2) == -5
+    assert lib.rdvc_corr_pair_host_wait(0) == 0 and lib.rdvc_corr_pair_host_wait(-1) == -5
     with pytest.raises(ValueError, match="RDVC_E_TOO_SMALL"):
         rc._cabi.check(build(h=15), "rdvc_corr_build")
     # rdvc_motion_warp(prev, flow, B, C, H, W, h_in, w_in, warped, flow_out, stream)

@@ -477,6 +477,21 @@ def test_pair_host_entry_point(lib):
     for i in range(iters):
         ref = blk.index_pyramid(centroids_coords=gpu(coords[i])).cpu().numpy()
         assert np.array_equal(out[i], ref)
+    # the split call: two pairs in flight on the two slots, each result in its own host buffer
+    out2 = [np.empty_like(out), np.empty_like(out)]
+    f1b, f2b = cn.synth_fmaps(B, D, h, w, seed=32)
+    for slot, (x1, x2) in enumerate(((f1, f2), (f1b, f2b))):
+        rc._cabi.check(lib.rdvc_corr_pair_host_submit(fp(x1), fp(x2), fp(coords), fp(out2[slot]), B, D, h, w, 4, 4,
+                                                      iters, rc.RDVC_DT_F32, slot), "submit")
+    assert lib.rdvc_corr_pair_host_submit(fp(f1), fp(f2), fp(coords), fp(out2[0]), B, D, h, w, 4, 4, iters,
+                                          rc.RDVC_DT_F32, 0) == -5          # slot 0 is still pending
+    for slot in (0, 1):
+        rc._cabi.check(lib.rdvc_corr_pair_host_wait(slot), "wait")
+    assert np.array_equal(out2[0], out)
+    blk.build_pyramid(gpu(f1b), gpu(f2b))
+    for i in range(iters):
+        assert np.array_equal(out2[1][i], blk.index_pyramid(centroids_coords=gpu(coords[i])).cpu().numpy())
+    assert lib.rdvc_corr_pair_host_wait(1) == 0 and lib.rdvc_corr_pair_host_wait(5) == -5
     lib.rdvc_corr_release()
 
 
