@@ -285,10 +285,11 @@ struct HostArena {  // scratch owned by rdvc_corr_pair_host*, one per (thread, s
     void* dev = nullptr;
     size_t bytes = 0;
     cudaStream_t compute = nullptr, copy = nullptr;
-    cudaEvent_t ev[2] = {nullptr, nullptr};
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};   // one per device-side result buffer
     bool pending = false;   // a submitted pair has not been waited for yet
 };
 constexpr int kHostSlots = 2;
+constexpr int kOutBufs = 4;     // lookups run ahead of their device->host copies by up to this many results
 thread_local HostArena g_arena[kHostSlots];
 
 void release_arena(HostArena& a) {
@@ -702,7 +703,7 @@ int rdvc_corr_pair_host_submit(const float* fmap1_host, const float* fmap2_host,
     const int layout = (g_opt_mode.load() == 1) ? RDVC_LAYOUT_ROWMAJOR : RDVC_LAYOUT_TILED;
     const size_t pyr_bytes = rdvc_corr_pyramid_bytes(B, h, w, num_levels, vol_dtype, layout);
     const size_t ws_bytes = rdvc_corr_workspace_bytes(B, D, h, w);
-    const size_t need = 2 * fmap_bytes + iters * coords_bytes + 2 * out_bytes + pyr_bytes + ws_bytes;
+    const size_t need = 2 * fmap_bytes + iters * coords_bytes + kOutBufs * out_bytes + pyr_bytes + ws_bytes;
 
     HostArena& a = g_arena[slot];
     cudaError_t e;
@@ -727,8 +728,9 @@ int rdvc_corr_pair_host_submit(const float* fmap1_host, const float* fmap2_host,
     uint8_t* d_f1 = base;
     uint8_t* d_f2 = d_f1 + fmap_bytes;
     uint8_t* d_co = d_f2 + fmap_bytes;
-    uint8_t* d_out[2] = {d_co + iters * coords_bytes, d_co + iters * coords_bytes + out_bytes};
-    uint8_t* d_pyr = d_out[1] + out_bytes;
+    uint8_t* d_out[kOutBufs];
+    for (int k = 0; k < kOutBufs; ++k) d_out[k] = d_co + iters * coords_bytes + k * out_bytes;
+    uint8_t* d_pyr = d_out[kOutBufs - 1] + out_bytes;
     uint8_t* d_ws = d_pyr + pyr_bytes;
 
     // inputs in (one copy each), then build
@@ -742,10 +744,10 @@ int rdvc_corr_pair_host_submit(const float* fmap1_host, const float* fmap2_host,
     a.pending = true;
     rc = rdvc_corr_build(d_f1, d_f2, B, D, h, w, RDVC_DT_F32, d_pyr, vol_dtype, layout, num_levels, d_ws, ws_bytes, a.compute);
     if (rc) return rc;
-    // lookups ping-pong between two device buffers; the copy stream drains them
-    bool used[2] = {false, false};
+    // lookups rotate over kOutBufs device buffers; the copy stream drains them
+    bool used[kOutBufs] = {};
     for (int it = 0; it < iters; ++it) {
-        const int s = it & 1;
+        const int s = it % kOutBufs;
         if (used[s]) {  // the D2H that last read this buffer must have finished
             if ((e = cudaStreamWaitEvent(a.compute, a.ev[s], 0)) != cudaSuccess) return cuda_fail(e, "wait event");
         }
