@@ -8,8 +8,9 @@ pyramid from two (1, 256, 136, 240) feature maps, then 12 radius-4 lookups with 
 coordinates.  Prints ONE JSON line (rank 0).  See DESIGN.md section "Measurement".
 
   value        pairs/s, inputs resident in HBM, CUDA events on the launching stream, max over ranks
-  e2e          pairs/s through the C-ABI host entry point rdvc_corr_pair_host: pinned HOST feature
-               maps + coords in, all 12 lookup tensors back to HOST, copies inside the timed region
+  e2e          pairs/s through the C-ABI host entry points rdvc_corr_pair_host_submit / _wait (two pairs in
+               flight): pinned HOST feature maps + coords in, all 12 lookup tensors of every pair back to HOST,
+               copies inside the timed region
   roofline     the build kernel alone: algorithmic bytes / its CUDA-event duration vs measured HBM peak
   cpu_baseline the reference's implementation (torchvision CorrBlock, CPU fp32) on this box's cores
 
