@@ -155,6 +155,18 @@ corr_pack_kernel(const __grid_constant__ PackParams p) {
                    p.dst[map][l] + (static_cast<size_t>(b) * p.img[map][l] + pix) * D + cg * PACK_CG) + lane;
     };
     const float* t0 = tile + (2 * lane) * PACK_PITCH + ry0 * PACK_TX + cx0;
+    // Address of the region's first pixel per level once; the other pixels are compile-time row offsets from
+    // it whenever the region maps onto whole layout tiles (raster order, or 4-row tiles 4 or 8 pixels wide --
+    // the defaults); other tile shapes (experiments) take the general per-pixel formula.
+    const int Yr = y0 + ry0, Xr = x0 + cx0;           // level-0 origin of this warp's 4 x 8 region
+    const bool tl = p.tiled[map] != 0;
+    const bool quick = !tl || (p.thl == 2 && (p.twl == 2 || p.twl == 3));
+    const bool w4 = tl && p.twl == 2, w8 = tl && p.twl == 3;
+    const size_t rstride = static_cast<size_t>(D) / 2;    // one operand row in 32-bit pairs
+    uint32_t* const b0 = row_ptr(0, Yr, Xr);
+    uint32_t* const b1 = (L > 1) ? row_ptr(1, Yr >> 1, Xr >> 1) : b0;
+    uint32_t* const b2p = (L > 2) ? row_ptr(2, Yr >> 2, Xr >> 2) : b0;
+    const int w0 = w, w1 = w >> 1;
     float s3a = 0.f, s3b = 0.f;                       // this warp's half of the level-3 sum (4 x 8 pixels)
 #pragma unroll
     for (int b2 = 0; b2 < 2; ++b2) {                  // the two 4 x 4 blocks of the region
@@ -167,20 +179,32 @@ corr_pack_kernel(const __grid_constant__ PackParams p) {
                 const int yy = (qd >> 1) * 2 + (e >> 1), xx = b2 * 4 + (qd & 1) * 2 + (e & 1);
                 const float v0 = t0[yy * PACK_TX + xx], v1 = t0[PACK_PITCH + yy * PACK_TX + xx];
                 s1a += v0; s1b += v1;
-                const int Y = y0 + ry0 + yy, X = x0 + cx0 + xx;
-                if (Y < h && X < w) *row_ptr(0, Y, X) = pack_pair(v0, v1, f16);
+                const int Y = Yr + yy, X = Xr + xx;
+                if (Y < h && X < w) {
+                    // row offset from b0: raster yy * w + xx; 4-wide tiles: next tile after 16; 8-wide: one tile
+                    const int off = w4 ? (xx >> 2) * 16 + yy * 4 + (xx & 3) : w8 ? yy * 8 + xx : yy * w0 + xx;
+                    uint32_t* dst = quick ? b0 + off * rstride : row_ptr(0, Y, X);
+                    *dst = pack_pair(v0, v1, f16);
+                }
             }
             s2a += s1a; s2b += s1b;
             if (L > 1) {
-                const int Y = (y0 + ry0) / 2 + (qd >> 1), X = (x0 + cx0) / 2 + b2 * 2 + (qd & 1);
-                if (Y < (h >> 1) && X < (w >> 1)) *row_ptr(1, Y, X) = pack_pair(s1a * 0.25f, s1b * 0.25f, f16);
+                const int qy = qd >> 1, qx = b2 * 2 + (qd & 1);
+                const int Y = (Yr >> 1) + qy, X = (Xr >> 1) + qx;
+                if (Y < (h >> 1) && X < (w >> 1)) {
+                    const int off = w4 ? qy * 4 + qx : w8 ? qy * 8 + qx : qy * w1 + qx;   // inside one tile
+                    uint32_t* dst = quick ? b1 + off * rstride : row_ptr(1, Y, X);
+                    *dst = pack_pair(s1a * 0.25f, s1b * 0.25f, f16);
+                }
             }
         }
         s3a += s2a; s3b += s2b;
         if (L > 2) {
-            const int Y = (y0 + ry0) / 4, X = (x0 + cx0) / 4 + b2;
-            if (Y < (h >> 2) && X < (w >> 2))
-                *row_ptr(2, Y, X) = pack_pair(s2a * (1.0f / 16.0f), s2b * (1.0f / 16.0f), f16);
+            const int Y = Yr >> 2, X = (Xr >> 2) + b2;
+            if (Y < (h >> 2) && X < (w >> 2)) {
+                uint32_t* dst = quick ? b2p + b2 * rstride : row_ptr(2, Y, X);               // x neighbour, same tile
+                *dst = pack_pair(s2a * (1.0f / 16.0f), s2b * (1.0f / 16.0f), f16);
+            }
         }
     }
     if (L > 3) {                                      // uniform over the block: all warps take it or none
