@@ -71,17 +71,19 @@ __device__ __forceinline__ uint32_t pack_pair(float a, float b, int f16) {
     return *reinterpret_cast<const uint32_t*>(&t);
 }
 
-// grid: (ceil(w/32), ceil(h/8), 2 * B * D/64); block: 256 threads; dynamic smem: PACK_SMEM_BYTES.
+// grid: (D/64 * ceil(w/32), ceil(h/8), 2 * B); block: 256 threads; dynamic smem: PACK_SMEM_BYTES.
 template <typename T>
 __global__ void __launch_bounds__(PACK_THREADS)
 corr_pack_kernel(const __grid_constant__ PackParams p) {
     extern __shared__ float tile[];  // [64][257], column = yy * 32 + xx
     const int D = p.D, h = p.h, w = p.w;
+    // the D/64 channel groups of one spatial block are neighbours in dispatch order (fastest grid index):
+    // the 128-byte pieces they write into the same 512-byte operand rows then meet in L2
     const int cgn = D / PACK_CG;
-    const int cg = blockIdx.z % cgn;
-    const int b = (blockIdx.z / cgn) % p.B;
-    const int map = blockIdx.z / (cgn * p.B);
-    const int y0 = blockIdx.y * PACK_TY, x0 = blockIdx.x * PACK_TX;
+    const int cg = blockIdx.x % cgn;
+    const int b = blockIdx.z % p.B;
+    const int map = blockIdx.z / p.B;
+    const int y0 = blockIdx.y * PACK_TY, x0 = (blockIdx.x / cgn) * PACK_TX;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const T* src = static_cast<const T*>(p.src[map]) +
                    (static_cast<size_t>(b) * D + static_cast<size_t>(cg) * PACK_CG) * h * w;

@@ -235,8 +235,8 @@ int launch_pack(const void* f1, const void* f2, void* a_km, void* const* b_km, i
     pp.f16 = f16;
     pp.img[0][0] = h * w;
     for (int l = 0; l < 4; ++l) pp.img[1][l] = static_cast<int>(nl_of[l]);
-    dim3 grid((w + rdvc::PACK_TX - 1) / rdvc::PACK_TX, (h + rdvc::PACK_TY - 1) / rdvc::PACK_TY,
-              2 * B * (D / rdvc::PACK_CG));
+    dim3 grid((D / rdvc::PACK_CG) * ((w + rdvc::PACK_TX - 1) / rdvc::PACK_TX), (h + rdvc::PACK_TY - 1) / rdvc::PACK_TY,
+              2 * B);
     kern<<<grid, rdvc::PACK_THREADS, rdvc::PACK_SMEM_BYTES, st>>>(pp);
     ++g_launches;
     cudaError_t e = cudaGetLastError();
