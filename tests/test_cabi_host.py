@@ -42,6 +42,19 @@ def test_header_symbols_exported(lib):
         assert hasattr(lib, name)
 
 
+def test_header_is_plain_c_and_example_links(lib, tmp_path):
+    """include/rdvc_corr.h is a C header (no C++ in the signatures): the plain-C host example compiles with
+    -std=c99 -Wall -Werror and links against the shared library (not executed here: no GPU)."""
+    src = os.path.join(ROOT, "examples", "host_pair.c")
+    obj = str(tmp_path / "host_pair.o")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), "-c", src, "-o", obj])
+    libdir = os.path.dirname(rc._cabi.lib_path())
+    exe = str(tmp_path / "host_pair")
+    subprocess.check_call(["gcc", obj, "-o", exe, "-L", libdir, "-lrdvc_corr", "-lm", "-Wl,-rpath," + libdir,
+                           "-Wl,--allow-shlib-undefined"])
+    assert os.path.exists(exe)
+
+
 def test_library_is_sm100a_with_tcgen05_and_tma():
     """The shipped kernels are Blackwell-native: tcgen05.mma (UTCHMMA), TMEM loads (LDTM) and TMA
     loads/stores (UTMALDG/UTMASTG) must be in the SASS."""
