@@ -148,6 +148,15 @@ int rdvc_corr_pair_host_submit(const float* fmap1_host, const float* fmap2_host,
                                int w, int num_levels, int radius, int iters, int vol_dtype, int slot);
 int rdvc_corr_pair_host_wait(int slot);
 
+/* ---- next row: frame preparation in front of RAFT / the codec ---------- *
+ * Replaces preprocess_frame_raft (R:codec_processing.py:751-761: TF.to_tensor + TF.resize(antialias=True),
+ * run on the CPU at :1430-1431) and preprocess_frame_codec (:763-769, to_tensor only: h_out = H, w_out = W).
+ * frame_hwc : device, (H, W, C) uint8, C in [1, 4]
+ * out       : device, (C, h_out, w_out) fp32 in [0, 1]: bilinear resize with aten's anti-aliasing filter
+ *             (_upsample_bilinear2d_aa, align_corners=False) of frame / 255; down-scaling up to 7x.        */
+int rdvc_preprocess_frame(const unsigned char* frame_hwc, int H, int W, int C, float* out, int h_out,
+                          int w_out, void* stream);
+
 /* Frees the per-thread scratch arenas of rdvc_corr_pair_host* (optional). */
 void rdvc_corr_release(void);
 

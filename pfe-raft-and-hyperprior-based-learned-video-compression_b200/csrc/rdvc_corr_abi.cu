@@ -17,6 +17,7 @@
 #include "corr_lookup.cuh"
 #include "corr_pack.cuh"
 #include "motion_warp.cuh"
+#include "preprocess.cuh"
 
 #ifndef RDVC_PAIR_DEFAULT
 #define RDVC_PAIR_DEFAULT 0   // the CTA-pair build kernel is opt-in (option key 12 = 2) until it wins
@@ -678,6 +679,28 @@ int rdvc_motion_warp(const float* prev, const float* flow, int B, int C, int H, 
     ++g_launches;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "motion_warp_kernel launch");
+    return RDVC_OK;
+}
+
+int rdvc_preprocess_frame(const unsigned char* frame_hwc, int H, int W, int C, float* out, int h_out, int w_out,
+                          void* stream) {
+    if (!frame_hwc || !out) return fail(RDVC_E_NULL, "null pointer argument");
+    if (H <= 0 || W <= 0 || h_out <= 0 || w_out <= 0) return fail(RDVC_E_SHAPE, "non-positive dimension H=%d W=%d h_out=%d w_out=%d", H, W, h_out, w_out);
+    if (C < 1 || C > 4) return fail(RDVC_E_UNSUPPORTED, "C=%d not in [1, 4]", C);
+    if (h_out > 65535) return fail(RDVC_E_UNSUPPORTED, "h_out must be <= 65535 (grid limit)");
+    const double sy = static_cast<double>(H) / h_out, sx = static_cast<double>(W) / w_out;
+    if (2.0 * (sy > 1 ? sy : 1) + 2 > rdvc::PREP_MAX_TAPS || 2.0 * (sx > 1 ? sx : 1) + 2 > rdvc::PREP_MAX_TAPS)
+        return fail(RDVC_E_UNSUPPORTED, "down-scaling by more than %dx is not supported", (rdvc::PREP_MAX_TAPS - 2) / 2);
+    rdvc::PrepParams p;
+    memset(&p, 0, sizeof(p));
+    p.src = frame_hwc; p.dst = out; p.H = H; p.W = W; p.C = C; p.h_out = h_out; p.w_out = w_out;
+    p.sy = static_cast<float>(H) / static_cast<float>(h_out);    // aten: area_pixel_compute_scale, fp32
+    p.sx = static_cast<float>(W) / static_cast<float>(w_out);
+    dim3 grid((w_out + 127) / 128, h_out);
+    rdvc::preprocess_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(p);
+    ++g_launches;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "preprocess_kernel launch");
     return RDVC_OK;
 }
 

@@ -26,14 +26,14 @@ def lib():
 def header_functions():
     src = open(HEADER).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    return sorted(set(re.findall(r"\b(rdvc_(?:corr|motion)_\w+)\s*\(", src)))
+    return sorted(set(re.findall(r"\b(rdvc_(?:corr|motion|preprocess)_\w+)\s*\(", src)))
 
 
 def test_header_symbols_exported(lib):
     declared = header_functions()
     assert len(declared) >= 10
     out = subprocess.check_output(["nm", "-D", "--defined-only", rc._cabi.lib_path()], text=True)
-    exported = set(re.findall(r"\bT (rdvc_(?:corr|motion)_\w+)", out))
+    exported = set(re.findall(r"\bT (rdvc_(?:corr|motion|preprocess)_\w+)", out))
     missing = [f for f in declared if f not in exported]
     assert not missing, f"header declares symbols the library does not export: {missing}"
     # and the ctypes table binds exactly the header's functions
@@ -149,6 +149,11 @@ def test_argument_validation_returns_negative_codes(lib):
     assert lib.rdvc_motion_warp(None, p, 1, 0, 8, 8, 8, 8, None, None, None) == -1  # nothing to do
     assert lib.rdvc_motion_warp(p, p, 1, 3, 0, 8, 8, 8, p, p, None) == -2
     assert lib.rdvc_motion_warp(p, p, 1, 3, 70000, 8, 8, 8, p, p, None) == -5
+    # rdvc_preprocess_frame(frame_hwc, H, W, C, out, h_out, w_out, stream)
+    assert lib.rdvc_preprocess_frame(None, 8, 8, 3, p, 8, 8, None) == -1
+    assert lib.rdvc_preprocess_frame(p, 8, 0, 3, p, 8, 8, None) == -2
+    assert lib.rdvc_preprocess_frame(p, 8, 8, 5, p, 8, 8, None) == -5
+    assert lib.rdvc_preprocess_frame(p, 800, 8, 3, p, 8, 8, None) == -5      # 100x down-scaling
 
 
 # ------------------------------------------------------------------ Python host mirror
@@ -239,6 +244,18 @@ def test_motion_warp_host_behaviour_matches_reference():
         rc.WarpingLayer()(x, torch.zeros(2, 2, 6, 8))
     with pytest.raises(ValueError, match="does not match"):
         rc.motion_warp(x, torch.zeros(2, 2, 3, 4), (6, 9))
+
+
+def test_preprocess_host_behaviour_matches_reference(capsys):
+    """preprocess_frame_raft / _codec keep the reference's contract: a failure is printed and None is returned
+    (R:codec_processing.py:760-761, :768-769) -- here: no GPU, and there is no CPU fallback to hide it."""
+    frame = np.zeros((16, 24, 3), np.uint8)
+    assert rc.preprocess_frame_raft(frame, (32, 48), torch.device("cpu")) is None
+    assert "Error preprocessing frame for RAFT" in capsys.readouterr().out
+    assert rc.preprocess_frame_codec(frame, "cpu") is None
+    assert "Error preprocessing frame for Codec" in capsys.readouterr().out
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        rc.frame_to_tensor(frame, None, "cpu")
 
 
 def test_coords_validation_without_gpu():

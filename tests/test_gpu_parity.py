@@ -616,3 +616,39 @@ def test_motion_warp_1080p_properties(lib):
     fl = torch.cat([lin * 0.001, lin * 0.0], 1).contiguous()             # resize is linear: exact on a ramp
     f = rc.resize_flow(fl, (H, W))
     assert torch.allclose(f[:, 0], (lin[:, 0, :H] * 0.001), atol=1e-5) and f.shape == (B, 2, H, W)
+
+
+# ------------------------------------------------------------------ next row: frame preparation
+TOL_PREP = 2e-5           # absolute on [0, 1]: fp32 triangle-filter sums in one pass instead of aten's two
+                          # (observed up to 9e-6 at 1080 -> 1088)
+
+
+def test_preprocess_matches_reference_fixtures(lib, golden_dir):
+    """rdvc_preprocess_frame vs the outputs of the reference's own preprocess_frame_raft / _codec."""
+    from oracle import preprocess as pp
+    g = np.load(os.path.join(golden_dir, "preprocess.npz"))
+    for name in sorted(k[: -len("_shape")] for k in g.files if k.endswith("_shape")):
+        H, W, C, h, w = [int(v) for v in g[f"{name}_shape"]]
+        frame = pp.synth_frame(H, W, C, seed=len(name))
+        fr = frame if C > 1 else frame[:, :, 0]
+        got = rc.preprocess_frame_raft(fr, (h, w), torch.device("cuda"))
+        assert got.shape == (1, C, h, w) and got.dtype == torch.float32
+        assert np.abs(got.cpu().numpy() - g[f"{name}_raft"]).max() < TOL_PREP, name
+        assert np.abs(rc.preprocess_frame_codec(fr, "cuda").cpu().numpy() - g[f"{name}_codec"]).max() < 1e-7, name
+
+
+def test_preprocess_1080p_vs_torchvision(lib):
+    """Full size against the reference's ops run on the GPU: 1080p -> 1088x1920 (what the 1080p runs need) and
+    1080p -> 368x640 (the reference's default RAFT size, 2.9x down with anti-aliasing)."""
+    import torchvision.transforms.functional as TF
+    from oracle import preprocess as pp
+    frame = pp.synth_frame(1080, 1920, 3, seed=3)
+    t = torch.from_numpy(frame).cuda().permute(2, 0, 1).float() / 255.0
+    for size in ((1088, 1920), (368, 640), (1080, 1920)):
+        n0 = lib.rdvc_corr_launch_count()
+        got = rc.preprocess_frame_raft(frame, size, "cuda")
+        assert lib.rdvc_corr_launch_count() - n0 == 1
+        ref = TF.resize(t, list(size), antialias=True).unsqueeze(0)
+        assert (got - ref).abs().max().item() < TOL_PREP, size
+    assert torch.equal(rc.preprocess_frame_codec(frame, "cuda")[0], (t * 255.0).round() / 255.0) or \
+        (rc.preprocess_frame_codec(frame, "cuda")[0] - t).abs().max().item() < 1e-7
