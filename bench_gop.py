@@ -83,6 +83,11 @@ def run_sharded(args):
     g = torch.Generator(device=dev).manual_seed(0)
     base = torch.rand(1, 3, h // 16 + 8, w // 16 + 8, device=dev, generator=g)
     big = F.interpolate(base, size=(h + 64, w + 64), mode="bicubic", align_corners=False).clamp(0, 1)
+    host_frames = None
+    if args.from_uint8:      # the ten distinct frames of the synthetic sequence as uint8 HWC host arrays, 8 rows shorter
+        fh_ = h - 8 if h % 16 == 0 and h > 64 else h
+        host_frames = [torch.from_numpy((frame_at(big, t, h, w)[0, :, :fh_].permute(1, 2, 0) * 255).round().to(torch.uint8).cpu().numpy()).pin_memory()
+                       for t in range(10)]
     gops = gs.split_gops(args.frames, args.gop)
     mine = gs.assign_gops(gops, world)[rank]
     ctx = lambda: torch.autocast("cuda", dtype=torch.float16, enabled=args.amp)
@@ -108,6 +113,14 @@ def run_sharded(args):
         small = F.avg_pool2d(flow.float(), 8)
         q = (small * 4).round().clamp(-127, 127).to(torch.int8).cpu().numpy().tobytes()
         return fmt.pframe_payload(tuple(small.shape[-2:]), q, (0, 0), b"")
+
+    def get_frame(t):
+        """Frame t as the encoder loop sees it: a (RAFT input, codec input) pair of device tensors."""
+        if host_frames is None:
+            f = frame_at(big, t, h, w)
+            return f
+        u8 = host_frames[t % 10]
+        return rc.preprocess_frame_raft(u8, (h, w), dev)      # R:codec_processing.py:1430-1431
 
     def enc_p_batch(prevs, curs):
         a, b = torch.cat(list(prevs), 0), torch.cat(list(curs), 0)
@@ -139,10 +152,9 @@ def run_sharded(args):
     barrier()
     t0 = time.perf_counter()
     if args.batch_gop:
-        local = {gp.index: gs.encode_gop_batched(gp, lambda t: frame_at(big, t, h, w), enc_i, enc_p_batch, enc_p)
-                 for gp in mine}
+        local = {gp.index: gs.encode_gop_batched(gp, get_frame, enc_i, enc_p_batch, enc_p) for gp in mine}
     else:
-        local = {gp.index: gs.encode_gop(gp, lambda t: frame_at(big, t, h, w), enc_i, enc_p) for gp in mine}
+        local = {gp.index: gs.encode_gop(gp, get_frame, enc_i, enc_p) for gp in mine}
     torch.cuda.synchronize()
     t_local = time.perf_counter() - t0
     stream = gs.gather_stream(local, len(gops), {"rdvc_version": "b200-bench", "iframe_interval": args.gop},
@@ -163,7 +175,8 @@ def run_sharded(args):
             "unit": "P-frames/s", "n_gpus": world, "scaling": "strong",
             "config": {"workload": f"{args.frames} synthetic frames {w}x{h}, GOP {args.gop}, 12 RAFT updates, "
                                    "seed-0 random-init raft_large, B200 correlation block, final-only upsampling",
-                       "amp_fp16": args.amp, "cuda_graph": args.graph, "batched_gop": args.batch_gop, "volume_dtype": args.volume, "gops": len(gops), "gops_per_rank_max": max(len(x) for x in gs.assign_gops(gops, world)),
+                       "amp_fp16": args.amp, "cuda_graph": args.graph, "batched_gop": args.batch_gop, "volume_dtype": args.volume, "frames_from_host_uint8": args.from_uint8,
+                       "gops": len(gops), "gops_per_rank_max": max(len(x) for x in gs.assign_gops(gops, world)),
                        "payload": "placeholder (codec networks out of scope)", "collective": "none on the data path; "
                        "host-side gather_object of per-GOP byte strings (gloo)"},
             "seconds_total_max_over_ranks": times[0].item(), "seconds_encode_max_over_ranks": times[1].item(),
@@ -185,6 +198,9 @@ def main():
     ap.add_argument("--amp", action="store_true", help="fp16 autocast like the reference's GPU default")
     ap.add_argument("--graph", action="store_true", help="replay rc.raft_flow as one CUDA graph (rc.GraphedRaftFlow)")
     ap.add_argument("--volume", choices=["fp32", "bf16"], default="fp32", help="storage type of the correlation pyramid")
+    ap.add_argument("--from-uint8", action="store_true",
+                    help="config 4: frames start as uint8 HWC host arrays (1080 rows) and go through "
+                         "rc.preprocess_frame_raft / _codec, like the reference's loop (R:codec_processing.py:1430-1450)")
     ap.add_argument("--batch-gop", action="store_true",
                     help="run all P-frames of a GOP through RAFT as one batch (the encoder is open loop)")
     args = ap.parse_args()
