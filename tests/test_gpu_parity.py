@@ -652,3 +652,34 @@ def test_preprocess_1080p_vs_torchvision(lib):
         assert (got - ref).abs().max().item() < TOL_PREP, size
     assert torch.equal(rc.preprocess_frame_codec(frame, "cuda")[0], (t * 255.0).round() / 255.0) or \
         (rc.preprocess_frame_codec(frame, "cuda")[0] - t).abs().max().item() < 1e-7
+
+
+# ------------------------------------------------------------------ randomized sweep over the parameter space
+def test_random_configurations_against_oracle(lib):
+    """24 seeded random configurations (batch, channels, odd sizes, levels, radius, storage type, layout):
+    build vs the fp64 statement of what the kernel multiplies, lookup vs the C oracle on the library's pyramid."""
+    rng = np.random.default_rng(2026)
+    for case in range(24):
+        levels = int(rng.integers(1, 5))
+        lo = 2 * 2 ** (levels - 1)
+        B, D = int(rng.integers(1, 3)), int(rng.choice([64, 128, 192, 256]))
+        h, w = int(rng.integers(lo, 41)), int(rng.integers(lo, 49))
+        radius = int(rng.integers(1, 5))
+        vol = torch.float32 if rng.random() < 0.5 else torch.bfloat16
+        layout = ROW if rng.random() < 0.4 else TILED
+        sigma = float(rng.choice([0.0, 0.5, 3.0, 30.0]))
+        tag = (case, B, D, h, w, levels, radius, str(vol), layout, sigma)
+        f1, f2 = cn.synth_fmaps(B, D, h, w, seed=100 + case)
+        pyr = rc.build_pyramid(gpu(f1), gpu(f2), levels, vol, layout=layout)
+        ref = ref_pyramid_linear(f1, f2, levels)
+        own = []
+        for l in range(levels):
+            got = pyr.level(l)[:, 0].float().cpu().numpy()
+            tol = TOL_SAME_OPERANDS_BF16 if vol == torch.bfloat16 else (TOL_SAME_OPERANDS_F32 if l == 0 else TOL_SAME_OPERANDS_POOLED)
+            assert rel_max(got, ref[l]) < tol, tag + (l,)
+            own.append(got)
+        co = cn.synth_coords(B, h, w, sigma, seed=case)
+        got = rc.index_pyramid(pyr, gpu(co), radius).cpu().numpy()
+        flat = np.concatenate([x.reshape(-1) for x in own])
+        assert got.shape == (B, levels * (2 * radius + 1) ** 2, h, w)
+        assert rel_max(got, cc.index_pyramid(flat, co, levels, radius)) < TOL_LOOKUP, tag
