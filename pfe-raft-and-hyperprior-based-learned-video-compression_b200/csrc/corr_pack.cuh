@@ -72,7 +72,12 @@ __device__ __forceinline__ uint32_t pack_pair(float a, float b, int f16) {
 }
 
 // grid: (D/64 * ceil(w/32), ceil(h/8), 2 * B); block: 256 threads; dynamic smem: PACK_SMEM_BYTES.
-template <typename T>
+// VEC: w % 4 == 0, rows can be fetched as 16-byte vectors.
+// QUICK: the layout is raster order or 4-row tiles 4 / 8 pixels wide (the defaults), so a warp's region maps onto
+// whole layout tiles and pixel addresses are compile-time offsets from one base per level; !QUICK keeps the general
+// per-pixel formula for other (experimental) tile shapes.  Two instantiations instead of a run-time choice: the
+// general formula inlined 43 times made the kernel 4096 instructions long.
+template <typename T, bool QUICK, bool VEC>
 __global__ void __launch_bounds__(PACK_THREADS)
 corr_pack_kernel(const __grid_constant__ PackParams p) {
     extern __shared__ float tile[];  // [64][257], column = yy * 32 + xx
@@ -93,7 +98,7 @@ corr_pack_kernel(const __grid_constant__ PackParams p) {
     // thread before the first is consumed; the 4 channels land 257 floats apart, so the four
     // scalar smem stores are conflict-free.  Scalar path: one 32-pixel row per instruction.
     constexpr int NWARP = PACK_THREADS / 32, PACK_MLP = 8;
-    if ((w & 3) == 0) {
+    if constexpr (VEC) {   // w % 4 == 0, chosen by the host: the two load loops are separate instantiations
         constexpr int ROWS4 = PACK_CG * PACK_TY / 4;   // 128 four-channel row groups
         static_assert(ROWS4 % (NWARP * PACK_MLP) == 0, "load loop shape");
         const int cl = lane >> 3, xq = (lane & 7) * 4;
@@ -162,7 +167,7 @@ corr_pack_kernel(const __grid_constant__ PackParams p) {
     // the defaults); other tile shapes (experiments) take the general per-pixel formula.
     const int Yr = y0 + ry0, Xr = x0 + cx0;           // level-0 origin of this warp's 4 x 8 region
     const bool tl = p.tiled[map] != 0;
-    const bool quick = !tl || (p.thl == 2 && (p.twl == 2 || p.twl == 3));
+    constexpr bool quick = QUICK;
     const bool w4 = tl && p.twl == 2, w8 = tl && p.twl == 3;
     const size_t rstride = static_cast<size_t>(D) / 2;    // one operand row in 32-bit pairs
     uint32_t* const b0 = row_ptr(0, Yr, Xr);
@@ -185,7 +190,8 @@ corr_pack_kernel(const __grid_constant__ PackParams p) {
                 if (Y < h && X < w) {
                     // row offset from b0: raster yy * w + xx; 4-wide tiles: next tile after 16; 8-wide: one tile
                     const int off = w4 ? (xx >> 2) * 16 + yy * 4 + (xx & 3) : w8 ? yy * 8 + xx : yy * w0 + xx;
-                    uint32_t* dst = quick ? b0 + off * rstride : row_ptr(0, Y, X);
+                    uint32_t* dst;
+                    if constexpr (quick) dst = b0 + off * rstride; else dst = row_ptr(0, Y, X);
                     *dst = pack_pair(v0, v1, f16);
                 }
             }
@@ -195,7 +201,8 @@ corr_pack_kernel(const __grid_constant__ PackParams p) {
                 const int Y = (Yr >> 1) + qy, X = (Xr >> 1) + qx;
                 if (Y < (h >> 1) && X < (w >> 1)) {
                     const int off = w4 ? qy * 4 + qx : w8 ? qy * 8 + qx : qy * w1 + qx;   // inside one tile
-                    uint32_t* dst = quick ? b1 + off * rstride : row_ptr(1, Y, X);
+                    uint32_t* dst;
+                    if constexpr (quick) dst = b1 + off * rstride; else dst = row_ptr(1, Y, X);
                     *dst = pack_pair(s1a * 0.25f, s1b * 0.25f, f16);
                 }
             }
@@ -204,7 +211,8 @@ corr_pack_kernel(const __grid_constant__ PackParams p) {
         if (L > 2) {
             const int Y = Yr >> 2, X = (Xr >> 2) + b2;
             if (Y < (h >> 2) && X < (w >> 2)) {
-                uint32_t* dst = quick ? b2p + b2 * rstride : row_ptr(2, Y, X);               // x neighbour, same tile
+                uint32_t* dst;                                                               // x neighbour, same tile
+                if constexpr (quick) dst = b2p + b2 * rstride; else dst = row_ptr(2, Y, X);
                 *dst = pack_pair(s2a * (1.0f / 16.0f), s2b * (1.0f / 16.0f), f16);
             }
         }

@@ -217,10 +217,10 @@ int launch_build_pair(const CUtensorMap& ta, const CUtensorMap* tb, const CUtens
 }
 
 // both feature maps -> K-major bf16 rows (fmap2 at `levels2` pyramid levels), one launch
-template <typename T>
-int launch_pack(const void* f1, const void* f2, void* a_km, void* const* b_km, int B, int D, int h, int w,
+template <typename T, bool QUICK, bool VEC>
+int launch_pack_impl(const void* f1, const void* f2, void* a_km, void* const* b_km, int B, int D, int h, int w,
                 int levels2, int layout, int twl, int thl, const size_t* nl_of, int f16, cudaStream_t st) {
-    auto kern = rdvc::corr_pack_kernel<T>;
+    auto kern = rdvc::corr_pack_kernel<T, QUICK, VEC>;
     static std::atomic<unsigned long long> attr_done{0};
     if (int rc = ensure_dynamic_smem(kern, rdvc::PACK_SMEM_BYTES, attr_done, "cudaFuncSetAttribute(pack, max dynamic smem)"))
         return rc;
@@ -247,6 +247,17 @@ int launch_pack(const void* f1, const void* f2, void* a_km, void* const* b_km, i
 
 // KIND: 0 / 1 = row-major layout, scalar / 128-bit loads; 2.. = tiled layout:
 //       2 + DBG (DBG in 0..2)
+template <typename T>
+int launch_pack(const void* f1, const void* f2, void* a_km, void* const* b_km, int B, int D, int h, int w,
+                int levels2, int layout, int twl, int thl, const size_t* nl_of, int f16, cudaStream_t st) {
+    const bool quick = (layout != RDVC_LAYOUT_TILED) || (thl == 2 && (twl == 2 || twl == 3));
+    const bool vec = (w % 4) == 0;
+    if (quick && vec) return launch_pack_impl<T, true, true>(f1, f2, a_km, b_km, B, D, h, w, levels2, layout, twl, thl, nl_of, f16, st);
+    if (quick) return launch_pack_impl<T, true, false>(f1, f2, a_km, b_km, B, D, h, w, levels2, layout, twl, thl, nl_of, f16, st);
+    if (vec) return launch_pack_impl<T, false, true>(f1, f2, a_km, b_km, B, D, h, w, levels2, layout, twl, thl, nl_of, f16, st);
+    return launch_pack_impl<T, false, false>(f1, f2, a_km, b_km, B, D, h, w, levels2, layout, twl, thl, nl_of, f16, st);
+}
+
 template <int R, typename VolT, int KIND>
 int launch_lookup(const rdvc::LookupParams& p, cudaStream_t st) {
     const unsigned grid = static_cast<unsigned>((p.total + 31) / 32);
