@@ -157,6 +157,47 @@ int rdvc_corr_pair_host_wait(int slot);
 int rdvc_preprocess_frame(const unsigned char* frame_hwc, int H, int W, int C, float* out, int h_out,
                           int w_out, void* stream);
 
+/* ---- next row f-4 (cont.): the motion-compensation network --------------- *
+ * Replaces MotionCompensationNetwork.forward (R:codec_processing.py:369-406, called per P-frame at :1458, built
+ * from ConvNormAct :117-156 and ResidualBlock :190-217) in inference mode:
+ *   refined = warped_ref * sigmoid(conv5x5(resblocks(lrelu(bn(conv5x5(cat(warped_ref, flow, ref_frame)))))))
+ * Every convolution is a tcgen05 implicit GEMM over fp16 activations with fp32 accumulation (csrc/mcn_conv_sm100.cuh).
+ * The host folds each BatchNorm into its convolution (w' = w * gamma / sqrt(var + eps), bias' = beta - mean * gamma /
+ * sqrt(var + eps)) and packs the folded weights once with rdvc_mcn_pack_weights.
+ *
+ * Activation layout ("plane", rdvc_mcn_plane_bytes): [B][H][ceil(W/2)][2 pixels][32 channels] fp16 -- NHWC with 32
+ * channels, rows padded to an even pixel count (the padding pixel holds 0).                                      */
+#define RDVC_MCN_ACT_NONE 0
+#define RDVC_MCN_ACT_LEAKY 1 /* LeakyReLU(0.2), R:codec_processing.py:110 */
+size_t rdvc_mcn_plane_bytes(int B, int H, int W);
+size_t rdvc_mcn_workspace_bytes(int B, int H, int W); /* three planes */
+/* HOST function (no GPU needed): conv weight (cout, cin, k, k) fp32, k in {3, 5}, cin <= 32, cout == 32 or <= 8 ->
+ * the per-tap fp16 matrices the kernel multiplies by (rdvc_mcn_packed_weight_bytes long; copy them to the device)
+ * and the mask of non-zero k-steps.                                                                              */
+size_t rdvc_mcn_packed_weight_bytes(int ksize, int cout);
+int rdvc_mcn_pack_weights(const float* weight, int cout, int cin, int ksize, void* packed_host,
+                          unsigned long long* kmask);
+/* cat(warped_ref, flow, ref_frame) (R:codec_processing.py:402), each (B, c_*, H, W) fp32 on the device -> plane. */
+int rdvc_mcn_pack_input(const float* warped, const float* flow, const float* ref, int B, int c_warped,
+                        int c_flow, int c_ref, int H, int W, void* act, void* stream);
+/* One 32 -> 32 layer: act_out = act(conv_k(act_in) + bias [+ residual]).  bias: 32 HOST floats (or NULL = 0), copied
+ * at call time.  residual: optional plane added before the activation (ResidualBlock, :212-216).  Not in place.   */
+int rdvc_mcn_conv(const void* act_in, const void* packed_weights, unsigned long long kmask,
+                  const float* bias, int ksize, int act, const void* residual, void* act_out, int B,
+                  int H, int W, void* stream);
+/* The output layer fused with the refinement (:403-404): out = warped * sigmoid(conv5x5(act_in) + bias), (B, cout, H, W)
+ * fp32, cout <= 8; bias: cout HOST floats.                                                                        */
+int rdvc_mcn_conv_out(const void* act_in, const void* packed_weights, unsigned long long kmask,
+                      const float* bias, int ksize, int cout, const float* warped, float* out, int B,
+                      int H, int W, void* stream);
+/* The whole network: 1 + (2 + 2 * num_res_blocks) launches.  packed_weights: HOST array of 2 + 2 * num_res_blocks
+ * DEVICE pointers in layer order; kmasks: HOST array, one per layer; biases: HOST, 32 floats per layer.
+ * warped / ref: (B, 3, H, W); flow: (B, 2, H, W); out: (B, 3, H, W), all fp32 on the device.                      */
+int rdvc_mcn_forward(const float* warped, const float* flow, const float* ref, int B, int H, int W,
+                     int num_res_blocks, const void* const* packed_weights,
+                     const unsigned long long* kmasks, const float* biases, void* workspace,
+                     size_t workspace_bytes, float* out, void* stream);
+
 /* Frees the per-thread scratch arenas of rdvc_corr_pair_host* (optional). */
 void rdvc_corr_release(void);
 

@@ -37,6 +37,18 @@ SYMBOLS = {
                             [_c.c_int] * 8),
     "rdvc_motion_warp": (_c.c_int, [_c.c_void_p, _c.c_void_p] + [_c.c_int] * 6 + [_c.c_void_p, _c.c_void_p, _c.c_void_p]),
     "rdvc_preprocess_frame": (_c.c_int, [_c.c_void_p] + [_c.c_int] * 3 + [_c.c_void_p, _c.c_int, _c.c_int, _c.c_void_p]),
+    "rdvc_mcn_plane_bytes": (_c.c_size_t, [_c.c_int] * 3),
+    "rdvc_mcn_workspace_bytes": (_c.c_size_t, [_c.c_int] * 3),
+    "rdvc_mcn_packed_weight_bytes": (_c.c_size_t, [_c.c_int] * 2),
+    "rdvc_mcn_pack_weights": (_c.c_int, [_c.c_void_p, _c.c_int, _c.c_int, _c.c_int, _c.c_void_p,
+                                         _c.POINTER(_c.c_ulonglong)]),
+    "rdvc_mcn_pack_input": (_c.c_int, [_c.c_void_p] * 3 + [_c.c_int] * 6 + [_c.c_void_p, _c.c_void_p]),
+    "rdvc_mcn_conv": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_ulonglong, _c.c_void_p, _c.c_int, _c.c_int,
+                                 _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int, _c.c_int, _c.c_void_p]),
+    "rdvc_mcn_conv_out": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_ulonglong, _c.c_void_p, _c.c_int, _c.c_int,
+                                     _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int, _c.c_int, _c.c_void_p]),
+    "rdvc_mcn_forward": (_c.c_int, [_c.c_void_p] * 3 + [_c.c_int] * 4 + [_c.c_void_p, _c.c_void_p, _c.c_void_p,
+                                    _c.c_void_p, _c.c_size_t, _c.c_void_p, _c.c_void_p]),
     "rdvc_corr_pair_host_submit": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p] +
                                    [_c.c_int] * 9),
     "rdvc_corr_pair_host_wait": (_c.c_int, [_c.c_int]),

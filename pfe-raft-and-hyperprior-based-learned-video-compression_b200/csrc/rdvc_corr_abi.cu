@@ -2,6 +2,7 @@
 // Argument checking, pyramid layout arithmetic, TMA descriptor encoding and the
 // kernel launches.  No torch, no C++ types across the boundary, no CPU fallback.
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
 #include <atomic>
@@ -16,6 +17,7 @@
 #include "corr_build2_sm100.cuh"
 #include "corr_lookup.cuh"
 #include "corr_pack.cuh"
+#include "mcn_conv_sm100.cuh"
 #include "motion_warp.cuh"
 #include "preprocess.cuh"
 
@@ -820,6 +822,205 @@ int rdvc_corr_pair_host(const float* fmap1_host, const float* fmap2_host, const 
                                     iters, vol_dtype, 0);
     const int rw = rdvc_corr_pair_host_wait(0);
     return rc ? rc : rw;
+}
+
+}  // extern "C"
+
+// ---- next row f-4 (cont.): motion compensation network ----------------------------------------
+namespace {
+
+int mcn_check_geometry(int B, int H, int W) {
+    if (B <= 0 || H <= 0 || W <= 0) return fail(RDVC_E_SHAPE, "non-positive dimension B=%d H=%d W=%d", B, H, W);
+    if (H > 65535 || B > 65535) return fail(RDVC_E_UNSUPPORTED, "H and B must be <= 65535 (grid limits)");
+    if (static_cast<long long>(B) * ((H + 7) / 8) * ((W + 31) / 32) >= (1LL << 31))
+        return fail(RDVC_E_UNSUPPORTED, "too many tiles for 32-bit tile indices");
+    return RDVC_OK;
+}
+
+template <int R, int NOUT>
+int launch_mcn_conv(const void* act_in, const void* packed_w, void* act_out, rdvc::McnConvParams& p, cudaStream_t st) {
+    using Cfg = rdvc::McnCfg<R, NOUT>;
+    auto kern = rdvc::mcn_conv_kernel<R, NOUT>;
+    static std::atomic<unsigned long long> attr_done{0};
+    if (int rc = ensure_dynamic_smem(kern, Cfg::SMEM_LAUNCH, attr_done, "cudaFuncSetAttribute(mcn_conv, max dynamic smem)"))
+        return rc;
+    const cuuint64_t Wsp = static_cast<cuuint64_t>(p.Wsp), H = static_cast<cuuint64_t>(p.H), B = static_cast<cuuint64_t>(p.B);
+    CUtensorMap tm_in, tm_w, tm_out;
+    {
+        const cuuint64_t dims[4] = {64, Wsp, H, B};
+        const cuuint64_t strides[3] = {128, Wsp * 128, H * Wsp * 128};
+        const cuuint32_t box_in[4] = {64, rdvc::MCN_TX, rdvc::MCN_TY, 1};
+        if (int rc = make_tmap(&tm_in, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, const_cast<void*>(act_in), 4, dims, strides, box_in))
+            return rc;
+        // the last layer writes NCHW fp32 itself; its store map is a placeholder on the input tensor
+        const cuuint32_t box_out[4] = {64, rdvc::MCN_TX, 2, 1};
+        if (int rc = make_tmap(&tm_out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, act_out ? act_out : const_cast<void*>(act_in), 4,
+                               dims, strides, box_out))
+            return rc;
+    }
+    {
+        const cuuint64_t dims[3] = {64, static_cast<cuuint64_t>(NOUT), static_cast<cuuint64_t>(Cfg::NTAPS)};
+        const cuuint64_t strides[2] = {128, static_cast<cuuint64_t>(NOUT) * 128};
+        const cuuint32_t box[3] = {64, static_cast<cuuint32_t>(NOUT), 1};
+        if (int rc = make_tmap(&tm_w, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, const_cast<void*>(packed_w), 3, dims, strides, box))
+            return rc;
+    }
+    long long grid = sm_count();
+    const long long n_tiles = static_cast<long long>(p.B) * p.ntx * p.nty;
+    if (grid > n_tiles) grid = n_tiles;
+    kern<<<static_cast<unsigned>(grid), rdvc::MCN_THREADS, Cfg::SMEM_LAUNCH, st>>>(tm_in, tm_w, tm_out, p);
+    ++g_launches;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "mcn_conv_kernel launch");
+    return RDVC_OK;
+}
+
+int mcn_fill_params(rdvc::McnConvParams& p, int B, int H, int W, unsigned long long kmask, const float* bias, int nbias) {
+    memset(&p, 0, sizeof(p));
+    p.B = B; p.H = H; p.W = W; p.Wsp = (W + 1) / 2;
+    p.ntx = (p.Wsp + rdvc::MCN_TX - 1) / rdvc::MCN_TX;
+    p.nty = (H + rdvc::MCN_TY - 1) / rdvc::MCN_TY;
+    p.kmask = kmask;
+    if (bias) for (int i = 0; i < nbias; ++i) p.bias[i] = bias[i];
+    return RDVC_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+size_t rdvc_mcn_plane_bytes(int B, int H, int W) {
+    if (B <= 0 || H <= 0 || W <= 0) return 0;
+    return align_up(static_cast<size_t>(B) * H * ((W + 1) / 2) * 128, 1024);
+}
+
+size_t rdvc_mcn_workspace_bytes(int B, int H, int W) { return 3 * rdvc_mcn_plane_bytes(B, H, W); }
+
+size_t rdvc_mcn_packed_weight_bytes(int ksize, int cout) {
+    if ((ksize != 3 && ksize != 5) || cout <= 0 || cout > rdvc::MCN_C) return 0;
+    const int nout = (cout > 8) ? 64 : 16;
+    return static_cast<size_t>(ksize) * 3 * nout * 64 * 2;
+}
+
+int rdvc_mcn_pack_weights(const float* weight, int cout, int cin, int ksize, void* packed_host,
+                          unsigned long long* kmask) {
+    if (!weight || !packed_host || !kmask) return fail(RDVC_E_NULL, "null pointer argument");
+    if (ksize != 3 && ksize != 5) return fail(RDVC_E_UNSUPPORTED, "kernel size %d not in {3, 5}", ksize);
+    if (cin <= 0 || cin > rdvc::MCN_C || cout <= 0 || cout > rdvc::MCN_C)
+        return fail(RDVC_E_UNSUPPORTED, "channel counts must be in [1, %d], got cin=%d cout=%d", rdvc::MCN_C, cin, cout);
+    const int R = ksize / 2, nout = (cout > 8) ? 64 : 16, co_n = nout / 2;
+    __half* out = static_cast<__half*>(packed_host);
+    unsigned long long mask = 0;
+    for (int dy = -R; dy <= R; ++dy)
+        for (int dsx = -1; dsx <= 1; ++dsx) {
+            const int t = (dy + R) * 3 + (dsx + 1);
+            for (int n = 0; n < nout; ++n) {
+                const int q = n / co_n, co = n % co_n;
+                for (int k = 0; k < 64; ++k) {
+                    const int pp = k / rdvc::MCN_C, ci = k % rdvc::MCN_C;
+                    const int dx = 2 * dsx + pp - q;
+                    float v = 0.f;
+                    if (co < cout && ci < cin && dx >= -R && dx <= R)
+                        v = weight[((static_cast<size_t>(co) * cin + ci) * ksize + (dy + R)) * ksize + (dx + R)];
+                    const __half hv = __float2half_rn(v);
+                    out[(static_cast<size_t>(t) * nout + n) * 64 + k] = hv;
+                    if (__half2float(hv) != 0.f) mask |= 1ull << (4 * t + k / 16);
+                }
+            }
+        }
+    *kmask = mask;
+    return RDVC_OK;
+}
+
+int rdvc_mcn_pack_input(const float* warped, const float* flow, const float* ref, int B, int c_warped, int c_flow,
+                        int c_ref, int H, int W, void* act, void* stream) {
+    if (!warped || !flow || !ref || !act) return fail(RDVC_E_NULL, "null pointer argument");
+    if (int rc = mcn_check_geometry(B, H, W)) return rc;
+    if (c_warped < 0 || c_flow < 0 || c_ref < 0 || c_warped + c_flow + c_ref > 8 || c_warped + c_flow + c_ref <= 0)
+        return fail(RDVC_E_UNSUPPORTED, "input channels %d + %d + %d must sum to 1..8", c_warped, c_flow, c_ref);
+    if (reinterpret_cast<uintptr_t>(act) % 16) return fail(RDVC_E_ALIGN, "activation buffer must be 16-byte aligned");
+    rdvc::McnInputParams p;
+    memset(&p, 0, sizeof(p));
+    p.src[0] = warped; p.src[1] = flow; p.src[2] = ref;
+    p.ch[0] = c_warped; p.ch[1] = c_flow; p.ch[2] = c_ref;
+    p.dst = static_cast<__half*>(act);
+    p.B = B; p.H = H; p.W = W; p.Wsp = (W + 1) / 2;
+    dim3 grid((2 * p.Wsp + 127) / 128, H, B);
+    rdvc::mcn_pack_input_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(p);
+    ++g_launches;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "mcn_pack_input_kernel launch");
+    return RDVC_OK;
+}
+
+int rdvc_mcn_conv(const void* act_in, const void* packed_weights, unsigned long long kmask, const float* bias,
+                  int ksize, int act, const void* residual, void* act_out, int B, int H, int W, void* stream) {
+    if (!act_in || !packed_weights || !act_out) return fail(RDVC_E_NULL, "null pointer argument");
+    if (ksize != 3 && ksize != 5) return fail(RDVC_E_UNSUPPORTED, "kernel size %d not in {3, 5}", ksize);
+    if (act != RDVC_MCN_ACT_NONE && act != RDVC_MCN_ACT_LEAKY) return fail(RDVC_E_UNSUPPORTED, "unknown activation %d", act);
+    if (int rc = mcn_check_geometry(B, H, W)) return rc;
+    if (act_in == act_out) return fail(RDVC_E_UNSUPPORTED, "a layer cannot run in place (neighbouring tiles read its input)");
+    if (reinterpret_cast<uintptr_t>(act_in) % 16 || reinterpret_cast<uintptr_t>(act_out) % 16 ||
+        reinterpret_cast<uintptr_t>(packed_weights) % 16 || reinterpret_cast<uintptr_t>(residual) % 16)
+        return fail(RDVC_E_ALIGN, "activation / weight buffers must be 16-byte aligned");
+    rdvc::McnConvParams p;
+    mcn_fill_params(p, B, H, W, kmask, bias, rdvc::MCN_C);
+    p.act = act;
+    p.residual = static_cast<const __half*>(residual);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    return ksize == 3 ? launch_mcn_conv<1, 64>(act_in, packed_weights, act_out, p, st)
+                      : launch_mcn_conv<2, 64>(act_in, packed_weights, act_out, p, st);
+}
+
+int rdvc_mcn_conv_out(const void* act_in, const void* packed_weights, unsigned long long kmask, const float* bias,
+                      int ksize, int cout, const float* warped, float* out, int B, int H, int W, void* stream) {
+    if (!act_in || !packed_weights || !warped || !out) return fail(RDVC_E_NULL, "null pointer argument");
+    if (ksize != 5) return fail(RDVC_E_UNSUPPORTED, "the output layer is 5x5 (got %d)", ksize);
+    if (cout <= 0 || cout > 8) return fail(RDVC_E_UNSUPPORTED, "output channels %d not in [1, 8]", cout);
+    if (int rc = mcn_check_geometry(B, H, W)) return rc;
+    if (reinterpret_cast<uintptr_t>(act_in) % 16 || reinterpret_cast<uintptr_t>(packed_weights) % 16)
+        return fail(RDVC_E_ALIGN, "activation / weight buffers must be 16-byte aligned");
+    if ((W % 2 == 0) && (reinterpret_cast<uintptr_t>(warped) % 8 || reinterpret_cast<uintptr_t>(out) % 8))
+        return fail(RDVC_E_ALIGN, "warped / out must be 8-byte aligned");
+    rdvc::McnConvParams p;
+    mcn_fill_params(p, B, H, W, kmask, bias, cout);
+    p.cout = cout;
+    p.warped = warped;
+    p.out = out;
+    return launch_mcn_conv<2, 16>(act_in, packed_weights, nullptr, p, static_cast<cudaStream_t>(stream));
+}
+
+int rdvc_mcn_forward(const float* warped, const float* flow, const float* ref, int B, int H, int W,
+                     int num_res_blocks, const void* const* packed_weights, const unsigned long long* kmasks,
+                     const float* biases, void* workspace, size_t workspace_bytes, float* out, void* stream) {
+    if (!warped || !flow || !ref || !packed_weights || !kmasks || !biases || !workspace || !out)
+        return fail(RDVC_E_NULL, "null pointer argument");
+    if (num_res_blocks < 0 || num_res_blocks > 64) return fail(RDVC_E_UNSUPPORTED, "num_res_blocks=%d", num_res_blocks);
+    if (int rc = mcn_check_geometry(B, H, W)) return rc;
+    const size_t plane = rdvc_mcn_plane_bytes(B, H, W);
+    if (workspace_bytes < 3 * plane)
+        return fail(RDVC_E_WORKSPACE, "workspace too small: %zu < %zu bytes", workspace_bytes, 3 * plane);
+    if (reinterpret_cast<uintptr_t>(workspace) % 256) return fail(RDVC_E_ALIGN, "workspace must be 256-byte aligned");
+    char* ws = static_cast<char*>(workspace);
+    void* t = ws;                 // network input, then every block's middle activation
+    void* x = ws + plane;         // block input (kept for the residual)
+    void* y = ws + 2 * plane;     // block output
+    const int n_layers = 2 + 2 * num_res_blocks;
+    if (int rc = rdvc_mcn_pack_input(warped, flow, ref, B, 3, 2, 3, H, W, t, stream)) return rc;
+    if (int rc = rdvc_mcn_conv(t, packed_weights[0], kmasks[0], biases, 5, RDVC_MCN_ACT_LEAKY, nullptr, x, B, H, W, stream))
+        return rc;
+    for (int r = 0; r < num_res_blocks; ++r) {
+        const int l = 1 + 2 * r;
+        if (int rc = rdvc_mcn_conv(x, packed_weights[l], kmasks[l], biases + l * 32, 3, RDVC_MCN_ACT_LEAKY, nullptr, t,
+                                   B, H, W, stream))
+            return rc;
+        if (int rc = rdvc_mcn_conv(t, packed_weights[l + 1], kmasks[l + 1], biases + (l + 1) * 32, 3, RDVC_MCN_ACT_LEAKY,
+                                   x, y, B, H, W, stream))
+            return rc;
+        void* tmp = x; x = y; y = tmp;
+    }
+    return rdvc_mcn_conv_out(x, packed_weights[n_layers - 1], kmasks[n_layers - 1], biases + (n_layers - 1) * 32, 5, 3,
+                             warped, out, B, H, W, stream);
 }
 
 }  // extern "C"
