@@ -17,19 +17,24 @@
 // at row (q, co), column (p, ci) with dx = 2 dsx + p - q, zero where |dx| > R (packed once on the
 // host by rdvc_mcn_pack_weights; k-steps whose 16 columns are all zero are skipped through a
 // 4-bit mask per tap, so a 3 x 3 layer issues 24 instead of 36 MMAs per tile).  The A operand of
-// a tap is the activation tensor itself, shifted: one 4-D TMA box (64 ch', 16 super-pixels,
-// 8 rows) at (x0 + dsx, y0 + dy); the zero padding of the convolution is TMA's out-of-bounds fill.
+// a tap is the activation tensor itself, shifted.  One 4-D TMA box (64 ch', 16 super-pixels,
+// 8 + 2R rows) at (x0 + dsx, y0 - R) serves all 2R + 1 vertical taps of a column offset dsx: a
+// tile row is 16 x 128 B = two whole 1 KB swizzle atoms, so the box shifted down by dy rows is
+// again a valid SWIZZLE_128B operand (descriptor start address + dy * 2 KB) -- 3 boxes of 20 / 24 KB
+// per tile instead of 9 / 15 of 16 KB (measured: L2->SM traffic was the limiter, 174 us per 3x3
+// layer at 1080p with one box per tap).  The zero padding of the convolution is TMA's
+// out-of-bounds fill.
 //
 // Persistent, one CTA per SM, warp-specialised like the correlation build:
-//   warp 0  TMA producer: all tap matrices once (stationary, 72 / 120 KB), then the shifted
-//           activation boxes through a 16 KB x STAGES ring
+//   warp 0  TMA producer: all tap matrices once (stationary, 72 / 120 KB), then the activation
+//           boxes through a ring of 6 (3 for the 5x5 32 -> 32 shape) stages
 //   warp 1  tcgen05.mma issuer: M128 x NOUT x K16, fp16 x fp16 -> fp32 in TMEM, two accumulators
 //   warp 2  TMEM allocator
 //   warps 4-7 epilogue: tcgen05.ld (thread = super-pixel) -> + bias (+ residual) -> LeakyReLU
 //           -> fp16 -> swizzled smem row -> one TMA store per warp of (64, 16, 2) = 4 KB;
 //           the last layer instead applies sigmoid x warped_ref and writes NCHW fp32.
-// Bound: the taps re-read the activation tile from L2 (9 or 15 x 16 KB per 256 pixels); HBM sees
-// each activation once in and once out (266 MB per layer at 1080p).
+// HBM sees each activation once in and once out (266 MB per layer at 1080p); L2 -> SM traffic is
+// 3 x (8 + 2R) / 8 of that.
 #pragma once
 #include <cuda.h>
 #include <cuda_fp16.h>
@@ -42,7 +47,7 @@ namespace rdvc {
 constexpr int MCN_C = 32;        // channels per pixel of the activation layout
 constexpr int MCN_TX = 16;       // tile width in super-pixels (32 pixels)
 constexpr int MCN_TY = 8;        // tile height in rows
-constexpr int MCN_A_BYTES = MCN_TX * MCN_TY * 128;   // 16 KB: one shifted activation box
+constexpr int MCN_ROW_BYTES = MCN_TX * 128;           // 2 KB: one tile row = two 1 KB swizzle atoms
 constexpr int MCN_STG_BYTES = 4096;                  // one epilogue warp's store box (32 rows x 128 B)
 constexpr int MCN_THREADS = 256;
 
@@ -53,10 +58,12 @@ struct McnCfg {
     static constexpr int NTAPS = (2 * R + 1) * 3;
     static constexpr int W_TAP_BYTES = NOUT * 128;
     static constexpr int W_BYTES = NTAPS * W_TAP_BYTES;          // 72 KB (3x3), 120 KB (5x5), 30 KB (last)
-    static constexpr int STAGES = (R == 2 && NOUT == 64) ? 4 : 6;
+    static constexpr int BOX_ROWS = MCN_TY + 2 * R;             // a box carries its dy halo
+    static constexpr int A_BYTES = BOX_ROWS * MCN_ROW_BYTES;    // 20 KB (3x3) / 24 KB (5x5)
+    static constexpr int STAGES = (R == 2 && NOUT == 64) ? 3 : 6;
     static constexpr int SMEM_W = 0;
     static constexpr int SMEM_A = W_BYTES;
-    static constexpr int SMEM_STG = SMEM_A + STAGES * MCN_A_BYTES;
+    static constexpr int SMEM_STG = SMEM_A + STAGES * A_BYTES;
     static constexpr int SMEM_BAR = SMEM_STG + 4 * 2 * MCN_STG_BYTES;
     static constexpr int SMEM_TOTAL = SMEM_BAR + 256;
     static constexpr int SMEM_LAUNCH = SMEM_TOTAL + 1024;        // slack for 1024-byte alignment
@@ -147,14 +154,11 @@ mcn_conv_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
                 const int b = tile / tiles_per_img, rem = tile % tiles_per_img;
                 const int y0 = (rem / p.ntx) * MCN_TY, x0 = (rem % p.ntx) * MCN_TX;
-                for (int dy = -R; dy <= R; ++dy) {
-                    for (int dsx = -1; dsx <= 1; ++dsx, ++a_it) {
-                        const uint32_t st = a_it % STAGES, ph = (a_it / STAGES) & 1;
-                        ptx::mbar_wait(bar(A_EMPTY + st), ph ^ 1);
-                        ptx::mbar_arrive_expect_tx(bar(A_FULL + st), MCN_A_BYTES);
-                        ptx::tma_load_4d(s_a + st * MCN_A_BYTES, &tm_in, bar(A_FULL + st), 0, x0 + dsx,
-                                         y0 + dy, b);
-                    }
+                for (int dsx = -1; dsx <= 1; ++dsx, ++a_it) {
+                    const uint32_t st = a_it % STAGES, ph = (a_it / STAGES) & 1;
+                    ptx::mbar_wait(bar(A_EMPTY + st), ph ^ 1);
+                    ptx::mbar_arrive_expect_tx(bar(A_FULL + st), Cfg::A_BYTES);
+                    ptx::tma_load_4d(s_a + st * Cfg::A_BYTES, &tm_in, bar(A_FULL + st), 0, x0 + dsx, y0 - R, b);
                 }
             }
         }
@@ -172,20 +176,25 @@ mcn_conv_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
                 ptx::tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * NOUT;
                 uint32_t accumulate = 0;
-                for (int t = 0; t < NTAPS; ++t, ++a_it) {
+                for (int dsx = 0; dsx < 3; ++dsx, ++a_it) {
                     const uint32_t st = a_it % STAGES, ph = (a_it / STAGES) & 1;
                     ptx::mbar_wait(bar(A_FULL + st), ph);
                     ptx::tc_fence_after();
-                    const uint32_t a_addr = s_a + st * MCN_A_BYTES;
-                    const uint32_t b_addr = s_w + t * Cfg::W_TAP_BYTES;
-                    uint32_t km = static_cast<uint32_t>(p.kmask >> (4 * t)) & 15u;
-                    if (t == 0) km |= 1u;   // the first MMA of a tile initialises the accumulator
+                    for (int dy = 0; dy < 2 * R + 1; ++dy) {
+                        // the tap's A operand is the box shifted down by dy rows: 2 KB = two whole swizzle
+                        // atoms, so the 128-byte swizzle phase of every row is unchanged
+                        const int t = dy * 3 + dsx;
+                        const uint32_t a_addr = s_a + st * Cfg::A_BYTES + dy * MCN_ROW_BYTES;
+                        const uint32_t b_addr = s_w + t * Cfg::W_TAP_BYTES;
+                        uint32_t km = static_cast<uint32_t>(p.kmask >> (4 * t)) & 15u;
+                        if (accumulate == 0) km |= 1u;   // the first MMA of a tile initialises the accumulator
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        if ((km >> k) & 1u) {
-                            ptx::umma_bf16(d_tmem, ptx::umma_desc_k_sw128(a_addr + k * 32),
-                                           ptx::umma_desc_k_sw128(b_addr + k * 32), idesc, accumulate);
-                            accumulate = 1;
+                        for (int k = 0; k < 4; ++k) {
+                            if ((km >> k) & 1u) {
+                                ptx::umma_bf16(d_tmem, ptx::umma_desc_k_sw128(a_addr + k * 32),
+                                               ptx::umma_desc_k_sw128(b_addr + k * 32), idesc, accumulate);
+                                accumulate = 1;
+                            }
                         }
                     }
                     ptx::umma_commit(bar(A_EMPTY + st));   // ring slot free when these MMAs retire

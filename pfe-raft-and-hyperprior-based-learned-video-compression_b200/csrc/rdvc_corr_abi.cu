@@ -849,7 +849,7 @@ int launch_mcn_conv(const void* act_in, const void* packed_w, void* act_out, rdv
     {
         const cuuint64_t dims[4] = {64, Wsp, H, B};
         const cuuint64_t strides[3] = {128, Wsp * 128, H * Wsp * 128};
-        const cuuint32_t box_in[4] = {64, rdvc::MCN_TX, rdvc::MCN_TY, 1};
+        const cuuint32_t box_in[4] = {64, rdvc::MCN_TX, static_cast<cuuint32_t>(Cfg::BOX_ROWS), 1};
         if (int rc = make_tmap(&tm_in, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, const_cast<void*>(act_in), 4, dims, strides, box_in))
             return rc;
         // the last layer writes NCHW fp32 itself; its store map is a placeholder on the input tensor
