@@ -15,8 +15,8 @@
 // taps (dy in [-R, R], dsx in {-1, 0, 1} super-pixels) of [128 super-pixels x 64] x [64 x NOUT]
 // GEMMs, NOUT = 2 pixels x 32 output channels; the weight matrix of a tap holds w[co][ci][dy][dx]
 // at row (q, co), column (p, ci) with dx = 2 dsx + p - q, zero where |dx| > R (packed once on the
-// host by rdvc_mcn_pack_weights; k-steps whose 16 columns are all zero are skipped through a
-// 4-bit mask per tap, so a 3 x 3 layer issues 24 instead of 36 MMAs per tile).  The A operand of
+// host by rdvc_mcn_pack_weights; k-steps whose 16 columns are all zero are left out of the
+// compile-time MMA schedule, so a 3 x 3 layer issues 24 instead of 36 MMAs per tile).  The A operand of
 // a tap is the activation tensor itself, shifted.  One 4-D TMA box (64 ch', 16 super-pixels,
 // 8 + 2R rows) at (x0 + dsx, y0 - R) serves all 2R + 1 vertical taps of a column offset dsx: a
 // tile row is 16 x 128 B = two whole 1 KB swizzle atoms, so the box shifted down by dy rows is
@@ -51,6 +51,31 @@ constexpr int MCN_ROW_BYTES = MCN_TX * 128;           // 2 KB: one tile row = tw
 constexpr int MCN_STG_BYTES = 4096;                  // one epilogue warp's store box (32 rows x 128 B)
 constexpr int MCN_THREADS = 256;
 
+// Which 16-column k-steps of a tap's 64-column matrix the MMA warp issues -- a COMPILE-TIME schedule, so the
+// issue loop is straight-line code (two 64-bit adds + one tcgen05.mma per step).  With M128 x N64 x K16 MMAs
+// (~32 tensor cycles each) a loop that tests a run-time mask and rebuilds descriptors (~25 dependent
+// single-thread instructions per MMA) made the ISSUE the bottleneck: 132 us per 3x3 layer at 1080p, tensor
+// pipe 19 % busy, producer and epilogue both waiting.
+//   MCN_K_FULL: every k-step.
+//   MCN_K_3X3 : 3x3 over all 32 channels: the left / right super-pixel column contributes through one of its
+//               two pixels only (dx = 2 dsx + p - q must lie in [-1, 1]).
+//   MCN_K_C16 : at most 16 input channels (the network's first layer has 8): k-steps 0 and 2.
+constexpr int MCN_K_FULL = 0, MCN_K_3X3 = 1, MCN_K_C16 = 2;
+__host__ __device__ constexpr bool mcn_kstep_on(int kpat, int dsx_idx, int k) {
+    return kpat == MCN_K_FULL  ? true
+           : kpat == MCN_K_3X3 ? (dsx_idx == 0 ? k >= 2 : dsx_idx == 1 ? true : k < 2)
+                               : (k == 0 || k == 2);
+}
+// the run-time mask (rdvc_mcn_pack_weights) a schedule covers: bit (4 t + k), t = dy_idx * 3 + dsx_idx
+inline unsigned long long mcn_pattern_mask(int kpat, int ksize) {
+    unsigned long long m = 0;
+    for (int dy = 0; dy < ksize; ++dy)
+        for (int dsx = 0; dsx < 3; ++dsx)
+            for (int k = 0; k < 4; ++k)
+                if (mcn_kstep_on(kpat, dsx, k)) m |= 1ull << (4 * (dy * 3 + dsx) + k);
+    return m;
+}
+
 template <int R, int NOUT>
 struct McnCfg {
     static_assert(R == 1 || R == 2, "3x3 or 5x5");
@@ -75,7 +100,6 @@ struct McnCfg {
 struct McnConvParams {
     int B, H, W, Wsp;
     int ntx, nty;                 // tiles along x (super-pixels / 16) and y (rows / 8)
-    unsigned long long kmask;     // bit (4 t + k): k-step k of tap t has non-zero weights
     int act;                      // 0 none, 1 LeakyReLU(0.2)
     int cout;                     // last layer: real output channels (<= 8)
     const __half* residual;       // optional, activation layout; added before the activation
@@ -94,7 +118,7 @@ __device__ __forceinline__ uint32_t mcn_pack_h2(float a, float b) {
     return *reinterpret_cast<uint32_t*>(&t);
 }
 
-template <int R, int NOUT>
+template <int R, int NOUT, int KPAT>
 __global__ void __launch_bounds__(MCN_THREADS, 1)
 mcn_conv_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_w,
                 const __grid_constant__ CUtensorMap tm_out, const McnConvParams p) {
@@ -169,31 +193,32 @@ mcn_conv_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
             const uint32_t idesc = ptx::umma_idesc(128, NOUT, 0);   // fp16 operands, fp32 accumulate
             ptx::mbar_wait(bar(W_FULL), 0);
             ptx::tc_fence_after();
+            const uint64_t b_desc0 = ptx::umma_desc_k_sw128(s_w);
             uint32_t a_it = 0, tile_it = 0;
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_it) {
                 const uint32_t acc = tile_it & 1, acc_ph = (tile_it >> 1) & 1;
                 ptx::mbar_wait(bar(T_EMPTY + acc), acc_ph ^ 1);
                 ptx::tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * NOUT;
-                uint32_t accumulate = 0;
+#pragma unroll
                 for (int dsx = 0; dsx < 3; ++dsx, ++a_it) {
                     const uint32_t st = a_it % STAGES, ph = (a_it / STAGES) & 1;
                     ptx::mbar_wait(bar(A_FULL + st), ph);
                     ptx::tc_fence_after();
+                    const uint64_t a_desc0 = ptx::umma_desc_k_sw128(s_a + st * Cfg::A_BYTES);
+#pragma unroll
                     for (int dy = 0; dy < 2 * R + 1; ++dy) {
                         // the tap's A operand is the box shifted down by dy rows: 2 KB = two whole swizzle
-                        // atoms, so the 128-byte swizzle phase of every row is unchanged
-                        const int t = dy * 3 + dsx;
-                        const uint32_t a_addr = s_a + st * Cfg::A_BYTES + dy * MCN_ROW_BYTES;
-                        const uint32_t b_addr = s_w + t * Cfg::W_TAP_BYTES;
-                        uint32_t km = static_cast<uint32_t>(p.kmask >> (4 * t)) & 15u;
-                        if (accumulate == 0) km |= 1u;   // the first MMA of a tile initialises the accumulator
+                        // atoms, so the 128-byte swizzle phase of every row is unchanged.  Descriptor
+                        // start addresses are in 16-byte units in the low bits: offsets are plain adds.
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
-                            if ((km >> k) & 1u) {
-                                ptx::umma_bf16(d_tmem, ptx::umma_desc_k_sw128(a_addr + k * 32),
-                                               ptx::umma_desc_k_sw128(b_addr + k * 32), idesc, accumulate);
-                                accumulate = 1;
+                            if (mcn_kstep_on(KPAT, dsx, k)) {
+                                constexpr int first_k = (KPAT == MCN_K_3X3) ? 2 : 0;   // first step issued at dsx = 0, dy = 0
+                                const bool first = (dsx == 0 && dy == 0 && k == first_k);
+                                ptx::umma_bf16(d_tmem, a_desc0 + ((dy * MCN_ROW_BYTES + k * 32) >> 4),
+                                               b_desc0 + (((dy * 3 + dsx) * Cfg::W_TAP_BYTES + k * 32) >> 4), idesc,
+                                               first ? 0u : 1u);
                             }
                         }
                     }

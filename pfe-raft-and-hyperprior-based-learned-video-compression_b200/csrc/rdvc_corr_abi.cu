@@ -837,10 +837,10 @@ int mcn_check_geometry(int B, int H, int W) {
     return RDVC_OK;
 }
 
-template <int R, int NOUT>
+template <int R, int NOUT, int KPAT>
 int launch_mcn_conv(const void* act_in, const void* packed_w, void* act_out, rdvc::McnConvParams& p, cudaStream_t st) {
     using Cfg = rdvc::McnCfg<R, NOUT>;
-    auto kern = rdvc::mcn_conv_kernel<R, NOUT>;
+    auto kern = rdvc::mcn_conv_kernel<R, NOUT, KPAT>;
     static std::atomic<unsigned long long> attr_done{0};
     if (int rc = ensure_dynamic_smem(kern, Cfg::SMEM_LAUNCH, attr_done, "cudaFuncSetAttribute(mcn_conv, max dynamic smem)"))
         return rc;
@@ -875,12 +875,11 @@ int launch_mcn_conv(const void* act_in, const void* packed_w, void* act_out, rdv
     return RDVC_OK;
 }
 
-int mcn_fill_params(rdvc::McnConvParams& p, int B, int H, int W, unsigned long long kmask, const float* bias, int nbias) {
+int mcn_fill_params(rdvc::McnConvParams& p, int B, int H, int W, const float* bias, int nbias) {
     memset(&p, 0, sizeof(p));
     p.B = B; p.H = H; p.W = W; p.Wsp = (W + 1) / 2;
     p.ntx = (p.Wsp + rdvc::MCN_TX - 1) / rdvc::MCN_TX;
     p.nty = (H + rdvc::MCN_TY - 1) / rdvc::MCN_TY;
-    p.kmask = kmask;
     if (bias) for (int i = 0; i < nbias; ++i) p.bias[i] = bias[i];
     return RDVC_OK;
 }
@@ -964,12 +963,18 @@ int rdvc_mcn_conv(const void* act_in, const void* packed_weights, unsigned long 
         reinterpret_cast<uintptr_t>(packed_weights) % 16 || reinterpret_cast<uintptr_t>(residual) % 16)
         return fail(RDVC_E_ALIGN, "activation / weight buffers must be 16-byte aligned");
     rdvc::McnConvParams p;
-    mcn_fill_params(p, B, H, W, kmask, bias, rdvc::MCN_C);
+    mcn_fill_params(p, B, H, W, bias, rdvc::MCN_C);
     p.act = act;
     p.residual = static_cast<const __half*>(residual);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    return ksize == 3 ? launch_mcn_conv<1, 64>(act_in, packed_weights, act_out, p, st)
-                      : launch_mcn_conv<2, 64>(act_in, packed_weights, act_out, p, st);
+    // the cheapest compile-time MMA schedule that covers the non-zero k-steps of these weights
+    auto covered = [&](int kpat) { return (kmask & ~rdvc::mcn_pattern_mask(kpat, ksize)) == 0; };
+    if (ksize == 3) {
+        if (covered(rdvc::MCN_K_3X3)) return launch_mcn_conv<1, 64, rdvc::MCN_K_3X3>(act_in, packed_weights, act_out, p, st);
+        return launch_mcn_conv<1, 64, rdvc::MCN_K_FULL>(act_in, packed_weights, act_out, p, st);
+    }
+    if (covered(rdvc::MCN_K_C16)) return launch_mcn_conv<2, 64, rdvc::MCN_K_C16>(act_in, packed_weights, act_out, p, st);
+    return launch_mcn_conv<2, 64, rdvc::MCN_K_FULL>(act_in, packed_weights, act_out, p, st);
 }
 
 int rdvc_mcn_conv_out(const void* act_in, const void* packed_weights, unsigned long long kmask, const float* bias,
@@ -983,11 +988,12 @@ int rdvc_mcn_conv_out(const void* act_in, const void* packed_weights, unsigned l
     if ((W % 2 == 0) && (reinterpret_cast<uintptr_t>(warped) % 8 || reinterpret_cast<uintptr_t>(out) % 8))
         return fail(RDVC_E_ALIGN, "warped / out must be 8-byte aligned");
     rdvc::McnConvParams p;
-    mcn_fill_params(p, B, H, W, kmask, bias, cout);
+    mcn_fill_params(p, B, H, W, bias, cout);
     p.cout = cout;
     p.warped = warped;
     p.out = out;
-    return launch_mcn_conv<2, 16>(act_in, packed_weights, nullptr, p, static_cast<cudaStream_t>(stream));
+    (void)kmask;   // the output layer always runs the full schedule
+    return launch_mcn_conv<2, 16, rdvc::MCN_K_FULL>(act_in, packed_weights, nullptr, p, static_cast<cudaStream_t>(stream));
 }
 
 int rdvc_mcn_forward(const float* warped, const float* flow, const float* ref, int B, int H, int W,
