@@ -30,8 +30,9 @@
 //           boxes through a ring of 6 (3 for the 5x5 32 -> 32 shape) stages
 //   warp 1  tcgen05.mma issuer: M128 x NOUT x K16, fp16 x fp16 -> fp32 in TMEM, two accumulators
 //   warp 2  TMEM allocator
-//   warps 4-7 epilogue: tcgen05.ld (thread = super-pixel) -> + bias (+ residual) -> LeakyReLU
-//           -> fp16 -> swizzled smem row -> one TMA store per warp of (64, 16, 2) = 4 KB;
+//   warps 4-7 epilogue: tcgen05.ld (thread = super-pixel) -> + bias (+ residual, a TMA load of the
+//           warp's 4 KB box into its staging buffer) -> LeakyReLU -> fp16 -> swizzled smem row
+//           -> one TMA store per warp of (64, 16, 2) = 4 KB;
 //           the last layer instead applies sigmoid x warped_ref and writes NCHW fp32.
 // HBM sees each activation once in and once out (266 MB per layer at 1080p); L2 -> SM traffic is
 // 3 x (8 + 2R) / 8 of that.
@@ -113,6 +114,14 @@ __device__ __forceinline__ void mcn_sts_16(uint32_t addr, uint4 v) {
                  "r"(v.w)
                  : "memory");
 }
+__device__ __forceinline__ uint4 mcn_lds_16(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                 : "r"(addr)
+                 : "memory");
+    return v;
+}
 __device__ __forceinline__ uint32_t mcn_pack_h2(float a, float b) {
     __half2 t = __floats2half2_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&t);
@@ -121,7 +130,8 @@ __device__ __forceinline__ uint32_t mcn_pack_h2(float a, float b) {
 template <int R, int NOUT, int KPAT>
 __global__ void __launch_bounds__(MCN_THREADS, 1)
 mcn_conv_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_w,
-                const __grid_constant__ CUtensorMap tm_out, const McnConvParams p) {
+                const __grid_constant__ CUtensorMap tm_out, const __grid_constant__ CUtensorMap tm_res,
+                const McnConvParams p) {
     using Cfg = McnCfg<R, NOUT>;
     constexpr int NTAPS = Cfg::NTAPS, STAGES = Cfg::STAGES;
     extern __shared__ uint8_t smem_raw[];
@@ -131,10 +141,10 @@ mcn_conv_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
     const uint32_t s_a = ptx::smem_u32(smem + Cfg::SMEM_A);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::SMEM_BAR);
     const uint32_t bar0 = ptx::smem_u32(bars);
-    constexpr int A_FULL = 0, A_EMPTY = 6, W_FULL = 12, T_FULL = 13, T_EMPTY = 15;
+    constexpr int A_FULL = 0, A_EMPTY = 6, W_FULL = 12, T_FULL = 13, T_EMPTY = 15, R_FULL = 17;
     static_assert(STAGES <= 6, "barrier slots");
     auto bar = [&](int i) { return bar0 + 8u * i; };
-    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(bars + 20);
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(bars + 24);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -154,6 +164,7 @@ mcn_conv_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
             ptx::mbar_init(bar(T_FULL + i), 1);
             ptx::mbar_init(bar(T_EMPTY + i), 4);
         }
+        for (int i = 0; i < 4; ++i) ptx::mbar_init(bar(R_FULL + i), 1);
         ptx::fence_mbar_init();
     }
     if (warp == 2) {
@@ -243,15 +254,19 @@ mcn_conv_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * NOUT;
 
             if constexpr (NOUT == 64) {
-                // residual row of this thread, requested before the accumulator is waited for
-                uint4 res[8];
-                const bool has_res = (p.residual != nullptr) && inside;
-                if (has_res) {
-                    const uint4* rp = reinterpret_cast<const uint4*>(
-                        p.residual + ((static_cast<size_t>(b) * p.H + y) * p.Wsp + sp) * 64);
-#pragma unroll
-                    for (int c = 0; c < 8; ++c) res[c] = __ldg(rp + c);
+                // The residual rows of this warp (the same 4 KB box the result goes out through) are fetched
+                // by TMA into the staging buffer before the accumulator is waited for: per-thread 128-byte
+                // global reads here cost 35 us per layer at 1080p.
+                const bool use_res = (p.residual != nullptr);
+                const uint32_t sb = stg + (tile_it & 1) * MCN_STG_BYTES;
+                if (lane == 0) {
+                    ptx::bulk_wait_read<1>();   // this warp's previous-but-one store has finished reading `sb`
+                    if (use_res) {
+                        ptx::mbar_arrive_expect_tx(bar(R_FULL + q), MCN_STG_BYTES);
+                        ptx::tma_load_4d(sb, &tm_res, bar(R_FULL + q), 0, x0, y0 + 2 * q, b);
+                    }
                 }
+                __syncwarp();
                 ptx::mbar_wait(bar(T_FULL + acc), acc_ph);
                 ptx::tc_fence_after();
                 float v[64];
@@ -263,10 +278,12 @@ mcn_conv_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
                 if (lane == 0) ptx::mbar_arrive(bar(T_EMPTY + acc));   // accumulator back to the MMA warp
 #pragma unroll
                 for (int i = 0; i < 64; ++i) v[i] += p.bias[i & 31];
-                if (has_res) {
+                if (use_res) {
+                    ptx::mbar_wait(bar(R_FULL + q), tile_it & 1);
 #pragma unroll
                     for (int c = 0; c < 8; ++c) {
-                        const uint32_t w4[4] = {res[c].x, res[c].y, res[c].z, res[c].w};
+                        const uint4 r4 = mcn_lds_16(sb + lane * 128 + ((c ^ (lane & 7)) << 4));
+                        const uint32_t w4[4] = {r4.x, r4.y, r4.z, r4.w};
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
                             const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w4[j]));
@@ -283,10 +300,6 @@ mcn_conv_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
 #pragma unroll
                     for (int i = 32; i < 64; ++i) v[i] = 0.f;
                 }
-                // this warp's previous-but-one store has finished reading its staging buffer
-                if (lane == 0) ptx::bulk_wait_read<1>();
-                __syncwarp();
-                const uint32_t sb = stg + (tile_it & 1) * MCN_STG_BYTES;
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
                     uint4 w;

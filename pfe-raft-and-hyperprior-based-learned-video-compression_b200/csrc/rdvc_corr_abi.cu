@@ -845,7 +845,7 @@ int launch_mcn_conv(const void* act_in, const void* packed_w, void* act_out, rdv
     if (int rc = ensure_dynamic_smem(kern, Cfg::SMEM_LAUNCH, attr_done, "cudaFuncSetAttribute(mcn_conv, max dynamic smem)"))
         return rc;
     const cuuint64_t Wsp = static_cast<cuuint64_t>(p.Wsp), H = static_cast<cuuint64_t>(p.H), B = static_cast<cuuint64_t>(p.B);
-    CUtensorMap tm_in, tm_w, tm_out;
+    CUtensorMap tm_in, tm_w, tm_out, tm_res;
     {
         const cuuint64_t dims[4] = {64, Wsp, H, B};
         const cuuint64_t strides[3] = {128, Wsp * 128, H * Wsp * 128};
@@ -857,6 +857,11 @@ int launch_mcn_conv(const void* act_in, const void* packed_w, void* act_out, rdv
         if (int rc = make_tmap(&tm_out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, act_out ? act_out : const_cast<void*>(act_in), 4,
                                dims, strides, box_out))
             return rc;
+        tm_res = tm_out;
+        if (p.residual)
+            if (int rc = make_tmap(&tm_res, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, const_cast<__half*>(p.residual), 4, dims,
+                                   strides, box_out))
+                return rc;
     }
     {
         const cuuint64_t dims[3] = {64, static_cast<cuuint64_t>(NOUT), static_cast<cuuint64_t>(Cfg::NTAPS)};
@@ -868,7 +873,7 @@ int launch_mcn_conv(const void* act_in, const void* packed_w, void* act_out, rdv
     long long grid = sm_count();
     const long long n_tiles = static_cast<long long>(p.B) * p.ntx * p.nty;
     if (grid > n_tiles) grid = n_tiles;
-    kern<<<static_cast<unsigned>(grid), rdvc::MCN_THREADS, Cfg::SMEM_LAUNCH, st>>>(tm_in, tm_w, tm_out, p);
+    kern<<<static_cast<unsigned>(grid), rdvc::MCN_THREADS, Cfg::SMEM_LAUNCH, st>>>(tm_in, tm_w, tm_out, tm_res, p);
     ++g_launches;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "mcn_conv_kernel launch");
