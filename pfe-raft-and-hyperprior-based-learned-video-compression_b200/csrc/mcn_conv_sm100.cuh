@@ -28,9 +28,10 @@
 // Persistent, one CTA per SM, warp-specialised like the correlation build:
 //   warp 0  TMA producer: all tap matrices once (stationary, 72 / 120 KB), then the activation
 //           boxes through a ring of 6 (3 for the 5x5 32 -> 32 shape) stages
-//   warp 1  tcgen05.mma issuer: M128 x NOUT x K16, fp16 x fp16 -> fp32 in TMEM, two accumulators
+//   warps 1, 3  tcgen05.mma issuers (even / odd tiles): M128 x NOUT x K16, fp16 x fp16 -> fp32 in TMEM,
+//           one accumulator each
 //   warp 2  TMEM allocator
-//   warps 4-7 epilogue: tcgen05.ld (thread = super-pixel) -> + bias (+ residual, a TMA load of the
+//   warps 4-11 epilogue (lane quarter x tile parity): tcgen05.ld (thread = super-pixel) -> + bias (+ residual, a TMA load of the
 //           warp's 4 KB box into its staging buffer) -> LeakyReLU -> fp16 -> swizzled smem row
 //           -> one TMA store per warp of (64, 16, 2) = 4 KB;
 //           the last layer instead applies sigmoid x warped_ref and writes NCHW fp32.
@@ -50,7 +51,7 @@ constexpr int MCN_TX = 16;       // tile width in super-pixels (32 pixels)
 constexpr int MCN_TY = 8;        // tile height in rows
 constexpr int MCN_ROW_BYTES = MCN_TX * 128;           // 2 KB: one tile row = two 1 KB swizzle atoms
 constexpr int MCN_STG_BYTES = 4096;                  // one epilogue warp's store box (32 rows x 128 B)
-constexpr int MCN_THREADS = 256;
+constexpr int MCN_THREADS = 384;                      // 4 service warps + 8 epilogue warps
 
 // Which 16-column k-steps of a tap's 64-column matrix the MMA warp issues -- a COMPILE-TIME schedule, so the
 // issue loop is straight-line code (two 64-bit adds + one tcgen05.mma per step).  With M128 x N64 x K16 MMAs
@@ -141,10 +142,10 @@ mcn_conv_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
     const uint32_t s_a = ptx::smem_u32(smem + Cfg::SMEM_A);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::SMEM_BAR);
     const uint32_t bar0 = ptx::smem_u32(bars);
-    constexpr int A_FULL = 0, A_EMPTY = 6, W_FULL = 12, T_FULL = 13, T_EMPTY = 15, R_FULL = 17;
+    constexpr int A_FULL = 0, A_EMPTY = 6, W_FULL = 12, T_FULL = 13, T_EMPTY = 15, R_FULL = 17;   // R_FULL: 8
     static_assert(STAGES <= 6, "barrier slots");
     auto bar = [&](int i) { return bar0 + 8u * i; };
-    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(bars + 24);
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(bars + 28);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -164,7 +165,7 @@ mcn_conv_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
             ptx::mbar_init(bar(T_FULL + i), 1);
             ptx::mbar_init(bar(T_EMPTY + i), 4);
         }
-        for (int i = 0; i < 4; ++i) ptx::mbar_init(bar(R_FULL + i), 1);
+        for (int i = 0; i < 8; ++i) ptx::mbar_init(bar(R_FULL + i), 1);
         ptx::fence_mbar_init();
     }
     if (warp == 2) {
@@ -198,19 +199,28 @@ mcn_conv_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
             }
         }
         __syncwarp();
-    } else if (warp == 1) {
+    } else if (warp == 1 || warp == 3) {
+        // Two issuing warps, one per accumulator: warp 1 takes the even tiles of this CTA, warp 3 the odd
+        // ones.  An M128 x N64 x K16 MMA occupies the tensor pipe for ~32 cycles but costs one thread ~65
+        // cycles to issue, so a single issuer left the pipe two-thirds idle (measured).
+        // (With the 3-stage ring of the 5x5 32 -> 32 shape both parities would share every ring slot and a
+        // parity wait could alias across the other warp's phase: that shape keeps one issuer.  With 6 stages
+        // even tiles own slots 0-2 and odd tiles slots 3-5.)
+        constexpr uint32_t ISSUERS = (STAGES == 6) ? 2 : 1;
+        const uint32_t mma_id = warp >> 1;
         // ===================== MMA issuer =====================
         if (lane == 0) {
             const uint32_t idesc = ptx::umma_idesc(128, NOUT, 0);   // fp16 operands, fp32 accumulate
             ptx::mbar_wait(bar(W_FULL), 0);
             ptx::tc_fence_after();
             const uint64_t b_desc0 = ptx::umma_desc_k_sw128(s_w);
-            uint32_t a_it = 0, tile_it = 0;
-            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_it) {
+            for (uint32_t tile_it = mma_id; mma_id < ISSUERS && blockIdx.x + static_cast<long long>(tile_it) * gridDim.x < n_tiles;
+                 tile_it += ISSUERS) {
                 const uint32_t acc = tile_it & 1, acc_ph = (tile_it >> 1) & 1;
                 ptx::mbar_wait(bar(T_EMPTY + acc), acc_ph ^ 1);
                 ptx::tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * NOUT;
+                uint32_t a_it = 3 * tile_it;
 #pragma unroll
                 for (int dsx = 0; dsx < 3; ++dsx, ++a_it) {
                     const uint32_t st = a_it % STAGES, ph = (a_it / STAGES) & 1;
@@ -241,16 +251,21 @@ mcn_conv_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
         __syncwarp();
     } else if (warp >= 4) {
         // ===================== epilogue =====================
-        const int q = warp - 4;                         // TMEM lane quarter = rows 32 q .. 32 q + 31 of the tile
+        // Eight warps: warp 4 + e reads TMEM lane quarter q = e % 4 (rows 32 q .. 32 q + 31 of a tile) and
+        // takes the tiles of parity e / 4, i.e. one accumulator -- two warps per scheduler hide each other's
+        // latencies (with four warps the epilogue was the second bottleneck, ~1500 cycles per tile).
+        const int e = warp - 4;
+        const int q = e & 3;
+        const uint32_t par = e >> 2;
         const int ty = q * 2 + (lane >> 4), tx = lane & 15;
-        const uint32_t stg = ptx::smem_u32(smem + Cfg::SMEM_STG) + q * 2 * MCN_STG_BYTES;
-        uint32_t tile_it = 0;
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_it) {
+        const uint32_t sb = ptx::smem_u32(smem + Cfg::SMEM_STG) + e * MCN_STG_BYTES;   // this warp's staging box
+        for (uint32_t tile_it = par; blockIdx.x + static_cast<long long>(tile_it) * gridDim.x < n_tiles; tile_it += 2) {
+            const int tile = blockIdx.x + tile_it * gridDim.x;
             const int b = tile / tiles_per_img, rem = tile % tiles_per_img;
             const int y0 = (rem / p.ntx) * MCN_TY, x0 = (rem % p.ntx) * MCN_TX;
             const int y = y0 + ty, sp = x0 + tx;
             const bool inside = (y < p.H) && (sp < p.Wsp);
-            const uint32_t acc = tile_it & 1, acc_ph = (tile_it >> 1) & 1;
+            const uint32_t acc = par, acc_ph = (tile_it >> 1) & 1;
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * NOUT;
 
             if constexpr (NOUT == 64) {
@@ -258,12 +273,11 @@ mcn_conv_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
                 // by TMA into the staging buffer before the accumulator is waited for: per-thread 128-byte
                 // global reads here cost 35 us per layer at 1080p.
                 const bool use_res = (p.residual != nullptr);
-                const uint32_t sb = stg + (tile_it & 1) * MCN_STG_BYTES;
                 if (lane == 0) {
-                    ptx::bulk_wait_read<1>();   // this warp's previous-but-one store has finished reading `sb`
+                    ptx::bulk_wait_read<0>();   // this warp's previous store has finished reading `sb`
                     if (use_res) {
-                        ptx::mbar_arrive_expect_tx(bar(R_FULL + q), MCN_STG_BYTES);
-                        ptx::tma_load_4d(sb, &tm_res, bar(R_FULL + q), 0, x0, y0 + 2 * q, b);
+                        ptx::mbar_arrive_expect_tx(bar(R_FULL + e), MCN_STG_BYTES);
+                        ptx::tma_load_4d(sb, &tm_res, bar(R_FULL + e), 0, x0, y0 + 2 * q, b);
                     }
                 }
                 __syncwarp();
@@ -279,7 +293,7 @@ mcn_conv_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
 #pragma unroll
                 for (int i = 0; i < 64; ++i) v[i] += p.bias[i & 31];
                 if (use_res) {
-                    ptx::mbar_wait(bar(R_FULL + q), tile_it & 1);
+                    ptx::mbar_wait(bar(R_FULL + e), (tile_it >> 1) & 1);
 #pragma unroll
                     for (int c = 0; c < 8; ++c) {
                         const uint4 r4 = mcn_lds_16(sb + lane * 128 + ((c ^ (lane & 7)) << 4));
