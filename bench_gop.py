@@ -101,6 +101,24 @@ def run_sharded(args):
     runner = (rc.GraphedRaftFlow(model, 12, amp_dtype=torch.float16 if args.amp else None, volume_dtype=vol)
               if args.graph else None)
 
+    mcn_net = None
+    if args.mcn:     # step 5b of the reference (R:codec_processing.py:1458); seeded weights, non-trivial BatchNorm statistics
+        mcn_net = rc.MotionCompensationNetwork()
+        gm = torch.Generator().manual_seed(1)
+        for m in mcn_net.modules():
+            if isinstance(m, torch.nn.BatchNorm2d):
+                m.running_mean.copy_(torch.randn(m.num_features, generator=gm) * 0.3)
+                m.running_var.copy_(torch.rand(m.num_features, generator=gm) * 1.5 + 0.25)
+        mcn_net = mcn_net.eval().to(dev)
+
+    def predict(warped, flow, prev_codec, cur_codec):
+        """Motion-compensated prediction and the mean |residual| the residual codec would see."""
+        if mcn_net is None:
+            return None
+        with torch.no_grad():
+            pred = mcn_net(warped, flow, prev_codec)
+        return (cur_codec - pred).abs().mean(dim=(1, 2, 3))
+
     def enc_p(prev, cur):
         if runner is not None:
             flow = runner(prev, cur)
@@ -109,10 +127,13 @@ def run_sharded(args):
                 flow = rc.raft_flow(model, prev, cur, 12)
         # steps 3 + 5a of the reference (R:codec_processing.py:1446,1456): flow to frame resolution and the
         # warped previous frame, one fused launch; the MCN / residual / codecs that consume them are out of scope
-        warped, flow = rc.motion_warp(prev[:, :, :fh].contiguous(), flow, (fh, w))
+        prev_codec = prev[:, :, :fh].contiguous()
+        warped, flow = rc.motion_warp(prev_codec, flow, (fh, w))
+        res = predict(warped, flow, prev_codec, cur[:, :, :fh])
         small = F.avg_pool2d(flow.float(), 8)
         q = (small * 4).round().clamp(-127, 127).to(torch.int8).cpu().numpy().tobytes()
-        return fmt.pframe_payload(tuple(small.shape[-2:]), q, (0, 0), b"")
+        rbytes = b"" if res is None else res.cpu().numpy().astype("<f4").tobytes()
+        return fmt.pframe_payload(tuple(small.shape[-2:]), q, (0, 0) if res is None else (1, 1), rbytes)
 
     def get_frame(t):
         """Frame t as the encoder loop sees it: a (RAFT input, codec input) pair of device tensors."""
@@ -129,10 +150,14 @@ def run_sharded(args):
         else:
             with torch.no_grad(), ctx():
                 flow = rc.raft_flow(model, a, b, 12)
-        warped, flow = rc.motion_warp(a[:, :, :fh].contiguous(), flow, (fh, w))
+        a_codec = a[:, :, :fh].contiguous()
+        warped, flow = rc.motion_warp(a_codec, flow, (fh, w))
+        res = predict(warped, flow, a_codec, b[:, :, :fh])
         small = F.avg_pool2d(flow.float(), 8)
         q = (small * 4).round().clamp(-127, 127).to(torch.int8).cpu().numpy()
-        return [fmt.pframe_payload(tuple(small.shape[-2:]), q[i].tobytes(), (0, 0), b"") for i in range(q.shape[0])]
+        rb = None if res is None else res.cpu().numpy().astype("<f4")
+        return [fmt.pframe_payload(tuple(small.shape[-2:]), q[i].tobytes(), (0, 0) if rb is None else (1, 1),
+                                   b"" if rb is None else rb[i].tobytes()) for i in range(q.shape[0])]
 
     def barrier():
         torch.cuda.synchronize()
@@ -176,6 +201,7 @@ def run_sharded(args):
             "config": {"workload": f"{args.frames} synthetic frames {w}x{h}, GOP {args.gop}, 12 RAFT updates, "
                                    "seed-0 random-init raft_large, B200 correlation block, final-only upsampling",
                        "amp_fp16": args.amp, "cuda_graph": args.graph, "batched_gop": args.batch_gop, "volume_dtype": args.volume, "frames_from_host_uint8": args.from_uint8,
+                       "motion_compensation_network": args.mcn,
                        "gops": len(gops), "gops_per_rank_max": max(len(x) for x in gs.assign_gops(gops, world)),
                        "payload": "placeholder (codec networks out of scope)", "collective": "none on the data path; "
                        "host-side gather_object of per-GOP byte strings (gloo)"},
@@ -201,6 +227,9 @@ def main():
     ap.add_argument("--from-uint8", action="store_true",
                     help="config 4: frames start as uint8 HWC host arrays (1080 rows) and go through "
                          "rc.preprocess_frame_raft / _codec, like the reference's loop (R:codec_processing.py:1430-1450)")
+    ap.add_argument("--mcn", action="store_true",
+                    help="also run the motion-compensation network on every P-frame (rc.MotionCompensationNetwork, "
+                         "R:codec_processing.py:1458) with seeded random weights")
     ap.add_argument("--batch-gop", action="store_true",
                     help="run all P-frames of a GOP through RAFT as one batch (the encoder is open loop)")
     args = ap.parse_args()
