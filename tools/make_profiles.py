@@ -22,7 +22,7 @@ WANT = ["Kernel Name", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__
 
 
 def short(name):
-    m = re.search(r"(corr_\w+?)_kernel", name)
+    m = re.search(r"((?:corr|mcn)_\w+?)_kernel", name)
     return m.group(1) if m else re.sub(r"\W+", "_", name)[:30]
 
 
