@@ -169,6 +169,8 @@ int rdvc_preprocess_frame(const unsigned char* frame_hwc, int H, int W, int C, f
  * channels, rows padded to an even pixel count (the padding pixel holds 0).                                      */
 #define RDVC_MCN_ACT_NONE 0
 #define RDVC_MCN_ACT_LEAKY 1 /* LeakyReLU(0.2), R:codec_processing.py:110 */
+#define RDVC_MCN_REVERSE_ORDER 0x100 /* OR into `act`: walk the tiles last-to-first (same result; lets a layer start on
+                                        the part of its input the previous launch wrote last, which is still in L2) */
 size_t rdvc_mcn_plane_bytes(int B, int H, int W);
 size_t rdvc_mcn_workspace_bytes(int B, int H, int W); /* three planes */
 /* HOST function (no GPU needed): conv weight (cout, cin, k, k) fp32, k in {3, 5}, cin <= 32, cout == 32 or <= 8 ->

@@ -29,7 +29,7 @@
 //   warp 0  TMA producer: all tap matrices once (stationary, 72 / 120 KB), then the activation
 //           boxes through a ring of 6 (3 for the 5x5 32 -> 32 shape) stages
 //   warps 1, 3  tcgen05.mma issuers (even / odd tiles): M128 x NOUT x K16, fp16 x fp16 -> fp32 in TMEM,
-//           one accumulator each
+//           two accumulators each
 //   warp 2  TMEM allocator
 //   warps 4-11 epilogue (lane quarter x tile parity): tcgen05.ld (thread = super-pixel) -> + bias (+ residual, a TMA load of the
 //           warp's 4 KB box into its staging buffer) -> LeakyReLU -> fp16 -> swizzled smem row
@@ -94,7 +94,7 @@ struct McnCfg {
     static constexpr int SMEM_BAR = SMEM_STG + 4 * 2 * MCN_STG_BYTES;
     static constexpr int SMEM_TOTAL = SMEM_BAR + 256;
     static constexpr int SMEM_LAUNCH = SMEM_TOTAL + 1024;        // slack for 1024-byte alignment
-    static constexpr int TMEM_COLS = (2 * NOUT < 32) ? 32 : 2 * NOUT;
+    static constexpr int TMEM_COLS = 4 * NOUT;                   // four accumulators: 256 / 64 columns
     static_assert(W_BYTES % 1024 == 0, "tap matrices keep the ring 1024-byte aligned");
     static_assert(SMEM_LAUNCH <= 227 * 1024, "shared memory");
 };
@@ -103,6 +103,7 @@ struct McnConvParams {
     int B, H, W, Wsp;
     int ntx, nty;                 // tiles along x (super-pixels / 16) and y (rows / 8)
     int act;                      // 0 none, 1 LeakyReLU(0.2)
+    int reverse;                  // walk the tiles last-to-first (see rdvc_mcn_forward: L2 reuse between layers)
     int cout;                     // last layer: real output channels (<= 8)
     const __half* residual;       // optional, activation layout; added before the activation
     const float* warped;          // last layer: (B, cout, H, W) fp32 multiplied by the sigmoid
@@ -142,10 +143,10 @@ mcn_conv_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
     const uint32_t s_a = ptx::smem_u32(smem + Cfg::SMEM_A);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::SMEM_BAR);
     const uint32_t bar0 = ptx::smem_u32(bars);
-    constexpr int A_FULL = 0, A_EMPTY = 6, W_FULL = 12, T_FULL = 13, T_EMPTY = 15, R_FULL = 17;   // R_FULL: 8
+    constexpr int A_FULL = 0, A_EMPTY = 6, W_FULL = 12, T_FULL = 13, T_EMPTY = 17, R_FULL = 21;   // 6, 6, 1, 4, 4, 8
     static_assert(STAGES <= 6, "barrier slots");
     auto bar = [&](int i) { return bar0 + 8u * i; };
-    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(bars + 28);
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(bars + 30);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -161,7 +162,7 @@ mcn_conv_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
             ptx::mbar_init(bar(A_EMPTY + i), 1);
         }
         ptx::mbar_init(bar(W_FULL), 1);
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < 4; ++i) {
             ptx::mbar_init(bar(T_FULL + i), 1);
             ptx::mbar_init(bar(T_EMPTY + i), 4);
         }
@@ -188,7 +189,8 @@ mcn_conv_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
                 ptx::tma_load_3d(s_w + t * Cfg::W_TAP_BYTES, &tm_w, bar(W_FULL), 0, 0, t);
             uint32_t a_it = 0;
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-                const int b = tile / tiles_per_img, rem = tile % tiles_per_img;
+                const int tw = p.reverse ? n_tiles - 1 - tile : tile;
+                const int b = tw / tiles_per_img, rem = tw % tiles_per_img;
                 const int y0 = (rem / p.ntx) * MCN_TY, x0 = (rem % p.ntx) * MCN_TX;
                 for (int dsx = -1; dsx <= 1; ++dsx, ++a_it) {
                     const uint32_t st = a_it % STAGES, ph = (a_it / STAGES) & 1;
@@ -200,8 +202,8 @@ mcn_conv_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
         }
         __syncwarp();
     } else if (warp == 1 || warp == 3) {
-        // Two issuing warps, one per accumulator: warp 1 takes the even tiles of this CTA, warp 3 the odd
-        // ones.  An M128 x N64 x K16 MMA occupies the tensor pipe for ~32 cycles but costs one thread ~65
+        // Two issuing warps: warp 1 takes the even tiles of this CTA, warp 3 the odd ones, each with two
+        // TMEM accumulators (four in all), so the next tile's MMAs do not wait for the epilogue of the last.  An M128 x N64 x K16 MMA occupies the tensor pipe for ~32 cycles but costs one thread ~65
         // cycles to issue, so a single issuer left the pipe two-thirds idle (measured).
         // (With the 3-stage ring of the 5x5 32 -> 32 shape both parities would share every ring slot and a
         // parity wait could alias across the other warp's phase: that shape keeps one issuer.  With 6 stages
@@ -216,7 +218,7 @@ mcn_conv_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
             const uint64_t b_desc0 = ptx::umma_desc_k_sw128(s_w);
             for (uint32_t tile_it = mma_id; mma_id < ISSUERS && blockIdx.x + static_cast<long long>(tile_it) * gridDim.x < n_tiles;
                  tile_it += ISSUERS) {
-                const uint32_t acc = tile_it & 1, acc_ph = (tile_it >> 1) & 1;
+                const uint32_t acc = tile_it & 3, acc_ph = (tile_it >> 2) & 1;   // four accumulators, two per issuer
                 ptx::mbar_wait(bar(T_EMPTY + acc), acc_ph ^ 1);
                 ptx::tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * NOUT;
@@ -261,11 +263,12 @@ mcn_conv_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
         const uint32_t sb = ptx::smem_u32(smem + Cfg::SMEM_STG) + e * MCN_STG_BYTES;   // this warp's staging box
         for (uint32_t tile_it = par; blockIdx.x + static_cast<long long>(tile_it) * gridDim.x < n_tiles; tile_it += 2) {
             const int tile = blockIdx.x + tile_it * gridDim.x;
-            const int b = tile / tiles_per_img, rem = tile % tiles_per_img;
+            const int tw = p.reverse ? n_tiles - 1 - tile : tile;
+            const int b = tw / tiles_per_img, rem = tw % tiles_per_img;
             const int y0 = (rem / p.ntx) * MCN_TY, x0 = (rem % p.ntx) * MCN_TX;
             const int y = y0 + ty, sp = x0 + tx;
             const bool inside = (y < p.H) && (sp < p.Wsp);
-            const uint32_t acc = par, acc_ph = (tile_it >> 1) & 1;
+            const uint32_t acc = tile_it & 3, acc_ph = (tile_it >> 2) & 1;
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * NOUT;
 
             if constexpr (NOUT == 64) {

@@ -961,6 +961,8 @@ int rdvc_mcn_conv(const void* act_in, const void* packed_weights, unsigned long 
                   int ksize, int act, const void* residual, void* act_out, int B, int H, int W, void* stream) {
     if (!act_in || !packed_weights || !act_out) return fail(RDVC_E_NULL, "null pointer argument");
     if (ksize != 3 && ksize != 5) return fail(RDVC_E_UNSUPPORTED, "kernel size %d not in {3, 5}", ksize);
+    const int reverse = (act & RDVC_MCN_REVERSE_ORDER) ? 1 : 0;
+    act &= ~RDVC_MCN_REVERSE_ORDER;
     if (act != RDVC_MCN_ACT_NONE && act != RDVC_MCN_ACT_LEAKY) return fail(RDVC_E_UNSUPPORTED, "unknown activation %d", act);
     if (int rc = mcn_check_geometry(B, H, W)) return rc;
     if (act_in == act_out) return fail(RDVC_E_UNSUPPORTED, "a layer cannot run in place (neighbouring tiles read its input)");
@@ -970,6 +972,7 @@ int rdvc_mcn_conv(const void* act_in, const void* packed_weights, unsigned long 
     rdvc::McnConvParams p;
     mcn_fill_params(p, B, H, W, bias, rdvc::MCN_C);
     p.act = act;
+    p.reverse = reverse;
     p.residual = static_cast<const __half*>(residual);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     // the cheapest compile-time MMA schedule that covers the non-zero k-steps of these weights
@@ -1018,15 +1021,20 @@ int rdvc_mcn_forward(const float* warped, const float* flow, const float* ref, i
     void* y = ws + 2 * plane;     // block output
     const int n_layers = 2 + 2 * num_res_blocks;
     if (int rc = rdvc_mcn_pack_input(warped, flow, ref, B, 3, 2, 3, H, W, t, stream)) return rc;
-    if (int rc = rdvc_mcn_conv(t, packed_weights[0], kmasks[0], biases, 5, RDVC_MCN_ACT_LEAKY, nullptr, x, B, H, W, stream))
+    // Successive layers walk the tiles in opposite directions: a plane (133 MB at 1080p) is about the size of
+    // the L2, so the part of it the previous launch wrote LAST is still cached when the next launch starts --
+    // reading it first turns those loads into L2 hits.  The input pack writes first-to-last, so layer 0 runs
+    // last-to-first; the output layer (odd index) runs first-to-last.
+    const int REV = RDVC_MCN_REVERSE_ORDER;
+    if (int rc = rdvc_mcn_conv(t, packed_weights[0], kmasks[0], biases, 5, RDVC_MCN_ACT_LEAKY | REV, nullptr, x, B, H, W, stream))
         return rc;
     for (int r = 0; r < num_res_blocks; ++r) {
         const int l = 1 + 2 * r;
         if (int rc = rdvc_mcn_conv(x, packed_weights[l], kmasks[l], biases + l * 32, 3, RDVC_MCN_ACT_LEAKY, nullptr, t,
-                                   B, H, W, stream))
+                                   B, H, W, stream))                                   // odd layer: first-to-last
             return rc;
-        if (int rc = rdvc_mcn_conv(t, packed_weights[l + 1], kmasks[l + 1], biases + (l + 1) * 32, 3, RDVC_MCN_ACT_LEAKY,
-                                   x, y, B, H, W, stream))
+        if (int rc = rdvc_mcn_conv(t, packed_weights[l + 1], kmasks[l + 1], biases + (l + 1) * 32, 3, RDVC_MCN_ACT_LEAKY | REV,
+                                   x, y, B, H, W, stream))                             // even layer: last-to-first
             return rc;
         void* tmp = x; x = y; y = tmp;
     }

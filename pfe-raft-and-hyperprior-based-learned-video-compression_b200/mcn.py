@@ -22,6 +22,7 @@ from torch import Tensor, nn
 from . import _cabi
 
 ACT_NONE, ACT_LEAKY = 0, 1
+REVERSE_ORDER = 0x100   # RDVC_MCN_REVERSE_ORDER: OR into `act`
 _C = 32   # channels of the activation layout == the only base_channels the kernels cover
 
 

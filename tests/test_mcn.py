@@ -154,6 +154,20 @@ def test_conv_layer_matches_oracle(B, H, W, k, cin, act, with_res):
 
 
 @pytest.mark.gpu
+def test_reverse_tile_order_is_bit_identical():
+    """RDVC_MCN_REVERSE_ORDER only changes the order in which a launch walks its tiles (L2 reuse between layers)."""
+    B, H, W, k = 2, 37, 150, 3
+    x, w, b, res = _layer_case(B, H, W, k, 32, seed=11, act=True, with_res=True)
+    packed, mask = hm.pack_conv_weights(torch.from_numpy(w))
+    plane, rplane = (hm.plane_from_nchw(torch.from_numpy(t).cuda()) for t in (x, res))
+    outs = [hm.conv_layer(plane, packed.cuda(), mask, torch.from_numpy(b), k, hm.ACT_LEAKY | flag, B, H, W, residual=rplane)
+            for flag in (0, hm.REVERSE_ORDER)]
+    torch.cuda.synchronize()
+    n = B * H * ((W + 1) // 2) * 128          # the plane proper (the buffer is rounded up to 1 KB)
+    assert torch.equal(outs[0][:n], outs[1][:n])
+
+
+@pytest.mark.gpu
 def test_pack_input_matches_concat():
     rng = np.random.default_rng(5)
     B, H, W = 2, 11, 27
