@@ -116,6 +116,38 @@ def test_mirror_error_behaviour(golden):
         rc.MotionCompensationNetwork(base_channels=64)
 
 
+def test_cabi_argument_errors_need_no_gpu():
+    """Argument checking happens before any CUDA call: negative RDVC_E_* codes, message in rdvc_corr_last_error."""
+    lib = rc._cabi.load()
+    assert lib.rdvc_mcn_plane_bytes(1, 1080, 1920) == 1080 * 960 * 128
+    assert lib.rdvc_mcn_plane_bytes(2, 5, 7) == 5120            # 2 * 5 * 4 super-pixels * 128 B (a multiple of 1 KB)
+    assert lib.rdvc_mcn_plane_bytes(1, 3, 3) == 1024            # 3 * 2 * 128 = 768, rounded up to 1 KB
+    assert lib.rdvc_mcn_workspace_bytes(1, 1080, 1920) == 3 * 1080 * 960 * 128
+    assert lib.rdvc_mcn_packed_weight_bytes(3, 32) == 9 * 64 * 128 and lib.rdvc_mcn_packed_weight_bytes(5, 3) == 15 * 16 * 128
+    assert lib.rdvc_mcn_packed_weight_bytes(7, 32) == 0 and lib.rdvc_mcn_packed_weight_bytes(3, 33) == 0
+    A, Bp, Cp = 4096, 8192, 12288                                # fake 16-byte-aligned device addresses (never dereferenced)
+    conv = lib.rdvc_mcn_conv
+    assert conv(None, Bp, 0, None, 3, 1, None, Cp, 1, 8, 8, None) == -1                      # RDVC_E_NULL
+    assert conv(A, Bp, 0, None, 4, 1, None, Cp, 1, 8, 8, None) == -5                         # kernel size
+    assert conv(A, Bp, 0, None, 3, 7, None, Cp, 1, 8, 8, None) == -5                         # activation
+    assert conv(A, Bp, 0, None, 3, 1, None, A, 1, 8, 8, None) == -5                          # in place
+    assert "in place" in rc._cabi.last_error()
+    assert conv(A, Bp, 0, None, 3, 1, None, Cp, 0, 8, 8, None) == -2                         # RDVC_E_SHAPE
+    assert conv(A + 4, Bp, 0, None, 3, 1, None, Cp, 1, 8, 8, None) == -7                     # RDVC_E_ALIGN
+    out = lib.rdvc_mcn_conv_out
+    assert out(A, Bp, 0, None, 3, 3, A, Cp, 1, 8, 8, None) == -5                             # the output layer is 5x5
+    assert out(A, Bp, 0, None, 5, 9, A, Cp, 1, 8, 8, None) == -5                             # at most 8 channels
+    fwd = lib.rdvc_mcn_forward
+    import ctypes
+    ptrs = (ctypes.c_void_p * 8)(*([Bp] * 8))
+    masks = (ctypes.c_ulonglong * 8)(*([0] * 8))
+    biases = (ctypes.c_float * 256)()
+    assert fwd(A, A, A, 1, 8, 8, 3, ptrs, masks, biases, Cp, 10, A, None) == -6              # RDVC_E_WORKSPACE
+    assert fwd(A, A, A, 1, 8, 8, -1, ptrs, masks, biases, Cp, 1 << 20, A, None) == -5
+    assert fwd(A, A, None, 1, 8, 8, 3, ptrs, masks, biases, Cp, 1 << 20, A, None) == -1
+    assert lib.rdvc_mcn_pack_input(A, A, A, 1, 3, 3, 3, 8, 8, Cp, None) == -5                # 9 input channels
+
+
 # ------------------------------------------------------------------ GPU
 def _layer_case(B, H, W, k, cin, seed, act, with_res):
     rng = np.random.default_rng(seed)
