@@ -223,7 +223,9 @@ void rdvc_corr_set_profile_events(void* start_event, void* stop_event);
  *   key 7 / 8: experiment: log2 tile width / height of RDVC_LAYOUT_TILED (0 = default)
  *   key 9: build epilogue warps (0 = auto: 8 for an fp32 volume, 4 for bf16; 4; 8)
  *   key 12: build kernel (0 = auto, 1 = one CTA per tile, 2 = CTA pairs / tcgen05 cta_group::2,
- *           opt-in: bit-identical results, measured slower at 1080p)           */
+ *           opt-in: bit-identical results, measured slower at 1080p)
+ *   key 13: experiment: MCN convolutions pull their boxes into L2 this many tiles ahead with TMA prefetches
+ *           (default 0 = off: no effect measured at 1-4, slower beyond)                        */
 int rdvc_corr_set_option(int key, int value);
 
 #ifdef __cplusplus

@@ -41,6 +41,7 @@ std::atomic<int> g_opt_twl{0};
 std::atomic<int> g_opt_thl{0};
 std::atomic<int> g_opt_epi_warps{0};
 std::atomic<int> g_opt_pair{0};
+std::atomic<int> g_opt_mcn_prefetch{0};   // measured: no effect at 1-4 tiles ahead, slower beyond
 
 int fail(int code, const char* fmt, ...) {
     va_list ap;
@@ -341,6 +342,7 @@ int rdvc_corr_set_option(int key, int value) {
     if (key == 8 && value >= 0 && value <= 4) { g_opt_thl = value; return RDVC_OK; }
     if (key == 9 && (value == 0 || value == 4 || value == 8)) { g_opt_epi_warps = value; return RDVC_OK; }
     if (key == 12 && value >= 0 && value <= 2) { g_opt_pair = value; return RDVC_OK; }
+    if (key == 13 && value >= 0 && value <= 16) { g_opt_mcn_prefetch = value; return RDVC_OK; }
     return fail(RDVC_E_UNSUPPORTED, "unknown option key=%d value=%d", key, value);
 }
 
@@ -886,6 +888,7 @@ int mcn_fill_params(rdvc::McnConvParams& p, int B, int H, int W, const float* bi
     p.ntx = (p.Wsp + rdvc::MCN_TX - 1) / rdvc::MCN_TX;
     p.nty = (H + rdvc::MCN_TY - 1) / rdvc::MCN_TY;
     if (bias) for (int i = 0; i < nbias; ++i) p.bias[i] = bias[i];
+    p.prefetch_dist = g_opt_mcn_prefetch.load();
     return RDVC_OK;
 }
 

@@ -58,6 +58,13 @@ def timed(fn, n=10, warm=3):
 
 
 with torch.no_grad():
+    sweep = {}
+    for d in [int(v) for v in os.environ.get("MCN_PF_SWEEP", "").split(",") if v]:
+        rc._cabi.load().rdvc_corr_set_option(13, d)
+        sweep[d] = round(timed(lambda: net(a, f, r), n=20), 3)
+    if sweep:
+        print("prefetch-distance sweep (ms):", sweep, file=sys.stderr)
+        rc._cabi.load().rdvc_corr_set_option(13, 0)
     ours_ms = timed(lambda: net(a, f, r), n=20)
     got = net(a, f, r)
     stock_fp32_ms = timed(lambda: stock(a, f, r))
