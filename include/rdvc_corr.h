@@ -225,7 +225,9 @@ void rdvc_corr_set_profile_events(void* start_event, void* stop_event);
  *   key 12: build kernel (0 = auto, 1 = one CTA per tile, 2 = CTA pairs / tcgen05 cta_group::2,
  *           opt-in: bit-identical results, measured slower at 1080p)
  *   key 13: experiment: MCN convolutions pull their boxes into L2 this many tiles ahead with TMA prefetches
- *           (default 0 = off: no effect measured at 1-4, slower beyond)                        */
+ *           (default 0 = off: no effect measured at 1-4, slower beyond)
+ *   key 14: MCN convolution kernel (0 = auto, 1 = three activation boxes per tile, 2 = one box per tile
+ *           with the x halo handled in the epilogue; same results up to fp32 summation order)     */
 int rdvc_corr_set_option(int key, int value);
 
 #ifdef __cplusplus

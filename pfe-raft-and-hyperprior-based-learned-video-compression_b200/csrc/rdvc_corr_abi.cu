@@ -18,6 +18,7 @@
 #include "corr_lookup.cuh"
 #include "corr_pack.cuh"
 #include "mcn_conv_sm100.cuh"
+#include "mcn_convx_sm100.cuh"
 #include "motion_warp.cuh"
 #include "preprocess.cuh"
 
@@ -41,7 +42,8 @@ std::atomic<int> g_opt_twl{0};
 std::atomic<int> g_opt_thl{0};
 std::atomic<int> g_opt_epi_warps{0};
 std::atomic<int> g_opt_pair{0};
-std::atomic<int> g_opt_mcn_prefetch{0};   // measured: no effect at 1-4 tiles ahead, slower beyond
+std::atomic<int> g_opt_mcn_prefetch{0};
+std::atomic<int> g_opt_mcn_kernel{0};     // 0 = auto, 1 = three boxes per tile, 2 = one box per tile (x halo)   // measured: no effect at 1-4 tiles ahead, slower beyond
 
 int fail(int code, const char* fmt, ...) {
     va_list ap;
@@ -343,6 +345,7 @@ int rdvc_corr_set_option(int key, int value) {
     if (key == 9 && (value == 0 || value == 4 || value == 8)) { g_opt_epi_warps = value; return RDVC_OK; }
     if (key == 12 && value >= 0 && value <= 2) { g_opt_pair = value; return RDVC_OK; }
     if (key == 13 && value >= 0 && value <= 16) { g_opt_mcn_prefetch = value; return RDVC_OK; }
+    if (key == 14 && value >= 0 && value <= 2) { g_opt_mcn_kernel = value; return RDVC_OK; }
     return fail(RDVC_E_UNSUPPORTED, "unknown option key=%d value=%d", key, value);
 }
 
@@ -839,13 +842,17 @@ int mcn_check_geometry(int B, int H, int W) {
     return RDVC_OK;
 }
 
-template <int R, int NOUT, int KPAT>
-int launch_mcn_conv(const void* act_in, const void* packed_w, void* act_out, rdvc::McnConvParams& p, cudaStream_t st) {
+// XH = false: mcn_conv_kernel (three boxes per tile); XH = true: mcn_convx_kernel (one box per tile, 14 output columns)
+template <int R, int NOUT, int KPAT, bool XH>
+int launch_mcn_conv_impl(const void* act_in, const void* packed_w, void* act_out, rdvc::McnConvParams& p, cudaStream_t st) {
     using Cfg = rdvc::McnCfg<R, NOUT>;
-    auto kern = rdvc::mcn_conv_kernel<R, NOUT, KPAT>;
+    constexpr int SMEM = XH ? rdvc::McnXCfg<R, NOUT>::SMEM_LAUNCH : Cfg::SMEM_LAUNCH;
+    auto kern = XH ? rdvc::mcn_convx_kernel<R, NOUT, KPAT> : rdvc::mcn_conv_kernel<R, NOUT, KPAT>;
     static std::atomic<unsigned long long> attr_done{0};
-    if (int rc = ensure_dynamic_smem(kern, Cfg::SMEM_LAUNCH, attr_done, "cudaFuncSetAttribute(mcn_conv, max dynamic smem)"))
+    if (int rc = ensure_dynamic_smem(kern, SMEM, attr_done, "cudaFuncSetAttribute(mcn_conv, max dynamic smem)"))
         return rc;
+    const int out_cols = XH ? rdvc::MCNX_TXO : rdvc::MCN_TX;
+    p.ntx = (p.Wsp + out_cols - 1) / out_cols;
     const cuuint64_t Wsp = static_cast<cuuint64_t>(p.Wsp), H = static_cast<cuuint64_t>(p.H), B = static_cast<cuuint64_t>(p.B);
     CUtensorMap tm_in, tm_w, tm_out, tm_res;
     {
@@ -855,7 +862,7 @@ int launch_mcn_conv(const void* act_in, const void* packed_w, void* act_out, rdv
         if (int rc = make_tmap(&tm_in, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, const_cast<void*>(act_in), 4, dims, strides, box_in))
             return rc;
         // the last layer writes NCHW fp32 itself; its store map is a placeholder on the input tensor
-        const cuuint32_t box_out[4] = {64, rdvc::MCN_TX, 2, 1};
+        const cuuint32_t box_out[4] = {64, static_cast<cuuint32_t>(out_cols), 2, 1};
         if (int rc = make_tmap(&tm_out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, act_out ? act_out : const_cast<void*>(act_in), 4,
                                dims, strides, box_out))
             return rc;
@@ -875,11 +882,21 @@ int launch_mcn_conv(const void* act_in, const void* packed_w, void* act_out, rdv
     long long grid = sm_count();
     const long long n_tiles = static_cast<long long>(p.B) * p.ntx * p.nty;
     if (grid > n_tiles) grid = n_tiles;
-    kern<<<static_cast<unsigned>(grid), rdvc::MCN_THREADS, Cfg::SMEM_LAUNCH, st>>>(tm_in, tm_w, tm_out, tm_res, p);
+    kern<<<static_cast<unsigned>(grid), rdvc::MCN_THREADS, SMEM, st>>>(tm_in, tm_w, tm_out, tm_res, p);
     ++g_launches;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "mcn_conv_kernel launch");
     return RDVC_OK;
+}
+
+template <int R, int NOUT, int KPAT>
+int launch_mcn_conv(const void* act_in, const void* packed_w, void* act_out, rdvc::McnConvParams& p, cudaStream_t st) {
+    // auto (measured at 1080p, us per layer, three boxes / one box): 3x3 68 / 58, first layer 103 / 89 -- but with a
+    // residual 77 / 81 and for the output layer 88 / 98 (the one-box epilogue does more work per tile)
+    const int k = g_opt_mcn_kernel.load();
+    const bool xh = (k == 2) || (k == 0 && NOUT == 64 && p.residual == nullptr);
+    return xh ? launch_mcn_conv_impl<R, NOUT, KPAT, true>(act_in, packed_w, act_out, p, st)
+              : launch_mcn_conv_impl<R, NOUT, KPAT, false>(act_in, packed_w, act_out, p, st);
 }
 
 int mcn_fill_params(rdvc::McnConvParams& p, int B, int H, int W, const float* bias, int nbias) {

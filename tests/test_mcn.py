@@ -149,6 +149,16 @@ def test_cabi_argument_errors_need_no_gpu():
 
 
 # ------------------------------------------------------------------ GPU
+@pytest.fixture(params=["auto", "three_boxes", "x_halo"])
+def mcn_kernel(request):
+    """Both convolution kernels (option key 14): three activation boxes per tile / one box with the x halo, and the
+    default that picks per layer."""
+    lib = rc._cabi.load()
+    assert lib.rdvc_corr_set_option(14, {"auto": 0, "three_boxes": 1, "x_halo": 2}[request.param]) == 0
+    yield request.param
+    lib.rdvc_corr_set_option(14, 0)
+
+
 def _layer_case(B, H, W, k, cin, seed, act, with_res):
     rng = np.random.default_rng(seed)
     x = np.zeros((B, 32, H, W), np.float32)
@@ -169,7 +179,7 @@ def _layer_case(B, H, W, k, cin, seed, act, with_res):
     (1, 5, 7, 3, 32, True, True),        # smaller than a tile
     (1, 70, 330, 3, 32, True, True),     # more tiles than SMs: the persistent loop and both accumulators wrap
 ])
-def test_conv_layer_matches_oracle(B, H, W, k, cin, act, with_res):
+def test_conv_layer_matches_oracle(mcn_kernel, B, H, W, k, cin, act, with_res):
     x, w, b, res = _layer_case(B, H, W, k, cin, seed=H * 1000 + W + k, act=act, with_res=with_res)
     packed, mask = hm.pack_conv_weights(torch.from_numpy(w))
     plane = hm.plane_from_nchw(torch.from_numpy(x).cuda())
@@ -186,7 +196,7 @@ def test_conv_layer_matches_oracle(B, H, W, k, cin, act, with_res):
 
 
 @pytest.mark.gpu
-def test_reverse_tile_order_is_bit_identical():
+def test_reverse_tile_order_is_bit_identical(mcn_kernel):
     """RDVC_MCN_REVERSE_ORDER only changes the order in which a launch walks its tiles (L2 reuse between layers)."""
     B, H, W, k = 2, 37, 150, 3
     x, w, b, res = _layer_case(B, H, W, k, 32, seed=11, act=True, with_res=True)
@@ -214,7 +224,7 @@ def test_pack_input_matches_concat():
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", CASES)
-def test_network_matches_reference_fixture(golden, name):
+def test_network_matches_reference_fixture(mcn_kernel, golden, name):
     z, params = golden
     net = mirror_with_reference_weights(params, "cuda")
     args = [torch.from_numpy(z[f"{name}:{k}"]).cuda() for k in ("warped", "flow", "ref")]
@@ -228,7 +238,7 @@ def test_network_matches_reference_fixture(golden, name):
 
 
 @pytest.mark.gpu
-def test_network_full_size_against_torch_on_the_same_gpu(golden):
+def test_network_full_size_against_torch_on_the_same_gpu(mcn_kernel, golden):
     """1080p: no CPU oracle finishes in seconds, so the comparison is against the same network evaluated by
     PyTorch/cuDNN in fp32 on the GPU (the definition is pinned by the fixture test above)."""
     _, params = golden

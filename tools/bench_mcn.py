@@ -58,6 +58,8 @@ def timed(fn, n=10, warm=3):
 
 
 with torch.no_grad():
+    if os.environ.get("MCN_KERNEL"):
+        assert rc._cabi.load().rdvc_corr_set_option(14, int(os.environ["MCN_KERNEL"])) == 0
     sweep = {}
     for d in [int(v) for v in os.environ.get("MCN_PF_SWEEP", "").split(",") if v]:
         rc._cabi.load().rdvc_corr_set_option(13, d)
@@ -110,7 +112,7 @@ hbm = px * 4 * (8 + 3 + 3) + plane_b * (1 + 2 * 7 + 3)                      # fp
 peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
 hbm_peak = peaks.get("hbm_gbs", 6650.0)
 print(json.dumps({
-    "metric": "motion_compensation_network_1080p_ms", "B": B, "ours_ms": round(ours_ms, 3),
+    "metric": "motion_compensation_network_1080p_ms", "B": B, "kernel_option_14": int(os.environ.get("MCN_KERNEL", 0)), "ours_ms": round(ours_ms, 3),
     "ours_layers_ms": {"pack_input": round(t_pack, 3), "conv5x5_8to32": round(t_first, 3), "conv3x3": round(t_mid, 3),
                        "conv3x3_residual": round(t_mid_res, 3), "conv5x5_32to3_sigmoid_mul": round(t_last, 3)},
     "torch_cudnn_fp32_ms": round(stock_fp32_ms, 3), "torch_cudnn_fp16_autocast_ms": round(stock_amp_ms, 3),
