@@ -119,3 +119,37 @@ def superpixel_gemm_conv(x: np.ndarray, packed: np.ndarray, ksize: int, nout: in
                     acc += a[..., 16 * k:16 * k + 16] @ taps[t][:, 16 * k:16 * k + 16].T
     co = nout // 2
     return acc.reshape(B, H, Wsp, 2, co).transpose(0, 4, 1, 2, 3).reshape(B, co, H, W)
+
+
+def superpixel_gemm_conv_xhalo(x: np.ndarray, packed: np.ndarray, ksize: int, nout: int, kmask: int) -> np.ndarray:
+    """The same convolution evaluated the way the ONE-BOX kernel (csrc/mcn_convx_sm100.cuh) organises it: every tap
+    multiplies the unshifted rows; the column-offset -1 taps accumulate into L (what a super-pixel sends to its right
+    neighbour), the +1 taps into R (to its left neighbour), and the result is C[sp] + L[sp-1] + R[sp+1].  For 3x3 only
+    the q = 0 rows of the L taps and the q = 1 rows of the R taps are used, as in the kernel (N = 32 MMAs)."""
+    B, C, H, W = x.shape
+    assert C == 32 and W % 2 == 0
+    R = ksize // 2
+    Wsp = W // 2
+    sp = x.reshape(B, 32, H, Wsp, 2).transpose(0, 2, 3, 4, 1).reshape(B, H, Wsp, 64).astype(np.float64)
+    pad = np.zeros((B, H + 2 * R, Wsp + 2, 64))                 # one halo column each side, R halo rows
+    pad[:, R:R + H, 1:1 + Wsp] = sp
+    taps = packed.reshape(ksize * 3, nout, 64).astype(np.float64)
+    half = nout // 2
+    acc_c = np.zeros((B, H, Wsp + 2, nout))
+    acc_l = np.zeros((B, H, Wsp + 2, nout))
+    acc_r = np.zeros((B, H, Wsp + 2, nout))
+    for dy in range(-R, R + 1):
+        a = pad[:, R + dy:R + dy + H]                           # unshifted in x, halo columns included
+        for dsx, acc in ((0, acc_c), (-1, acc_l), (1, acc_r)):
+            t = (dy + R) * 3 + dsx + 1
+            rows = slice(0, nout)
+            if R == 1 and dsx == -1:
+                rows = slice(0, half)
+            if R == 1 and dsx == 1:
+                rows = slice(half, nout)
+            for k in range(4):
+                if (kmask >> (4 * t + k)) & 1:
+                    acc[..., rows] += a[..., 16 * k:16 * k + 16] @ taps[t][rows, 16 * k:16 * k + 16].T
+    out = acc_c[:, :, 1:1 + Wsp] + acc_l[:, :, 0:Wsp] + acc_r[:, :, 2:2 + Wsp]
+    co = nout // 2
+    return out.reshape(B, H, Wsp, 2, co).transpose(0, 4, 1, 2, 3).reshape(B, co, H, W)

@@ -70,6 +70,9 @@ def test_packed_weights_reproduce_the_convolution(cout, cin, k):
     got = om.superpixel_gemm_conv(x, packed, k, nout, mask)[:, :cout]
     want = om.conv2d_same(x[:, :cin], w.astype(np.float16).astype(np.float64))
     assert np.abs(got - want).max() <= 1e-9 * max(1.0, np.abs(want).max())
+    # ... and the way the one-box kernel walks them (L / R accumulators shifted on the output side)
+    got_x = om.superpixel_gemm_conv_xhalo(x, packed, k, nout, mask)[:, :cout]
+    assert np.abs(got_x - want).max() <= 1e-9 * max(1.0, np.abs(want).max())
     # k-steps: 16-channel groups beyond cin are skipped, and for 3x3 the outer super-pixel columns need one pixel only
     groups = (cin + 15) // 16
     for t in range(3 * k):
