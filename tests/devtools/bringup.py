@@ -2,8 +2,8 @@
 """GPU bring-up diagnostics (developer tool, not a test): each stage runs in its own
 process under a timeout so one faulting kernel cannot take the rest down.
 
-    python tools/bringup.py all            # on the GPU box
-    python tools/bringup.py lookup|build_small|build_odd|build_ref|perf
+    python tests/devtools/bringup.py all            # on the GPU box
+    python tests/devtools/bringup.py lookup|build_small|build_odd|build_ref|perf
 """
 from __future__ import annotations
 
@@ -12,7 +12,7 @@ import subprocess
 import sys
 import time
 
-ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), "..", ".."))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 

@@ -4,7 +4,7 @@ random weights) with an error breakdown by channel / pixel parity / row, so a la
 import os
 import sys
 
-ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), "..", ".."))
 sys.path.insert(0, ROOT)
 import numpy as np
 import torch

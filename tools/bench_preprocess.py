@@ -8,10 +8,12 @@ sys.path.insert(0, ROOT)
 import numpy as np, torch
 import torchvision.transforms.functional as TF
 import rdvc_corr_b200 as rc
-from oracle import preprocess as pp
 
 dev = torch.device("cuda", 0)
-frame = pp.synth_frame(1080, 1920, 3, seed=1)
+rng = np.random.default_rng(1)      # a deterministic uint8 frame with smooth and noisy content
+yy, xx = np.meshgrid(np.linspace(0, 6.0, 1080), np.linspace(0, 9.0, 1920), indexing="ij")
+frame = np.clip(127.5 + 100.0 * np.sin(yy[..., None] + np.arange(3)) * np.cos(xx[..., None]) + rng.integers(-20, 21, (1080, 1920, 3)),
+                0, 255).astype(np.uint8)
 pinned = torch.from_numpy(frame).pin_memory()
 torch.set_num_threads(os.cpu_count() or 1)
 for size in ((1088, 1920), (368, 640)):

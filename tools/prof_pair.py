@@ -5,7 +5,6 @@ ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
 sys.path.insert(0, ROOT)
 import torch
 import rdvc_corr_b200 as rc
-from oracle import corr_numpy as cn
 
 tile = int(sys.argv[1]) if len(sys.argv) > 1 else 0
 vol = torch.bfloat16 if (len(sys.argv) > 2 and sys.argv[2] == "bf16") else torch.float32
@@ -23,7 +22,8 @@ blk = rc.TVCorrBlock(volume_dtype=vol)
 for _ in range(nb):
     blk.build_pyramid(f1, f2)
 for i in range(3):
-    co = torch.from_numpy(cn.synth_coords(B, h, w, 1.0 + i, seed=i)).cuda()
+    ys, xs = torch.meshgrid(torch.arange(h, device="cuda"), torch.arange(w, device="cuda"), indexing="ij")
+    co = torch.stack([xs, ys]).float()[None] + (1.0 + i) * torch.randn(B, 2, h, w, device="cuda", generator=g)
     blk.index_pyramid(co)
 torch.cuda.synchronize()
 print("done")
