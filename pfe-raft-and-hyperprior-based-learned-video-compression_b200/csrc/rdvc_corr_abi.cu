@@ -837,7 +837,7 @@ namespace {
 int mcn_check_geometry(int B, int H, int W) {
     if (B <= 0 || H <= 0 || W <= 0) return fail(RDVC_E_SHAPE, "non-positive dimension B=%d H=%d W=%d", B, H, W);
     if (H > 65535 || B > 65535) return fail(RDVC_E_UNSUPPORTED, "H and B must be <= 65535 (grid limits)");
-    if (static_cast<long long>(B) * ((H + 7) / 8) * ((W + 31) / 32) >= (1LL << 31))
+    if (static_cast<long long>(B) * ((H + 7) / 8) * (((W + 1) / 2 + rdvc::MCNX_TXO - 1) / rdvc::MCNX_TXO) >= (1LL << 31))
         return fail(RDVC_E_UNSUPPORTED, "too many tiles for 32-bit tile indices");
     return RDVC_OK;
 }
