@@ -36,7 +36,8 @@
 //           -> one TMA store per warp of (64, 16, 2) = 4 KB;
 //           the last layer instead applies sigmoid x warped_ref and writes NCHW fp32.
 // HBM sees each activation once in and once out (266 MB per layer at 1080p); L2 -> SM traffic is
-// 3 x (8 + 2R) / 8 of that.
+// 3 x (8 + 2R) / 8 of that -- measured to be what bounds this kernel.  mcn_convx_sm100.cuh is the variant
+// with ONE box per tile (the x shift moved to the output side); the ABI picks per layer (option key 14).
 #pragma once
 #include <cuda.h>
 #include <cuda_fp16.h>
