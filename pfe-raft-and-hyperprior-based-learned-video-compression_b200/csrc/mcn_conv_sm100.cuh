@@ -228,7 +228,12 @@ mcn_conv_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
         constexpr uint32_t ISSUERS = (STAGES == 6) ? 2 : 1;
         const uint32_t mma_id = warp >> 1;
         // ===================== MMA issuer =====================
-        if (lane == 0) {
+        // The WHOLE warp runs the loops and the barrier waits; only the tcgen05 instructions sit under
+        // elect_one().  With `if (lane == 0)` around everything the compiler keeps the descriptors in per-thread
+        // registers and wraps every MMA in an elect / R2UR.BROADCAST / branch sequence (~9 instructions, ~65
+        // cycles per MMA for a lone thread); in converged code they live in uniform registers and the MMAs of a
+        // box are issued back to back, one instruction each (checked with cuobjdump).
+        {
             const uint32_t idesc = ptx::umma_idesc(128, NOUT, 0);   // fp16 operands, fp32 accumulate
             ptx::mbar_wait(bar(W_FULL), 0);
             ptx::tc_fence_after();
@@ -246,6 +251,7 @@ mcn_conv_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
                     ptx::mbar_wait(bar(A_FULL + st), ph);
                     ptx::tc_fence_after();
                     const uint64_t a_desc0 = ptx::umma_desc_k_sw128(s_a + st * Cfg::A_BYTES);
+                    if (ptx::elect_one()) {
 #pragma unroll
                     for (int dy = 0; dy < 2 * R + 1; ++dy) {
                         // the tap's A operand is the box shifted down by dy rows: 2 KB = two whole swizzle
@@ -263,8 +269,10 @@ mcn_conv_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
                         }
                     }
                     ptx::umma_commit(bar(A_EMPTY + st));   // ring slot free when these MMAs retire
+                    if (dsx == 2) ptx::umma_commit(bar(T_FULL + acc));
+                    }
+                    __syncwarp();
                 }
-                ptx::umma_commit(bar(T_FULL + acc));
             }
         }
         __syncwarp();

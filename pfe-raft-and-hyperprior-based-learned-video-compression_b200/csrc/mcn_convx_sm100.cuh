@@ -118,7 +118,7 @@ mcn_convx_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constan
     } else if (warp == 1 || warp == 3) {
         // ===================== MMA issuers (even / odd tiles) =====================
         const uint32_t mma_id = warp >> 1;
-        if (lane == 0 && mma_id < Cfg::ISSUERS) {
+        if (mma_id < Cfg::ISSUERS) {      // the whole warp runs the loop; only the tcgen05 instructions are elected (see mcn_conv_kernel)
             const uint32_t idesc_c = ptx::umma_idesc(128, NOUT, 0);   // fp16 operands, fp32 accumulate
             const uint32_t idesc_s = ptx::umma_idesc(128, NLR, 0);
             ptx::mbar_wait(bar(W_FULL), 0);
@@ -137,6 +137,7 @@ mcn_convx_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constan
                 const uint64_t a_desc0 = ptx::umma_desc_k_sw128(s_a + st * Cfg::A_BYTES);
                 // rows of a side tap that can be non-zero: 3x3 -> q = 0 (first half) for L, q = 1 (second half) for R
                 constexpr int R_ROW0 = (R == 1) ? NOUT / 2 : 0;
+                if (ptx::elect_one()) {
 #pragma unroll
                 for (int dy = 0; dy < 2 * R + 1; ++dy) {
 #pragma unroll
@@ -162,6 +163,8 @@ mcn_convx_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constan
                 }
                 ptx::umma_commit(bar(A_EMPTY + st));
                 ptx::umma_commit(bar(T_FULL + acc));
+                }
+                __syncwarp();
             }
         }
         __syncwarp();
