@@ -55,7 +55,7 @@
 extern "C" {
 #endif
 
-#define RDVC_CORR_VERSION 102 /* 0.1.2 */
+#define RDVC_CORR_VERSION 103 /* 0.1.3 */
 
 /* element types */
 #define RDVC_DT_BF16 0
@@ -65,6 +65,14 @@ extern "C" {
 /* pyramid layouts (see "Pyramid layout" above) */
 #define RDVC_LAYOUT_ROWMAJOR 0
 #define RDVC_LAYOUT_TILED 1
+
+/* forms of the lookup result (rdvc_corr_lookup_ex) */
+#define RDVC_OUT_NCHW 0   /* (B, L*S*S, h, w): what torchvision's index_pyramid returns                      */
+#define RDVC_OUT_KMAJOR 1 /* [B*h*w][rdvc_corr_feat_pitch] 16-bit rows: the A operand of rdvc_conv1x1        */
+
+/* activations of rdvc_conv1x1 */
+#define RDVC_ACT_NONE 0
+#define RDVC_ACT_RELU 1
 
 /* argument errors (negative); CUDA errors are returned as positive cudaError_t */
 #define RDVC_OK 0
@@ -79,6 +87,10 @@ extern "C" {
 
 int rdvc_corr_version(void);
 const char* rdvc_corr_last_error(void);
+/* "RDVC_SRC_HASH=<sha256 of csrc/ + include/> version=<n> experiments=<0|1>": which sources this binary was built
+ * from (the Python loader refuses a library whose hash differs from the tree's) and whether the experiment knobs
+ * are compiled in (the product build: 0).                                                                       */
+const char* rdvc_corr_build_info(void);
 
 /* ---- sizes ------------------------------------------------------------- */
 /* vol_dtype: RDVC_DT_F32 or RDVC_DT_BF16 (storage type of the pyramid). */
@@ -99,8 +111,7 @@ size_t rdvc_corr_workspace_bytes(int B, int D, int h, int w);
  * Computes  pyr[0][b*N+i][y][x] = sum_c fmap1[b,c,i] * fmap2[b,c,y*w+x] / sqrt(D)
  * with bf16 operands (fp16 operands when in_dtype is F16: nothing of an fp16 input is lost) and fp32
  * accumulation (tcgen05), and pyr[l+1] = 2x2 mean of
- * pyr[l] over (y,x) with the odd trailing row/column dropped.  The fused-epilogue build
- * mode (option key 4 = 1) supports RDVC_LAYOUT_ROWMAJOR only.                       */
+ * pyr[l] over (y,x) with the odd trailing row/column dropped.                        */
 int rdvc_corr_build(const void* fmap1, const void* fmap2, int B, int D, int h, int w,
                     int in_dtype, void* pyramid, int vol_dtype, int layout, int num_levels,
                     void* workspace, size_t workspace_bytes, void* stream);
@@ -114,6 +125,39 @@ int rdvc_corr_build(const void* fmap1, const void* fmap2, int B, int D, int h, i
  * zero outside the level, pixel centres at integers (align_corners=True).     */
 int rdvc_corr_lookup(const void* pyramid, int vol_dtype, int layout, const float* coords, int B,
                      int h, int w, int num_levels, int radius, float* out, void* stream);
+
+/* The same lookup with a choice of result type and form (TILED pyramids; ROWMAJOR supports F32 / NCHW only):
+ *   out_form RDVC_OUT_NCHW,   out_dtype F32 | F16 : (B, L*S*S, h, w); F16 is what the consumer casts the features to
+ *                                                   under the reference's default autocast (R:codec_processing.py:1436)
+ *   out_form RDVC_OUT_KMAJOR, out_dtype BF16 | F16: feature rows [B*h*w][rdvc_corr_feat_pitch(L, r)], 16-byte aligned;
+ *            column l*PL + j*S + i holds torchvision channel l*S*S + i*S + j (PL = S*S rounded up to 8), padding
+ *            columns hold 0 -- the A operand of rdvc_conv1x1.                                                     */
+int rdvc_corr_lookup_ex(const void* pyramid, int vol_dtype, int layout, const float* coords, int B, int h,
+                        int w, int num_levels, int radius, void* out, int out_dtype, int out_form, void* stream);
+/* elements per K-major feature row: num_levels * PL rounded up to 16 (352 for 4 levels x radius 4); 0 if unsupported */
+size_t rdvc_corr_feat_pitch(int num_levels, int radius);
+
+/* ---- next row f-1: lookup fused with MotionEncoder.convcorr1 ------------- *
+ * Replaces index_pyramid (TV:raft.py:394-422) + convcorr1 = Conv2d(L*S*S -> cout, kernel 1) + ReLU (TV:raft.py:185
+ * construction, :202 call): the (B, 324, h, w) fp32 lookup tensor (42 MB per iteration at 1080p) is never written;
+ * the lookup emits 16-bit K-major feature rows (23 MB, L2-resident) and a tcgen05 GEMM with the bias + ReLU epilogue
+ * writes the (B, cout, h, w) tensor convcorr2 reads.  16-bit operands, fp32 accumulation.
+ *
+ * rdvc_conv1x1_pack_weights (HOST, no GPU needed): conv weight (cout, L*S*S) fp32 in torchvision's channel order ->
+ *   [cout][K padded to 64] 16-bit rows in the lookup's column order, zero padded; copy them to the device.
+ *   cout: multiple of 32, <= 256.  feat_dtype: BF16 or F16 (must match the lookup's).
+ * rdvc_conv1x1: out[b, n, y, x] = act(sum_k feat[b*h*w + y*w + x][k] * Wp[n][k] + bias[n]);  bias: cout DEVICE floats
+ *   or NULL; out: (B, cout, h, w) F32 | F16 | BF16.
+ * rdvc_corr_lookup_conv1x1: both steps (2 launches); feat_ws: DEVICE scratch of B*h*w*rdvc_corr_feat_pitch*2 bytes. */
+size_t rdvc_conv1x1_packed_weight_bytes(int cout, int num_levels, int radius);
+int rdvc_conv1x1_pack_weights(const float* weight, int cout, int num_levels, int radius, int feat_dtype,
+                              void* packed_host);
+int rdvc_conv1x1(const void* feat, int feat_dtype, const void* packed_w, const float* bias, int B, int h, int w,
+                 int num_levels, int radius, int cout, int act, void* out, int out_dtype, void* stream);
+int rdvc_corr_lookup_conv1x1(const void* pyramid, int vol_dtype, int layout, const float* coords, int B, int h,
+                             int w, int num_levels, int radius, const void* packed_w, const float* bias, int cout,
+                             int act, int feat_dtype, void* feat_ws, size_t feat_ws_bytes, void* out, int out_dtype,
+                             void* stream);
 
 /* ---- one frame pair from host memory (blocking) ------------------------ *
  * fmap1_host, fmap2_host : host fp32 (B, D, h, w)
@@ -147,6 +191,12 @@ int rdvc_corr_pair_host_submit(const float* fmap1_host, const float* fmap2_host,
                                const float* coords_host, float* out_host, int B, int D, int h,
                                int w, int num_levels, int radius, int iters, int vol_dtype, int slot);
 int rdvc_corr_pair_host_wait(int slot);
+/* _submit with a choice of result type: out_dtype F32, or F16 (out_host then holds __half: half the bytes over PCIe;
+ * the reference's default consumer runs under autocast and casts the features to fp16 anyway).                   */
+int rdvc_corr_pair_host_submit_ex(const float* fmap1_host, const float* fmap2_host,
+                                  const float* coords_host, void* out_host, int B, int D, int h,
+                                  int w, int num_levels, int radius, int iters, int vol_dtype,
+                                  int out_dtype, int slot);
 
 /* ---- next row: frame preparation in front of RAFT / the codec ---------- *
  * Replaces preprocess_frame_raft (R:codec_processing.py:751-761: TF.to_tensor + TF.resize(antialias=True),
@@ -210,20 +260,24 @@ unsigned long long rdvc_corr_launch_count(void);
  * the main build kernel of the next rdvc_corr_build calls on this thread (NULL, NULL = off).
  * Lets a bench time the dominant kernel alone, on the stream it runs on.             */
 void rdvc_corr_set_profile_events(void* start_event, void* stop_event);
-/* Debug/tuning knobs; unknown keys return RDVC_E_UNSUPPORTED.
+/* How many rdvc_corr_build calls of this process found their plan (TMA descriptors + work split) in the cache. */
+unsigned long long rdvc_corr_plan_cache_hits(void);
+/* Tuning knobs; unknown keys return RDVC_E_UNSUPPORTED.  [EXP] = accepted only by a library compiled with
+ * -DRDVC_EXPERIMENTS (lib/librdvc_corr_exp.so, never the product build): knobs that skip work for timing
+ * experiments and the build variants that lost their measurements.
  *   key 0: lookup variant   (0 = auto, 1 = scalar loads, 2 = 128-bit loads,
- *                            3 / 4 = timing only: skip the volume loads / the output stores)
- *   key 1: build tile shape (0 = auto, 1 = 16x16, 2 = 8x32 fmap2 pixels)
+ *                            [EXP] 3 / 4 = timing only: skip the volume loads / the output stores)
+ *   key 1: [EXP] fused-mode build tile shape (0 = auto, 1 = 16x16, 2 = 8x32 fmap2 pixels)
  *   key 2: build m-range slices per fmap2 tile (0 = auto)
- *   key 3: debug: bit mask of pyramid levels the build writes (default 15)
- *   key 4: build mode (0 = auto, 1 = fused pooling epilogue, 2 = pooled-fmap2 rows)
+ *   key 3: [EXP] bit mask of pyramid levels the build writes (default 15)
+ *   key 4: build mode (0 = auto, [EXP] 1 = fused pooling epilogue, 2 = pooled-fmap2 rows)
  *   key 5: linear-mode output path (1 = auto: TMA boxes 16 rows x 256 B where the row pitch allows,
  *          else 32 rows x 128 B, else staged stores; 2 = never the wide boxes; 0 = staged only)
- *   key 6: debug: L2 policy of the TMA stores (0 default, 1 evict_last, 2 evict_first)
+ *   key 6: [EXP] L2 policy of the TMA stores (0 default, 1 evict_last, 2 evict_first)
  *   key 7 / 8: experiment: log2 tile width / height of RDVC_LAYOUT_TILED (0 = default)
  *   key 9: build epilogue warps (0 = auto: 8 for an fp32 volume, 4 for bf16; 4; 8)
- *   key 12: build kernel (0 = auto, 1 = one CTA per tile, 2 = CTA pairs / tcgen05 cta_group::2,
- *           opt-in: bit-identical results, measured slower at 1080p)
+ *   key 12: build kernel (0 = auto, 1 = one CTA per tile, [EXP] 2 = CTA pairs / tcgen05 cta_group::2:
+ *           bit-identical results, measured slower at 1080p)
  *   key 13: experiment: MCN convolutions pull their boxes into L2 this many tiles ahead with TMA prefetches
  *           (default 0 = off: no effect measured at 1-4, slower beyond)
  *   key 14: MCN convolution kernel (0 = auto, 1 = three activation boxes per tile, 2 = one box per tile

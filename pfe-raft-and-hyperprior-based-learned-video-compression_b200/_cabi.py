@@ -12,6 +12,8 @@ from . import _build
 
 RDVC_DT_BF16, RDVC_DT_F32, RDVC_DT_F16 = 0, 1, 2
 RDVC_LAYOUT_ROWMAJOR, RDVC_LAYOUT_TILED = 0, 1
+RDVC_OUT_NCHW, RDVC_OUT_KMAJOR = 0, 1
+RDVC_ACT_NONE, RDVC_ACT_RELU = 0, 1
 
 RDVC_E = {
     -1: "RDVC_E_NULL", -2: "RDVC_E_SHAPE", -3: "RDVC_E_TOO_SMALL", -4: "RDVC_E_DTYPE",
@@ -23,6 +25,7 @@ _c = ctypes
 SYMBOLS = {
     "rdvc_corr_version": (_c.c_int, []),
     "rdvc_corr_last_error": (_c.c_char_p, []),
+    "rdvc_corr_build_info": (_c.c_char_p, []),
     "rdvc_corr_pyramid_bytes": (_c.c_size_t, [_c.c_int] * 6),
     "rdvc_corr_level_offset_bytes": (_c.c_size_t, [_c.c_int] * 6),
     "rdvc_corr_level_image_elems": (_c.c_size_t, [_c.c_int] * 5),
@@ -33,6 +36,19 @@ SYMBOLS = {
                                    _c.c_size_t, _c.c_void_p]),
     "rdvc_corr_lookup": (_c.c_int, [_c.c_void_p, _c.c_int, _c.c_int, _c.c_void_p, _c.c_int, _c.c_int,
                                     _c.c_int, _c.c_int, _c.c_int, _c.c_void_p, _c.c_void_p]),
+    "rdvc_corr_lookup_ex": (_c.c_int, [_c.c_void_p, _c.c_int, _c.c_int, _c.c_void_p, _c.c_int, _c.c_int,
+                                       _c.c_int, _c.c_int, _c.c_int, _c.c_void_p, _c.c_int, _c.c_int, _c.c_void_p]),
+    "rdvc_corr_feat_pitch": (_c.c_size_t, [_c.c_int, _c.c_int]),
+    "rdvc_conv1x1_packed_weight_bytes": (_c.c_size_t, [_c.c_int] * 3),
+    "rdvc_conv1x1_pack_weights": (_c.c_int, [_c.c_void_p, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_void_p]),
+    "rdvc_conv1x1": (_c.c_int, [_c.c_void_p, _c.c_int, _c.c_void_p, _c.c_void_p] + [_c.c_int] * 7 +
+                     [_c.c_void_p, _c.c_int, _c.c_void_p]),
+    "rdvc_corr_lookup_conv1x1": (_c.c_int, [_c.c_void_p, _c.c_int, _c.c_int, _c.c_void_p] + [_c.c_int] * 5 +
+                                 [_c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int, _c.c_int, _c.c_void_p, _c.c_size_t,
+                                  _c.c_void_p, _c.c_int, _c.c_void_p]),
+    "rdvc_corr_pair_host_submit_ex": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p] +
+                                      [_c.c_int] * 10),
+    "rdvc_corr_plan_cache_hits": (_c.c_ulonglong, []),
     "rdvc_corr_pair_host": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p] +
                             [_c.c_int] * 8),
     "rdvc_motion_warp": (_c.c_int, [_c.c_void_p, _c.c_void_p] + [_c.c_int] * 6 + [_c.c_void_p, _c.c_void_p, _c.c_void_p]),
@@ -79,6 +95,14 @@ def load():
             "`python -c 'import __graft_entry__ as g; g.build()'` (needs nvcc). "
             "There is no CPU or PyTorch fallback for this path."
         )
+    # the library must have been built from exactly the sources in this tree (content hash compiled into it):
+    # a stale binary that happens to sit next to newer sources is an error, not something to run
+    built_from, tree = _build.embedded_hash(path), _build.source_hash()
+    if built_from != tree and not os.environ.get("RDVC_CORR_ALLOW_STALE"):
+        raise RuntimeError(
+            f"{path} was built from other sources (library {str(built_from)[:12]}, tree {tree[:12]}): rebuild with "
+            "`python -c 'import __graft_entry__ as g; g.build()'`."
+        )
     L = ctypes.CDLL(path)
     for name, (res, args) in SYMBOLS.items():
         fn = getattr(L, name)  # AttributeError if the .so does not export it
@@ -86,6 +110,11 @@ def load():
         fn.argtypes = args
     _lib = L
     return L
+
+
+def has_experiments() -> bool:
+    """True if the loaded library was compiled with -DRDVC_EXPERIMENTS (never the product build)."""
+    return b"experiments=1" in load().rdvc_corr_build_info()
 
 
 def last_error() -> str:

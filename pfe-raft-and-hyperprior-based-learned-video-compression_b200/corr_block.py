@@ -164,10 +164,7 @@ def build_pyramid(fmap1: Tensor, fmap2: Tensor, num_levels: int = 4,
     return pyr
 
 
-def index_pyramid(pyr: CorrPyramid, coords: Tensor, radius: int = 4,
-                  out: Optional[Tensor] = None) -> Tensor:
-    """(B, 2, h, w) coords -> (B, L*(2r+1)^2, h, w) fp32 through ``rdvc_corr_lookup``."""
-    lib = _cabi.load()
+def _check_coords(pyr: CorrPyramid, coords: Tensor) -> Tensor:
     if coords.dim() != 4 or coords.shape[1] != 2:
         raise ValueError(f"coords should be (B, 2, h, w), got {tuple(coords.shape)}")
     B, _, h, w = coords.shape
@@ -177,18 +174,113 @@ def index_pyramid(pyr: CorrPyramid, coords: Tensor, radius: int = 4,
         )
     if not coords.is_cuda:
         raise RuntimeError("rdvc_corr_b200 runs on an sm_100 GPU only; got CPU coords.")
+    return coords.detach().to(torch.float32).contiguous()
+
+
+def index_pyramid(pyr: CorrPyramid, coords: Tensor, radius: int = 4,
+                  out: Optional[Tensor] = None, out_dtype: torch.dtype = torch.float32) -> Tensor:
+    """(B, 2, h, w) coords -> (B, L*(2r+1)^2, h, w) through ``rdvc_corr_lookup_ex``: fp32 like torchvision's
+    ``index_pyramid``, or fp16 (``out_dtype=torch.float16``: what the consumer casts the features to under the
+    reference's default autocast, R:codec_processing.py:1436; tiled pyramids only)."""
+    lib = _cabi.load()
+    c = _check_coords(pyr, coords)
+    B, _, h, w = coords.shape
     dev = coords.device
-    c = coords.detach().to(torch.float32).contiguous()
+    if out_dtype not in (torch.float32, torch.float16):
+        raise ValueError(f"out_dtype must be float32 or float16, got {out_dtype}")
     S = 2 * radius + 1
     C = pyr.num_levels * S * S
     if out is None:
-        out = torch.empty((B, C, h, w), dtype=torch.float32, device=dev)
-    elif tuple(out.shape) != (B, C, h, w) or out.dtype != torch.float32 or not out.is_contiguous():
-        raise ValueError("out must be a contiguous fp32 tensor of shape (B, L*(2r+1)^2, h, w)")
+        out = torch.empty((B, C, h, w), dtype=out_dtype, device=dev)
+    elif tuple(out.shape) != (B, C, h, w) or out.dtype != out_dtype or not out.is_contiguous():
+        raise ValueError(f"out must be a contiguous {out_dtype} tensor of shape (B, L*(2r+1)^2, h, w)")
     with torch.cuda.device(dev):
-        rc = lib.rdvc_corr_lookup(pyr.buffer.data_ptr(), _VOL_DTYPES[pyr.volume_dtype], pyr.layout, c.data_ptr(),
-                                  B, h, w, pyr.num_levels, radius, out.data_ptr(), _stream_ptr(dev))
-    _cabi.check(rc, "rdvc_corr_lookup")
+        rc = lib.rdvc_corr_lookup_ex(pyr.buffer.data_ptr(), _VOL_DTYPES[pyr.volume_dtype], pyr.layout, c.data_ptr(),
+                                     B, h, w, pyr.num_levels, radius, out.data_ptr(), _IN_DTYPES[out_dtype],
+                                     _cabi.RDVC_OUT_NCHW, _stream_ptr(dev))
+    _cabi.check(rc, "rdvc_corr_lookup_ex")
+    return out
+
+
+_FEAT_DTYPES = {torch.bfloat16: _cabi.RDVC_DT_BF16, torch.float16: _cabi.RDVC_DT_F16}
+
+
+def feat_pitch(num_levels: int = 4, radius: int = 4) -> int:
+    """Elements per K-major feature row (include/rdvc_corr.h: rdvc_corr_feat_pitch)."""
+    return int(_cabi.load().rdvc_corr_feat_pitch(num_levels, radius))
+
+
+def index_pyramid_kmajor(pyr: CorrPyramid, coords: Tensor, radius: int = 4, feat_dtype: torch.dtype = torch.bfloat16,
+                         out: Optional[Tensor] = None) -> Tensor:
+    """The lookup as K-major 16-bit feature rows (B*h*w, feat_pitch): column l*PL + j*S + i holds torchvision
+    channel l*S*S + i*S + j (PL = S*S rounded up to 8), padding columns hold 0 -- the A operand of the 1x1
+    convolution (``conv1x1``)."""
+    lib = _cabi.load()
+    c = _check_coords(pyr, coords)
+    B, _, h, w = coords.shape
+    dev = coords.device
+    kp = feat_pitch(pyr.num_levels, radius)
+    if kp == 0 or feat_dtype not in _FEAT_DTYPES:
+        raise ValueError(f"unsupported (levels, radius, feat_dtype) = ({pyr.num_levels}, {radius}, {feat_dtype})")
+    if out is None:
+        out = torch.empty((B * h * w, kp), dtype=feat_dtype, device=dev)
+    elif tuple(out.shape) != (B * h * w, kp) or out.dtype != feat_dtype or not out.is_contiguous():
+        raise ValueError(f"out must be a contiguous {feat_dtype} tensor of shape (B*h*w, {kp})")
+    with torch.cuda.device(dev):
+        rc = lib.rdvc_corr_lookup_ex(pyr.buffer.data_ptr(), _VOL_DTYPES[pyr.volume_dtype], pyr.layout, c.data_ptr(),
+                                     B, h, w, pyr.num_levels, radius, out.data_ptr(), _FEAT_DTYPES[feat_dtype],
+                                     _cabi.RDVC_OUT_KMAJOR, _stream_ptr(dev))
+    _cabi.check(rc, "rdvc_corr_lookup_ex")
+    return out
+
+
+class PackedConv1x1:
+    """A 1x1 convolution's weight (cout, L*S*S[, 1, 1]) packed for ``rdvc_conv1x1`` (host function
+    ``rdvc_conv1x1_pack_weights``: permuted to the lookup's column order, zero padded, 16-bit) + its bias, on the
+    device.  Built once per (module, feat_dtype); rebuilt if the parameters change version or device."""
+
+    def __init__(self, weight: Tensor, bias: Optional[Tensor], num_levels: int, radius: int, feat_dtype: torch.dtype,
+                 device):
+        import ctypes
+        import numpy as np
+        lib = _cabi.load()
+        cout = weight.shape[0]
+        w2 = weight.detach().to(torch.float32).reshape(cout, -1).cpu().contiguous().numpy()
+        S = 2 * radius + 1
+        if w2.shape[1] != num_levels * S * S:
+            raise ValueError(f"weight has {w2.shape[1]} input channels, the lookup produces {num_levels * S * S}")
+        nbytes = lib.rdvc_conv1x1_packed_weight_bytes(cout, num_levels, radius)
+        if nbytes == 0:
+            raise ValueError(f"unsupported 1x1 convolution: cout={cout} (multiple of 32, <= 256), levels={num_levels}, radius={radius}")
+        packed = np.zeros(nbytes // 2, np.uint16)
+        _cabi.check(lib.rdvc_conv1x1_pack_weights(w2.ctypes.data_as(ctypes.c_void_p), cout, num_levels, radius,
+                                                  _FEAT_DTYPES[feat_dtype], packed.ctypes.data_as(ctypes.c_void_p)),
+                    "rdvc_conv1x1_pack_weights")
+        self.cout = cout
+        self.feat_dtype = feat_dtype
+        self.weight = torch.from_numpy(packed.view(np.int16)).to(device)       # raw 16-bit patterns
+        self.bias = None if bias is None else bias.detach().to(torch.float32).to(device).contiguous()
+        self.key = _param_key(weight, bias, feat_dtype, device)
+
+
+def _param_key(weight, bias, feat_dtype, device):
+    return (weight.data_ptr(), weight._version, None if bias is None else (bias.data_ptr(), bias._version),
+            feat_dtype, torch.device(device))
+
+
+def conv1x1(feat: Tensor, packed: PackedConv1x1, B: int, h: int, w: int, num_levels: int = 4, radius: int = 4,
+            relu: bool = True, out_dtype: torch.dtype = torch.float32, out: Optional[Tensor] = None) -> Tensor:
+    """(B*h*w, feat_pitch) K-major feature rows -> (B, cout, h, w) = act(W . feat + bias) through ``rdvc_conv1x1``."""
+    lib = _cabi.load()
+    dev = feat.device
+    if out is None:
+        out = torch.empty((B, packed.cout, h, w), dtype=out_dtype, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib.rdvc_conv1x1(feat.data_ptr(), _FEAT_DTYPES[feat.dtype], packed.weight.data_ptr(),
+                              0 if packed.bias is None else packed.bias.data_ptr(), B, h, w, num_levels, radius,
+                              packed.cout, _cabi.RDVC_ACT_RELU if relu else _cabi.RDVC_ACT_NONE, out.data_ptr(),
+                              _IN_DTYPES[out.dtype], _stream_ptr(dev))
+    _cabi.check(rc, "rdvc_conv1x1")
     return out
 
 
@@ -210,6 +302,8 @@ class TVCorrBlock(nn.Module):
         self._pyr: Optional[CorrPyramid] = None
         self._workspace: Optional[Tensor] = None
         self._levels: Optional[List[Tensor]] = None
+        self._packed: Optional[PackedConv1x1] = None     # convcorr1 weights packed for rdvc_conv1x1
+        self._feat: Optional[Tensor] = None              # K-major feature rows between the two launches
 
     @property
     def corr_pyramid(self) -> List[Tensor]:
@@ -239,11 +333,48 @@ class TVCorrBlock(nn.Module):
             )
         return corr_features
 
+    def index_pyramid_convcorr1(self, centroids_coords: Tensor, weight: Tensor, bias: Optional[Tensor] = None,
+                                relu: bool = True, out_dtype: Optional[torch.dtype] = None,
+                                feat_dtype: Optional[torch.dtype] = None) -> Tensor:
+        """``relu(conv1x1(index_pyramid(coords), weight, bias))`` -- the lookup fused with
+        ``MotionEncoder.convcorr1`` (TV:raft.py:185,202) through ``rdvc_corr_lookup_conv1x1``: the (B, 324, h, w)
+        fp32 lookup tensor is never written.  ``weight``: (cout, L*S*S[, 1, 1]) in torchvision's channel order.
+        16-bit operands (bf16; fp16 under fp16 autocast, where the stock convolution runs in fp16 too), fp32
+        accumulation; the result is fp32, or the autocast dtype when autocast is on."""
+        if self._pyr is None:
+            raise RuntimeError("index_pyramid_convcorr1 called before build_pyramid")
+        pyr = self._pyr
+        c = _check_coords(pyr, centroids_coords)
+        B, _, h, w = centroids_coords.shape
+        dev = centroids_coords.device
+        amp = torch.is_autocast_enabled("cuda")
+        if out_dtype is None:
+            out_dtype = torch.get_autocast_dtype("cuda") if amp else torch.float32
+        if feat_dtype is None:
+            feat_dtype = torch.float16 if (amp and torch.get_autocast_dtype("cuda") == torch.float16) else torch.bfloat16
+        key = _param_key(weight, bias, feat_dtype, dev)
+        if self._packed is None or self._packed.key != key:
+            self._packed = PackedConv1x1(weight, bias, self.num_levels, self.radius, feat_dtype, dev)
+        kp = feat_pitch(self.num_levels, self.radius)
+        if self._feat is None or self._feat.shape != (B * h * w, kp) or self._feat.dtype != feat_dtype or self._feat.device != dev:
+            self._feat = torch.empty((B * h * w, kp), dtype=feat_dtype, device=dev)
+        out = torch.empty((B, self._packed.cout, h, w), dtype=out_dtype, device=dev)
+        lib = _cabi.load()
+        with torch.cuda.device(dev):
+            rc = lib.rdvc_corr_lookup_conv1x1(
+                pyr.buffer.data_ptr(), _VOL_DTYPES[pyr.volume_dtype], pyr.layout, c.data_ptr(), B, h, w, self.num_levels,
+                self.radius, self._packed.weight.data_ptr(), 0 if self._packed.bias is None else self._packed.bias.data_ptr(),
+                self._packed.cout, _cabi.RDVC_ACT_RELU if relu else _cabi.RDVC_ACT_NONE, _FEAT_DTYPES[feat_dtype],
+                self._feat.data_ptr(), self._feat.numel() * 2, out.data_ptr(), _IN_DTYPES[out_dtype], _stream_ptr(dev))
+        _cabi.check(rc, "rdvc_corr_lookup_conv1x1")
+        return out
+
     def release(self) -> None:
         """Drop the pyramid (5.7 GB at 1080p fp32) back to torch's allocator."""
         self._pyr = None
         self._workspace = None
         self._levels = None
+        self._feat = None
 
 
 class CorrBlock:

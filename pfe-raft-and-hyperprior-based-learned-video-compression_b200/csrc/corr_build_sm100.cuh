@@ -93,8 +93,8 @@ struct BuildParams {
     int msplit;         // m-range slices per fmap2 tile (work item = tile x slice)
     float scale;        // 1 / sqrt(D)
     int ab_format;      // tcgen05 kind::f16 operand format: 1 = bf16, 0 = fp16
-    int dbg_store_mask; // debug: bit l set = write level l (default 15)
-    int dbg_policy;     // debug: TMA-store L2 policy (0 default, 1 evict_last, 2 evict_first)
+    int dbg_store_mask; // RDVC_EXPERIMENTS builds only: bit l set = write level l (default 15)
+    int dbg_policy;     // RDVC_EXPERIMENTS builds only: TMA-store L2 policy (0 default, 1 evict_last, 2 evict_first)
     int tma_out;        // MODE_LINEAR: 2 bits per level: how level l is written --
                         //   0 staged st.global, 1 = TMA boxes 32 rows x 128 B (3-D map {n_l, N, B}),
                         //   2 = TMA boxes 16 rows x 256 B (4-D map {128 B, n_l*es/128, N, B})
@@ -283,7 +283,9 @@ corr_build_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
 
     if (warp == 0) {
         // ===================== TMA producer =====================
-        if (lane == 0) {
+        // The whole warp runs the loops and the barrier waits (converged: tensor-map pointers, coordinates and
+        // barrier addresses stay in uniform registers); only the arrive / TMA instructions sit under elect_one().
+        {
             uint32_t a_it = 0, b_it = 0;
             for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
                 const int u = item % units, sl = item / units;
@@ -293,33 +295,45 @@ corr_build_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
                 if (mb0 == mb1) continue;
                 // new stationary fmap2 tile: wait until the MMAs reading the old one retired
                 ptx::mbar_wait(bar(B_EMPTY), (b_it & 1) ^ 1);
-                ptx::mbar_arrive_expect_tx(bar(B_FULL), kc_n * BLD_B_SLAB_BYTES);
                 if constexpr (MODE == MODE_FUSED) {
                     const int y0 = (nt / p.ntx) * TILE_Y, x0 = (nt % p.ntx) * TILE_X;
-                    for (int kc = 0; kc < kc_n; ++kc)
-                        ptx::tma_load_4d(s_b + kc * BLD_B_SLAB_BYTES, &tm_b0, bar(B_FULL),
-                                         kc * BLD_BLOCK_K, x0, y0, b);
+                    if (ptx::elect_one()) {
+                        ptx::mbar_arrive_expect_tx(bar(B_FULL), kc_n * BLD_B_SLAB_BYTES);
+                        for (int kc = 0; kc < kc_n; ++kc)
+                            ptx::tma_load_4d(s_b + kc * BLD_B_SLAB_BYTES, &tm_b0, bar(B_FULL),
+                                             kc * BLD_BLOCK_K, x0, y0, b);
+                    }
                 } else {
                     int l = 0;
                     while (l + 1 < p.num_levels && nt >= p.tile_start[l + 1]) ++l;
                     const CUtensorMap* tm = (l == 0) ? &tm_b0 : (l == 1) ? &tm_b1 : (l == 2) ? &tm_b2 : &tm_b3;
                     const int c0 = (nt - p.tile_start[l]) * BLD_BLOCK_N;
-                    for (int kc = 0; kc < kc_n; ++kc)
-                        ptx::tma_load_3d(s_b + kc * BLD_B_SLAB_BYTES, tm, bar(B_FULL),
-                                         kc * BLD_BLOCK_K, c0, b);
+                    if (ptx::elect_one()) {
+                        ptx::mbar_arrive_expect_tx(bar(B_FULL), kc_n * BLD_B_SLAB_BYTES);
+                        for (int kc = 0; kc < kc_n; ++kc)
+                            ptx::tma_load_3d(s_b + kc * BLD_B_SLAB_BYTES, tm, bar(B_FULL),
+                                             kc * BLD_BLOCK_K, c0, b);
+                    }
                 }
+                __syncwarp();
                 ++b_it;
                 for (int mb = mb0; mb < mb1; ++mb) {
                     for (int kc = 0; kc < kc_n; ++kc, ++a_it) {
                         const uint32_t st = a_it % BLD_A_STAGES, ph = (a_it / BLD_A_STAGES) & 1;
                         ptx::mbar_wait(bar(A_EMPTY + st), ph ^ 1);
-                        if ((p.dbg_store_mask & 16) && a_it >= BLD_A_STAGES) {  // debug: no A traffic
-                            ptx::mbar_arrive(bar(A_FULL + st));
-                            continue;
+                        if (ptx::elect_one()) {
+#ifdef RDVC_EXPERIMENTS
+                            if ((p.dbg_store_mask & 16) && a_it >= BLD_A_STAGES) {  // debug: no A traffic
+                                ptx::mbar_arrive(bar(A_FULL + st));
+                            } else
+#endif
+                            {
+                                ptx::mbar_arrive_expect_tx(bar(A_FULL + st), BLD_A_STAGE_BYTES);
+                                ptx::tma_load_3d(s_a + st * BLD_A_STAGE_BYTES, &tm_a, bar(A_FULL + st),
+                                                 kc * BLD_BLOCK_K, mb * BLD_BLOCK_M, b);
+                            }
                         }
-                        ptx::mbar_arrive_expect_tx(bar(A_FULL + st), BLD_A_STAGE_BYTES);
-                        ptx::tma_load_3d(s_a + st * BLD_A_STAGE_BYTES, &tm_a, bar(A_FULL + st),
-                                         kc * BLD_BLOCK_K, mb * BLD_BLOCK_M, b);
+                        __syncwarp();
                     }
                 }
             }
@@ -327,7 +341,12 @@ corr_build_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
         __syncwarp();
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
+        // Converged warp, tcgen05 instructions under elect_one() (the form the MCN kernels use): with
+        // `if (lane == 0)` around the loops every tcgen05.mma sat in an elect / R2UR.BROADCAST / branch wrapper
+        // of ~9 instructions; here the descriptors live in uniform registers and the four MMAs of a k-block
+        // are issued back to back.  Every commit is issued inside the SAME elect block as the MMAs it covers
+        // (tcgen05.commit tracks the executing thread's operations).
+        {
             const uint32_t idesc = ptx::umma_idesc(BLD_BLOCK_M, BLD_BLOCK_N, p.ab_format);   // 1 = bf16, 0 = fp16 operands
             uint32_t a_it = 0, b_it = 0, tile_it = 0;
             for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
@@ -346,19 +365,23 @@ corr_build_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
                         const uint32_t st = a_it % BLD_A_STAGES, ph = (a_it / BLD_A_STAGES) & 1;
                         ptx::mbar_wait(bar(A_FULL + st), ph);
                         ptx::tc_fence_after();
-                        const uint32_t a_addr = s_a + st * BLD_A_STAGE_BYTES;
-                        const uint32_t b_addr = s_b + kc * BLD_B_SLAB_BYTES;
+                        const uint64_t a_desc0 = ptx::umma_desc_k_sw128(s_a + st * BLD_A_STAGE_BYTES);
+                        const uint64_t b_desc0 = ptx::umma_desc_k_sw128(s_b + kc * BLD_B_SLAB_BYTES);
+                        if (ptx::elect_one()) {
 #pragma unroll
-                        for (int k = 0; k < BLD_BLOCK_K / BLD_UMMA_K; ++k) {
-                            ptx::umma_bf16(d_tmem, ptx::umma_desc_k_sw128(a_addr + k * BLD_UMMA_K * 2),
-                                           ptx::umma_desc_k_sw128(b_addr + k * BLD_UMMA_K * 2), idesc,
-                                           (kc | k) != 0 ? 1u : 0u);
+                            for (int k = 0; k < BLD_BLOCK_K / BLD_UMMA_K; ++k)
+                                ptx::umma_bf16(d_tmem, a_desc0 + ((k * BLD_UMMA_K * 2) >> 4),
+                                               b_desc0 + ((k * BLD_UMMA_K * 2) >> 4), idesc, (kc | k) != 0 ? 1u : 0u);
+                            ptx::umma_commit(bar(A_EMPTY + st));  // frees the ring slot when the MMAs retire
+                            if (kc == kc_n - 1) {
+                                ptx::umma_commit(bar(T_FULL + acc));      // accumulator ready for the epilogue
+                                // every MMA that reads this fmap2 tile has been issued
+                                if (mb == mb1 - 1) ptx::umma_commit(bar(B_EMPTY));
+                            }
                         }
-                        ptx::umma_commit(bar(A_EMPTY + st));  // frees the ring slot when the MMAs retire
+                        __syncwarp();
                     }
-                    ptx::umma_commit(bar(T_FULL + acc));      // accumulator ready for the epilogue
                 }
-                ptx::umma_commit(bar(B_EMPTY));  // every MMA that reads this fmap2 tile has been issued
             }
         }
         __syncwarp();
@@ -372,7 +395,13 @@ corr_build_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
         uint32_t box_it = 0;  // TMA boxes issued by this warp (selects the staging buffer)
         const float scale = p.scale;
         const int L = p.num_levels;
-        const int smask = p.dbg_store_mask;
+#ifdef RDVC_EXPERIMENTS
+        const int smask = p.dbg_store_mask;     // experiments only: levels to write, bit 5 = skip the TMEM reads
+        const int dbg_policy = p.dbg_policy;
+#else
+        constexpr int smask = 15;
+        constexpr int dbg_policy = 0;
+#endif
         uint32_t tile_it = 0;
 
         if constexpr (MODE == MODE_LINEAR) {
@@ -475,9 +504,9 @@ corr_build_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
                                 ptx::fence_proxy_async_smem();
                                 __syncwarp();
                                 if (lane == 0) {
-                                    if (p.dbg_policy == 0) ptx::tma_store_4d(tmo, sb, 0, (col0 + g * GC) / EPB, m0 + 16 * hh, b);
+                                    if (dbg_policy == 0) ptx::tma_store_4d(tmo, sb, 0, (col0 + g * GC) / EPB, m0 + 16 * hh, b);
                                     else ptx::tma_store_4d_hint(tmo, sb, 0, (col0 + g * GC) / EPB, m0 + 16 * hh, b,
-                                                                p.dbg_policy == 1 ? ptx::policy_evict_last()
+                                                                dbg_policy == 1 ? ptx::policy_evict_last()
                                                                                   : ptx::policy_evict_first());
                                     ptx::bulk_commit();
                                 }
@@ -521,9 +550,9 @@ corr_build_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
                                 ptx::fence_proxy_async_smem();
                                 __syncwarp();
                                 if (lane == 0) {
-                                    if (p.dbg_policy == 0) ptx::tma_store_3d(tmo, sb, col0 + j * CW, m0, b);
+                                    if (dbg_policy == 0) ptx::tma_store_3d(tmo, sb, col0 + j * CW, m0, b);
                                     else ptx::tma_store_3d_hint(tmo, sb, col0 + j * CW, m0, b,
-                                                                p.dbg_policy == 1 ? ptx::policy_evict_last()
+                                                                dbg_policy == 1 ? ptx::policy_evict_last()
                                                                                   : ptx::policy_evict_first());
                                     ptx::bulk_commit();
                                 }

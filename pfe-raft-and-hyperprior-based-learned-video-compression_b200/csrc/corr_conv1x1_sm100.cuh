@@ -1,0 +1,239 @@
+// corr_conv1x1_sm100.cuh -- "next" row f-1: the 1x1 convolution + bias + ReLU that consumes the correlation
+// features (MotionEncoder.convcorr1, TV:raft.py:185 construction, :202 call), as a tcgen05 GEMM over the K-major
+// feature rows the lookup kernel emits (corr_lookup.cuh, LKP_OUT_KM_*):
+//
+//   out[b, n, y, x] = act( sum_k feat[b*N + y*w + x][k] * Wp[n][k] + bias[n] ),   n < cout <= 256
+//
+// feat: [B*N][kp] bf16 / fp16 (kp = rdvc_corr_feat_pitch, 352 for 4 levels x radius 4), Wp: the convolution's
+// weight permuted to the lookup's column order and zero-padded (rdvc_conv1x1_pack_weights), fp32 accumulation
+// in TMEM, bias + ReLU in the epilogue, result written ONCE as the (B, cout, h, w) tensor convcorr2 reads --
+// the (B, 324, h, w) fp32 lookup tensor (42 MB per iteration at 1080p) and its re-read by cuDNN are gone.
+//
+// Shape of the computation at 1080p: M = 32640 pixels, N = 256, K = 352: 5.9 GFLOP (3.5 us at the bf16 peak),
+// 23 MB of features in (L2-resident: the lookup wrote them a moment ago), 33 MB fp32 out (5.1 us at the HBM
+// peak).  What has to be avoided is re-streaming the 176 KB weight matrix per 128-pixel tile through L2 -> SM
+// (the feed ceiling measured on the MCN layers, ~7 TB/s): so CTA PAIRS (tcgen05 cta_group::2, M = 256): each
+// CTA keeps only its HALF of the output channels' weights (6 k-blocks x 16 KB = 96 KB) stationary for the
+// whole kernel and streams its own 128 pixel rows through a 6-stage ring (a whole tile in flight).  Every CTA
+// owns a contiguous pixel range (total / grid, rounded to 32), so the output bytes per SM are equal.
+//
+// Protocol as in corr_build2_sm100.cuh ("leader" = cluster rank 0; barriers at the same offset in both CTAs):
+//   W_FULL, A_FULL[s]   leader only; armed by the leader's producer for BOTH CTAs' bytes, completed by each
+//                       CTA's TMA loads.
+//   A_EMPTY[s], T_FULL[a]  both CTAs, tcgen05.commit multicast from the leader's issuing warp.
+//   T_EMPTY[a]          leader only, 16 arrivals (every epilogue warp of both CTAs).
+// The issuing warp runs converged; only the tcgen05 instructions sit under elect_one().
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cstdint>
+
+#include "ptx_sm100.cuh"
+
+namespace rdvc {
+
+constexpr int C1_BLOCK_M = 128;                 // pixel rows per CTA and tile
+constexpr int C1_BLOCK_K = 64;                  // 16-bit elements per 128-byte swizzle row
+constexpr int C1_MAX_KB = 6;                    // K <= 384
+constexpr int C1_MAX_COUT = 256;
+constexpr int C1_A_STAGES = 6;
+constexpr int C1_A_STAGE_BYTES = C1_BLOCK_M * C1_BLOCK_K * 2;            // 16 KB
+constexpr int C1_W_SLAB_BYTES = (C1_MAX_COUT / 2) * C1_BLOCK_K * 2;      // 16 KB: half the channels x one k-block
+constexpr int C1_EPI_WARPS = 8;
+constexpr int C1_THREADS = 128 + C1_EPI_WARPS * 32;
+constexpr int C1_SMEM_W = 0;
+constexpr int C1_SMEM_A = C1_SMEM_W + C1_MAX_KB * C1_W_SLAB_BYTES;       // 98304
+constexpr int C1_SMEM_BIAS = C1_SMEM_A + C1_A_STAGES * C1_A_STAGE_BYTES; // 196608
+constexpr int C1_SMEM_BAR = C1_SMEM_BIAS + C1_MAX_COUT * 4;
+constexpr int C1_SMEM_TOTAL = C1_SMEM_BAR + 256;
+constexpr int C1_SMEM_LAUNCH = C1_SMEM_TOTAL + 1024;                     // slack for 1024-byte alignment
+
+struct Conv1x1Params {
+    void* out;              // (B, cout, n_pix) OutT
+    const float* bias;      // cout floats on the device, or nullptr
+    long long m_total;      // B * n_pix feature rows
+    int n_pix;              // h * w
+    int cout;               // multiple of 32, <= 256
+    int kp;                 // feature-row pitch in elements (multiple of 16, <= 384)
+    int rows_per_cta;       // pixel rows owned by one CTA (multiple of 32)
+    int tiles_per_cta;      // ceil(rows_per_cta / 128)
+    int relu;
+    int ab_format;          // tcgen05 kind::f16 operand format: 1 = bf16, 0 = fp16
+};
+
+template <typename OutT> __device__ __forceinline__ OutT c1_cvt(float x);
+template <> __device__ __forceinline__ float c1_cvt<float>(float x) { return x; }
+template <> __device__ __forceinline__ __half c1_cvt<__half>(float x) { return __float2half_rn(x); }
+template <> __device__ __forceinline__ __nv_bfloat16 c1_cvt<__nv_bfloat16>(float x) { return __float2bfloat16_rn(x); }
+
+// grid: an even number of CTAs (clusters of 2); block: C1_THREADS; dynamic smem: C1_SMEM_LAUNCH.
+// tm_a: features as a {kp, m_total, 1} tensor, box {64, 128, 1}; tm_w: packed weights {kpw, cout, 1}, box {64, cout / 2, 1}.
+template <typename OutT>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(C1_THREADS, 1)
+corr_conv1x1_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_w,
+                    const Conv1x1Params p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>(
+        (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    const uint32_t s_w = ptx::smem_u32(smem + C1_SMEM_W);
+    const uint32_t s_a = ptx::smem_u32(smem + C1_SMEM_A);
+    float* bias_s = reinterpret_cast<float*>(smem + C1_SMEM_BIAS);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C1_SMEM_BAR);
+    const uint32_t bar0 = ptx::smem_u32(bars);
+    constexpr int A_FULL = 0, A_EMPTY = C1_A_STAGES, W_FULL = 2 * C1_A_STAGES, T_FULL = W_FULL + 1, T_EMPTY = T_FULL + 2;
+    auto bar = [&](int i) { return bar0 + 8u * i; };
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(bars + T_EMPTY + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t rank = ptx::cluster_ctarank();
+    const bool leader = (rank == 0);
+
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tensormap(&tm_a);
+        ptx::prefetch_tensormap(&tm_w);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < C1_A_STAGES; ++i) {
+            ptx::mbar_init(bar(A_FULL + i), 1);
+            ptx::mbar_init(bar(A_EMPTY + i), 1);
+        }
+        ptx::mbar_init(bar(W_FULL), 1);
+        for (int i = 0; i < 2; ++i) {
+            ptx::mbar_init(bar(T_FULL + i), 1);
+            ptx::mbar_init(bar(T_EMPTY + i), 2 * C1_EPI_WARPS);
+        }
+        ptx::fence_mbar_init();
+    }
+    if (warp == 2) {
+        ptx::tmem_alloc_2sm(ptx::smem_u32(const_cast<uint32_t*>(tmem_slot)), 512);
+        ptx::tmem_relinquish_2sm();
+    }
+    if (warp == 3) {
+        for (int i = lane; i < p.cout; i += 32) bias_s[i] = p.bias ? __ldg(p.bias + i) : 0.f;
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::cluster_sync_all();          // the peer's barriers are initialised before anyone signals them
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int n_kb = (p.kp + C1_BLOCK_K - 1) / C1_BLOCK_K;      // k-blocks (the last may be partial)
+    const int n_ksteps = p.kp / 16;                              // UMMA k-steps over the whole K
+    const int half = p.cout / 2;                                 // output channels whose weights this CTA holds
+    const long long row_base = static_cast<long long>(blockIdx.x) * p.rows_per_cta;
+    const int n_tiles = p.tiles_per_cta;
+
+    if (warp == 0) {
+        // ===================== TMA producer (both CTAs) =====================
+        if (lane == 0) {
+            if (leader) ptx::mbar_arrive_expect_tx(bar(W_FULL), 2u * n_kb * half * 128u);
+            for (int kb = 0; kb < n_kb; ++kb)
+                ptx::tma_load_3d_2sm(s_w + kb * C1_W_SLAB_BYTES, &tm_w, bar(W_FULL), kb * C1_BLOCK_K,
+                                     static_cast<int>(rank) * half, 0);
+            uint32_t a_it = 0;
+            for (int t = 0; t < n_tiles; ++t) {
+                long long m0 = row_base + static_cast<long long>(t) * C1_BLOCK_M;
+                if (m0 > p.m_total - 1) m0 = p.m_total - 1;      // a range past the end: rows are masked in the epilogue
+                for (int kb = 0; kb < n_kb; ++kb, ++a_it) {
+                    const uint32_t st = a_it % C1_A_STAGES, ph = (a_it / C1_A_STAGES) & 1;
+                    ptx::mbar_wait(bar(A_EMPTY + st), ph ^ 1);
+                    if (leader) ptx::mbar_arrive_expect_tx(bar(A_FULL + st), 2 * C1_A_STAGE_BYTES);
+                    ptx::tma_load_3d_2sm(s_a + st * C1_A_STAGE_BYTES, &tm_a, bar(A_FULL + st), kb * C1_BLOCK_K,
+                                         static_cast<int>(m0), 0);
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ===================== MMA issuer (leader CTA only; converged warp, tcgen05 under elect_one) =====================
+        if (leader) {
+            const uint32_t idesc = ptx::umma_idesc(2 * C1_BLOCK_M, p.cout, p.ab_format);
+            ptx::mbar_wait(bar(W_FULL), 0);
+            ptx::tc_fence_after();
+            const uint64_t b_desc0 = ptx::umma_desc_k_sw128(s_w);
+            uint32_t a_it = 0;
+            for (int t = 0; t < n_tiles; ++t) {
+                const uint32_t acc = t & 1, acc_ph = (t >> 1) & 1;
+                ptx::mbar_wait(bar(T_EMPTY + acc), acc_ph ^ 1);
+                ptx::tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * C1_MAX_COUT;
+                for (int kb = 0; kb < n_kb; ++kb, ++a_it) {
+                    const uint32_t st = a_it % C1_A_STAGES, ph = (a_it / C1_A_STAGES) & 1;
+                    ptx::mbar_wait(bar(A_FULL + st), ph);
+                    ptx::tc_fence_after();
+                    const uint64_t a_desc0 = ptx::umma_desc_k_sw128(s_a + st * C1_A_STAGE_BYTES);
+                    const int ks = n_ksteps - kb * 4;            // k-steps left: 4 for a full block
+                    if (ptx::elect_one()) {
+                        const uint64_t b_desc = b_desc0 + ((kb * C1_W_SLAB_BYTES) >> 4);
+                        if (ks >= 4) {                            // a full k-block: four MMAs back to back
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                ptx::umma_bf16_2sm(d_tmem, a_desc0 + ((k * 32) >> 4), b_desc + ((k * 32) >> 4), idesc,
+                                                   (kb | k) != 0 ? 1u : 0u);
+                        } else {                                  // the partial last block (K = 352: two k-steps)
+                            for (int k = 0; k < ks; ++k)
+                                ptx::umma_bf16_2sm(d_tmem, a_desc0 + ((k * 32) >> 4), b_desc + ((k * 32) >> 4), idesc,
+                                                   (kb | k) != 0 ? 1u : 0u);
+                        }
+                        ptx::umma_commit_2sm(bar(A_EMPTY + st), 3);                   // ring slot free in both CTAs
+                        if (kb == n_kb - 1) ptx::umma_commit_2sm(bar(T_FULL + acc), 3);  // accumulator ready in both
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp >= 4) {
+        // ===================== epilogue (both CTAs) =====================
+        // warp 4 + e: TMEM lane quarter q = e % 4 (pixel rows 32 q .. 32 q + 31 of the tile), channel half e / 4.
+        // A thread is one pixel: for a fixed channel the 32 lanes are 32 consecutive pixels, so every store is a
+        // coalesced line of the (B, cout, h, w) tensor straight from registers -- no staging.
+        const int e = warp - 4;
+        const int q = e & 3;
+        const int ch0 = (e >> 2) * half;
+        const uint32_t t_empty_leader0 = ptx::mapa(bar(T_EMPTY), 0);
+        for (int t = 0; t < n_tiles; ++t) {
+            const int row = t * C1_BLOCK_M + q * 32 + lane;                 // row inside this CTA's range
+            const long long pix = row_base + row;
+            const bool ok = (row < p.rows_per_cta) && (pix < p.m_total);
+            const long long b = ok ? pix / p.n_pix : 0;
+            const long long qp = ok ? pix - b * p.n_pix : 0;
+            OutT* o = static_cast<OutT*>(p.out) + (b * p.cout + ch0) * p.n_pix + qp;
+            const uint32_t acc = t & 1, acc_ph = (t >> 1) & 1;
+            ptx::mbar_wait(bar(T_FULL + acc), acc_ph);
+            ptx::tc_fence_after();
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * C1_MAX_COUT + ch0;
+            for (int c = 0; c < half; c += 32) {
+                float v[32];
+                const bool two = (c + 16 < half);
+                ptx::tmem_ld_x16(taddr + c, v);
+                if (two) ptx::tmem_ld_x16(taddr + c + 16, v + 16);
+                ptx::tmem_ld_wait();
+                if (c + 32 >= half) {
+                    // every TMEM read of this tile is done: hand the accumulator back (to the leader)
+                    ptx::tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) ptx::mbar_arrive_cluster(t_empty_leader0 + 8u * acc);
+                }
+                const int nch = two ? 32 : 16;
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    if (i < nch) {
+                        float x = v[i] + bias_s[ch0 + c + i];
+                        if (p.relu) x = fmaxf(x, 0.f);
+                        if (ok) o[static_cast<long long>(c + i) * p.n_pix] = c1_cvt<OutT>(x);
+                    }
+                }
+            }
+        }
+    }
+
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::cluster_sync_all();          // the leader's MMAs read the peer's shared memory until the very end
+    if (warp == 2) ptx::tmem_dealloc_2sm(tmem_base, 512);
+}
+
+}  // namespace rdvc

@@ -23,7 +23,9 @@
 // row-major rows; padding pixels are zeros, so no per-element masking either.
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cstdint>
+#include <type_traits>
 
 namespace rdvc {
 
@@ -37,7 +39,8 @@ struct LookupParams {
     int tiles_w[LKP_MAX_LEVELS];     // RDVC_LAYOUT_TILED: tiles per image row
     int twl, thl;                    // RDVC_LAYOUT_TILED: log2 tile width / height
     const float* coords;  // (B, 2, N)
-    float* out;           // (B, L*S*S, N)
+    void* out;            // LKP_OUT_NCHW_*: (B, L*S*S, N);  LKP_OUT_KM_*: (B*N, feat_pitch) 16-bit rows
+    int feat_pitch;       // LKP_OUT_KM_*: elements per feature row (rdvc_corr_feat_pitch)
     int B, N;
     int num_levels;
     long long total;      // B * N
@@ -188,6 +191,40 @@ struct LookupSite {
     }
 };
 
+// ---- output forms of the tiled kernel ---------------------------------------------------------
+// NCHW: the (B, L*S*S, h, w) tensor torchvision's index_pyramid returns, fp32 (what RAFT.forward consumes) or
+//       fp16 (what the consumer casts it to under the reference's default autocast, R:codec_processing.py:1436).
+// KM  : "K-major" 16-bit feature rows [B*N][feat_pitch] -- the A operand of the 1x1 convolution that follows the
+//       lookup in MotionEncoder (TV:raft.py:185,202; corr_conv1x1_sm100.cuh).  A thread's S*S taps of one level
+//       are written in the order it produces them (window row j outer, x index i inner) at columns
+//       l * PL + j * S + i, PL = S*S rounded up to 8 (one 16-byte store per 8 taps; padding columns hold 0);
+//       the convolution's weight matrix is permuted to match on the host (rdvc_conv1x1_pack_weights).
+constexpr int LKP_OUT_NCHW_F32 = 0, LKP_OUT_NCHW_F16 = 1, LKP_OUT_KM_BF16 = 2, LKP_OUT_KM_F16 = 3;
+
+__host__ __device__ constexpr int lkp_level_pitch(int radius) {
+    return ((2 * radius + 1) * (2 * radius + 1) + 7) / 8 * 8;
+}
+__host__ __device__ constexpr int lkp_feat_pitch(int num_levels, int radius) {
+    return (num_levels * lkp_level_pitch(radius) + 15) / 16 * 16;      // whole UMMA k-steps
+}
+
+template <bool F16>
+__device__ __forceinline__ uint4 lkp_pack8(const float* v) {
+    uint4 w;
+    if constexpr (F16) {
+        const __half2 a = __floats2half2_rn(v[0], v[1]), b = __floats2half2_rn(v[2], v[3]);
+        const __half2 c = __floats2half2_rn(v[4], v[5]), d = __floats2half2_rn(v[6], v[7]);
+        w.x = *reinterpret_cast<const uint32_t*>(&a); w.y = *reinterpret_cast<const uint32_t*>(&b);
+        w.z = *reinterpret_cast<const uint32_t*>(&c); w.w = *reinterpret_cast<const uint32_t*>(&d);
+    } else {
+        const __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
+        const __nv_bfloat162 c = __floats2bfloat162_rn(v[4], v[5]), d = __floats2bfloat162_rn(v[6], v[7]);
+        w.x = *reinterpret_cast<const uint32_t*>(&a); w.y = *reinterpret_cast<const uint32_t*>(&b);
+        w.z = *reinterpret_cast<const uint32_t*>(&c); w.w = *reinterpret_cast<const uint32_t*>(&d);
+    }
+    return w;
+}
+
 // ---- RDVC_LAYOUT_TILED kernel -------------------------------------------------------------
 // One CTA = 32 consecutive query pixels x all levels: warp = level, lane = pixel.
 // Measured at 1080p and rejected (tools/exp_lookup.py history): splitting a window's rows over
@@ -206,8 +243,8 @@ struct LookupSite {
 // need) and its 42 MB result out: 145 MB in 28.5 us = 5.1 TB/s of scattered traffic, 0.78 of the
 // measured copy peak.  (ncu's single cold launch shows only 13 MB written -- the rest is still
 // dirty in L2 when it ends -- which is why loads-only 18.7 us + stores-only 15 us looked additive.)
-// DBG (timing experiments only): 1 = no volume loads, 2 = no output stores.
-template <int R, typename VolT, int DBG>
+// DBG (timing experiments, RDVC_EXPERIMENTS builds only): 1 = no volume loads, 2 = no output stores.
+template <int R, typename VolT, int OUT, int DBG>
 __global__ void __launch_bounds__(32 * LKP_MAX_LEVELS)
 corr_lookup_tiled_kernel(const __grid_constant__ LookupParams p) {
     constexpr int S = 2 * R + 1;
@@ -248,9 +285,15 @@ corr_lookup_tiled_kernel(const __grid_constant__ LookupParams p) {
         }
     };
 
+    constexpr bool KM = (OUT == LKP_OUT_KM_BF16 || OUT == LKP_OUT_KM_F16);
+    using OutT = typename std::conditional<OUT == LKP_OUT_NCHW_F32, float, __half>::type;   // NCHW element type
     const size_t C_out = static_cast<size_t>(p.num_levels) * S * S;
-    float* outp = p.out + (static_cast<size_t>(site.b) * C_out + static_cast<size_t>(l) * S * S) * p.N + site.q;
+    OutT* outp = static_cast<OutT*>(p.out) + (static_cast<size_t>(site.b) * C_out + static_cast<size_t>(l) * S * S) * p.N + site.q;
     const size_t chan_i = static_cast<size_t>(S) * p.N;   // stride of the window's x index
+    // K-major form: this thread's S*S taps go to columns [l * PL, l * PL + PL) of feature row `pix`
+    constexpr int PL = lkp_level_pitch(R);
+    uint16_t* featp = static_cast<uint16_t*>(p.out) + static_cast<size_t>(pix) * p.feat_pitch + l * PL;
+    float stash[8];
 
     TRow buf[2];
     fetch(ya, buf[0]);
@@ -265,16 +308,35 @@ corr_lookup_tiled_kernel(const __grid_constant__ LookupParams p) {
 #pragma unroll
         for (int i = 0; i < S; ++i) hrow[i] = c[i] * (1.0f - fx) + c[i + 1] * fx;
         if (rr > 0) {                               // window row j = rr - 1: ys = cy + (j - R)
-            float* o = outp + static_cast<size_t>(rr - 1) * p.N;
+            OutT* o = outp + static_cast<size_t>(rr - 1) * p.N;
 #pragma unroll
             for (int i = 0; i < S; ++i) {
                 const float v = prev[i] * (1.0f - fy) + hrow[i] * fy;
-                if (DBG != 2 || v == 12345.678f) __stcs(o, v);
-                o += chan_i;
+                if constexpr (KM) {
+                    const int idx = (rr - 1) * S + i;          // a compile-time constant once unrolled
+                    stash[idx & 7] = v;
+                    if ((idx & 7) == 7 || idx == S * S - 1) {
+#pragma unroll
+                        for (int z = (idx & 7) + 1; z < 8; ++z) stash[z] = 0.f;    // padding columns of the level
+                        const uint4 wv = lkp_pack8<OUT == LKP_OUT_KM_F16>(stash);
+                        if (DBG != 2 || v == 12345.678f) *reinterpret_cast<uint4*>(featp + (idx >> 3) * 8) = wv;
+                    }
+                } else if constexpr (OUT == LKP_OUT_NCHW_F16) {
+                    if (DBG != 2 || v == 12345.678f) *o = __float2half_rn(v);
+                    o += chan_i;
+                } else {
+                    if (DBG != 2 || v == 12345.678f) __stcs(o, v);
+                    o += chan_i;
+                }
             }
         }
 #pragma unroll
         for (int i = 0; i < S; ++i) prev[i] = hrow[i];
+    }
+    if constexpr (KM) {
+        if (l == p.num_levels - 1)
+            for (int c = PL; l * PL + c < p.feat_pitch; c += 8)
+                *reinterpret_cast<uint4*>(featp + c) = make_uint4(0u, 0u, 0u, 0u);
     }
 }
 
@@ -299,7 +361,7 @@ corr_lookup_kernel(const __grid_constant__ LookupParams p) {
     const VolT* lvl = static_cast<const VolT*>(p.lvl[l]);
     const long long img_ge = pix * p.img[l];  // element offset of this pixel's image
     const size_t C_out = static_cast<size_t>(p.num_levels) * S * S;
-    float* outp = p.out + (static_cast<size_t>(site.b) * C_out + static_cast<size_t>(l) * S * S) * p.N + site.q;
+    float* outp = static_cast<float*>(p.out) + (static_cast<size_t>(site.b) * C_out + static_cast<size_t>(l) * S * S) * p.N + site.q;
 
     // whole window left/right of the level: every tap is zero
     const bool x_dead = (xa + R2 <= 0) || (xa >= wl);

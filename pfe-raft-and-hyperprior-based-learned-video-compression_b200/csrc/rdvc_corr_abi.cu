@@ -11,10 +11,14 @@
 #include <cstdio>
 #include <cstring>
 #include <mutex>
+#include <vector>
 
 #include "../../include/rdvc_corr.h"
 #include "corr_build_sm100.cuh"
+#ifdef RDVC_EXPERIMENTS
 #include "corr_build2_sm100.cuh"
+#endif
+#include "corr_conv1x1_sm100.cuh"
 #include "corr_lookup.cuh"
 #include "corr_pack.cuh"
 #include "mcn_conv_sm100.cuh"
@@ -25,6 +29,20 @@
 #ifndef RDVC_PAIR_DEFAULT
 #define RDVC_PAIR_DEFAULT 0   // the CTA-pair build kernel is opt-in (option key 12 = 2) until it wins
 #endif
+// RDVC_EXPERIMENTS (off in the product build, `python -m ..._build --experiments` turns it on in a SEPARATE
+// library, lib/librdvc_corr_exp.so): compiles in the knobs that skip work for timing experiments (level store
+// mask, no-load / no-store lookups, L2 store policies) and the build variants that lost their measurements
+// (fused pooling epilogue, CTA-pair kernel).  The product library accepts none of them.
+#ifdef RDVC_EXPERIMENTS
+#define RDVC_HAS_EXPERIMENTS 1
+#else
+#define RDVC_HAS_EXPERIMENTS 0
+#endif
+#ifndef RDVC_SRC_HASH
+#define RDVC_SRC_HASH "unknown"
+#endif
+#define RDVC_STR2(x) #x
+#define RDVC_STR(x) RDVC_STR2(x)
 
 namespace {
 
@@ -80,6 +98,8 @@ void tile_log2(int vol_dtype, int* twl, int* thl) {
 
 // elements of one level image in the given layout (TILED pads both sides to whole tiles)
 size_t level_image_elems(int h, int w, int level, int vol_dtype, int layout) {
+    if (vol_dtype != RDVC_DT_F32 && vol_dtype != RDVC_DT_BF16) return 0;   // size queries answer 0 for a bad enum
+    if (h <= 0 || w <= 0 || level < 0 || level >= 31) return 0;
     const size_t hl = h >> level, wl = w >> level;
     if (layout != RDVC_LAYOUT_TILED) return hl * wl;
     int twl, thl;
@@ -201,6 +221,7 @@ int launch_build(const CUtensorMap& ta, const CUtensorMap* tb, const CUtensorMap
     return RDVC_OK;
 }
 
+#ifdef RDVC_EXPERIMENTS
 template <typename OutT>
 int launch_build_pair(const CUtensorMap& ta, const CUtensorMap* tb, const CUtensorMap* to, const rdvc::BuildParams& p,
                       cudaStream_t st) {
@@ -220,6 +241,8 @@ int launch_build_pair(const CUtensorMap& ta, const CUtensorMap* tb, const CUtens
     if (e != cudaSuccess) return cuda_fail(e, "corr_build2_kernel launch");
     return RDVC_OK;
 }
+
+#endif
 
 // both feature maps -> K-major bf16 rows (fmap2 at `levels2` pyramid levels), one launch
 template <typename T, bool QUICK, bool VEC>
@@ -256,21 +279,21 @@ template <typename T>
 int launch_pack(const void* f1, const void* f2, void* a_km, void* const* b_km, int B, int D, int h, int w,
                 int levels2, int layout, int twl, int thl, const size_t* nl_of, int f16, cudaStream_t st) {
     const bool quick = (layout != RDVC_LAYOUT_TILED) || (thl == 2 && (twl == 2 || twl == 3));
-    const bool vec = (w % 4) == 0;
+    // 4-element vector loads need w % 4 == 0 AND 4-element-aligned bases (a contiguous torch view can start at
+    // an odd storage offset); anything else takes the scalar instantiation
+    const uintptr_t amask = 4 * sizeof(T) - 1;
+    const bool vec = (w % 4) == 0 && !((reinterpret_cast<uintptr_t>(f1) | reinterpret_cast<uintptr_t>(f2)) & amask);
     if (quick && vec) return launch_pack_impl<T, true, true>(f1, f2, a_km, b_km, B, D, h, w, levels2, layout, twl, thl, nl_of, f16, st);
     if (quick) return launch_pack_impl<T, true, false>(f1, f2, a_km, b_km, B, D, h, w, levels2, layout, twl, thl, nl_of, f16, st);
     if (vec) return launch_pack_impl<T, false, true>(f1, f2, a_km, b_km, B, D, h, w, levels2, layout, twl, thl, nl_of, f16, st);
     return launch_pack_impl<T, false, false>(f1, f2, a_km, b_km, B, D, h, w, levels2, layout, twl, thl, nl_of, f16, st);
 }
 
+// row-major kernels: KIND 0 / 1 = scalar / 128-bit loads
 template <int R, typename VolT, int KIND>
 int launch_lookup(const rdvc::LookupParams& p, cudaStream_t st) {
     const unsigned grid = static_cast<unsigned>((p.total + 31) / 32);
-    if constexpr (KIND < 2) {
-        rdvc::corr_lookup_kernel<R, VolT, KIND == 1><<<grid, 32 * p.num_levels, 0, st>>>(p);
-    } else {
-        rdvc::corr_lookup_tiled_kernel<R, VolT, KIND - 2><<<grid, 32 * p.num_levels, 0, st>>>(p);
-    }
+    rdvc::corr_lookup_kernel<R, VolT, KIND == 1><<<grid, 32 * p.num_levels, 0, st>>>(p);
     ++g_launches;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "corr_lookup_kernel launch");
@@ -288,13 +311,281 @@ int dispatch_lookup_radius(int radius, const rdvc::LookupParams& p, cudaStream_t
     }
 }
 
-template <typename VolT>
-int dispatch_lookup_tiled(int dbg, int radius, const rdvc::LookupParams& p, cudaStream_t st) {
-    switch (dbg) {
-        case 1: return dispatch_lookup_radius<VolT, 3>(radius, p, st);
-        case 2: return dispatch_lookup_radius<VolT, 4>(radius, p, st);
-        default: return dispatch_lookup_radius<VolT, 2>(radius, p, st);
+// tiled kernel: OUT = output form (rdvc::LKP_OUT_*), DBG = timing experiments (RDVC_EXPERIMENTS builds only)
+template <int R, typename VolT, int OUT, int DBG>
+int launch_lookup_tiled(const rdvc::LookupParams& p, cudaStream_t st) {
+    const unsigned grid = static_cast<unsigned>((p.total + 31) / 32);
+    rdvc::corr_lookup_tiled_kernel<R, VolT, OUT, DBG><<<grid, 32 * p.num_levels, 0, st>>>(p);
+    ++g_launches;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "corr_lookup_tiled_kernel launch");
+    return RDVC_OK;
+}
+
+template <typename VolT, int OUT, int DBG>
+int dispatch_lookup_tiled_radius(int radius, const rdvc::LookupParams& p, cudaStream_t st) {
+    switch (radius) {
+        case 1: return launch_lookup_tiled<1, VolT, OUT, DBG>(p, st);
+        case 2: return launch_lookup_tiled<2, VolT, OUT, DBG>(p, st);
+        case 3: return launch_lookup_tiled<3, VolT, OUT, DBG>(p, st);
+        case 4: return launch_lookup_tiled<4, VolT, OUT, DBG>(p, st);
+        default: return fail(RDVC_E_UNSUPPORTED, "radius=%d not in [1, 4]", radius);
     }
+}
+
+template <typename VolT>
+int dispatch_lookup_tiled(int out_mode, int dbg, int radius, const rdvc::LookupParams& p, cudaStream_t st) {
+#ifdef RDVC_EXPERIMENTS
+    if (dbg == 1 && out_mode == rdvc::LKP_OUT_NCHW_F32) return dispatch_lookup_tiled_radius<VolT, rdvc::LKP_OUT_NCHW_F32, 1>(radius, p, st);
+    if (dbg == 2 && out_mode == rdvc::LKP_OUT_NCHW_F32) return dispatch_lookup_tiled_radius<VolT, rdvc::LKP_OUT_NCHW_F32, 2>(radius, p, st);
+    if (dbg == 1 && out_mode == rdvc::LKP_OUT_KM_BF16) return dispatch_lookup_tiled_radius<VolT, rdvc::LKP_OUT_KM_BF16, 1>(radius, p, st);
+    if (dbg == 2 && out_mode == rdvc::LKP_OUT_KM_BF16) return dispatch_lookup_tiled_radius<VolT, rdvc::LKP_OUT_KM_BF16, 2>(radius, p, st);
+#else
+    (void)dbg;
+#endif
+    switch (out_mode) {
+        case rdvc::LKP_OUT_NCHW_F16: return dispatch_lookup_tiled_radius<VolT, rdvc::LKP_OUT_NCHW_F16, 0>(radius, p, st);
+        case rdvc::LKP_OUT_KM_BF16: return dispatch_lookup_tiled_radius<VolT, rdvc::LKP_OUT_KM_BF16, 0>(radius, p, st);
+        case rdvc::LKP_OUT_KM_F16: return dispatch_lookup_tiled_radius<VolT, rdvc::LKP_OUT_KM_F16, 0>(radius, p, st);
+        default: return dispatch_lookup_tiled_radius<VolT, rdvc::LKP_OUT_NCHW_F32, 0>(radius, p, st);
+    }
+}
+
+template <typename OutT>
+cudaError_t launch_conv1x1(const CUtensorMap& tm_a, const CUtensorMap& tm_w, const rdvc::Conv1x1Params& p, unsigned grid,
+                           cudaStream_t st) {
+    auto kern = rdvc::corr_conv1x1_kernel<OutT>;
+    static std::atomic<unsigned long long> attr_done{0};
+    if (ensure_dynamic_smem(kern, rdvc::C1_SMEM_LAUNCH, attr_done, "cudaFuncSetAttribute(conv1x1, max dynamic smem)"))
+        return cudaErrorInvalidValue;
+    kern<<<grid, rdvc::C1_THREADS, rdvc::C1_SMEM_LAUNCH, st>>>(tm_a, tm_w, p);
+    ++g_launches;
+    return cudaGetLastError();
+}
+
+// ---- build plan: everything rdvc_corr_build derives from its arguments and the options, cached ----
+struct BuildKey {            // compared with memcmp: no padding (2 pointers + 20 ints), zeroed before it is filled
+    void* pyramid;
+    void* workspace;
+    int device, B, D, h, w, f16_ops, vol_dtype, layout, num_levels;
+    int opt_mode, opt_tile, opt_msplit, opt_tma_out, opt_epi, opt_pair, opt_twl, opt_thl, opt_store_mask, opt_policy;
+    int reserved;
+};
+static_assert(sizeof(BuildKey) == 2 * sizeof(void*) + 20 * sizeof(int), "BuildKey must have no padding");
+
+struct BuildPlan {
+    BuildKey key;
+    void* a_km;                              // fmap1 as (B, N, D) 16-bit rows
+    void* b_km[rdvc::BLD_MAX_LEVELS];        // fmap2 level l as (B, n_l, D)
+    size_t nl_of[rdvc::BLD_MAX_LEVELS];      // pixels (operand rows / output columns) of level l in this layout
+    int twl, thl;
+    void* memset_ptr;
+    size_t memset_bytes;
+    bool linear, pair;
+    int tile, ew;
+    CUtensorMap ta, tb[rdvc::BLD_MAX_LEVELS], to[rdvc::BLD_MAX_LEVELS], tb2[rdvc::BLD_MAX_LEVELS];
+    rdvc::BuildParams p, p2;
+};
+
+constexpr size_t kPlanCacheSize = 8;
+std::mutex g_plan_mutex;
+std::vector<BuildPlan> g_plans;              // most recently used first
+std::atomic<unsigned long long> g_plan_hits{0}, g_plan_misses{0};
+
+bool plan_cache_get(const BuildKey& key, BuildPlan* out) {
+    std::lock_guard<std::mutex> lock(g_plan_mutex);
+    for (size_t i = 0; i < g_plans.size(); ++i)
+        if (memcmp(&g_plans[i].key, &key, sizeof(key)) == 0) {
+            if (i) std::swap(g_plans[0], g_plans[i]);
+            *out = g_plans[0];
+            ++g_plan_hits;
+            return true;
+        }
+    ++g_plan_misses;
+    return false;
+}
+
+void plan_cache_put(const BuildPlan& plan) {
+    std::lock_guard<std::mutex> lock(g_plan_mutex);
+    if (g_plans.size() >= kPlanCacheSize) g_plans.pop_back();
+    g_plans.insert(g_plans.begin(), plan);
+}
+
+// m-range slices per fmap2 tile: enough (tile, slice) items to fill `G` CTAs (or pairs) in whole waves.
+// cost = waves x (m-blocks per slice + ~0.5 for the tile reload); a mild bias toward few slices keeps
+// concurrent CTAs on the same query rows (see the kernel).
+int choose_msplit(long long units, int m_blks, int G, int forced) {
+    int best = 1;
+    double best_cost = 1e300;
+    const int s_max = m_blks < 64 ? m_blks : 64;
+    for (int S = 1; S <= s_max; ++S) {
+        const long long waves = (units * S + G - 1) / G;
+        const double cost = waves * ((m_blks + S - 1) / S + 0.5) * (1.0 + 0.005 * S);
+        if (cost < best_cost) { best_cost = cost; best = S; }
+    }
+    return (forced > 0) ? (forced < m_blks ? forced : m_blks) : best;
+}
+
+int make_build_plan(const BuildKey& k, BuildPlan* plan) {
+    BuildPlan& pl = *plan;
+    memset(&pl, 0, sizeof(pl));
+    pl.key = k;
+    const int B = k.B, D = k.D, h = k.h, w = k.w, num_levels = k.num_levels, vol_dtype = k.vol_dtype, layout = k.layout;
+    const int N = h * w;
+    uint8_t* ws = static_cast<uint8_t*>(k.workspace);
+    pl.a_km = ws;
+    {
+        size_t off = align_up(static_cast<size_t>(B) * N * D * 2, 256);
+        for (int l = 0; l < rdvc::BLD_MAX_LEVELS; ++l) {
+            pl.b_km[l] = ws + off;
+            off += align_up(static_cast<size_t>(B) * operand_rows_max(h, w, l) * D * 2, 256);
+        }
+    }
+    int mode = k.opt_mode;
+    if (mode == 0) mode = 2;  // default: linear (pooled fmap2 rows), see corr_build_sm100.cuh
+    pl.linear = (mode == 2);
+    if (!pl.linear && !RDVC_HAS_EXPERIMENTS)
+        return fail(RDVC_E_UNSUPPORTED, "the fused-epilogue build mode exists in RDVC_EXPERIMENTS builds only");
+    if (!pl.linear && layout != RDVC_LAYOUT_ROWMAJOR)
+        return fail(RDVC_E_UNSUPPORTED, "the fused-epilogue build mode writes RDVC_LAYOUT_ROWMAJOR only");
+    for (int l = 0; l < rdvc::BLD_MAX_LEVELS; ++l) pl.nl_of[l] = level_image_elems(h, w, l, vol_dtype, layout);
+    if (layout == RDVC_LAYOUT_TILED) {
+        tile_log2(vol_dtype, &pl.twl, &pl.thl);
+        int first = -1;
+        for (int l = 0; l < num_levels && first < 0; ++l)
+            if (pl.nl_of[l] != static_cast<size_t>(h >> l) * (w >> l)) first = l;
+        if (first >= 0) {
+            uint8_t* lo = static_cast<uint8_t*>(pl.b_km[first]);
+            uint8_t* hi = static_cast<uint8_t*>(pl.b_km[num_levels - 1]) + static_cast<size_t>(B) * pl.nl_of[num_levels - 1] * D * 2;
+            pl.memset_ptr = lo;
+            pl.memset_bytes = static_cast<size_t>(hi - lo);
+        }
+    }
+    // operand format: fp16 inputs (the reference's default autocast, R:codec_processing.py:1436) stay fp16
+    // -- same tensor-core rate, 11 instead of 8 mantissa bits; everything else is multiplied as bf16
+    const CUtensorMapDataType op_dt = k.f16_ops ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+
+    // fused mode tile shape: 16x16 fmap2 pixels unless 8x32 wastes less padding
+    int tile = k.opt_tile;
+    auto padded = [&](int ty, int tx) {
+        return static_cast<long long>((h + ty - 1) / ty) * ty * ((w + tx - 1) / tx) * tx;
+    };
+    if (tile == 0) tile = (padded(8, 32) < padded(16, 16)) ? 2 : 1;
+    pl.tile = tile;
+    const int TY = (tile == 1) ? 16 : 8, TX = (tile == 1) ? 16 : 32;
+
+    // TMA descriptors over the repacked maps
+    int rc;
+    {
+        cuuint64_t dims[3] = {(cuuint64_t)D, (cuuint64_t)N, (cuuint64_t)B};
+        cuuint64_t str[2] = {(cuuint64_t)D * 2, (cuuint64_t)N * D * 2};
+        cuuint32_t box[3] = {rdvc::BLD_BLOCK_K, rdvc::BLD_BLOCK_M, 1};
+        rc = make_tmap(&pl.ta, op_dt, pl.a_km, 3, dims, str, box);
+        if (rc) return rc;
+    }
+    if (pl.linear) {
+        for (int l = 0; l < rdvc::BLD_MAX_LEVELS; ++l) {
+            const int ll = l < num_levels ? l : 0;  // unused slots alias level 0
+            const cuuint64_t nl = (cuuint64_t)pl.nl_of[ll];
+            cuuint64_t dims[3] = {(cuuint64_t)D, nl, (cuuint64_t)B};
+            cuuint64_t str[2] = {(cuuint64_t)D * 2, nl * D * 2};
+            cuuint32_t box[3] = {rdvc::BLD_BLOCK_K, rdvc::BLD_BLOCK_N, 1};
+            rc = make_tmap(&pl.tb[l], op_dt, pl.b_km[ll], 3, dims, str, box);
+            if (rc) return rc;
+        }
+    } else {
+        cuuint64_t dims[4] = {(cuuint64_t)D, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)B};
+        cuuint64_t str[3] = {(cuuint64_t)D * 2, (cuuint64_t)w * D * 2, (cuuint64_t)N * D * 2};
+        cuuint32_t box[4] = {rdvc::BLD_BLOCK_K, (cuuint32_t)TX, (cuuint32_t)TY, 1};
+        rc = make_tmap(&pl.tb[0], op_dt, pl.b_km[0], 4, dims, str, box);
+        if (rc) return rc;
+        pl.tb[1] = pl.tb[2] = pl.tb[3] = pl.tb[0];
+    }
+
+    rdvc::BuildParams& p = pl.p;
+    for (int l = 0; l < num_levels; ++l) {
+        p.lvl[l] = static_cast<uint8_t*>(k.pyramid) + rdvc_corr_level_offset_bytes(B, h, w, l, vol_dtype, layout);
+        p.hl[l] = h >> l;
+        p.wl[l] = w >> l;
+        p.nl[l] = static_cast<int>(pl.nl_of[l]);
+    }
+    p.B = B; p.h = h; p.w = w; p.N = N;
+    p.num_levels = num_levels;
+    p.kc = D / 64;
+    p.m_blks = (N + rdvc::BLD_BLOCK_M - 1) / rdvc::BLD_BLOCK_M;
+    p.nty = (h + TY - 1) / TY;
+    p.ntx = (w + TX - 1) / TX;
+    if (pl.linear) {
+        int t = 0;
+        for (int l = 0; l < rdvc::BLD_MAX_LEVELS; ++l) {
+            p.tile_start[l] = t;
+            if (l < num_levels) t += (p.nl[l] + rdvc::BLD_BLOCK_N - 1) / rdvc::BLD_BLOCK_N;
+        }
+        p.ntiles = t;
+    } else {
+        p.ntiles = p.nty * p.ntx;
+    }
+    p.scale = static_cast<float>(1.0 / std::sqrt(static_cast<double>(D)));
+    p.ab_format = k.f16_ops ? 0 : 1;
+    p.dbg_store_mask = RDVC_HAS_EXPERIMENTS ? k.opt_store_mask : 15;
+    p.dbg_policy = RDVC_HAS_EXPERIMENTS ? k.opt_policy : 0;
+    p.msplit = choose_msplit(static_cast<long long>(B) * p.ntiles, p.m_blks, sm_count(), k.opt_msplit);
+
+    // output descriptors (linear mode).  Row pitch a multiple of 128 bytes (always, in the tiled
+    // layout): level l as a {128 B, pitch/128, N, B} tensor written in boxes of 16 query rows x 256
+    // contiguous bytes.  Row pitch only 16-byte aligned: a {n_l, N, B} tensor, boxes of 32 rows x 128
+    // bytes.  Anything else takes the staged-store path.  (option key 5: 0 = staged only, 1 = auto,
+    // 2 = never the wide boxes)
+    for (int l = 0; l < rdvc::BLD_MAX_LEVELS; ++l) pl.to[l] = pl.ta;
+    const int tma_opt = k.opt_tma_out;
+    if (pl.linear && tma_opt) {
+        const bool f32 = (vol_dtype == RDVC_DT_F32);
+        const cuuint64_t es = f32 ? 4 : 2;
+        const CUtensorMapDataType dt = f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+        for (int l = 0; l < num_levels; ++l) {
+            const cuuint64_t nl = (cuuint64_t)p.nl[l];
+            if ((nl * es) % 128 == 0 && tma_opt == 1) {
+                cuuint64_t dims[4] = {128 / es, nl * es / 128, (cuuint64_t)N, (cuuint64_t)B};
+                cuuint64_t str[3] = {128, nl * es, (cuuint64_t)N * nl * es};
+                cuuint32_t box[4] = {(cuuint32_t)(128 / es), 2, 16, 1};
+                rc = make_tmap(&pl.to[l], dt, p.lvl[l], 4, dims, str, box);
+                if (rc) return rc;
+                p.tma_out |= 2 << (2 * l);
+            } else if ((nl * es) % 16 == 0) {
+                cuuint64_t dims[3] = {nl, (cuuint64_t)N, (cuuint64_t)B};
+                cuuint64_t str[2] = {nl * es, (cuuint64_t)N * nl * es};
+                cuuint32_t box[3] = {(cuuint32_t)(128 / es), 32, 1};
+                rc = make_tmap(&pl.to[l], dt, p.lvl[l], 3, dims, str, box);
+                if (rc) return rc;
+                p.tma_out |= 1 << (2 * l);
+            }
+        }
+    }
+    // epilogue shape per storage type: see BuildCfg (option key 9: 0 = auto, 4 / 8 = force)
+    pl.ew = k.opt_epi ? k.opt_epi : ((vol_dtype == RDVC_DT_F32) ? 8 : 4);
+
+#ifdef RDVC_EXPERIMENTS
+    // CTA-pair kernel (cta_group::2): linear mode with every level on the wide-box path (always true for
+    // the tiled layout).  Option key 12: 0 = auto, 1 = single-CTA kernel, 2 = pair kernel where possible.
+    bool pair_ok = pl.linear && (sm_count() >= 2);
+    for (int l = 0; l < num_levels; ++l) pair_ok = pair_ok && (((p.tma_out >> (2 * l)) & 3) == 2);
+    if (pair_ok && (k.opt_pair == 2 || (k.opt_pair == 0 && RDVC_PAIR_DEFAULT))) {
+        for (int l = 0; l < rdvc::BLD_MAX_LEVELS; ++l) {
+            const int ll = l < num_levels ? l : 0;
+            const cuuint64_t nl = (cuuint64_t)pl.nl_of[ll];
+            cuuint64_t dims[3] = {(cuuint64_t)D, nl, (cuuint64_t)B};
+            cuuint64_t str[2] = {(cuuint64_t)D * 2, nl * D * 2};
+            cuuint32_t box[3] = {rdvc::BLD_BLOCK_K, rdvc::BLD_BLOCK_N / 2, 1};   // each CTA loads half the tile
+            rc = make_tmap(&pl.tb2[l], op_dt, pl.b_km[ll], 3, dims, str, box);
+            if (rc) return rc;
+        }
+        pl.p2 = p;
+        pl.p2.m_blks = (N + 2 * rdvc::BLD_BLOCK_M - 1) / (2 * rdvc::BLD_BLOCK_M);
+        pl.p2.msplit = choose_msplit(static_cast<long long>(B) * pl.p2.ntiles, pl.p2.m_blks, sm_count() / 2, k.opt_msplit);
+        pl.pair = true;
+    }
+#endif
+    return RDVC_OK;
 }
 
 struct HostArena {  // scratch owned by rdvc_corr_pair_host*, one per (thread, slot), bound to one device
@@ -302,7 +593,8 @@ struct HostArena {  // scratch owned by rdvc_corr_pair_host*, one per (thread, s
     void* dev = nullptr;
     size_t bytes = 0;
     cudaStream_t compute = nullptr, copy = nullptr;
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};   // one per device-side result buffer
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};   // one per device-side result buffer: its D2H copy finished
+    cudaEvent_t done[4] = {nullptr, nullptr, nullptr, nullptr}; // one per device-side result buffer: its lookup finished
     bool pending = false;   // a submitted pair has not been waited for yet
 };
 constexpr int kHostSlots = 2;
@@ -316,6 +608,7 @@ void release_arena(HostArena& a) {
     if (a.compute) cudaStreamDestroy(a.compute);
     if (a.copy) cudaStreamDestroy(a.copy);
     for (auto& e : a.ev) if (e) cudaEventDestroy(e);
+    for (auto& e : a.done) if (e) cudaEventDestroy(e);
     a = HostArena();
 }
 
@@ -333,21 +626,30 @@ void rdvc_corr_set_profile_events(void* start, void* stop) {
 }
 
 int rdvc_corr_set_option(int key, int value) {
-    if (key == 0 && value >= 0 && value <= 4) { g_opt_lookup = value; return RDVC_OK; }
+    const bool exp = RDVC_HAS_EXPERIMENTS;
+    if (key == 0 && value >= 0 && value <= (exp ? 4 : 2)) { g_opt_lookup = value; return RDVC_OK; }
     if (key == 1 && value >= 0 && value <= 2) { g_opt_tile = value; return RDVC_OK; }
     if (key == 2 && value >= 0) { g_opt_msplit = value; return RDVC_OK; }
-    if (key == 3 && value >= 0 && value <= 63) { g_opt_store_mask = value; return RDVC_OK; }
-    if (key == 4 && value >= 0 && value <= 2) { g_opt_mode = value; return RDVC_OK; }
+    if (key == 3 && value >= 0 && value <= 63 && (exp || value == 15)) { g_opt_store_mask = value; return RDVC_OK; }
+    if (key == 4 && value >= 0 && value <= 2 && (exp || value != 1)) { g_opt_mode = value; return RDVC_OK; }
     if (key == 5 && value >= 0 && value <= 2) { g_opt_tma_out = value; return RDVC_OK; }
-    if (key == 6 && value >= 0 && value <= 2) { g_opt_policy = value; return RDVC_OK; }
+    if (key == 6 && value >= 0 && value <= 2 && (exp || value == 0)) { g_opt_policy = value; return RDVC_OK; }
     if (key == 7 && value >= 0 && value <= 4) { g_opt_twl = value; return RDVC_OK; }
     if (key == 8 && value >= 0 && value <= 4) { g_opt_thl = value; return RDVC_OK; }
     if (key == 9 && (value == 0 || value == 4 || value == 8)) { g_opt_epi_warps = value; return RDVC_OK; }
-    if (key == 12 && value >= 0 && value <= 2) { g_opt_pair = value; return RDVC_OK; }
+    if (key == 12 && value >= 0 && value <= 2 && (exp || value != 2)) { g_opt_pair = value; return RDVC_OK; }
     if (key == 13 && value >= 0 && value <= 16) { g_opt_mcn_prefetch = value; return RDVC_OK; }
     if (key == 14 && value >= 0 && value <= 2) { g_opt_mcn_kernel = value; return RDVC_OK; }
-    return fail(RDVC_E_UNSUPPORTED, "unknown option key=%d value=%d", key, value);
+    return fail(RDVC_E_UNSUPPORTED, "unknown option key=%d value=%d%s", key, value,
+                exp ? "" : " (work-skipping knobs and the fused / CTA-pair build variants exist in RDVC_EXPERIMENTS builds only)");
 }
+
+const char* rdvc_corr_build_info(void) {
+    // the marker lets _build.py read the hash out of the file without loading it
+    return "RDVC_SRC_HASH=" RDVC_SRC_HASH " version=" RDVC_STR(RDVC_CORR_VERSION) " experiments=" RDVC_STR(RDVC_HAS_EXPERIMENTS);
+}
+
+unsigned long long rdvc_corr_plan_cache_hits(void) { return g_plan_hits.load(); }
 
 size_t rdvc_corr_level_image_elems(int h, int w, int level, int vol_dtype, int layout) {
     if (elem_size(vol_dtype) == 0 || h <= 0 || w <= 0 || level < 0) return 0;
@@ -366,6 +668,7 @@ int rdvc_corr_tile_shape(int vol_dtype, int* tile_w, int* tile_h) {
 }
 
 size_t rdvc_corr_level_offset_bytes(int B, int h, int w, int level, int vol_dtype, int layout) {
+    if ((vol_dtype != RDVC_DT_F32 && vol_dtype != RDVC_DT_BF16) || B <= 0 || h <= 0 || w <= 0 || level < 0) return 0;
     size_t off = 0;
     for (int l = 0; l < level; ++l) off += align_up(level_bytes(B, h, w, l, vol_dtype, layout), 256);
     return off;
@@ -409,227 +712,76 @@ int rdvc_corr_build(const void* fmap1, const void* fmap2, int B, int D, int h, i
         return fail(RDVC_E_UNSUPPORTED, "h*w too large for 32-bit pixel indices");
 
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const int N = h * w;
-    uint8_t* ws = static_cast<uint8_t*>(workspace);
-    void* a_km = ws;  // fmap1 as (B, N, D) bf16
-    void* b_km[rdvc::BLD_MAX_LEVELS];  // fmap2 level l as (B, n_l, D) bf16
-    {
-        size_t off = align_up(static_cast<size_t>(B) * N * D * 2, 256);
-        for (int l = 0; l < rdvc::BLD_MAX_LEVELS; ++l) {
-            b_km[l] = ws + off;
-            off += align_up(static_cast<size_t>(B) * operand_rows_max(h, w, l) * D * 2, 256);
-        }
+    BuildKey key;
+    memset(&key, 0, sizeof(key));
+    key.device = current_device();
+    key.pyramid = pyramid; key.workspace = workspace;
+    key.B = B; key.D = D; key.h = h; key.w = w; key.f16_ops = (in_dtype == RDVC_DT_F16) ? 1 : 0;
+    key.vol_dtype = vol_dtype; key.layout = layout; key.num_levels = num_levels;
+    key.opt_mode = g_opt_mode.load(); key.opt_tile = g_opt_tile.load(); key.opt_msplit = g_opt_msplit.load();
+    key.opt_tma_out = g_opt_tma_out.load(); key.opt_epi = g_opt_epi_warps.load(); key.opt_pair = g_opt_pair.load();
+    key.opt_twl = g_opt_twl.load(); key.opt_thl = g_opt_thl.load();
+    key.opt_store_mask = g_opt_store_mask.load(); key.opt_policy = g_opt_policy.load();
+
+    // The plan (pointers into the workspace, 9 TMA descriptors, work split) depends only on the key: a per-process,
+    // mutex-guarded cache of the last few plans makes a repeated call (RAFT calls build once per frame pair with
+    // the same buffers) skip the descriptor encoding and the m-split search.
+    BuildPlan plan;
+    if (!plan_cache_get(key, &plan)) {
+        rc = make_build_plan(key, &plan);
+        if (rc) return rc;
+        plan_cache_put(plan);
     }
-    int mode = g_opt_mode.load();
-    if (mode == 0) mode = 2;  // default: linear (pooled fmap2 rows), see corr_build_sm100.cuh
-    const bool linear = (mode == 2);
-    if (!linear && layout != RDVC_LAYOUT_ROWMAJOR)
-        return fail(RDVC_E_UNSUPPORTED, "the fused-epilogue build mode writes RDVC_LAYOUT_ROWMAJOR only");
-    // pixels (K-major operand rows / output columns) of level l in this layout
-    size_t nl_of[rdvc::BLD_MAX_LEVELS];
-    for (int l = 0; l < rdvc::BLD_MAX_LEVELS; ++l) nl_of[l] = level_image_elems(h, w, l, vol_dtype, layout);
-    int twl = 0, thl = 0;
-    if (layout == RDVC_LAYOUT_TILED) {
-        tile_log2(vol_dtype, &twl, &thl);
+
+    if (plan.memset_bytes) {
         // padding pixels of a level must come out of the GEMM as exact zeros: clear the operand rows of
         // the levels that have any (the pack kernel writes only real pixels) -- ONE memset from the first
         // padded level to the end of the last level (the per-level buffers are contiguous)
-        int first = -1;
-        for (int l = 0; l < num_levels && first < 0; ++l)
-            if (nl_of[l] != static_cast<size_t>(h >> l) * (w >> l)) first = l;
-        if (first >= 0) {
-            uint8_t* lo = static_cast<uint8_t*>(b_km[first]);
-            uint8_t* hi = static_cast<uint8_t*>(b_km[num_levels - 1]) + static_cast<size_t>(B) * nl_of[num_levels - 1] * D * 2;
-            cudaError_t e = cudaMemsetAsync(lo, 0, static_cast<size_t>(hi - lo), st);
-            if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(padded operand rows)");
-        }
+        cudaError_t e = cudaMemsetAsync(plan.memset_ptr, 0, plan.memset_bytes, st);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(padded operand rows)");
     }
-
-    // operand format: fp16 inputs (the reference's default autocast, R:codec_processing.py:1436) stay fp16
-    // -- same tensor-core rate, 11 instead of 8 mantissa bits; everything else is multiplied as bf16
-    const int f16_ops = (in_dtype == RDVC_DT_F16) ? 1 : 0;
-    const CUtensorMapDataType op_dt = f16_ops ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
-
     // 1. repack to K-major 16-bit rows; the linear mode also needs the pooled fmap2 levels
     {
-        const int levels2 = linear ? num_levels : 1;
-        if (in_dtype == RDVC_DT_F32) rc = launch_pack<float>(fmap1, fmap2, a_km, b_km, B, D, h, w, levels2, layout, twl, thl, nl_of, f16_ops, st);
-        else if (in_dtype == RDVC_DT_BF16) rc = launch_pack<__nv_bfloat16>(fmap1, fmap2, a_km, b_km, B, D, h, w, levels2, layout, twl, thl, nl_of, f16_ops, st);
-        else rc = launch_pack<__half>(fmap1, fmap2, a_km, b_km, B, D, h, w, levels2, layout, twl, thl, nl_of, f16_ops, st);
+        const int levels2 = plan.linear ? num_levels : 1;
+        if (in_dtype == RDVC_DT_F32) rc = launch_pack<float>(fmap1, fmap2, plan.a_km, plan.b_km, B, D, h, w, levels2, layout, plan.twl, plan.thl, plan.nl_of, key.f16_ops, st);
+        else if (in_dtype == RDVC_DT_BF16) rc = launch_pack<__nv_bfloat16>(fmap1, fmap2, plan.a_km, plan.b_km, B, D, h, w, levels2, layout, plan.twl, plan.thl, plan.nl_of, key.f16_ops, st);
+        else rc = launch_pack<__half>(fmap1, fmap2, plan.a_km, plan.b_km, B, D, h, w, levels2, layout, plan.twl, plan.thl, plan.nl_of, key.f16_ops, st);
         if (rc) return rc;
     }
-
-    // 2. fused mode tile shape: 16x16 fmap2 pixels unless 8x32 wastes less padding
-    int tile = g_opt_tile.load();
-    auto padded = [&](int ty, int tx) {
-        return static_cast<long long>((h + ty - 1) / ty) * ty * ((w + tx - 1) / tx) * tx;
-    };
-    if (tile == 0) tile = (padded(8, 32) < padded(16, 16)) ? 2 : 1;
-    const int TY = (tile == 1) ? 16 : 8, TX = (tile == 1) ? 16 : 32;
-
-    // 3. TMA descriptors over the repacked maps
-    CUtensorMap ta, tb[rdvc::BLD_MAX_LEVELS];
-    {
-        cuuint64_t dims[3] = {(cuuint64_t)D, (cuuint64_t)N, (cuuint64_t)B};
-        cuuint64_t str[2] = {(cuuint64_t)D * 2, (cuuint64_t)N * D * 2};
-        cuuint32_t box[3] = {rdvc::BLD_BLOCK_K, rdvc::BLD_BLOCK_M, 1};
-        rc = make_tmap(&ta, op_dt, a_km, 3, dims, str, box);
-        if (rc) return rc;
-    }
-    if (linear) {
-        for (int l = 0; l < rdvc::BLD_MAX_LEVELS; ++l) {
-            const int ll = l < num_levels ? l : 0;  // unused slots alias level 0
-            const cuuint64_t nl = (cuuint64_t)nl_of[ll];
-            cuuint64_t dims[3] = {(cuuint64_t)D, nl, (cuuint64_t)B};
-            cuuint64_t str[2] = {(cuuint64_t)D * 2, nl * D * 2};
-            cuuint32_t box[3] = {rdvc::BLD_BLOCK_K, rdvc::BLD_BLOCK_N, 1};
-            rc = make_tmap(&tb[l], op_dt, b_km[ll], 3, dims, str, box);
-            if (rc) return rc;
-        }
-    } else {
-        cuuint64_t dims[4] = {(cuuint64_t)D, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)B};
-        cuuint64_t str[3] = {(cuuint64_t)D * 2, (cuuint64_t)w * D * 2, (cuuint64_t)N * D * 2};
-        cuuint32_t box[4] = {rdvc::BLD_BLOCK_K, (cuuint32_t)TX, (cuuint32_t)TY, 1};
-        rc = make_tmap(&tb[0], op_dt, b_km[0], 4, dims, str, box);
-        if (rc) return rc;
-        tb[1] = tb[2] = tb[3] = tb[0];
-    }
-
-    rdvc::BuildParams p;
-    memset(&p, 0, sizeof(p));
-    for (int l = 0; l < num_levels; ++l) {
-        p.lvl[l] = static_cast<uint8_t*>(pyramid) + rdvc_corr_level_offset_bytes(B, h, w, l, vol_dtype, layout);
-        p.hl[l] = h >> l;
-        p.wl[l] = w >> l;
-        p.nl[l] = static_cast<int>(nl_of[l]);
-    }
-    p.B = B; p.h = h; p.w = w; p.N = N;
-    p.num_levels = num_levels;
-    p.kc = D / 64;
-    p.m_blks = (N + rdvc::BLD_BLOCK_M - 1) / rdvc::BLD_BLOCK_M;
-    p.nty = (h + TY - 1) / TY;
-    p.ntx = (w + TX - 1) / TX;
-    if (linear) {
-        int t = 0;
-        for (int l = 0; l < rdvc::BLD_MAX_LEVELS; ++l) {
-            p.tile_start[l] = t;
-            if (l < num_levels) t += (p.nl[l] + rdvc::BLD_BLOCK_N - 1) / rdvc::BLD_BLOCK_N;
-        }
-        p.ntiles = t;
-    } else {
-        p.ntiles = p.nty * p.ntx;
-    }
-    p.scale = static_cast<float>(1.0 / std::sqrt(static_cast<double>(D)));
-    p.ab_format = f16_ops ? 0 : 1;
-    p.dbg_store_mask = g_opt_store_mask.load();
-    p.dbg_policy = g_opt_policy.load();
-    {
-        // m-range slices per fmap2 tile: enough (tile, slice) items to fill the SMs in whole
-        // waves.  cost = waves x (m-blocks per slice + ~0.5 for the 128 KB tile reload); a mild
-        // bias toward few slices keeps concurrent CTAs on the same query rows (see kernel).
-        const long long units = static_cast<long long>(B) * p.ntiles;
-        const int G = sm_count();
-        int best = 1;
-        double best_cost = 1e300;
-        const int s_max = p.m_blks < 64 ? p.m_blks : 64;
-        for (int S = 1; S <= s_max; ++S) {
-            const long long waves = (units * S + G - 1) / G;
-            const double cost = waves * ((p.m_blks + S - 1) / S + 0.5) * (1.0 + 0.005 * S);
-            if (cost < best_cost) { best_cost = cost; best = S; }
-        }
-        const int forced = g_opt_msplit.load();
-        p.msplit = (forced > 0) ? (forced < p.m_blks ? forced : p.m_blks) : best;
-    }
-
-    // output descriptors (linear mode).  Row pitch a multiple of 128 bytes (always, in the tiled
-    // layout): level l as a {128 B, pitch/128, N, B} tensor written in boxes of 16 query rows x 256
-    // contiguous bytes.  Row pitch only 16-byte aligned: a {n_l, N, B} tensor, boxes of 32 rows x 128
-    // bytes.  Anything else takes the staged-store path.  (option key 5: 0 = staged only, 1 = auto,
-    // 2 = never the wide boxes)
-    CUtensorMap to[rdvc::BLD_MAX_LEVELS];
-    for (int l = 0; l < rdvc::BLD_MAX_LEVELS; ++l) to[l] = ta;
-    const int tma_opt = g_opt_tma_out.load();
-    if (linear && tma_opt) {
-        const bool f32 = (vol_dtype == RDVC_DT_F32);
-        const cuuint64_t es = f32 ? 4 : 2;
-        const CUtensorMapDataType dt = f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
-        for (int l = 0; l < num_levels; ++l) {
-            const cuuint64_t nl = (cuuint64_t)p.nl[l];
-            if ((nl * es) % 128 == 0 && tma_opt == 1) {
-                cuuint64_t dims[4] = {128 / es, nl * es / 128, (cuuint64_t)N, (cuuint64_t)B};
-                cuuint64_t str[3] = {128, nl * es, (cuuint64_t)N * nl * es};
-                cuuint32_t box[4] = {(cuuint32_t)(128 / es), 2, 16, 1};
-                rc = make_tmap(&to[l], dt, p.lvl[l], 4, dims, str, box);
-                if (rc) return rc;
-                p.tma_out |= 2 << (2 * l);
-            } else if ((nl * es) % 16 == 0) {
-                cuuint64_t dims[3] = {nl, (cuuint64_t)N, (cuuint64_t)B};
-                cuuint64_t str[2] = {nl * es, (cuuint64_t)N * nl * es};
-                cuuint32_t box[3] = {(cuuint32_t)(128 / es), 32, 1};
-                rc = make_tmap(&to[l], dt, p.lvl[l], 3, dims, str, box);
-                if (rc) return rc;
-                p.tma_out |= 1 << (2 * l);
-            }
-        }
-    }
-
-    using rdvc::MODE_FUSED;
+    // 2. the GEMM
+    const CUtensorMap& ta = plan.ta;
+    const CUtensorMap* tb = plan.tb;
+    const CUtensorMap* to = plan.to;
+    const rdvc::BuildParams& p = plan.p;
     using rdvc::MODE_LINEAR;
-    // CTA-pair kernel (cta_group::2): linear mode with every level on the wide-box path (always true for
-    // the tiled layout).  Option key 12: 0 = auto, 1 = single-CTA kernel, 2 = pair kernel where possible.
-    bool pair_ok = linear && (sm_count() >= 2);
-    for (int l = 0; l < num_levels; ++l) pair_ok = pair_ok && (((p.tma_out >> (2 * l)) & 3) == 2);
-    const int pair_opt = g_opt_pair.load();
-    if (pair_ok && (pair_opt == 2 || (pair_opt == 0 && RDVC_PAIR_DEFAULT))) {
-        CUtensorMap tb2[rdvc::BLD_MAX_LEVELS];
-        for (int l = 0; l < rdvc::BLD_MAX_LEVELS; ++l) {
-            const int ll = l < num_levels ? l : 0;
-            const cuuint64_t nl = (cuuint64_t)nl_of[ll];
-            cuuint64_t dims[3] = {(cuuint64_t)D, nl, (cuuint64_t)B};
-            cuuint64_t str[2] = {(cuuint64_t)D * 2, nl * D * 2};
-            cuuint32_t box[3] = {rdvc::BLD_BLOCK_K, rdvc::BLD_BLOCK_N / 2, 1};   // each CTA loads half the tile
-            rc = make_tmap(&tb2[l], op_dt, b_km[ll], 3, dims, str, box);
-            if (rc) return rc;
-        }
-        rdvc::BuildParams p2 = p;
-        p2.m_blks = (N + 2 * rdvc::BLD_BLOCK_M - 1) / (2 * rdvc::BLD_BLOCK_M);
-        {
-            const long long units = static_cast<long long>(B) * p2.ntiles;
-            const int G = sm_count() / 2;
-            int best = 1;
-            double best_cost = 1e300;
-            const int s_max = p2.m_blks < 64 ? p2.m_blks : 64;
-            for (int S = 1; S <= s_max; ++S) {
-                const long long waves = (units * S + G - 1) / G;
-                const double cost = waves * ((p2.m_blks + S - 1) / S + 0.5) * (1.0 + 0.005 * S);
-                if (cost < best_cost) { best_cost = cost; best = S; }
-            }
-            const int forced = g_opt_msplit.load();
-            p2.msplit = (forced > 0) ? (forced < p2.m_blks ? forced : p2.m_blks) : best;
-        }
-        return (vol_dtype == RDVC_DT_F32) ? launch_build_pair<float>(ta, tb2, to, p2, st)
-                                          : launch_build_pair<__nv_bfloat16>(ta, tb2, to, p2, st);
-    }
-    if (linear) {
-        // epilogue shape per storage type: see BuildCfg (option key 9: 0 = auto, 4 / 8 = force)
-        int ew = g_opt_epi_warps.load();
-        if (ew == 0) ew = (vol_dtype == RDVC_DT_F32) ? 8 : 4;
+#ifdef RDVC_EXPERIMENTS
+    using rdvc::MODE_FUSED;
+    if (plan.pair)
+        return (vol_dtype == RDVC_DT_F32) ? launch_build_pair<float>(ta, plan.tb2, to, plan.p2, st)
+                                          : launch_build_pair<__nv_bfloat16>(ta, plan.tb2, to, plan.p2, st);
+    if (!plan.linear) {
         if (vol_dtype == RDVC_DT_F32)
-            return ew == 8 ? launch_build<MODE_LINEAR, 16, 16, float, 8>(ta, tb, to, p, st)
-                           : launch_build<MODE_LINEAR, 16, 16, float, 4>(ta, tb, to, p, st);
-        return ew == 8 ? launch_build<MODE_LINEAR, 16, 16, __nv_bfloat16, 8>(ta, tb, to, p, st)
-                       : launch_build<MODE_LINEAR, 16, 16, __nv_bfloat16, 4>(ta, tb, to, p, st);
+            return (plan.tile == 1) ? launch_build<MODE_FUSED, 16, 16, float, 8>(ta, tb, to, p, st)
+                                    : launch_build<MODE_FUSED, 8, 32, float, 8>(ta, tb, to, p, st);
+        return (plan.tile == 1) ? launch_build<MODE_FUSED, 16, 16, __nv_bfloat16, 8>(ta, tb, to, p, st)
+                                : launch_build<MODE_FUSED, 8, 32, __nv_bfloat16, 8>(ta, tb, to, p, st);
     }
-    if (vol_dtype == RDVC_DT_F32) {
-        return (tile == 1) ? launch_build<MODE_FUSED, 16, 16, float, 8>(ta, tb, to, p, st)
-                           : launch_build<MODE_FUSED, 8, 32, float, 8>(ta, tb, to, p, st);
-    }
-    return (tile == 1) ? launch_build<MODE_FUSED, 16, 16, __nv_bfloat16, 8>(ta, tb, to, p, st)
-                       : launch_build<MODE_FUSED, 8, 32, __nv_bfloat16, 8>(ta, tb, to, p, st);
+#endif
+    // epilogue shape per storage type: see BuildCfg (option key 9: 0 = auto, 4 / 8 = force)
+    if (vol_dtype == RDVC_DT_F32)
+        return plan.ew == 8 ? launch_build<MODE_LINEAR, 16, 16, float, 8>(ta, tb, to, p, st)
+                            : launch_build<MODE_LINEAR, 16, 16, float, 4>(ta, tb, to, p, st);
+    return plan.ew == 8 ? launch_build<MODE_LINEAR, 16, 16, __nv_bfloat16, 8>(ta, tb, to, p, st)
+                        : launch_build<MODE_LINEAR, 16, 16, __nv_bfloat16, 4>(ta, tb, to, p, st);
 }
 
-int rdvc_corr_lookup(const void* pyramid, int vol_dtype, int layout, const float* coords, int B, int h,
-                     int w, int num_levels, int radius, float* out, void* stream) {
+size_t rdvc_corr_feat_pitch(int num_levels, int radius) {
+    if (num_levels < 1 || num_levels > rdvc::LKP_MAX_LEVELS || radius < 1 || radius > 4) return 0;
+    return static_cast<size_t>(rdvc::lkp_feat_pitch(num_levels, radius));
+}
+
+int rdvc_corr_lookup_ex(const void* pyramid, int vol_dtype, int layout, const float* coords, int B, int h,
+                        int w, int num_levels, int radius, void* out, int out_dtype, int out_form, void* stream) {
     if (!pyramid || !coords || !out) return fail(RDVC_E_NULL, "null pointer argument");
     int rc = check_geometry(B, h, w, num_levels);
     if (rc) return rc;
@@ -639,6 +791,22 @@ int rdvc_corr_lookup(const void* pyramid, int vol_dtype, int layout, const float
         return fail(RDVC_E_UNSUPPORTED, "unknown pyramid layout %d", layout);
     if (reinterpret_cast<uintptr_t>(pyramid) & 15)
         return fail(RDVC_E_ALIGN, "pyramid must be 16-byte aligned");
+    if (radius < 1 || radius > 4) return fail(RDVC_E_UNSUPPORTED, "radius=%d not in [1, 4]", radius);
+    int out_mode;
+    if (out_form == RDVC_OUT_NCHW) {
+        if (out_dtype == RDVC_DT_F32) out_mode = rdvc::LKP_OUT_NCHW_F32;
+        else if (out_dtype == RDVC_DT_F16) out_mode = rdvc::LKP_OUT_NCHW_F16;
+        else return fail(RDVC_E_DTYPE, "NCHW lookup output must be F32 or F16, got out_dtype=%d", out_dtype);
+    } else if (out_form == RDVC_OUT_KMAJOR) {
+        if (out_dtype == RDVC_DT_BF16) out_mode = rdvc::LKP_OUT_KM_BF16;
+        else if (out_dtype == RDVC_DT_F16) out_mode = rdvc::LKP_OUT_KM_F16;
+        else return fail(RDVC_E_DTYPE, "K-major feature rows must be BF16 or F16, got out_dtype=%d", out_dtype);
+        if (reinterpret_cast<uintptr_t>(out) & 15) return fail(RDVC_E_ALIGN, "feature rows must be 16-byte aligned");
+    } else {
+        return fail(RDVC_E_UNSUPPORTED, "unknown lookup output form %d", out_form);
+    }
+    if (out_mode != rdvc::LKP_OUT_NCHW_F32 && layout != RDVC_LAYOUT_TILED)
+        return fail(RDVC_E_UNSUPPORTED, "fp16 / K-major lookup outputs need RDVC_LAYOUT_TILED");
     rdvc::LookupParams p;
     memset(&p, 0, sizeof(p));
     for (int l = 0; l < num_levels; ++l) {
@@ -653,6 +821,7 @@ int rdvc_corr_lookup(const void* pyramid, int vol_dtype, int layout, const float
     }
     p.coords = coords;
     p.out = out;
+    p.feat_pitch = rdvc::lkp_feat_pitch(num_levels, radius);
     p.B = B;
     p.N = h * w;
     p.num_levels = num_levels;
@@ -661,14 +830,124 @@ int rdvc_corr_lookup(const void* pyramid, int vol_dtype, int layout, const float
     const int variant = g_opt_lookup.load();
     if (layout == RDVC_LAYOUT_TILED) {
         const int dbg = variant >= 3 ? variant - 2 : 0;
-        return (vol_dtype == RDVC_DT_F32) ? dispatch_lookup_tiled<float>(dbg, radius, p, st)
-                                          : dispatch_lookup_tiled<__nv_bfloat16>(dbg, radius, p, st);
+        return (vol_dtype == RDVC_DT_F32) ? dispatch_lookup_tiled<float>(out_mode, dbg, radius, p, st)
+                                          : dispatch_lookup_tiled<__nv_bfloat16>(out_mode, dbg, radius, p, st);
     }
     if (vol_dtype == RDVC_DT_F32) {
         if (variant == 1) return dispatch_lookup_radius<float, 0>(radius, p, st);
         return dispatch_lookup_radius<float, 1>(radius, p, st);
     }
     return dispatch_lookup_radius<__nv_bfloat16, 0>(radius, p, st);
+}
+
+int rdvc_corr_lookup(const void* pyramid, int vol_dtype, int layout, const float* coords, int B, int h,
+                     int w, int num_levels, int radius, float* out, void* stream) {
+    return rdvc_corr_lookup_ex(pyramid, vol_dtype, layout, coords, B, h, w, num_levels, radius, out, RDVC_DT_F32,
+                               RDVC_OUT_NCHW, stream);
+}
+
+// ---- next row f-1: lookup + MotionEncoder.convcorr1 ------------------------------------------
+size_t rdvc_conv1x1_packed_weight_bytes(int cout, int num_levels, int radius) {
+    const size_t kp = rdvc_corr_feat_pitch(num_levels, radius);
+    if (kp == 0 || cout <= 0 || cout > rdvc::C1_MAX_COUT || cout % 32 != 0) return 0;
+    return static_cast<size_t>(cout) * align_up(kp, 64) * 2;
+}
+
+int rdvc_conv1x1_pack_weights(const float* weight, int cout, int num_levels, int radius, int feat_dtype,
+                              void* packed_host) {
+    if (!weight || !packed_host) return fail(RDVC_E_NULL, "null pointer argument");
+    if (feat_dtype != RDVC_DT_BF16 && feat_dtype != RDVC_DT_F16)
+        return fail(RDVC_E_DTYPE, "feat_dtype must be BF16 or F16, got %d", feat_dtype);
+    const size_t kp = rdvc_corr_feat_pitch(num_levels, radius);
+    if (kp == 0) return fail(RDVC_E_UNSUPPORTED, "num_levels=%d / radius=%d not supported", num_levels, radius);
+    if (cout <= 0 || cout > rdvc::C1_MAX_COUT || cout % 32 != 0)
+        return fail(RDVC_E_UNSUPPORTED, "cout=%d must be a multiple of 32 and <= %d", cout, rdvc::C1_MAX_COUT);
+    const int S = 2 * radius + 1, PL = rdvc::lkp_level_pitch(radius);
+    const size_t kpw = align_up(kp, 64);
+    const int cin = num_levels * S * S;
+    uint16_t* out = static_cast<uint16_t*>(packed_host);
+    memset(out, 0, static_cast<size_t>(cout) * kpw * 2);
+    for (int n = 0; n < cout; ++n)
+        for (int l = 0; l < num_levels; ++l)
+            for (int i = 0; i < S; ++i)          // torchvision channel = l*S*S + i*S + j  (i moves x, TV:raft.py:404-412)
+                for (int j = 0; j < S; ++j) {
+                    const float v = weight[static_cast<size_t>(n) * cin + l * S * S + i * S + j];
+                    uint16_t bits;
+                    if (feat_dtype == RDVC_DT_F16) { const __half hv = __float2half_rn(v); memcpy(&bits, &hv, 2); }
+                    else { const __nv_bfloat16 bv = __float2bfloat16_rn(v); memcpy(&bits, &bv, 2); }
+                    out[static_cast<size_t>(n) * kpw + l * PL + j * S + i] = bits;   // the lookup's column order
+                }
+    return RDVC_OK;
+}
+
+int rdvc_conv1x1(const void* feat, int feat_dtype, const void* packed_w, const float* bias, int B, int h, int w,
+                 int num_levels, int radius, int cout, int act, void* out, int out_dtype, void* stream) {
+    if (!feat || !packed_w || !out) return fail(RDVC_E_NULL, "null pointer argument");
+    if (B <= 0 || h <= 0 || w <= 0) return fail(RDVC_E_SHAPE, "non-positive dimension B=%d h=%d w=%d", B, h, w);
+    if (feat_dtype != RDVC_DT_BF16 && feat_dtype != RDVC_DT_F16)
+        return fail(RDVC_E_DTYPE, "feat_dtype must be BF16 or F16, got %d", feat_dtype);
+    if (out_dtype != RDVC_DT_F32 && out_dtype != RDVC_DT_F16 && out_dtype != RDVC_DT_BF16)
+        return fail(RDVC_E_DTYPE, "unsupported out_dtype=%d", out_dtype);
+    if (act != RDVC_ACT_NONE && act != RDVC_ACT_RELU) return fail(RDVC_E_UNSUPPORTED, "unknown activation %d", act);
+    const size_t kp = rdvc_corr_feat_pitch(num_levels, radius);
+    if (kp == 0) return fail(RDVC_E_UNSUPPORTED, "num_levels=%d / radius=%d not supported", num_levels, radius);
+    if (cout <= 0 || cout > rdvc::C1_MAX_COUT || cout % 32 != 0)
+        return fail(RDVC_E_UNSUPPORTED, "cout=%d must be a multiple of 32 and <= %d", cout, rdvc::C1_MAX_COUT);
+    if ((reinterpret_cast<uintptr_t>(feat) & 15) || (reinterpret_cast<uintptr_t>(packed_w) & 15))
+        return fail(RDVC_E_ALIGN, "feature rows and packed weights must be 16-byte aligned");
+    const long long m_total = static_cast<long long>(B) * h * w;
+    if (m_total >= (1LL << 31) - 256) return fail(RDVC_E_UNSUPPORTED, "too many pixels for 32-bit TMA coordinates");
+    const size_t kpw = align_up(kp, 64);
+    const CUtensorMapDataType op_dt = (feat_dtype == RDVC_DT_F16) ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+    CUtensorMap tm_a, tm_w;
+    {
+        cuuint64_t dims[3] = {(cuuint64_t)kp, (cuuint64_t)m_total, 1};
+        cuuint64_t str[2] = {(cuuint64_t)kp * 2, (cuuint64_t)m_total * kp * 2};
+        cuuint32_t box[3] = {rdvc::C1_BLOCK_K, rdvc::C1_BLOCK_M, 1};
+        if (int rc = make_tmap(&tm_a, op_dt, const_cast<void*>(feat), 3, dims, str, box)) return rc;
+    }
+    {
+        cuuint64_t dims[3] = {(cuuint64_t)kpw, (cuuint64_t)cout, 1};
+        cuuint64_t str[2] = {(cuuint64_t)kpw * 2, (cuuint64_t)cout * kpw * 2};
+        cuuint32_t box[3] = {rdvc::C1_BLOCK_K, (cuuint32_t)(cout / 2), 1};
+        if (int rc = make_tmap(&tm_w, op_dt, const_cast<void*>(packed_w), 3, dims, str, box)) return rc;
+    }
+    rdvc::Conv1x1Params p;
+    memset(&p, 0, sizeof(p));
+    p.out = out; p.bias = bias; p.m_total = m_total; p.n_pix = h * w; p.cout = cout; p.kp = static_cast<int>(kp);
+    p.relu = (act == RDVC_ACT_RELU); p.ab_format = (feat_dtype == RDVC_DT_F16) ? 0 : 1;
+    // every CTA owns a contiguous range of pixel rows (a multiple of 32, one warp's rows), as equal as possible
+    const int G = sm_count() & ~1;
+    if (G < 2) return fail(RDVC_E_UNSUPPORTED, "the 1x1 convolution runs on CTA pairs: needs at least 2 SMs");
+    long long rows = (m_total + G - 1) / G;
+    rows = (rows + 31) / 32 * 32;
+    p.rows_per_cta = static_cast<int>(rows);
+    p.tiles_per_cta = static_cast<int>((rows + rdvc::C1_BLOCK_M - 1) / rdvc::C1_BLOCK_M);
+    long long grid = (m_total + rows - 1) / rows;
+    grid = (grid + 1) & ~1LL;                                  // whole CTA pairs (a trailing CTA may own no rows)
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    cudaError_t e;
+    if (out_dtype == RDVC_DT_F32) e = launch_conv1x1<float>(tm_a, tm_w, p, static_cast<unsigned>(grid), st);
+    else if (out_dtype == RDVC_DT_F16) e = launch_conv1x1<__half>(tm_a, tm_w, p, static_cast<unsigned>(grid), st);
+    else e = launch_conv1x1<__nv_bfloat16>(tm_a, tm_w, p, static_cast<unsigned>(grid), st);
+    if (e != cudaSuccess) return cuda_fail(e, "corr_conv1x1_kernel launch");
+    return RDVC_OK;
+}
+
+int rdvc_corr_lookup_conv1x1(const void* pyramid, int vol_dtype, int layout, const float* coords, int B, int h,
+                             int w, int num_levels, int radius, const void* packed_w, const float* bias, int cout,
+                             int act, int feat_dtype, void* feat_ws, size_t feat_ws_bytes, void* out, int out_dtype,
+                             void* stream) {
+    if (!feat_ws) return fail(RDVC_E_NULL, "null pointer argument");
+    const size_t kp = rdvc_corr_feat_pitch(num_levels, radius);
+    if (kp == 0) return fail(RDVC_E_UNSUPPORTED, "num_levels=%d / radius=%d not supported", num_levels, radius);
+    if (B <= 0 || h <= 0 || w <= 0) return fail(RDVC_E_SHAPE, "non-positive dimension B=%d h=%d w=%d", B, h, w);
+    const size_t need = static_cast<size_t>(B) * h * w * kp * 2;
+    if (feat_ws_bytes < need) return fail(RDVC_E_WORKSPACE, "feature workspace %zu < required %zu", feat_ws_bytes, need);
+    int rc = rdvc_corr_lookup_ex(pyramid, vol_dtype, layout, coords, B, h, w, num_levels, radius, feat_ws, feat_dtype,
+                                 RDVC_OUT_KMAJOR, stream);
+    if (rc) return rc;
+    return rdvc_conv1x1(feat_ws, feat_dtype, packed_w, bias, B, h, w, num_levels, radius, cout, act, out, out_dtype, stream);
 }
 
 int rdvc_motion_warp(const float* prev, const float* flow, int B, int C, int H, int W, int h_in, int w_in,
@@ -726,21 +1005,27 @@ void rdvc_corr_release(void) {
     for (auto& a : g_arena) release_arena(a);
 }
 
-int rdvc_corr_pair_host_submit(const float* fmap1_host, const float* fmap2_host, const float* coords_host,
-                               float* out_host, int B, int D, int h, int w, int num_levels, int radius,
-                               int iters, int vol_dtype, int slot) {
+int rdvc_corr_pair_host_submit_ex(const float* fmap1_host, const float* fmap2_host, const float* coords_host,
+                                  void* out_host, int B, int D, int h, int w, int num_levels, int radius,
+                                  int iters, int vol_dtype, int out_dtype, int slot) {
     if (!fmap1_host || !fmap2_host || !coords_host || !out_host) return fail(RDVC_E_NULL, "null pointer argument");
     if (slot < 0 || slot >= kHostSlots) return fail(RDVC_E_UNSUPPORTED, "slot=%d not in [0, %d)", slot, kHostSlots);
+    // validated before any size arithmetic or allocation (a bad enum is an argument error, not a crash)
+    if (vol_dtype != RDVC_DT_F32 && vol_dtype != RDVC_DT_BF16)
+        return fail(RDVC_E_DTYPE, "unsupported vol_dtype=%d", vol_dtype);
+    if (out_dtype != RDVC_DT_F32 && out_dtype != RDVC_DT_F16)
+        return fail(RDVC_E_DTYPE, "out_dtype must be F32 or F16, got %d", out_dtype);
     int rc = check_geometry(B, h, w, num_levels);
     if (rc) return rc;
     if (iters <= 0 || D <= 0) return fail(RDVC_E_SHAPE, "iters=%d D=%d must be positive", iters, D);
     if (radius < 1 || radius > 4) return fail(RDVC_E_UNSUPPORTED, "radius=%d not in [1, 4]", radius);
     const size_t N = static_cast<size_t>(h) * w;
     const size_t S = 2 * radius + 1;
+    const size_t oes = (out_dtype == RDVC_DT_F32) ? 4 : 2;
     const size_t fmap_bytes = align_up(static_cast<size_t>(B) * D * N * 4, 256);
     const size_t coords_bytes = align_up(static_cast<size_t>(B) * 2 * N * 4, 256);
     const size_t out_elems = static_cast<size_t>(B) * num_levels * S * S * N;
-    const size_t out_bytes = align_up(out_elems * 4, 256);
+    const size_t out_bytes = align_up(out_elems * oes, 256);
     const int layout = (g_opt_mode.load() == 1) ? RDVC_LAYOUT_ROWMAJOR : RDVC_LAYOUT_TILED;
     const size_t pyr_bytes = rdvc_corr_pyramid_bytes(B, h, w, num_levels, vol_dtype, layout);
     const size_t ws_bytes = rdvc_corr_workspace_bytes(B, D, h, w);
@@ -757,6 +1042,8 @@ int rdvc_corr_pair_host_submit(const float* fmap1_host, const float* fmap2_host,
         if ((e = cudaStreamCreateWithFlags(&a.compute, cudaStreamNonBlocking)) != cudaSuccess) return cuda_fail(e, "stream create");
         if ((e = cudaStreamCreateWithFlags(&a.copy, cudaStreamNonBlocking)) != cudaSuccess) return cuda_fail(e, "stream create");
         for (auto& ev : a.ev)
+            if ((e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess) return cuda_fail(e, "event create");
+        for (auto& ev : a.done)
             if ((e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess) return cuda_fail(e, "event create");
     }
     if (a.bytes < need) {
@@ -792,19 +1079,25 @@ int rdvc_corr_pair_host_submit(const float* fmap1_host, const float* fmap2_host,
         if (used[s]) {  // the D2H that last read this buffer must have finished
             if ((e = cudaStreamWaitEvent(a.compute, a.ev[s], 0)) != cudaSuccess) return cuda_fail(e, "wait event");
         }
-        rc = rdvc_corr_lookup(d_pyr, vol_dtype, layout, reinterpret_cast<const float*>(d_co + it * coords_bytes), B, h, w,
-                              num_levels, radius, reinterpret_cast<float*>(d_out[s]), a.compute);
+        rc = rdvc_corr_lookup_ex(d_pyr, vol_dtype, layout, reinterpret_cast<const float*>(d_co + it * coords_bytes), B, h, w,
+                                 num_levels, radius, d_out[s], out_dtype, RDVC_OUT_NCHW, a.compute);
         if (rc) return rc;
-        cudaEvent_t done;  // lookup finished -> copy stream may read
-        if ((e = cudaEventCreateWithFlags(&done, cudaEventDisableTiming)) != cudaSuccess) return cuda_fail(e, "event create");
-        cudaEventRecord(done, a.compute);
-        cudaStreamWaitEvent(a.copy, done, 0);
-        cudaEventDestroy(done);
-        if ((e = cudaMemcpyAsync(out_host + it * out_elems, d_out[s], out_elems * 4, cudaMemcpyDeviceToHost, a.copy)) != cudaSuccess) return cuda_fail(e, "D2H out");
+        // lookup finished -> copy stream may read (the slot's own events, created once with the arena)
+        if ((e = cudaEventRecord(a.done[s], a.compute)) != cudaSuccess) return cuda_fail(e, "event record");
+        if ((e = cudaStreamWaitEvent(a.copy, a.done[s], 0)) != cudaSuccess) return cuda_fail(e, "wait event");
+        if ((e = cudaMemcpyAsync(static_cast<uint8_t*>(out_host) + it * out_elems * oes, d_out[s], out_elems * oes,
+                                 cudaMemcpyDeviceToHost, a.copy)) != cudaSuccess) return cuda_fail(e, "D2H out");
         cudaEventRecord(a.ev[s], a.copy);
         used[s] = true;
     }
     return RDVC_OK;
+}
+
+int rdvc_corr_pair_host_submit(const float* fmap1_host, const float* fmap2_host, const float* coords_host,
+                               float* out_host, int B, int D, int h, int w, int num_levels, int radius,
+                               int iters, int vol_dtype, int slot) {
+    return rdvc_corr_pair_host_submit_ex(fmap1_host, fmap2_host, coords_host, out_host, B, D, h, w, num_levels, radius,
+                                         iters, vol_dtype, RDVC_DT_F32, slot);
 }
 
 int rdvc_corr_pair_host_wait(int slot) {

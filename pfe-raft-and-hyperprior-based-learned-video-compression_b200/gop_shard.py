@@ -9,8 +9,12 @@ a host-side gather of per-GOP byte strings into the `.rdvc` writer on rank 0.
 """
 from __future__ import annotations
 
+import logging
+import traceback
 from dataclasses import dataclass
 from typing import Callable, Dict, List, Optional, Sequence, Tuple
+
+log = logging.getLogger("rdvc_corr_b200.gop_shard")
 
 from . import rdvc_format as fmt
 
@@ -51,12 +55,19 @@ def assign_gops(gops: Sequence[Gop], world_size: int) -> List[List[Gop]]:
     return out
 
 
+def _is_fatal(exc: BaseException) -> bool:
+    """Errors a retry on the next frame cannot fix: CUDA runtime failures (sticky) and memory exhaustion."""
+    name = type(exc).__name__
+    msg = str(exc)
+    return isinstance(exc, MemoryError) or name in ("OutOfMemoryError", "AcceleratorError") or "CUDA error" in msg
+
+
 def encode_gop(gop: Gop, frames: Callable[[int], object], encode_iframe: Callable[[object], bytes],
-               encode_pframe: Callable[[object, object], bytes]) -> bytes:
+               encode_pframe: Callable[[object, object], bytes], failures: Optional[List[int]] = None) -> bytes:
     """Frame records of one GOP.  `frames(t)` returns frame t; `encode_iframe(frame)` returns the I
     payload; `encode_pframe(prev_original, cur)` the P payload (motion branch + codec).  A failing
     P-frame turns the NEXT frame into an I-frame, as the reference does
-    (R:codec_processing.py:1501-1506)."""
+    (R:codec_processing.py:1501-1506); the indices of failed frames are appended to `failures` when given."""
     parts: List[bytes] = []
     prev = None
     force_i = True
@@ -68,7 +79,18 @@ def encode_gop(gop: Gop, frames: Callable[[int], object], encode_iframe: Callabl
         else:
             try:
                 parts.append(fmt.FrameRecord(t, "P", encode_pframe(prev, cur)).pack())
-            except Exception:
+            except Exception as exc:
+                # the reference prints the error and its traceback and goes on (R:codec_processing.py:1501-1506);
+                # here the failed frame additionally gets an EMPTY P record (0x0 shapes, no bitstreams) so that the
+                # frame indices of the stream stay dense -- a deliberate divergence: a decoder must treat an empty
+                # P record as "repeat the previous reconstruction".  Errors that will not go away by themselves
+                # (a sticky CUDA error, out of memory) are re-raised instead of degrading the whole stream silently.
+                log.error("P-frame %d failed (%s: %s); next frame forced to I\n%s", t, type(exc).__name__, exc,
+                          traceback.format_exc())
+                if _is_fatal(exc):
+                    raise
+                if failures is not None:
+                    failures.append(t)
                 parts.append(fmt.FrameRecord(t, "P", fmt.pframe_payload((0, 0), b"", (0, 0), b"")).pack())
                 force_i = True
         prev = cur   # open loop: the ORIGINAL frame is the next reference
@@ -77,7 +99,8 @@ def encode_gop(gop: Gop, frames: Callable[[int], object], encode_iframe: Callabl
 
 def encode_gop_batched(gop: Gop, frames: Callable[[int], object], encode_iframe: Callable[[object], bytes],
                        encode_pframes: Callable[[Sequence[object], Sequence[object]], Sequence[bytes]],
-                       encode_pframe: Optional[Callable[[object, object], bytes]] = None) -> bytes:
+                       encode_pframe: Optional[Callable[[object, object], bytes]] = None,
+                       failures: Optional[List[int]] = None) -> bytes:
     """Like :func:`encode_gop`, but all P-frames of the GOP go through ONE call
     `encode_pframes([prev originals], [current frames]) -> [payloads]`: the encoder is open loop, so every
     (previous original, current) pair of a GOP is known up front and RAFT can run them as one batch.  If the
@@ -93,10 +116,12 @@ def encode_gop_batched(gop: Gop, frames: Callable[[int], object], encode_iframe:
             payloads = list(encode_pframes(fr[:-1], fr[1:]))
             if len(payloads) != len(ts) - 1:
                 raise RuntimeError("encode_pframes returned the wrong number of payloads")
-        except Exception:
-            if encode_pframe is None:
+        except Exception as exc:
+            log.error("batched P-frames of GOP %d failed (%s: %s); redoing the GOP frame by frame\n%s", gop.index,
+                      type(exc).__name__, exc, traceback.format_exc())
+            if encode_pframe is None or _is_fatal(exc):
                 raise
-            return encode_gop(gop, lambda t: fr[t - gop.start], encode_iframe, encode_pframe)
+            return encode_gop(gop, lambda t: fr[t - gop.start], encode_iframe, encode_pframe, failures)
         parts += [fmt.FrameRecord(t, "P", pl).pack() for t, pl in zip(ts[1:], payloads)]
     return b"".join(parts)
 

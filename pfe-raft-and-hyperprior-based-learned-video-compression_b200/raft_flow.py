@@ -7,7 +7,15 @@ flows.  :func:`raft_flow` executes the same modules in the same order but upsamp
 end -- bit-identical final flow, 11 mask-predictor + upsample passes fewer -- and uses the
 correlation block's preallocated output so the refinement loop allocates nothing.
 
-All convolutions stay stock PyTorch/cuDNN; only the correlation block is this library's.
+With ``fuse_convcorr1=True`` (default) the lookup and the first layer of the motion encoder --
+``MotionEncoder.convcorr1`` = 1x1 convolution 324 -> 256 + ReLU, TV:raft.py:185,202 -- run as
+``TVCorrBlock.index_pyramid_convcorr1`` ("next" row f-1): the (B, 324, h, w) fp32 lookup tensor is never
+written, and the rest of ``MotionEncoder.forward`` / ``UpdateBlock.forward`` (TV:raft.py:200-210, 278-285)
+is restated module by module.  The 1x1 convolution then multiplies 16-bit operands with fp32 accumulation
+(the stock fp32 path multiplies in TF32 / fp32): flows differ by ~1e-3 px, far inside the 0.05 px budget;
+``fuse_convcorr1=False`` keeps the stock modules and is bit-identical to ``RAFT.forward``.
+
+All other convolutions stay stock PyTorch/cuDNN; only the correlation block (and that 1x1) is this library's.
 
 :class:`GraphedRaftFlow` replays the whole call as ONE CUDA graph per input shape.  At the reference's
 default RAFT size (368x640, R:codec_processing.py:649-650) a P-frame's ~700 kernel launches cost more
@@ -32,8 +40,39 @@ def _coords_grid(batch: int, h: int, w: int, device) -> Tensor:
 
 
 @torch.no_grad()
+def _update_block_fused(model, blk: TVCorrBlock, hidden_state: Tensor, context: Tensor, coords1: Tensor, flow: Tensor):
+    """``UpdateBlock.forward`` (TV:raft.py:278-285) with ``MotionEncoder.forward`` (TV:raft.py:200-210) inlined and its
+    first step -- ``convcorr1(index_pyramid(coords1))`` -- replaced by the fused call."""
+    ub = model.update_block
+    me = ub.motion_encoder
+    conv = me.convcorr1[0]                              # Conv2dNormActivation(324, 256, norm_layer=None, kernel_size=1): [Conv2d, ReLU]
+    corr = blk.index_pyramid_convcorr1(coords1, conv.weight, conv.bias, relu=True)
+    corr = me.convcorr2(corr)
+    flow_orig = flow
+    f = me.convflow2(me.convflow1(flow))
+    corr_flow = me.conv(torch.cat([corr, f], dim=1))
+    motion_features = torch.cat([corr_flow, flow_orig], dim=1)
+    x = torch.cat([context, motion_features], dim=1)
+    hidden_state = ub.recurrent_block(hidden_state, x)
+    return hidden_state, ub.flow_head(hidden_state)
+
+
+def _can_fuse_convcorr1(model) -> bool:
+    """convcorr1 must be exactly Conv2d(k=1, stride 1, no padding, groups 1) + ReLU with cout a multiple of 32 <= 256."""
+    try:
+        seq = model.update_block.motion_encoder.convcorr1
+        conv, act = seq[0], seq[1]
+    except Exception:
+        return False
+    return (len(seq) == 2 and isinstance(conv, torch.nn.Conv2d) and isinstance(act, torch.nn.ReLU)
+            and conv.kernel_size == (1, 1) and conv.stride == (1, 1) and conv.padding == (0, 0) and conv.groups == 1
+            and conv.out_channels % 32 == 0 and conv.out_channels <= 256)
+
+
+@torch.no_grad()
 def raft_flow(model, image1: Tensor, image2: Tensor, num_flow_updates: int = 12,
-              corr_block: Optional[TVCorrBlock] = None, all_predictions: bool = False):
+              corr_block: Optional[TVCorrBlock] = None, all_predictions: bool = False,
+              fuse_convcorr1: bool = True):
     """Final optical flow (B, 2, H, W) of a torchvision RAFT ``model`` for one frame pair.
 
     ``corr_block`` defaults to ``model.corr_block``, which must be a :class:`TVCorrBlock`
@@ -53,7 +92,10 @@ def raft_flow(model, image1: Tensor, image2: Tensor, num_flow_updates: int = 12,
 
     fmaps = model.feature_encoder(torch.cat([image1, image2], dim=0))
     fmap1, fmap2 = torch.chunk(fmaps, chunks=2, dim=0)
+    if fmap1.shape[-2:] != (h // 8, w // 8):            # TV:raft.py:494-495
+        raise ValueError("The feature encoder should downsample H and W by 8")
     blk.build_pyramid(fmap1, fmap2)
+    fuse = fuse_convcorr1 and blk.layout == 1 and _can_fuse_convcorr1(model)      # 1 = RDVC_LAYOUT_TILED
 
     context_out = model.context_encoder(image1)
     hidden_size = model.update_block.hidden_state_size
@@ -63,12 +105,16 @@ def raft_flow(model, image1: Tensor, image2: Tensor, num_flow_updates: int = 12,
 
     coords0 = _coords_grid(batch, h // 8, w // 8, fmap1.device)
     coords1 = coords0.clone()
-    corr_out = torch.empty((batch, blk.out_channels, h // 8, w // 8), dtype=torch.float32, device=fmap1.device)
+    corr_out = None if fuse else torch.empty((batch, blk.out_channels, h // 8, w // 8), dtype=torch.float32,
+                                             device=fmap1.device)
     preds: List[Tensor] = []
     for it in range(num_flow_updates):
-        corr_features = index_pyramid(blk._pyr, coords1, blk.radius, out=corr_out)
         flow = coords1 - coords0
-        hidden_state, delta_flow = model.update_block(hidden_state, context, corr_features, flow)
+        if fuse:
+            hidden_state, delta_flow = _update_block_fused(model, blk, hidden_state, context, coords1, flow)
+        else:
+            corr_features = index_pyramid(blk._pyr, coords1, blk.radius, out=corr_out)
+            hidden_state, delta_flow = model.update_block(hidden_state, context, corr_features, flow)
         coords1 = coords1 + delta_flow
         if all_predictions or it == num_flow_updates - 1:
             up_mask = None if model.mask_predictor is None else model.mask_predictor(hidden_state)
@@ -87,18 +133,32 @@ class GraphedRaftFlow:
     """
 
     def __init__(self, model, num_flow_updates: int = 12, amp_dtype: Optional[torch.dtype] = None,
-                 volume_dtype: torch.dtype = torch.float32):
+                 volume_dtype: torch.dtype = torch.float32, fuse_convcorr1: bool = True, max_entries: int = 4):
         if not isinstance(model.corr_block, TVCorrBlock):
             raise TypeError("GraphedRaftFlow needs a model built with corr_block=rdvc_corr_b200.TVCorrBlock()")
+        if model.training:
+            # a graph captured in train mode would update BatchNorm running statistics on every replay
+            raise RuntimeError("GraphedRaftFlow is inference only: call model.eval() first")
         self.model = model
         self.num_flow_updates = num_flow_updates
         self.amp_dtype = amp_dtype
         self.volume_dtype = volume_dtype
-        self._entries = {}
+        self.fuse_convcorr1 = fuse_convcorr1
+        self.max_entries = max_entries        # every captured shape pins a pyramid (5.7 GB at 1080p fp32)
+        self._entries = {}                    # insertion-ordered: least recently used first
 
     def _run(self, blk, a, b):
         with torch.autocast("cuda", dtype=self.amp_dtype or torch.float16, enabled=self.amp_dtype is not None):
-            return raft_flow(self.model, a, b, self.num_flow_updates, corr_block=blk)
+            return raft_flow(self.model, a, b, self.num_flow_updates, corr_block=blk, fuse_convcorr1=self.fuse_convcorr1)
+
+    def release(self, key=None) -> None:
+        """Drop the captured graph(s) and the pyramids they pin (all shapes, or one ``(shape, dtype, device)`` key)."""
+        keys = list(self._entries) if key is None else [key]
+        for k in keys:
+            e = self._entries.pop(k, None)
+            if e is not None:
+                e["graph"] = None
+                e["blk"].release()
 
     def _capture(self, image1: Tensor, image2: Tensor):
         dev = image1.device
@@ -123,10 +183,15 @@ class GraphedRaftFlow:
             raise RuntimeError("rdvc_corr_b200 runs on an sm_100 GPU only; got CPU frames.")
         if image1.shape != image2.shape or image1.dtype != image2.dtype:
             raise ValueError(f"input images should have the same shape and dtype, got {image1.shape} / {image2.shape}")
+        if self.model.training:
+            raise RuntimeError("GraphedRaftFlow is inference only: the model was switched back to train mode")
         key = (tuple(image1.shape), image1.dtype, image1.device)
-        e = self._entries.get(key)
+        e = self._entries.pop(key, None)
         if e is None:
-            e = self._entries[key] = self._capture(image1, image2)
+            while len(self._entries) >= self.max_entries:          # evict the least recently used shape
+                self.release(next(iter(self._entries)))
+            e = self._capture(image1, image2)
+        self._entries[key] = e                                      # most recently used last
         e["in1"].copy_(image1)
         e["in2"].copy_(image2)
         e["graph"].replay()

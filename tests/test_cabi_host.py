@@ -26,14 +26,14 @@ def lib():
 def header_functions():
     src = open(HEADER).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    return sorted(set(re.findall(r"\b(rdvc_(?:corr|motion|preprocess|mcn)_\w+)\s*\(", src)))
+    return sorted(set(re.findall(r"\b(rdvc_(?:corr|motion|preprocess|mcn|conv1x1)\w*)\s*\(", src)))
 
 
 def test_header_symbols_exported(lib):
     declared = header_functions()
     assert len(declared) >= 10
     out = subprocess.check_output(["nm", "-D", "--defined-only", rc._cabi.lib_path()], text=True)
-    exported = set(re.findall(r"\bT (rdvc_(?:corr|motion|preprocess|mcn)_\w+)", out))
+    exported = set(re.findall(r"\bT (rdvc_(?:corr|motion|preprocess|mcn|conv1x1)\w*)", out))
     missing = [f for f in declared if f not in exported]
     assert not missing, f"header declares symbols the library does not export: {missing}"
     # and the ctypes table binds exactly the header's functions
@@ -68,7 +68,7 @@ def test_library_is_sm100a_with_tcgen05_and_tma():
 
 
 def test_version_and_sizes(lib):
-    assert lib.rdvc_corr_version() == 102
+    assert lib.rdvc_corr_version() == 103
     F32, BF16 = rc.RDVC_DT_F32, rc.RDVC_DT_BF16
     ROW, TILED = rc.RDVC_LAYOUT_ROWMAJOR, rc.RDVC_LAYOUT_TILED
     # 1080p: 136x240 -> 32640 query pixels, levels 136x240, 68x120, 34x60, 17x30
@@ -266,3 +266,84 @@ def test_coords_validation_without_gpu():
         rc.index_pyramid(pyr, torch.zeros(1, 2, 46, 81))
     with pytest.raises(RuntimeError, match="GPU only"):
         rc.index_pyramid(pyr, torch.zeros(1, 2, 46, 80))
+
+
+# ------------------------------------------------------------------ round 2: validation, build identity, f-1 host side
+def test_bad_volume_dtype_is_an_error_not_a_crash(lib):
+    """A bad vol_dtype enum used to divide by zero inside the size queries (SIGILL with the TILED layout)."""
+    for layout in (rc.RDVC_LAYOUT_ROWMAJOR, rc.RDVC_LAYOUT_TILED):
+        for bad in (7, -1, rc.RDVC_DT_F16):
+            assert lib.rdvc_corr_pyramid_bytes(1, 46, 80, 4, bad, layout) == 0
+            assert lib.rdvc_corr_level_offset_bytes(1, 46, 80, 2, bad, layout) == 0
+            assert lib.rdvc_corr_level_image_elems(46, 80, 0, bad, layout) == 0
+    buf = np.zeros(16, np.float32)
+    fp = buf.ctypes.data_as(ctypes.c_void_p)
+    # validated before any size arithmetic, allocation or CUDA call: works without a GPU
+    assert lib.rdvc_corr_pair_host_submit(fp, fp, fp, fp, 1, 64, 16, 16, 4, 4, 1, 7, 0) == -4
+    assert b"vol_dtype" in lib.rdvc_corr_last_error()
+    assert lib.rdvc_corr_pair_host_submit_ex(fp, fp, fp, fp, 1, 64, 16, 16, 4, 4, 1, rc.RDVC_DT_F32, rc.RDVC_DT_BF16, 0) == -4
+    assert lib.rdvc_corr_pair_host(fp, fp, fp, fp, 1, 64, 16, 16, 4, 4, 1, 7) == -4
+
+
+def test_library_is_built_from_this_tree(lib):
+    """The content hash of csrc/ + include/ is compiled into the library; the loader refuses a mismatch."""
+    info = lib.rdvc_corr_build_info().decode()
+    assert f"RDVC_SRC_HASH={rc._build.source_hash()}" in info and "version=103" in info
+    assert rc._build.embedded_hash(rc._cabi.lib_path()) == rc._build.source_hash()
+    assert not rc._build.is_stale(rc._cabi.lib_path())
+    if os.environ.get("RDVC_CORR_LIB") is None:
+        assert "experiments=0" in info and not rc._cabi.has_experiments()
+
+
+def test_stale_library_is_refused(tmp_path, monkeypatch):
+    fake = tmp_path / "librdvc_corr.so"
+    blob = open(rc._build.LIB_PATH, "rb").read().replace(rc._build.source_hash().encode(), b"0" * 64)
+    fake.write_bytes(blob)
+    monkeypatch.setenv("RDVC_CORR_LIB", str(fake))
+    monkeypatch.setattr(rc._cabi, "_lib", None)
+    with pytest.raises(RuntimeError, match="built from other sources"):
+        rc._cabi.load()
+
+
+def test_product_build_has_no_work_skipping_knobs(lib):
+    if rc._cabi.has_experiments():
+        pytest.skip("experiments build")
+    for key, value in [(0, 3), (0, 4), (3, 7), (4, 1), (6, 1), (12, 2)]:
+        assert lib.rdvc_corr_set_option(key, value) == -5, (key, value)
+    for key, value in [(0, 0), (3, 15), (4, 2), (4, 0), (6, 0), (12, 0), (12, 1)]:
+        assert lib.rdvc_corr_set_option(key, value) == 0, (key, value)
+    syms = subprocess.check_output(["nm", "-C", rc._cabi.lib_path()], text=True)
+    assert "corr_build2_kernel" not in syms                       # the CTA-pair build variant
+    assert "corr_build_kernel<0," not in syms                     # MODE_FUSED
+    assert "corr_conv1x1_kernel<float>" in syms and "corr_lookup_tiled_kernel<4, float, 2, 0>" in syms
+
+
+def test_conv1x1_weight_packing(lib):
+    """rdvc_conv1x1_pack_weights (pure host C): torchvision channel l*S*S + i*S + j lands in column l*PL + j*S + i
+    of a row padded to whole 64-element k-blocks; everything else is zero."""
+    assert lib.rdvc_corr_feat_pitch(4, 4) == 352 and lib.rdvc_corr_feat_pitch(4, 3) == 224
+    assert lib.rdvc_corr_feat_pitch(3, 4) == 272 and lib.rdvc_corr_feat_pitch(5, 4) == 0
+    for (L, r, cout, fd) in [(4, 4, 256, rc.RDVC_DT_BF16), (4, 3, 96, rc.RDVC_DT_F16), (2, 2, 32, rc.RDVC_DT_BF16)]:
+        S = 2 * r + 1
+        PL = (S * S + 7) // 8 * 8
+        kp = lib.rdvc_corr_feat_pitch(L, r)
+        kpw = (kp + 63) // 64 * 64
+        assert lib.rdvc_conv1x1_packed_weight_bytes(cout, L, r) == cout * kpw * 2
+        rng = np.random.default_rng(cout)
+        wgt = rng.standard_normal((cout, L * S * S)).astype(np.float32)
+        packed = np.full(cout * kpw, 0x7FFF, np.uint16)
+        rc._cabi.check(lib.rdvc_conv1x1_pack_weights(wgt.ctypes.data_as(ctypes.c_void_p), cout, L, r, fd,
+                                                     packed.ctypes.data_as(ctypes.c_void_p)), "pack")
+        t = torch.from_numpy(packed.view(np.int16).reshape(cout, kpw))
+        vals = t.view(torch.bfloat16 if fd == rc.RDVC_DT_BF16 else torch.float16).float().numpy()
+        want = np.zeros((cout, kpw), np.float32)
+        rnd = torch.bfloat16 if fd == rc.RDVC_DT_BF16 else torch.float16
+        for l in range(L):
+            for i in range(S):
+                for j in range(S):
+                    want[:, l * PL + j * S + i] = torch.from_numpy(wgt[:, l * S * S + i * S + j]).to(rnd).float().numpy()
+        assert np.array_equal(vals, want)
+    w = np.zeros((48, 324), np.float32)
+    assert lib.rdvc_conv1x1_pack_weights(w.ctypes.data_as(ctypes.c_void_p), 48, 4, 4, rc.RDVC_DT_BF16,
+                                         w.ctypes.data_as(ctypes.c_void_p)) == -5          # cout % 32 != 0
+    assert lib.rdvc_conv1x1_packed_weight_bytes(48, 4, 4) == 0

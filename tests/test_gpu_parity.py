@@ -57,6 +57,13 @@ def gpu(x):
     return torch.from_numpy(np.ascontiguousarray(x)).cuda()
 
 
+def need_experiments(mode=None):
+    """The fused-pooling build mode, the CTA-pair build kernel and the work-skipping knobs are compiled into
+    lib/librdvc_corr_exp.so only (-DRDVC_EXPERIMENTS; `RDVC_CORR_LIB=.../librdvc_corr_exp.so pytest -m gpu`)."""
+    if mode in (None, "fused") and not rc._cabi.has_experiments():
+        pytest.skip("needs the RDVC_EXPERIMENTS build of the library (not the product build)")
+
+
 # ------------------------------------------------------------------ lookup
 @pytest.mark.parametrize("path", list(LOOKUP_PATHS))
 @pytest.mark.parametrize("shape", [(2, 8, 18, 22), (1, 8, 46, 80), (1, 4, 16, 16), (1, 4, 17, 19)])
@@ -154,6 +161,7 @@ BUILD_SHAPES = [(1, 64, 16, 16), (2, 64, 18, 22), (1, 128, 33, 47), (1, 256, 46,
 @pytest.mark.parametrize("mode", ["fused", "linear"])
 @pytest.mark.parametrize("shape", BUILD_SHAPES)
 def test_build_fp32_volume(lib, shape, mode):
+    need_experiments(mode)
     B, D, h, w = shape
     f1, f2 = cn.synth_fmaps(B, D, h, w, seed=5)
     ref32 = cn.build_pyramid(f1, f2, 4)                       # fp64 math on the un-rounded inputs
@@ -179,6 +187,7 @@ def test_build_fp32_volume(lib, shape, mode):
 
 @pytest.mark.parametrize("mode", ["fused", "linear"])
 def test_build_bf16_volume(lib, mode):
+    need_experiments(mode)
     B, D, h, w = 1, 128, 46, 80
     f1, f2 = cn.synth_fmaps(B, D, h, w, seed=5)
     ref32 = cn.build_pyramid(f1, f2, 4)
@@ -213,6 +222,7 @@ def test_build_cta_pair_kernel_is_bit_identical(lib, vol):
     """The opt-in CTA-pair build (tcgen05 cta_group::2, M = 256 over two SMs; option key 12 = 2) performs the
     same MMAs in the same K order as the single-CTA kernel: the pyramids must be bit-identical, including
     partial 256-row blocks (N = 396: the peer CTA's rows fall off the end), partial tiles and B > 1."""
+    need_experiments()
     for (B, D, h, w) in [(2, 64, 18, 22), (1, 128, 33, 47), (1, 256, 46, 80)]:
         f1, f2 = cn.synth_fmaps(B, D, h, w, seed=17)
         set_opts(lib, pair=1)
@@ -314,50 +324,121 @@ def test_build_is_linear_and_deterministic(lib):
 
 
 # ------------------------------------------------------------------ full size: 1920x1088
-def test_1080p_properties(lib):
-    """BASELINE.json config 2 shape: the oracle cannot hold the 5.7 GB pyramid in seconds, so
-    check size-independent properties + sampled rows against a torch fp32 matmul."""
+@pytest.mark.parametrize("vol", [torch.float32, torch.bfloat16], ids=["fp32vol", "bf16vol"])
+def test_1080p_properties(lib, vol):
+    """BASELINE.json config 2 shape, BOTH pyramid storage types (the bf16 volume takes another build
+    instantiation -- 4 epilogue warps, 2 staging buffers, 4-stage ring -- and another lookup instantiation): the
+    oracle cannot hold the 5.7 GB pyramid in seconds, so check size-independent properties + sampled rows
+    against a torch fp64 matmul of the same rounded operands."""
     B, D, h, w = 1, 256, 136, 240
     N = h * w
+    bf = vol == torch.bfloat16
     g = torch.Generator(device="cuda").manual_seed(0)
     f1 = torch.randn(B, D, h, w, device="cuda", generator=g)
     f2 = torch.randn(B, D, h, w, device="cuda", generator=g)
-    blk = rc.TVCorrBlock()
+    blk = rc.TVCorrBlock(volume_dtype=vol)
     blk.build_pyramid(f1, f2)
-    lv = blk.corr_pyramid
-    assert [tuple(x.shape) for x in lv] == [(N, 1, 136, 240), (N, 1, 68, 120), (N, 1, 34, 60), (N, 1, 17, 30)]
+    pyr = blk._pyr
     a = f1.to(torch.bfloat16).float().view(D, N)
     f2p = [f2] + [torch.nn.functional.avg_pool2d(f2, 2 ** l) for l in (1, 2, 3)]
     rows = torch.tensor([0, 1, 127, 128, 4097, 17000, N - 129, N - 1], device="cuda")
+    shapes = [(136, 240), (68, 120), (34, 60), (17, 30)]
     for l in range(4):
         b = f2p[l].to(torch.bfloat16).float().view(D, -1)
         ref = (a[:, rows].t().double() @ b.double() / 16.0).float()
-        got = lv[l][rows, 0].reshape(len(rows), -1)
+        got4 = pyr.level(l, rows)
+        assert tuple(got4.shape) == (len(rows), 1) + shapes[l] and got4.dtype == vol
+        got = got4[:, 0].reshape(len(rows), -1).float()
         err = (got - ref).abs().max().item() / ref.abs().max().item()
-        assert err < (TOL_SAME_OPERANDS_F32 if l == 0 else TOL_SAME_OPERANDS_POOLED), (l, err)
+        tol = TOL_SAME_OPERANDS_BF16 if bf else (TOL_SAME_OPERANDS_F32 if l == 0 else TOL_SAME_OPERANDS_POOLED)
+        assert err < tol, (l, err)
     # pyramid consistency: level l+1 is the 2x2 mean of level l (to bf16-operand accuracy)
-    sl = slice(5000, 5256)
+    sl = torch.arange(5000, 5256, device="cuda")
     for l in range(3):
-        pooled = torch.nn.functional.avg_pool2d(lv[l][sl], 2)
-        err = (pooled - lv[l + 1][sl]).abs().max().item() / lv[l + 1][sl].abs().max().item()
+        lo, hi = pyr.level(l, sl).float(), pyr.level(l + 1, sl).float()
+        pooled = torch.nn.functional.avg_pool2d(lo, 2)
+        err = (pooled - hi).abs().max().item() / hi.abs().max().item()
         assert err < TOL_VOLUME, (l, err)
     # checksum of checksums: sum over fmap2 pixels == fmap1 . sum(fmap2)
-    tot = lv[0][rows, 0].double().sum(dim=(1, 2))
+    tot = pyr.level(0, rows)[:, 0].double().sum(dim=(1, 2))
     ref = (a[:, rows].t().double() @ f2.to(torch.bfloat16).double().view(D, N).sum(dim=1)) / 16.0
-    assert ((tot - ref).abs().max() / ref.abs().max()).item() < 1e-3
+    assert ((tot - ref).abs().max() / ref.abs().max()).item() < (2e-2 if bf else 1e-3)
     # lookup at the identity grid: centre tap of level 0 is the volume diagonal
     co = gpu(cn.make_coords_grid(B, h, w))
     out = blk.index_pyramid(centroids_coords=co)
     assert out.shape == (B, 324, h, w) and out.is_contiguous() and out.dtype == torch.float32
-    diag = lv[0].view(N, N).diagonal()
-    assert torch.equal(out[0, 4 * 9 + 4].reshape(-1), diag)
-    # and a drifting lookup against torchvision's own index_pyramid ON OUR PYRAMID
+    lv0 = pyr.level(0)                                   # (N, 1, h, w): 4.3 GB fp32 / 2.1 GB bf16
+    assert torch.equal(out[0, 4 * 9 + 4].reshape(-1), lv0.view(N, N).diagonal().float())
+    del lv0
+    # and a drifting lookup against torchvision's own index_pyramid ON OUR PYRAMID (up-cast for the bf16 volume:
+    # the kernel reads bf16 and interpolates in fp32, which is what grid_sample does on the up-cast copy)
     co2 = gpu(cn.synth_coords(B, h, w, 3.0, seed=4))
     got = blk.index_pyramid(centroids_coords=co2)
-    ref = tv.index_pyramid([x for x in lv], co2, 4)
+    ref = tv.index_pyramid([pyr.level(l).float() for l in range(4)], co2, 4)
     err = (got - ref).abs().max().item() / ref.abs().max().item()
     assert err < TOL_LOOKUP, err
     blk.release()
+
+
+# ------------------------------------------------------------------ config 5: the resolution sweep, asserted
+def _lookup_rows_reference(levels_rows, coords_rows, radius):
+    """torchvision's index_pyramid arithmetic (TV:raft.py:394-422) on a SUBSET of query pixels: levels_rows[l] is
+    (R, 1, h_l, w_l) fp32 (the rows' level images), coords_rows (R, 2) their (x, y) centroids -> (R, L*S*S)."""
+    from torchvision.models.optical_flow._utils import grid_sample
+    S = 2 * radius + 1
+    di = torch.linspace(-radius, radius, S, device=coords_rows.device)
+    delta = torch.stack(torch.meshgrid(di, di, indexing="ij"), dim=-1).view(1, S, S, 2)
+    cc = coords_rows.view(-1, 1, 1, 2)
+    out = []
+    for lv in levels_rows:
+        out.append(grid_sample(lv, cc + delta, align_corners=True, mode="bilinear").view(lv.shape[0], S * S))
+        cc = cc / 2
+    return torch.cat(out, dim=1)
+
+
+@pytest.mark.parametrize("frame,vol", [((1280, 720), torch.float32), ((1280, 720), torch.bfloat16),
+                                       ((2560, 1440), torch.float32), ((2560, 1440), torch.bfloat16),
+                                       ((3840, 2160), torch.bfloat16)],
+                         ids=["720p-fp32", "720p-bf16", "1440p-fp32", "1440p-bf16", "4k-bf16"])
+def test_resolution_sweep_parity(lib, frame, vol):
+    """BASELINE.json config 5 shapes: build AND lookup parity on sampled query rows, including the
+    last one, at sizes where pix * image_elems crosses 2^32 elements (1440p, 4K).  The volumes do not fit twice
+    (4K bf16: 45 GB), so rows are read back with CorrPyramid.level(l, rows) and the lookup reference is
+    torchvision's grid_sample arithmetic on just those rows' level images."""
+    W, H = frame
+    B, D, h, w = 1, 256, H // 8, W // 8
+    N = h * w
+    bf = vol == torch.bfloat16
+    g = torch.Generator(device="cuda").manual_seed(7)
+    f1 = torch.randn(B, D, h, w, device="cuda", generator=g)
+    f2 = torch.randn(B, D, h, w, device="cuda", generator=g)
+    blk = rc.TVCorrBlock(volume_dtype=vol)
+    blk.build_pyramid(f1, f2)
+    pyr = blk._pyr
+    # incl. the first rows whose element offset pix * image_elems passes 2^31 and 2^32 (where they exist)
+    rows = torch.tensor([0, 1, w - 1, w, N // 3, N // 2 + 7, min(N - 3, (1 << 31) // N + 1), min(N - 4, (1 << 32) // N + 1),
+                         N - w - 1, N - 2, N - 1], device="cuda")
+    a = f1.to(torch.bfloat16).float().view(D, N)[:, rows].t().double()
+    lv_rows = []
+    for l in range(4):
+        b = torch.nn.functional.avg_pool2d(f2, 2 ** l) if l else f2
+        ref = (a @ b.to(torch.bfloat16).double().view(D, -1) / 16.0).float()
+        got = pyr.level(l, rows)
+        assert tuple(got.shape) == (len(rows), 1, h >> l, w >> l)
+        lv_rows.append(got.float())
+        err = ((got[:, 0].reshape(len(rows), -1).float() - ref).abs().max() / ref.abs().max()).item()
+        tol = TOL_SAME_OPERANDS_BF16 if bf else (TOL_SAME_OPERANDS_F32 if l == 0 else TOL_SAME_OPERANDS_POOLED)
+        assert err < tol, (frame, l, err)
+    # lookups of the whole frame; compare the sampled rows (fractional drift + some windows off the border)
+    ys, xs = torch.meshgrid(torch.arange(h, device="cuda"), torch.arange(w, device="cuda"), indexing="ij")
+    co = torch.stack([xs, ys], 0).float()[None] + 2.5 * torch.randn(1, 2, h, w, device="cuda", generator=g)
+    out = blk.index_pyramid(centroids_coords=co)                       # (1, 324, h, w)
+    got = out.view(324, N)[:, rows].t()
+    ref = _lookup_rows_reference(lv_rows, co.view(2, N)[:, rows].t().contiguous(), 4)
+    err = ((got - ref).abs().max() / ref.abs().max()).item()
+    assert err < TOL_LOOKUP, (frame, err)
+    blk.release()
+    torch.cuda.empty_cache()
 
 
 # ------------------------------------------------------------------ drop-in: torchvision RAFT
@@ -419,10 +500,12 @@ def test_raft_flow_runner_matches_forward(lib, golden_dir):
     model = _seeded_raft(rc.TVCorrBlock())
     with torch.no_grad():
         ref = model(a, b, num_flow_updates=12)
-        got = rc.raft_flow(model, a, b, num_flow_updates=12)
-        every = rc.raft_flow(model, a, b, num_flow_updates=12, all_predictions=True)
+        got = rc.raft_flow(model, a, b, num_flow_updates=12, fuse_convcorr1=False)
+        every = rc.raft_flow(model, a, b, num_flow_updates=12, all_predictions=True, fuse_convcorr1=False)
     assert torch.allclose(got, ref[-1], rtol=0, atol=1e-5)
     assert len(every) == 12 and all(torch.allclose(x, y, rtol=0, atol=1e-5) for x, y in zip(every, ref))
+    fused = rc.raft_flow(model, a, b, num_flow_updates=12)      # default: lookup fused with convcorr1 (16-bit operands)
+    assert (fused - ref[-1]).pow(2).sum(dim=1).sqrt().mean().item() < TOL_EPE
     with pytest.raises(TypeError):
         rc.raft_flow(_seeded_raft(), a, b)
     with pytest.raises(ValueError, match="divisible by 8"):
@@ -449,6 +532,10 @@ def test_graphed_raft_flow_is_bit_identical(lib, golden_dir):
     assert torch.equal(runner(a, b), eager_ab)
     with pytest.raises(TypeError):
         rc.GraphedRaftFlow(_seeded_raft())
+    with pytest.raises(RuntimeError, match="inference only"):
+        rc.GraphedRaftFlow(_seeded_raft(rc.TVCorrBlock()).train())
+    runner.release()
+    assert not runner._entries
 
 
 def test_princeton_facade(lib):
@@ -460,6 +547,146 @@ def test_princeton_facade(lib):
     own = np.concatenate([x[:, 0].cpu().numpy().reshape(-1) for x in corr.corr_pyramid])
     assert got.shape == (B, 324, h, w)
     assert rel_max(got, cc.index_pyramid(own, co, 4, 4)) < TOL_LOOKUP
+
+
+# ------------------------------------------------------------------ other forms of the lookup result
+@pytest.mark.parametrize("vol", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("radius,levels", [(4, 4), (3, 4), (4, 3), (2, 2)])
+def test_lookup_output_forms(lib, radius, levels, vol):
+    """rdvc_corr_lookup_ex: the fp16 NCHW result is the fp32 result rounded once; the K-major feature rows hold the
+    same numbers (bf16 / fp16 rounded) at column l*PL + j*S + i for torchvision channel l*S*S + i*S + j, zeros in
+    the padding columns."""
+    B, C, h, w = 2, 8, 18, 22
+    S = 2 * radius + 1
+    f1, f2 = cn.synth_fmaps(B, C, h, w, seed=23)
+    flat = cc.build_pyramid(f1, f2, levels)
+    pyr = pyramid_from_levels(rc, cc.split_levels(flat, B, h, w, levels), B, h, w, vol)
+    co = gpu(cn.synth_coords(B, h, w, 3.0, seed=2))
+    ref = rc.index_pyramid(pyr, co, radius)                                     # (B, L*S*S, h, w) fp32
+    assert torch.equal(rc.index_pyramid(pyr, co, radius, out_dtype=torch.float16), ref.half())
+    kp = rc.corr_block.feat_pitch(levels, radius)
+    PL = (S * S + 7) // 8 * 8
+    assert kp == (levels * PL + 15) // 16 * 16
+    # torchvision channel (l, i, j) -> column l*PL + j*S + i
+    l_, i_, j_ = torch.meshgrid(torch.arange(levels), torch.arange(S), torch.arange(S), indexing="ij")
+    col = (l_ * PL + j_ * S + i_).reshape(-1).cuda()
+    for fd in (torch.bfloat16, torch.float16):
+        km = torch.full((B * h * w, kp), float("nan"), dtype=fd, device="cuda")
+        rc.corr_block.index_pyramid_kmajor(pyr, co, radius, fd, out=km)
+        want = torch.zeros((B * h * w, kp), dtype=fd, device="cuda")
+        want[:, col] = ref.permute(0, 2, 3, 1).reshape(B * h * w, levels * S * S).to(fd)
+        assert torch.equal(km, want), (fd, radius, levels)
+    with pytest.raises(ValueError, match="RDVC_LAYOUT_TILED"):
+        rc.index_pyramid(pyramid_from_levels(rc, cc.split_levels(flat, B, h, w, levels), B, h, w, vol, layout=ROW),
+                         co, radius, out_dtype=torch.float16)
+
+
+TOL_CONV1X1_SAME_OPERANDS = 2e-5     # vs fp64 on the same 16-bit operands: fp32 accumulation over K = 324
+TOL_CONV1X1 = 1e-2                   # vs the stock fp32 convolution of the un-rounded features (bf16 operands)
+
+
+@pytest.mark.parametrize("shape", [(1, 46, 80), (2, 18, 22), (1, 17, 19), (3, 24, 40)])
+@pytest.mark.parametrize("cout,fd,od", [(256, torch.bfloat16, torch.float32), (256, torch.float16, torch.float16),
+                                        (96, torch.bfloat16, torch.bfloat16), (32, torch.float16, torch.float32)])
+def test_conv1x1_matches_fp64(lib, shape, cout, fd, od):
+    """rdvc_conv1x1 alone: random K-major feature rows (incl. garbage-free padding) x packed weights + bias, ReLU."""
+    B, h, w = shape
+    kp = rc.corr_block.feat_pitch(4, 4)
+    g = torch.Generator(device="cuda").manual_seed(h * w + cout)
+    feats_tv = torch.randn(B * h * w, 324, device="cuda", generator=g) * 3.0     # torchvision channel order
+    weight = torch.randn(cout, 324, 1, 1, device="cuda", generator=g) * 0.1
+    bias = torch.randn(cout, device="cuda", generator=g)
+    l_, i_, j_ = torch.meshgrid(torch.arange(4), torch.arange(9), torch.arange(9), indexing="ij")
+    col = (l_ * 88 + j_ * 9 + i_).reshape(-1).cuda()
+    km = torch.zeros(B * h * w, kp, dtype=fd, device="cuda")
+    km[:, col] = feats_tv.to(fd)
+    packed = rc.corr_block.PackedConv1x1(weight, bias, 4, 4, fd, "cuda")
+    for relu in (True, False):
+        got = rc.corr_block.conv1x1(km, packed, B, h, w, relu=relu, out_dtype=od)
+        assert got.shape == (B, cout, h, w) and got.dtype == od
+        ref = feats_tv.to(fd).double() @ weight.view(cout, 324).to(fd).double().t() + bias.double()
+        if relu:
+            ref = ref.clamp(min=0)
+        ref = ref.view(B, h, w, cout).permute(0, 3, 1, 2)
+        tol = TOL_CONV1X1_SAME_OPERANDS if od == torch.float32 else (1e-3 if od == torch.float16 else 8e-3)
+        err = ((got.double() - ref).abs().max() / ref.abs().max()).item()
+        assert err < tol, (shape, cout, fd, od, relu, err)
+
+
+@pytest.mark.parametrize("hw,vol", [((46, 80), torch.float32), ((46, 80), torch.bfloat16), ((136, 240), torch.float32)])
+def test_lookup_convcorr1_vs_stock_modules(lib, hw, vol):
+    """Row f-1: TVCorrBlock.index_pyramid_convcorr1 == MotionEncoder.convcorr1(index_pyramid(coords)) (TV:raft.py:185,
+    202) of a seed-0 raft_large, at RDVC's default RAFT size and at 1080p: <= 1e-2 max-norm relative (bf16 operands)
+    in fp32 mode, and under fp16 autocast (fp16 operands, like the stock fp16 convolution)."""
+    h, w = hw
+    B, D = 1, 256
+    model = _seeded_raft(rc.TVCorrBlock(volume_dtype=vol))
+    conv = model.update_block.motion_encoder.convcorr1
+    g = torch.Generator(device="cuda").manual_seed(11)
+    f1 = torch.randn(B, D, h, w, device="cuda", generator=g)
+    f2 = torch.randn(B, D, h, w, device="cuda", generator=g)
+    blk = model.corr_block
+    blk.build_pyramid(f1, f2)
+    co = gpu(cn.synth_coords(B, h, w, 2.0, seed=3))
+    with torch.no_grad():
+        torch.backends.cudnn.allow_tf32 = False
+        ref = conv(blk.index_pyramid(centroids_coords=co))
+        torch.backends.cudnn.allow_tf32 = True
+        n0 = lib.rdvc_corr_launch_count()
+        got = blk.index_pyramid_convcorr1(co, conv[0].weight, conv[0].bias)
+        assert lib.rdvc_corr_launch_count() - n0 == 2                   # lookup (K-major rows) + GEMM
+        assert got.shape == ref.shape == (B, 256, h, w) and got.dtype == torch.float32
+        err = ((got - ref).abs().max() / ref.abs().max()).item()
+        assert err < TOL_CONV1X1, err
+        assert (got >= 0).all()
+        with torch.autocast("cuda", dtype=torch.float16):
+            ref16 = conv(blk.index_pyramid(centroids_coords=co))
+            got16 = blk.index_pyramid_convcorr1(co, conv[0].weight, conv[0].bias)
+        assert got16.dtype == ref16.dtype == torch.float16
+        err16 = ((got16.float() - ref16.float()).abs().max() / ref16.float().abs().max()).item()
+        assert err16 < 5e-3, err16
+    blk.release()
+
+
+@pytest.mark.parametrize("size", [(368, 640), (1088, 1920)], ids=["368x640", "1080p"])
+def test_raft_flow_fused_convcorr1_epe(lib, golden_dir, size):
+    """rc.raft_flow with the lookup fused into convcorr1 (its default) vs STOCK torchvision RAFT.forward: mean EPE
+    < 0.05 px at RDVC's default RAFT size and at 1920x1088 (BASELINE.json config 3's frame size), 12 updates;
+    2 + 2 x 12 launches of this library per pair."""
+    g = np.load(os.path.join(golden_dir, "frames_im1_im2.npz"))
+    a = _preprocess(g["im1"], size).cuda()
+    b = _preprocess(g["im2"], size).cuda()
+    with torch.no_grad():
+        ref = _seeded_raft()(a, b, num_flow_updates=12)[-1]
+        model = _seeded_raft(rc.TVCorrBlock())
+        n0 = lib.rdvc_corr_launch_count()
+        got = rc.raft_flow(model, a, b, 12)
+        assert lib.rdvc_corr_launch_count() - n0 == 2 + 2 * 12
+        unfused = rc.raft_flow(model, a, b, 12, fuse_convcorr1=False)
+    assert torch.isfinite(got).all()
+    epe = (got - ref).pow(2).sum(dim=1).sqrt().mean().item()
+    epe_u = (unfused - ref).pow(2).sum(dim=1).sqrt().mean().item()
+    assert epe < TOL_EPE and epe_u < TOL_EPE, (epe, epe_u)
+    model.corr_block.release()
+
+
+def test_build_plan_cache(lib):
+    """A repeated rdvc_corr_build with the same buffers, shape and options finds its TMA descriptors and work split
+    in the per-process cache and writes the same bits; another shape or option misses."""
+    B, D, h, w = 1, 64, 24, 40
+    f1, f2 = cn.synth_fmaps(B, D, h, w, seed=51)
+    blk = rc.TVCorrBlock()
+    blk.build_pyramid(gpu(f1), gpu(f2))
+    first = blk._pyr.buffer.clone()
+    h0 = lib.rdvc_corr_plan_cache_hits()
+    blk.build_pyramid(gpu(f1), gpu(f2))                 # same pyramid buffer and workspace are reused by the block
+    assert lib.rdvc_corr_plan_cache_hits() == h0 + 1
+    assert torch.equal(blk._pyr.buffer, first)
+    set_opts(lib, msplit=3)
+    blk.build_pyramid(gpu(f1), gpu(f2))                 # an option changed: new plan, same result
+    assert lib.rdvc_corr_plan_cache_hits() == h0 + 1
+    assert torch.equal(blk._pyr.buffer, first)
+    set_opts(lib, msplit=0)
 
 
 # ------------------------------------------------------------------ ABI details
@@ -492,6 +719,14 @@ def test_pair_host_entry_point(lib):
     for i in range(iters):
         assert np.array_equal(out2[1][i], blk.index_pyramid(centroids_coords=gpu(coords[i])).cpu().numpy())
     assert lib.rdvc_corr_pair_host_wait(1) == 0 and lib.rdvc_corr_pair_host_wait(5) == -5
+    # fp16 results (half the bytes over PCIe): the fp32 results rounded once
+    out16 = np.empty((iters, B, 324, h, w), np.float16)
+    rc._cabi.check(lib.rdvc_corr_pair_host_submit_ex(fp(f1), fp(f2), fp(coords), fp(out16), B, D, h, w, 4, 4, iters,
+                                                     rc.RDVC_DT_F32, rc.RDVC_DT_F16, 0), "submit_ex")
+    rc._cabi.check(lib.rdvc_corr_pair_host_wait(0), "wait")
+    assert np.array_equal(out16, out.astype(np.float16))
+    assert lib.rdvc_corr_pair_host_submit_ex(fp(f1), fp(f2), fp(coords), fp(out16), B, D, h, w, 4, 4, iters,
+                                             7, rc.RDVC_DT_F16, 0) == -4            # bad vol_dtype: RDVC_E_DTYPE
     lib.rdvc_corr_release()
 
 
@@ -501,6 +736,7 @@ def test_no_out_of_bounds_writes(lib, mode, layout, vol):
     """compute-sanitizer is closed on this pool, so bounds are checked with canaries: every byte
     outside the pyramid levels / lookup output / workspace (guard bands before and after, and the
     256-byte padding between levels) must survive a build + lookups on odd shapes."""
+    need_experiments(mode)
     CANARY, GUARD = 0xAB, 4096
     vd = rc.RDVC_DT_F32 if vol == torch.float32 else rc.RDVC_DT_BF16
     es = 4 if vol == torch.float32 else 2
