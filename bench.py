@@ -11,10 +11,17 @@ coordinates.  Prints ONE JSON line (rank 0).  See DESIGN.md section "Measurement
   e2e          pairs/s through the C-ABI host entry points rdvc_corr_pair_host_submit / _wait (two pairs in
                flight): pinned HOST feature maps + coords in, all 12 lookup tensors of every pair back to HOST,
                copies inside the timed region
+  e2e_f16_out  the same with fp16 results (rdvc_corr_pair_host_submit_ex): half the bytes back over PCIe -- what the
+               reference's default consumer casts the features to anyway (autocast, R:codec_processing.py:1436)
   roofline     the build kernel alone: algorithmic bytes / its CUDA-event duration vs measured HBM peak
-  cpu_baseline the reference's implementation (torchvision CorrBlock, CPU fp32) on this box's cores
+  cpu_baseline the reference's implementation (torchvision CorrBlock, CPU fp32) on this box's cores, one FULL pair
+  gpu_library_baseline   stock torchvision CorrBlock on the SAME B200 (fp32 and fp16 autocast): the library-call bar
+  gop_sharded  BASELINE.json configs 3 / 4 at this N: P-frames/s of the 600-frame synthetic 1080p sequence (GOP 10)
+               through the motion branch's RAFT call, sharded over the ranks (bench_gop.run_sharded), + at N = 1 the
+               CPU comparator (stock RAFT.forward on the host cores for one P-frame)
 
---impl reference times that same CPU implementation as its own arm (rank 0 only).
+--impl reference times the reference's own CPU implementation as its own arm (rank 0 only): every step is one FULL
+1920x1088 pair through torchvision's CorrBlock.build_pyramid + 12 x index_pyramid, warm-up included.
 No number here is taken under a profiler.
 """
 from __future__ import annotations
@@ -38,6 +45,8 @@ B, D, H8, W8 = 1, 256, 136, 240          # 1920x1088 frames -> 1/8-resolution fe
 LEVELS, RADIUS, ITERS = 4, 4, 12
 N = H8 * W8
 RING = 4                                   # distinct input sets rotated through (268 MB > 126 MB L2)
+WORKLOAD = ("1 frame pair 1920x1088 per step per GPU: corr volume + 4-level pyramid + 12 radius-4 lookups "
+            "(BASELINE.json configs[1])")
 
 
 # ----------------------------------------------------------------------------- workload maths
@@ -60,13 +69,16 @@ def measured_peaks():
 
 def ncu_traffic(vol: str):
     """dram bytes read+write of the build kernel from the committed ncu capture (or None)."""
-    path = os.path.join(ROOT, "profiles", "r01_build_kernel_ncu.json")
-    try:
-        with open(path) as f:
-            d = json.load(f)
-        return d.get(vol, {}).get("dram_bytes_read_plus_write")
-    except Exception:
-        return None
+    for name in ("r02_build_kernel_ncu.json", "r01_build_kernel_ncu.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as f:
+                d = json.load(f)
+            v = d.get(vol, {}).get("dram_bytes_read_plus_write")
+            if v is not None:
+                return v
+        except Exception:
+            continue
+    return None
 
 
 # ----------------------------------------------------------------------------- clocks sampler
@@ -114,14 +126,10 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------- reference arm
-def reference_pair_seconds(steps: int, warmup: int, budget_s: float = 170.0):
-    """torchvision CorrBlock (what RDVC's encoder executes, R:codec_processing.py:1442) on the host
-    cores, fp32.  Returns (seconds per FULL pair, description of the sample, threads)."""
+def reference_inputs():
+    """The synthetic pair of BASELINE.json configs[1] on the host: seed-0 randn feature maps, 12 drifting coordinate fields."""
     import torch
     from oracle import corr_numpy as cn
-    from oracle import tv_corr as tv
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
     g = torch.Generator().manual_seed(0)
     f1 = torch.randn(B, D, H8, W8, generator=g)
     f2 = torch.randn(B, D, H8, W8, generator=g)
@@ -132,48 +140,59 @@ def reference_pair_seconds(steps: int, warmup: int, budget_s: float = 170.0):
     for _ in range(ITERS):
         c = c + 0.5 * torch.randn(c.shape, generator=g1)
         coords.append(c.clone())
+    return f1, f2, coords
 
-    # calibrate on a 1/16 slice of the query rows with the same torch ops the CorrBlock uses
-    def sliced(frac_rows: int):
-        import torch.nn.functional as F
-        from torchvision.models.optical_flow._utils import grid_sample
-        a = f1.view(B, D, N)[:, :, :frac_rows]
-        vol = torch.matmul(a.transpose(1, 2), f2.view(B, D, N)).view(frac_rows, 1, H8, W8)
-        vol = vol / torch.sqrt(torch.tensor(float(D)))
-        pyr = [vol]
-        for _ in range(LEVELS - 1):
-            pyr.append(F.avg_pool2d(pyr[-1], 2, 2))
-        di = torch.linspace(-RADIUS, RADIUS, 2 * RADIUS + 1)
-        delta = torch.stack(torch.meshgrid(di, di, indexing="ij"), dim=-1).view(1, 9, 9, 2)
-        for c_ in coords:
-            cc = c_.permute(0, 2, 3, 1).reshape(N, 1, 1, 2)[:frac_rows]
-            for lv in pyr:
-                grid_sample(lv, cc + delta, align_corners=True, mode="bilinear")
-                cc = cc / 2
 
-    t0 = time.perf_counter(); sliced(N // 16); t_cal = (time.perf_counter() - t0) * 16
-    total = steps + warmup
-    if total * t_cal <= budget_s:
-        frac, sample = 1, f"1 full frame pair 1920x1088 per step through torchvision CorrBlock.build_pyramid + {ITERS}x index_pyramid"
-    else:
-        frac = 2
-        while total * t_cal / frac > budget_s and frac < 64:
-            frac *= 2
-        sample = (f"1/{frac} of the query rows of one 1920x1088 pair per step (same torch ops as CorrBlock: "
-                  f"matmul, avg_pool2d x3, grid_sample x4 x{ITERS}), scaled x{frac} to a full pair")
+REFERENCE_SAMPLE = (f"1 full frame pair 1920x1088 per step through the stock torchvision CorrBlock "
+                    f"(build_pyramid + {ITERS} x index_pyramid), CPU fp32, all host threads")
+
+
+def reference_pair_seconds(steps: int, warmup: int):
+    """torchvision CorrBlock (what RDVC's encoder executes, R:codec_processing.py:1442) on the host cores, fp32:
+    EVERY step -- warm-up steps included -- is one full 1920x1088 pair through the stock class, nothing sliced,
+    restated or extrapolated.  Returns (mean seconds per pair over the timed steps, sample description, threads)."""
+    import torch
+    from oracle import tv_corr as tv
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    f1, f2, coords = reference_inputs()
     times = []
-    for i in range(total):
+    for i in range(warmup + steps):
         t0 = time.perf_counter()
-        if frac == 1:
-            with torch.no_grad():
-                tv.build_and_lookup(f1, f2, coords, LEVELS, RADIUS)
-        else:
-            with torch.no_grad():
-                sliced(N // frac)
-        dt = (time.perf_counter() - t0) * frac
+        with torch.no_grad():
+            tv.build_and_lookup(f1, f2, coords, LEVELS, RADIUS)
+        dt = time.perf_counter() - t0
         if i >= warmup:
             times.append(dt)
-    return sum(times) / len(times), sample, cores
+    return sum(times) / len(times), REFERENCE_SAMPLE, cores
+
+
+def gpu_library_pair_ms(dev, reps: int = 3):
+    """Stock torchvision CorrBlock on the SAME GPU (the "library-call" comparator and
+    what RDVC executes today, R:codec_processing.py:1442): build_pyramid + 12 x index_pyramid on one 1920x1088 pair,
+    fp32 and under fp16 autocast (the reference's GPU default, R:codec_processing.py:1436).  Median of `reps`
+    after one warm-up, CUDA events."""
+    import torch
+    from oracle import tv_corr as tv
+    f1, f2, coords = (x.to(dev) if hasattr(x, "to") else [c.to(dev) for c in x] for x in reference_inputs())
+    out = {}
+    for name, amp in (("fp32", False), ("autocast_fp16", True)):
+        ms = []
+        for i in range(reps + 1):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize(dev)
+            e0.record()
+            with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16, enabled=amp):
+                a, b_ = (f1.half(), f2.half()) if amp else (f1, f2)      # the feature encoder emits fp16 under autocast
+                tv.build_and_lookup(a, b_, coords, LEVELS, RADIUS)
+            e1.record()
+            torch.cuda.synchronize(dev)
+            if i > 0:
+                ms.append(e0.elapsed_time(e1))
+        out[name] = {"ms_per_pair": statistics.median(ms), "value": 1e3 / statistics.median(ms), "unit": UNIT}
+        torch.cuda.empty_cache()
+    out["note"] = "stock torchvision CorrBlock.build_pyramid + 12 x index_pyramid on this GPU, median of %d after 1 warm-up" % reps
+    return out
 
 
 def run_reference(args):
@@ -186,8 +205,8 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "1 frame pair 1920x1088: corr volume + 4-level pyramid + 12 radius-4 lookups",
-                   "fmap": [B, D, H8, W8], "host": "cpu"},
+        "config": {"workload": WORKLOAD, "fmap": [B, D, H8, W8], "iters": ITERS, "volume_dtype": "fp32",
+                   "host": "cpu: stock torchvision CorrBlock, every step one full pair"},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "reference", "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -332,18 +351,52 @@ def run_ours(args):
     e2e_run(args.steps)
     barrier()
     e2e_s = time.perf_counter() - t0
+    # the same with fp16 results: half the bytes back (the reference's consumer runs under autocast)
+    del h_out
+    h_out16 = [torch.empty((ITERS, B, LEVELS * (2 * RADIUS + 1) ** 2, H8, W8), dtype=torch.float16).pin_memory()
+               for _ in range(2)]
+
+    def e2e16_submit(i):
+        f1, f2 = h_f[i % 2]
+        rc_ = lib.rdvc_corr_pair_host_submit_ex(f1.data_ptr(), f2.data_ptr(), h_co.data_ptr(), h_out16[i % 2].data_ptr(),
+                                                B, D, H8, W8, LEVELS, RADIUS, ITERS, vd, rc.RDVC_DT_F16, i % 2)
+        rc._cabi.check(rc_, "rdvc_corr_pair_host_submit_ex")
+
+    def e2e16_run(n):
+        e2e16_submit(0)
+        for i in range(1, n):
+            e2e16_submit(i)
+            e2e_wait(i - 1)
+        e2e_wait(n - 1)
+
+    e2e16_run(2)
+    barrier()
+    t0 = time.perf_counter()
+    e2e16_run(args.steps)
+    barrier()
+    e2e16_s = time.perf_counter() - t0
     clocks = sampler.stop()
+    del h_out16
     h2d = 2 * B * D * N * 4 + ITERS * B * 2 * N * 4
     d2h = ITERS * B * LEVELS * (2 * RADIUS + 1) ** 2 * N * 4
 
     # ---- max over ranks
     alt_ms = alt[1] if alt is not None else 0.0
     if dist is not None:
-        t = torch.tensor([ms_total, e2e_s, alt_ms], device=dev, dtype=torch.float64)
+        t = torch.tensor([ms_total, e2e_s, alt_ms, e2e16_s], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total, e2e_s, alt_ms = t[0].item(), t[1].item(), t[2].item()
+        ms_total, e2e_s, alt_ms, e2e16_s = t[0].item(), t[1].item(), t[2].item(), t[3].item()
     value = world * args.steps / (ms_total / 1e3)
     e2e_value = world * args.steps / e2e_s
+    lib.rdvc_corr_release()
+    torch.cuda.empty_cache()
+
+    # ---- BASELINE.json configs 3 / 4 at this N: the 600-frame GOP-sharded motion branch (every rank takes part)
+    gop_line = None
+    if not args.no_gop:
+        import bench_gop
+        gop_line = bench_gop.run_sharded(bench_gop.sharded_args(frames=args.gop_frames), own_process_group=False)
+        torch.cuda.empty_cache()
 
     line = None
     if rank == 0:
@@ -357,15 +410,21 @@ def run_ours(args):
             "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {
-                "workload": "1 frame pair 1920x1088 per step per GPU: corr volume + 4-level pyramid + 12 radius-4 lookups (BASELINE.json configs[1])",
+                "workload": WORKLOAD,
                 "fmap": [B, D, H8, W8], "volume_dtype": args.volume_dtype, "operands": "bf16, fp32 accumulate",
                 "iters": ITERS, "sharding": "independent frame pairs per GPU, no collective",
                 "l2": f"inputs rotate over {RING} fmap sets (268 MB) and the 5.7 GB pyramid is rewritten every step: working set >> 126 MB L2",
             },
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "api": "rdvc_corr_pair_host_submit / _wait, 2 slots (C ABI, pinned host buffers, all 12 lookup tensors "
-                           "of every pair copied back; consecutive pairs overlap)"},
+                    "api": "rdvc_corr_pair_host_submit / _wait, 2 slots (C ABI, pinned host buffers, all 12 fp32 lookup tensors "
+                           "of every pair copied back; consecutive pairs overlap)",
+                    "bound": "PCIe device->host: %.0f MB of results per pair" % (d2h / 1e6),
+                    "d2h_gb_per_s": e2e_value / world * d2h / 1e9},
+            "e2e_f16_out": {"value": world * args.steps / e2e16_s, "unit": UNIT, "h2d_bytes_per_step": h2d,
+                            "d2h_bytes_per_step": d2h // 2,
+                            "api": "rdvc_corr_pair_host_submit_ex(out_dtype = F16) / _wait: the same call with fp16 results "
+                                   "(what the reference's autocast consumer casts the features to); not the headline"},
             "gpu_launches": int(launches) * world,
             "roofline": {
                 "bound": "hbm", "kernel": "corr_build_kernel (MODE_LINEAR)", "achieved": achieved, "peak": peak,
@@ -390,12 +449,24 @@ def run_ours(args):
                 "whole_step_frac_of_roofline": ((bb + ITERS * bl) / (peak * 1e9) * 1e3) / (alt_ms / args.steps),
                 "note": "same timed loop, other pyramid storage type; not the headline",
             }
+        if gop_line is not None:
+            line["gop_sharded"] = {k: gop_line[k] for k in ("metric", "value", "unit", "n_gpus", "scaling", "p_frames",
+                                                             "seconds_total_max_over_ranks", "seconds_encode_max_over_ranks",
+                                                             "stream_bytes", "total_pframe_payload_bytes", "config")}
+        if world == 1 and not args.no_gpu_baseline:
+            line["gpu_library_baseline"] = gpu_library_pair_ms(dev)
         if world == 1 and not args.no_cpu_baseline:
-            sec, sample, cores = reference_pair_seconds(steps=1, warmup=0)
+            sec, sample, cores = reference_pair_seconds(steps=1, warmup=1)
             line["cpu_baseline"] = {"value": 1.0 / sec, "unit": UNIT, "cores": cores, "kind": "reference",
-                                    "sample": sample}
+                                    "sample": sample + " (1 warm-up pair, 1 timed pair)"}
+            if gop_line is not None:
+                import bench_gop
+                sec_p, cores_p = bench_gop.cpu_raft_pframe_seconds(1088, 1920, 1)
+                line["gop_sharded"]["cpu_baseline"] = {
+                    "value": 1.0 / sec_p, "unit": "P-frames/s", "cores": cores_p, "kind": "reference",
+                    "sample": "1 P-frame 1920x1088: stock torchvision raft_large forward (its own CorrBlock), 12 updates, "
+                              "fp32, all host threads"}
         print(json.dumps(line), flush=True)
-    lib.rdvc_corr_release()
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
@@ -411,6 +482,9 @@ def main():
     ap.add_argument("--volume-dtype", choices=["fp32", "bf16"], default="fp32")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-alt", action="store_true", help="skip the extra timed loop with the other volume dtype")
+    ap.add_argument("--no-gpu-baseline", action="store_true", help="skip the stock-torchvision-on-this-GPU comparator")
+    ap.add_argument("--no-gop", action="store_true", help="skip the GOP-sharded motion-branch run (configs 3 / 4)")
+    ap.add_argument("--gop-frames", type=int, default=600, help="frames of the GOP-sharded run (config 4: 600)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3   # timing rule: at least 3 warm-up steps

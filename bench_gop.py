@@ -61,8 +61,21 @@ def frame_at(big, t, h, w):
     return big[:, :, 32 - dy:32 - dy + h, 32 - dx:32 - dx + w].contiguous()
 
 
-def run_sharded(args):
-    """BASELINE.json config 4: `--frames` frames in GOPs of `--gop`, sharded over the ranks."""
+def sharded_args(**kw):
+    """The argument namespace of run_sharded with its command-line defaults (for callers such as bench.py)."""
+    d = dict(frames=600, height=1088, width=1920, gop=10, amp=False, graph=True, volume="fp32", from_uint8=False,
+             mcn=False, batch_gop=True, shard="frames", fuse_convcorr1=True, entropy=True)
+    d.update(kw)
+    return argparse.Namespace(**d)
+
+
+def run_sharded(args, own_process_group=True):
+    """BASELINE.json config 4: `--frames` frames in GOPs of `--gop`, sharded over the ranks -- by whole GOPs
+    (`--shard gops`, the north star's unit: 60 GOPs / 8 ranks caps at 7.5x) or by frame spans (`--shard frames`,
+    the default: the encoder is open loop, so every rank takes a contiguous span with the same number of P-frames,
+    540 / 8 -> 67 or 68: 7.94x).  Either way the `.rdvc` stream is byte-identical to the 1-rank encode.
+    Returns the JSON line (a dict) on rank 0, None elsewhere.  With own_process_group=False the caller has
+    already initialised torch.distributed (NCCL) and keeps it."""
     import torch.distributed as dist
     import rdvc_corr_b200 as rc
     from torchvision.models.optical_flow import raft_large
@@ -74,7 +87,8 @@ def run_sharded(args):
     dev = torch.device("cuda", local_rank)
     host_group = None
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        if own_process_group:
+            dist.init_process_group("nccl", device_id=dev)
         host_group = dist.new_group(backend="gloo")      # byte strings travel over the host
     torch.manual_seed(0)
     vol = torch.float32 if args.volume == "fp32" else torch.bfloat16
@@ -90,6 +104,8 @@ def run_sharded(args):
                        for t in range(10)]
     gops = gs.split_gops(args.frames, args.gop)
     mine = gs.assign_gops(gops, world)[rank]
+    spans = gs.assign_frames(args.frames, args.gop, world)
+    by_frames = (args.shard == "frames")
     ctx = lambda: torch.autocast("cuda", dtype=torch.float16, enabled=args.amp)
 
     def enc_i(frame):
@@ -98,8 +114,9 @@ def run_sharded(args):
 
     fh = args.height - 8 if args.height % 16 == 0 and args.height > 64 else args.height   # 1088 -> 1080 codec frame
 
-    runner = (rc.GraphedRaftFlow(model, 12, amp_dtype=torch.float16 if args.amp else None, volume_dtype=vol)
-              if args.graph else None)
+    runner = (rc.GraphedRaftFlow(model, 12, amp_dtype=torch.float16 if args.amp else None, volume_dtype=vol,
+                                 fuse_convcorr1=args.fuse_convcorr1) if args.graph else None)
+    coder = rc.entropy_coder.FlowCoder() if args.entropy else None
 
     mcn_net = None
     if args.mcn:     # step 5b of the reference (R:codec_processing.py:1458); seeded weights, non-trivial BatchNorm statistics
@@ -124,16 +141,25 @@ def run_sharded(args):
             flow = runner(prev, cur)
         else:
             with torch.no_grad(), ctx():
-                flow = rc.raft_flow(model, prev, cur, 12)
+                flow = rc.raft_flow(model, prev, cur, 12, fuse_convcorr1=args.fuse_convcorr1)
         # steps 3 + 5a of the reference (R:codec_processing.py:1446,1456): flow to frame resolution and the
         # warped previous frame, one fused launch; the MCN / residual / codecs that consume them are out of scope
         prev_codec = prev[:, :, :fh].contiguous()
         warped, flow = rc.motion_warp(prev_codec, flow, (fh, w))
         res = predict(warped, flow, prev_codec, cur[:, :, :fh])
         small = F.avg_pool2d(flow.float(), 8)
-        q = (small * 4).round().clamp(-127, 127).to(torch.int8).cpu().numpy().tobytes()
+        q = motion_bytes((small * 4).round().clamp(-127, 127).to(torch.int8).cpu().numpy())[0]
         rbytes = b"" if res is None else res.cpu().numpy().astype("<f4").tobytes()
         return fmt.pframe_payload(tuple(small.shape[-2:]), q, (0, 0) if res is None else (1, 1), rbytes)
+
+    def motion_bytes(q_int8):
+        """(n, 2, h/8, w/8) int8 quantised flow -> one motion bitstream per frame.  With --entropy (default) through
+        the factorised-prior range coder stand-in (rc.entropy_coder; the reference's EntropyBottleneck.compress is
+        compressai's, absent here: bitstream parity unpinned) so the byte counts follow the symbol statistics;
+        otherwise the raw int8 dump."""
+        if coder is None:
+            return [q_int8[i].tobytes() for i in range(q_int8.shape[0])]
+        return [coder.compress(q_int8[i]) for i in range(q_int8.shape[0])]
 
     def get_frame(t):
         """Frame t as the encoder loop sees it: a (RAFT input, codec input) pair of device tensors."""
@@ -149,46 +175,63 @@ def run_sharded(args):
             flow = runner(a, b)
         else:
             with torch.no_grad(), ctx():
-                flow = rc.raft_flow(model, a, b, 12)
+                flow = rc.raft_flow(model, a, b, 12, fuse_convcorr1=args.fuse_convcorr1)
         a_codec = a[:, :, :fh].contiguous()
         warped, flow = rc.motion_warp(a_codec, flow, (fh, w))
         res = predict(warped, flow, a_codec, b[:, :, :fh])
         small = F.avg_pool2d(flow.float(), 8)
-        q = (small * 4).round().clamp(-127, 127).to(torch.int8).cpu().numpy()
+        q = motion_bytes((small * 4).round().clamp(-127, 127).to(torch.int8).cpu().numpy())
         rb = None if res is None else res.cpu().numpy().astype("<f4")
-        return [fmt.pframe_payload(tuple(small.shape[-2:]), q[i].tobytes(), (0, 0) if rb is None else (1, 1),
-                                   b"" if rb is None else rb[i].tobytes()) for i in range(q.shape[0])]
+        return [fmt.pframe_payload(tuple(small.shape[-2:]), q[i], (0, 0) if rb is None else (1, 1),
+                                   b"" if rb is None else rb[i].tobytes()) for i in range(len(q))]
 
     def barrier():
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
 
-    if args.batch_gop:                                    # warm-up at the batched shape (and graph capture)
-        npf = min(args.gop, args.frames) - 1
-        for _ in range(2):
-            enc_p_batch([frame_at(big, t, h, w) for t in range(npf)], [frame_at(big, t + 1, h, w) for t in range(npf)])
+    batch = max(1, min(args.gop, args.frames) - 1)        # P-frames per RAFT batch: a GOP's worth
+    if args.batch_gop:                                    # warm-up at the batched shape(s) (and graph capture)
+        shapes = {batch}
+        if by_frames:                                     # a span's last batch may be short
+            n_p = sum(1 for t in spans[rank] if not gs.is_iframe(t, args.gop))
+            if n_p % batch:
+                shapes.add(n_p % batch)
+            if 0 < n_p < batch:
+                shapes = {n_p}
+        for npf in sorted(shapes, reverse=True):
+            for _ in range(2):
+                enc_p_batch([frame_at(big, t, h, w) for t in range(npf)], [frame_at(big, t + 1, h, w) for t in range(npf)])
     if runner is not None:                                # warm-up: capture the graph outside the timed region
         for _ in range(2):
             runner(frame_at(big, 0, h, w), frame_at(big, 1, h, w))
     with torch.no_grad(), ctx():                          # warm-up: cuDNN autotune + allocator
         for _ in range(2):
-            rc.raft_flow(model, frame_at(big, 0, h, w), frame_at(big, 1, h, w), 12)
+            rc.raft_flow(model, frame_at(big, 0, h, w), frame_at(big, 1, h, w), 12, fuse_convcorr1=args.fuse_convcorr1)
     barrier()
     t0 = time.perf_counter()
-    if args.batch_gop:
-        local = {gp.index: gs.encode_gop_batched(gp, get_frame, enc_i, enc_p_batch, enc_p) for gp in mine}
+    meta_in = {"rdvc_version": "b200-bench", "iframe_interval": args.gop}
+    if by_frames:
+        data, tail_failed = gs.encode_span(spans[rank], args.gop, get_frame, enc_i, enc_p,
+                                           enc_p_batch if args.batch_gop else None, batch=batch)
+        torch.cuda.synchronize()
+        t_local = time.perf_counter() - t0
+        stream = gs.gather_spans(data, tail_failed, spans, meta_in, rank, world, host_group,
+                                 reencode_iframe=lambda t: enc_i(get_frame(t)))
     else:
-        local = {gp.index: gs.encode_gop(gp, get_frame, enc_i, enc_p) for gp in mine}
-    torch.cuda.synchronize()
-    t_local = time.perf_counter() - t0
-    stream = gs.gather_stream(local, len(gops), {"rdvc_version": "b200-bench", "iframe_interval": args.gop},
-                              rank, world, host_group)
+        if args.batch_gop:
+            local = {gp.index: gs.encode_gop_batched(gp, get_frame, enc_i, enc_p_batch, enc_p) for gp in mine}
+        else:
+            local = {gp.index: gs.encode_gop(gp, get_frame, enc_i, enc_p) for gp in mine}
+        torch.cuda.synchronize()
+        t_local = time.perf_counter() - t0
+        stream = gs.gather_stream(local, len(gops), meta_in, rank, world, host_group)
     barrier()
     t_all = time.perf_counter() - t0
     times = torch.tensor([t_all, t_local], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    line = None
     if rank == 0:
         meta, recs = fmt.read_stream(stream)
         n_p = sum(1 for r in recs if r.kind == "P")
@@ -201,17 +244,45 @@ def run_sharded(args):
             "config": {"workload": f"{args.frames} synthetic frames {w}x{h}, GOP {args.gop}, 12 RAFT updates, "
                                    "seed-0 random-init raft_large, B200 correlation block, final-only upsampling",
                        "amp_fp16": args.amp, "cuda_graph": args.graph, "batched_gop": args.batch_gop, "volume_dtype": args.volume, "frames_from_host_uint8": args.from_uint8,
-                       "motion_compensation_network": args.mcn,
+                       "motion_compensation_network": args.mcn, "lookup_fused_with_convcorr1": args.fuse_convcorr1,
+                       "sharding": ("frame spans (contiguous, P-frames balanced to one)" if by_frames else "whole GOPs (LPT)"),
                        "gops": len(gops), "gops_per_rank_max": max(len(x) for x in gs.assign_gops(gops, world)),
-                       "payload": "placeholder (codec networks out of scope)", "collective": "none on the data path; "
-                       "host-side gather_object of per-GOP byte strings (gloo)"},
+                       "pframes_per_rank_max": (max(sum(1 for t in sp if not gs.is_iframe(t, args.gop)) for sp in spans)
+                                                if by_frames else max(sum(g_.num_pframes for g_ in x) for x in gs.assign_gops(gops, world))),
+                       "payload": ("motion: 1/8-resolution quantised flow through the factorised-prior range coder stand-in "
+                                   "(bitstream parity unpinned: compressai absent); codec networks out of scope" if args.entropy
+                                   else "placeholder int8 dump (codec networks out of scope)"),
+                       "collective": "none on the data path; host-side gather_object of per-rank byte strings (gloo)"},
             "seconds_total_max_over_ranks": times[0].item(), "seconds_encode_max_over_ranks": times[1].item(),
             "p_frames": n_p, "stream_bytes": len(stream), "total_frames_processed": meta["total_frames_processed"],
         }
-        print(json.dumps(line), flush=True)
+        line["total_pframe_payload_bytes"] = meta["total_pframe_payload_bytes"]
+    if runner is not None:
+        runner.release()
+    model.corr_block.release()
     if world > 1:
         dist.barrier()
-        dist.destroy_process_group()
+        if own_process_group:
+            dist.destroy_process_group()
+    return line
+
+
+def cpu_raft_pframe_seconds(height=1088, width=1920, frames=1):
+    """CPU comparator for configs 3 / 4: the reference's motion-branch RAFT call -- stock torchvision
+    raft_large (seed 0, its own CorrBlock), 12 updates, fp32 -- on the host cores for `frames` P-frames."""
+    from torchvision.models.optical_flow import raft_large
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(0)
+    model = raft_large(weights=None).eval()
+    g = torch.Generator().manual_seed(0)
+    base = torch.rand(1, 3, height // 16 + 8, width // 16 + 8, generator=g)
+    big = F.interpolate(base, size=(height + 64, width + 64), mode="bicubic", align_corners=False).clamp(0, 1)
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        for t in range(frames):
+            model(frame_at(big, t, height, width), frame_at(big, t + 1, height, width), num_flow_updates=12)
+    return (time.perf_counter() - t0) / frames, cores
 
 
 def main():
@@ -232,9 +303,23 @@ def main():
                          "R:codec_processing.py:1458) with seeded random weights")
     ap.add_argument("--batch-gop", action="store_true",
                     help="run all P-frames of a GOP through RAFT as one batch (the encoder is open loop)")
+    ap.add_argument("--shard", choices=["gops", "frames"], default="frames",
+                    help="config 4: partition by whole GOPs or by contiguous frame spans (P-frames balanced to one)")
+    ap.add_argument("--no-fuse-convcorr1", dest="fuse_convcorr1", action="store_false",
+                    help="keep the stock convcorr1 module after an fp32 lookup instead of the fused lookup + 1x1 GEMM")
+    ap.add_argument("--no-entropy", dest="entropy", action="store_false",
+                    help="config 4: raw int8 motion payload instead of the range coder stand-in")
+    ap.add_argument("--cpu-baseline", action="store_true", help="also time stock RAFT on the host cores for 1 P-frame")
     args = ap.parse_args()
     if args.frames > 0:
-        return run_sharded(args)
+        line = run_sharded(args)
+        if line is not None:
+            if args.cpu_baseline:
+                sec, cores = cpu_raft_pframe_seconds(args.height, args.width, 1)
+                line["cpu_baseline"] = {"value": 1.0 / sec, "unit": "P-frames/s", "cores": cores, "kind": "reference",
+                                        "sample": "1 P-frame: stock torchvision raft_large forward, 12 updates, fp32, host cores"}
+            print(json.dumps(line), flush=True)
+        return
     import rdvc_corr_b200 as rc
     from torchvision.models.optical_flow import raft_large
     dev = torch.device("cuda", 0)
@@ -247,7 +332,8 @@ def main():
 
     ctx = lambda: torch.autocast("cuda", dtype=torch.float16, enabled=args.amp)
 
-    runner = rc.GraphedRaftFlow(ours, 12, amp_dtype=torch.float16 if args.amp else None) if args.graph else None
+    runner = (rc.GraphedRaftFlow(ours, 12, amp_dtype=torch.float16 if args.amp else None,
+                                 fuse_convcorr1=args.fuse_convcorr1) if args.graph else None)
 
     def run_ours():
         if args.batch_gop:
@@ -255,11 +341,11 @@ def main():
             if runner is not None:
                 return list(runner(a_, b_).split(1, 0))
             with torch.no_grad(), ctx():
-                return list(rc.raft_flow(ours, a_, b_, 12).split(1, 0))
+                return list(rc.raft_flow(ours, a_, b_, 12, fuse_convcorr1=args.fuse_convcorr1).split(1, 0))
         if runner is not None:
             return [runner(a, b) for a, b in pairs]
         with torch.no_grad(), ctx():
-            return [rc.raft_flow(ours, a, b, 12) for a, b in pairs]
+            return [rc.raft_flow(ours, a, b, 12, fuse_convcorr1=args.fuse_convcorr1) for a, b in pairs]
 
     def run_stock():
         with torch.no_grad(), ctx():
@@ -271,7 +357,8 @@ def main():
     line = {
         "metric": "raft_motion_branch_p_frames_per_s_1080p", "unit": "P-frames/s", "n_gpus": 1,
         "config": {"workload": f"synthetic GOP of {args.gop} frames {args.width}x{args.height}, 12 RAFT updates, "
-                               "seed-0 random-init raft_large", "amp_fp16": args.amp, "cuda_graph": args.graph, "batched_gop": args.batch_gop},
+                               "seed-0 random-init raft_large", "amp_fp16": args.amp, "cuda_graph": args.graph, "batched_gop": args.batch_gop,
+                   "lookup_fused_with_convcorr1": args.fuse_convcorr1},
         "ours": {"value": len(pairs) / t_ours, "ms_per_pframe": 1e3 * t_ours / len(pairs), "pframes": len(pairs)},
         "stock_torchvision_same_gpu": {"value": args.stock_pframes / t_stock,
                                        "ms_per_pframe": 1e3 * t_stock / args.stock_pframes,

@@ -250,6 +250,24 @@ int rdvc_mcn_forward(const float* warped, const float* flow, const float* ref, i
                      const unsigned long long* kmasks, const float* biases, void* workspace,
                      size_t workspace_bytes, float* out, void* stream);
 
+/* ---- next row f-4 (last piece): entropy-coder stand-in (HOST functions) ---- *
+ * Stands in for the range coder behind EntropyBottleneck.compress / .decompress (R:codec_processing.py:433,447
+ * construction, :488-497 compress, :509-536 decompress; compressai's RansEncoder.encode_with_indexes /
+ * RansDecoder.decode_with_indexes).  compressai is absent from this image: the BITSTREAM IS NOT the reference's
+ * (parity unpinned); interface and modelling contract are: per-index quantised CDF tables of 16-bit precision
+ * (cdfs: n_tables rows of max_len entries, row i valid for cdf_lengths[i] entries, first 0, last 65536, strictly
+ * increasing; the last slot of a table is the escape for symbols outside [offsets[i], offsets[i] + cdf_lengths[i] - 2),
+ * coded with 4-bit bypass digits), rANS with a 32-bit state and 16-bit words.  encode -> decode is bit exact.
+ * _encode returns the number of bytes written (0 = error, see rdvc_corr_last_error); out_capacity >=
+ * rdvc_ec_max_encoded_bytes(n) always suffices.  _decode returns 0 or a negative RDVC_E_*.                      */
+size_t rdvc_ec_max_encoded_bytes(size_t n);
+size_t rdvc_ec_encode_with_indexes(const int* symbols, const int* indexes, size_t n, const unsigned int* cdfs,
+                                   const int* cdf_lengths, const int* offsets, int n_tables, int max_len,
+                                   unsigned char* out, size_t out_capacity);
+int rdvc_ec_decode_with_indexes(const unsigned char* in, size_t nbytes, const int* indexes, size_t n,
+                                const unsigned int* cdfs, const int* cdf_lengths, const int* offsets, int n_tables,
+                                int max_len, int* symbols_out);
+
 /* Frees the per-thread scratch arenas of rdvc_corr_pair_host* (optional). */
 void rdvc_corr_release(void);
 

@@ -13,7 +13,7 @@ Contents: ``csrc/`` (hand-written sm_100a kernels + the C ABI of
 ``include/rdvc_corr.h``), ``_build`` (nvcc driver), ``_cabi`` (ctypes binding),
 ``corr_block`` (host-side mirror of the reference interface).
 """
-from . import _build, _cabi, gop_shard, rdvc_format  # noqa: F401
+from . import _build, _cabi, entropy_coder, gop_shard, rdvc_format  # noqa: F401
 from ._cabi import (RDVC_DT_BF16, RDVC_DT_F16, RDVC_DT_F32,  # noqa: F401
                     RDVC_LAYOUT_ROWMAJOR, RDVC_LAYOUT_TILED)
 from .corr_block import (  # noqa: F401

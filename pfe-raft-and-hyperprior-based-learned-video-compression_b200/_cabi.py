@@ -49,6 +49,11 @@ SYMBOLS = {
     "rdvc_corr_pair_host_submit_ex": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p] +
                                       [_c.c_int] * 10),
     "rdvc_corr_plan_cache_hits": (_c.c_ulonglong, []),
+    "rdvc_ec_max_encoded_bytes": (_c.c_size_t, [_c.c_size_t]),
+    "rdvc_ec_encode_with_indexes": (_c.c_size_t, [_c.c_void_p, _c.c_void_p, _c.c_size_t, _c.c_void_p, _c.c_void_p,
+                                                  _c.c_void_p, _c.c_int, _c.c_int, _c.c_void_p, _c.c_size_t]),
+    "rdvc_ec_decode_with_indexes": (_c.c_int, [_c.c_void_p, _c.c_size_t, _c.c_void_p, _c.c_size_t, _c.c_void_p,
+                                               _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int, _c.c_void_p]),
     "rdvc_corr_pair_host": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p] +
                             [_c.c_int] * 8),
     "rdvc_motion_warp": (_c.c_int, [_c.c_void_p, _c.c_void_p] + [_c.c_int] * 6 + [_c.c_void_p, _c.c_void_p, _c.c_void_p]),

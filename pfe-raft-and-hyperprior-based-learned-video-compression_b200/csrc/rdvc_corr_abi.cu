@@ -21,6 +21,7 @@
 #include "corr_conv1x1_sm100.cuh"
 #include "corr_lookup.cuh"
 #include "corr_pack.cuh"
+#include "entropy_coder.h"
 #include "mcn_conv_sm100.cuh"
 #include "mcn_convx_sm100.cuh"
 #include "motion_warp.cuh"
@@ -1353,6 +1354,36 @@ int rdvc_mcn_forward(const float* warped, const float* flow, const float* ref, i
     }
     return rdvc_mcn_conv_out(x, packed_weights[n_layers - 1], kmasks[n_layers - 1], biases + (n_layers - 1) * 32, 5, 3,
                              warped, out, B, H, W, stream);
+}
+
+}  // extern "C"
+
+// ---- next row f-4 (last piece): entropy-coder stand-in (host only) ----------------------------
+extern "C" {
+
+size_t rdvc_ec_max_encoded_bytes(size_t n) { return rdvc::ec::max_encoded_bytes(n); }
+
+size_t rdvc_ec_encode_with_indexes(const int* symbols, const int* indexes, size_t n, const unsigned int* cdfs,
+                                   const int* cdf_lengths, const int* offsets, int n_tables, int max_len,
+                                   unsigned char* out, size_t out_capacity) {
+    if ((n && (!symbols || !indexes)) || !cdfs || !cdf_lengths || !offsets || !out) {
+        fail(RDVC_E_NULL, "null pointer argument");
+        return 0;
+    }
+    const size_t r = rdvc::ec::encode_with_indexes(symbols, indexes, n, cdfs, cdf_lengths, offsets, n_tables, max_len,
+                                                   out, out_capacity);
+    if (r == 0) fail(RDVC_E_UNSUPPORTED, "entropy encode failed: malformed CDF table / index, or output buffer too small");
+    return r;
+}
+
+int rdvc_ec_decode_with_indexes(const unsigned char* in, size_t nbytes, const int* indexes, size_t n,
+                                const unsigned int* cdfs, const int* cdf_lengths, const int* offsets, int n_tables,
+                                int max_len, int* symbols_out) {
+    if ((n && (!in || !indexes || !symbols_out)) || !cdfs || !cdf_lengths || !offsets)
+        return fail(RDVC_E_NULL, "null pointer argument");
+    if (rdvc::ec::decode_with_indexes(in, nbytes, indexes, n, cdfs, cdf_lengths, offsets, n_tables, max_len, symbols_out))
+        return fail(RDVC_E_UNSUPPORTED, "entropy decode failed: truncated or malformed stream / table");
+    return RDVC_OK;
 }
 
 }  // extern "C"

@@ -6,6 +6,18 @@ I-frame, `iframe_interval` frames, R:codec_processing.py:634,1392) depends on no
 One process per GPU takes whole GOPs; the motion branch of every P-frame runs RAFT with the
 B200 correlation block.  There is NO collective on the data path: the only cross-rank step is
 a host-side gather of per-GOP byte strings into the `.rdvc` writer on rank 0.
+
+Two partitions of the same stream (both give a byte-identical `.rdvc` file to the 1-rank encode):
+
+* whole GOPs (`split_gops` / `assign_gops` / `encode_gop[_batched]` / `gather_stream`): the north star's unit.
+  60 GOPs on 8 ranks is 8 + 7 x ... = at best 7.5x.
+* frame spans (`assign_frames` / `encode_span` / `gather_spans`): because the encoder is open loop, a P-frame
+  needs only the two ORIGINAL frames (t-1, t), so the cut between two ranks may fall anywhere -- every rank
+  takes one contiguous span of frames holding (almost) the same number of P-frames (540 / 8 -> 67 or 68: 7.94x),
+  reads the one frame before its span, and batches its P-frames `batch` at a time across GOP boundaries.
+  The only cross-rank coupling is the reference's failure rule (a failed P-frame forces the next frame to I):
+  a span reports whether its LAST frame failed and rank 0 re-encodes the first frame of the next span as an
+  I-frame in that (rare) case, so the stream stays identical to the serial encode even then.
 """
 from __future__ import annotations
 
@@ -152,3 +164,136 @@ def gather_stream(local: Dict[int, bytes], num_gops: int, metadata: dict, rank: 
     meta["total_frames_processed"] = len(records)
     meta["total_pframe_payload_bytes"] = fmt.pframe_payload_bytes(records)
     return fmt.write_stream(meta, ordered)
+
+
+# ---------------------------------------------------------------- frame-level sharding ("frame-level
+# sharding is also legal for the encoder")
+def is_iframe(t: int, iframe_interval: int) -> bool:
+    """R:codec_processing.py:1392."""
+    return t % iframe_interval == 0
+
+
+def assign_frames(num_frames: int, iframe_interval: int, world_size: int) -> List[range]:
+    """One contiguous span of frames per rank, balanced by P-frame count (the I-frames cost the GPU nothing):
+    rank r owns the P-frames number floor(r P / W) .. floor((r+1) P / W) - 1 of the sequence and the I-frames
+    between them; an I-frame sitting right before a span's first P-frame goes with that span.  Deterministic,
+    identical on every rank without communication; spans may be empty when there are more ranks than P-frames."""
+    if num_frames < 0 or iframe_interval <= 0 or world_size <= 0:
+        raise ValueError("num_frames must be >= 0, iframe_interval and world_size > 0")
+    p_frames = [t for t in range(num_frames) if not is_iframe(t, iframe_interval)]
+    P = len(p_frames)
+    cuts = [0]
+    for r in range(1, world_size):
+        k = r * P // world_size                      # first P-frame (by P index) of rank r
+        if k >= P:
+            cuts.append(num_frames)
+            continue
+        c = p_frames[k]
+        if c > 0 and is_iframe(c - 1, iframe_interval):
+            c -= 1                                   # keep the I-frame with the P-frames that follow it
+        cuts.append(max(c, cuts[-1]))
+    cuts.append(num_frames)
+    if P == 0:                                       # I-frames only: spread them evenly
+        cuts = [r * num_frames // world_size for r in range(world_size + 1)]
+    return [range(cuts[r], cuts[r + 1]) for r in range(world_size)]
+
+
+def encode_span(span: range, iframe_interval: int, frames: Callable[[int], object],
+                encode_iframe: Callable[[object], bytes],
+                encode_pframe: Optional[Callable[[object, object], bytes]] = None,
+                encode_pframes: Optional[Callable[[Sequence[object], Sequence[object]], Sequence[bytes]]] = None,
+                batch: int = 9, failures: Optional[List[int]] = None,
+                force_first_i: bool = False) -> Tuple[bytes, bool]:
+    """Frame records of the frames in `span` and whether the span's LAST frame was a failed P-frame (the next
+    span's first frame must then become an I-frame, `gather_spans` does that).  With `encode_pframes` all
+    P-frames of the span are encoded `batch` at a time, across GOP boundaries (only the last batch may be
+    short); if a batch fails and `encode_pframe` is given, the span is redone frame by frame with the
+    reference's failure rule (R:codec_processing.py:1501-1506).  `frames(span.start - 1)` is read when the
+    span starts with a P-frame: the previous ORIGINAL frame, whichever rank encodes it."""
+    if encode_pframe is None and encode_pframes is None:
+        raise ValueError("need encode_pframe and/or encode_pframes")
+    if batch <= 0:
+        raise ValueError("batch must be positive")
+    ts = list(span)
+    if not ts:
+        return b"", False
+
+    def kind(t):
+        return "I" if (is_iframe(t, iframe_interval) or (force_first_i and t == ts[0])) else "P"
+
+    if encode_pframes is not None:
+        try:
+            ts_p = [t for t in ts if kind(t) == "P"]
+            payloads: Dict[int, bytes] = {}
+            for k in range(0, len(ts_p), batch):
+                chunk = ts_p[k:k + batch]
+                out = list(encode_pframes([frames(t - 1) for t in chunk], [frames(t) for t in chunk]))
+                if len(out) != len(chunk):
+                    raise RuntimeError("encode_pframes returned the wrong number of payloads")
+                payloads.update(zip(chunk, out))
+            recs = [fmt.FrameRecord(t, "I", encode_iframe(frames(t))).pack() if kind(t) == "I"
+                    else fmt.FrameRecord(t, "P", payloads[t]).pack() for t in ts]
+            return b"".join(recs), False
+        except Exception as exc:
+            log.error("batched P-frames of span [%d, %d) failed (%s: %s); redoing the span frame by frame\n%s",
+                      ts[0], ts[-1] + 1, type(exc).__name__, exc, traceback.format_exc())
+            if encode_pframe is None or _is_fatal(exc):
+                raise
+    parts: List[bytes] = []
+    force_i = False
+    for t in ts:
+        if kind(t) == "I" or force_i:
+            parts.append(fmt.FrameRecord(t, "I", encode_iframe(frames(t))).pack())
+            force_i = False
+            continue
+        try:
+            parts.append(fmt.FrameRecord(t, "P", encode_pframe(frames(t - 1), frames(t))).pack())
+        except Exception as exc:                      # same policy as encode_gop
+            log.error("P-frame %d failed (%s: %s); next frame forced to I\n%s", t, type(exc).__name__, exc,
+                      traceback.format_exc())
+            if _is_fatal(exc):
+                raise
+            if failures is not None:
+                failures.append(t)
+            parts.append(fmt.FrameRecord(t, "P", fmt.pframe_payload((0, 0), b"", (0, 0), b"")).pack())
+            force_i = True
+    return b"".join(parts), force_i
+
+
+def gather_spans(local: bytes, tail_failed: bool, spans: Sequence[range], metadata: dict, rank: int = 0,
+                 world_size: int = 1, group=None,
+                 reencode_iframe: Optional[Callable[[int], bytes]] = None) -> Optional[bytes]:
+    """Host-side gather of every rank's span records (rank order = frame order); rank 0 returns the `.rdvc`
+    stream.  If span r-1 ended on a failed P-frame, the first frame of span r is re-encoded as an I-frame with
+    `reencode_iframe(t) -> I payload` (the rule a serial encode applies in line)."""
+    if world_size > 1:
+        import torch.distributed as dist
+        gathered = [None] * world_size if rank == 0 else None
+        dist.gather_object((local, bool(tail_failed)), gathered, dst=0, group=group)
+        if rank != 0:
+            return None
+    else:
+        gathered = [(local, bool(tail_failed))]
+    import io
+    chunks: List[bytes] = []
+    prev_failed = False
+    for r, (data, failed) in enumerate(gathered):
+        if prev_failed and len(spans[r]) > 0:
+            recs = list(fmt.iter_frames(io.BytesIO(data)))
+            if recs and recs[0].kind == "P":
+                if reencode_iframe is None:
+                    raise RuntimeError(f"frame {recs[0].index} must become an I-frame (the frame before it failed) "
+                                       "but no reencode_iframe callback was given")
+                recs[0] = fmt.FrameRecord(recs[0].index, "I", reencode_iframe(recs[0].index))
+                data = b"".join(x.pack() for x in recs)
+        if len(spans[r]) > 0:
+            prev_failed = failed
+        chunks.append(data)
+    records = [x for b in chunks for x in fmt.iter_frames(io.BytesIO(b))]
+    want = [t for sp in spans for t in sp]
+    if [x.index for x in records] != want:
+        raise RuntimeError("frame records missing or out of order in the gather")
+    meta = dict(metadata)
+    meta["total_frames_processed"] = len(records)
+    meta["total_pframe_payload_bytes"] = fmt.pframe_payload_bytes(records)
+    return fmt.write_stream(meta, chunks)

@@ -20,6 +20,12 @@ def test_reference_arm_json_line():
     assert d["value"] > 0 and d["steps"] == 1 and d["n_gpus"] == 1
     assert d["cpu_baseline"]["kind"] == "reference" and d["cpu_baseline"]["cores"] >= 1
     assert d["cpu_baseline"]["value"] == d["value"] and "sample" in d["cpu_baseline"]
+    # the arm runs the STOCK class on the FULL configuration every step: no slicing, no extrapolation
+    assert "1 full frame pair 1920x1088" in d["cpu_baseline"]["sample"] and "stock torchvision CorrBlock" in d["cpu_baseline"]["sample"]
+    assert "scaled" not in d["cpu_baseline"]["sample"] and "1/" not in d["cpu_baseline"]["sample"]
+    sys.path.insert(0, ROOT)
+    import bench
+    assert d["config"]["workload"] == bench.WORKLOAD and d["config"]["fmap"] == [1, 256, 136, 240]
     assert d["e2e"] == {"value": d["value"], "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
 
 

@@ -176,3 +176,115 @@ def test_encode_gop_batched_matches_per_frame_and_falls_back():
     assert gs.encode_gop_batched(gs.Gop(0, 5, 5), frames, enc_i, enc_batch) == b""
     lone = gs.encode_gop_batched(gs.Gop(0, 7, 8), frames, enc_i, enc_batch)
     assert [r.kind for r in fmt.iter_frames(io.BytesIO(lone))] == ["I"]
+
+
+# ------------------------------------------------------------------ frame-level sharding (spans)
+@pytest.mark.parametrize("world", [1, 2, 3, 4, 8])
+@pytest.mark.parametrize("frames_interval", [(600, 10), (47, 5), (25, 10), (7, 32), (9, 1)])
+def test_assign_frames_is_a_balanced_contiguous_partition(world, frames_interval):
+    n, I = frames_interval
+    spans = gs.assign_frames(n, I, world)
+    assert len(spans) == world and [t for sp in spans for t in sp] == list(range(n))     # contiguous partition
+    loads = [sum(1 for t in sp if t % I != 0) for sp in spans]
+    assert max(loads) - min(loads) <= 1                                                  # P-frames balanced to one
+    assert gs.assign_frames(n, I, world) == spans
+    for sp in spans:                      # a span never starts right after "its" I-frame went to the previous rank
+        if len(sp) and sp.start > 0 and sp.start % I != 0:
+            assert (sp.start - 1) % I != 0
+    if (n, I, world) == (600, 10, 8):
+        assert max(loads) == 68 and min(loads) == 67                                     # 540 / 8: 7.94x, not 7.5x
+
+
+def _span_stream(num_frames, interval, world, enc_p_factory=None, batch=4, batched=True):
+    frames, enc_i, enc_p = _fake_encoders()
+    if enc_p_factory is not None:
+        enc_p = enc_p_factory(frames, enc_p)
+    enc_batch = (lambda prevs, curs: [enc_p(a, b) for a, b in zip(prevs, curs)]) if batched else None
+    spans = gs.assign_frames(num_frames, interval, world)
+    out, failed = [], []
+    for sp in spans:
+        data, tail = gs.encode_span(sp, interval, frames, enc_i, enc_p, enc_batch, batch=batch)
+        out.append(data); failed.append(tail)
+    if world == 1:
+        return gs.gather_spans(out[0], failed[0], spans, {"rdvc_version": "1.0"}, 0, 1)
+    # emulate the multi-rank gather in one process: rank 0 receives every rank's (bytes, tail_failed)
+    import unittest.mock as um
+    fake = list(zip(out, failed))
+    with um.patch("torch.distributed.gather_object",
+                  lambda obj, lst, dst=0, group=None: lst.__setitem__(slice(None), fake)):
+        return gs.gather_spans(out[0], failed[0], spans, {"rdvc_version": "1.0"}, 0, world,
+                               reencode_iframe=lambda t: enc_i(frames(t)))
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 8])
+def test_span_sharding_equals_gop_serial_stream(world):
+    """Frame spans (batched across GOP boundaries) give the SAME bytes as the serial whole-GOP encode."""
+    for (n, I) in [(47, 5), (25, 10), (12, 4)]:
+        assert _span_stream(n, I, world) == _serial_stream(n, I, {"rdvc_version": "1.0"}), (n, I, world)
+        assert _span_stream(n, I, world, batched=False) == _serial_stream(n, I, {"rdvc_version": "1.0"})
+
+
+def test_span_sharding_failure_rule_across_a_cut():
+    """A failing P-frame forces the next frame to I even when the cut between two ranks falls right after it."""
+    n, I = 20, 10
+    frames, enc_i, enc_p = _fake_encoders()
+    for bad in range(1, n):
+        if bad % I == 0:
+            continue
+
+        def factory(frames_, enc_p_, bad=bad):
+            def flaky(prev, cur):
+                if cur == frames_(bad):
+                    raise RuntimeError("boom")
+                return enc_p_(prev, cur)
+            return flaky
+        gops = gs.split_gops(n, I)
+        serial = gs.gather_stream({g.index: gs.encode_gop(g, frames, enc_i, factory(frames, enc_p)) for g in gops},
+                                  len(gops), {"rdvc_version": "1.0"})
+        for world in (2, 3, 6):
+            assert _span_stream(n, I, world, factory) == serial, (bad, world)
+
+
+def _span_worker(rank, world, port, num_frames, interval, out_path):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    frames, enc_i, enc_p = _fake_encoders()
+    spans = gs.assign_frames(num_frames, interval, world)
+    data, tail = gs.encode_span(spans[rank], interval, frames, enc_i, enc_p,
+                                lambda prevs, curs: [enc_p(a, b) for a, b in zip(prevs, curs)], batch=3)
+    out = gs.gather_spans(data, tail, spans, {"rdvc_version": "1.0"}, rank, world,
+                          reencode_iframe=lambda t: enc_i(frames(t)))
+    if rank == 0:
+        with open(out_path, "wb") as f:
+            f.write(out)
+    else:
+        assert out is None
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(180)
+def test_two_rank_span_gather_equals_serial(tmp_path):
+    out = str(tmp_path / "two_rank_spans.rdvc")
+    mp.spawn(_span_worker, args=(2, _free_port(), 47, 5, out), nprocs=2, join=True)
+    with open(out, "rb") as f:
+        assert f.read() == _serial_stream(47, 5, {"rdvc_version": "1.0"})
+
+
+def test_encode_gop_logs_and_reraises_fatal_errors(caplog):
+    """A failed P-frame is logged with its frame index (the reference prints the traceback,
+    R:codec_processing.py:1501-1506); errors a retry cannot fix are re-raised instead of silently degrading."""
+    frames, enc_i, enc_p = _fake_encoders()
+
+    def flaky(prev, cur):
+        raise RuntimeError("boom")
+    failures = []
+    with caplog.at_level("ERROR", logger="rdvc_corr_b200.gop_shard"):
+        gs.encode_gop(gs.Gop(0, 0, 3), frames, enc_i, flaky, failures)
+    assert failures == [1] and "P-frame 1 failed" in caplog.text and "boom" in caplog.text
+
+    def fatal(prev, cur):
+        raise RuntimeError("CUDA error: an illegal memory access was encountered")
+    with pytest.raises(RuntimeError, match="CUDA error"):
+        gs.encode_gop(gs.Gop(0, 0, 3), frames, enc_i, fatal)
