@@ -129,13 +129,19 @@ int rdvc_corr_lookup(const void* pyramid, int vol_dtype, int layout, const float
 /* The same lookup with a choice of result type and form (TILED pyramids; ROWMAJOR supports F32 / NCHW only):
  *   out_form RDVC_OUT_NCHW,   out_dtype F32 | F16 : (B, L*S*S, h, w); F16 is what the consumer casts the features to
  *                                                   under the reference's default autocast (R:codec_processing.py:1436)
- *   out_form RDVC_OUT_KMAJOR, out_dtype BF16 | F16: feature rows [B*h*w][rdvc_corr_feat_pitch(L, r)], 16-byte aligned;
- *            column l*PL + j*S + i holds torchvision channel l*S*S + i*S + j (PL = S*S rounded up to 8), padding
- *            columns hold 0 -- the A operand of rdvc_conv1x1.                                                     */
+ *   out_form RDVC_OUT_KMAJOR, out_dtype BF16 | F16: the K-major A operand of rdvc_conv1x1, rdvc_corr_feat_bytes long,
+ *            16-byte aligned.  Feature k = l*PL + j*S + i of query pixel m holds torchvision channel l*S*S + i*S + j
+ *            (PL = S*S rounded up to 8; padding features hold 0) and lives at element
+ *            ((k / 8) * rdvc_corr_feat_rows + m) * 8 + k % 8 -- chunk-major [K/8][rows][8]: a warp of 32 consecutive
+ *            pixels stores 8 taps of all of them as one contiguous 512-byte run, and a TMA box of it is the
+ *            un-swizzled tcgen05 core-matrix layout.  Rows m >= B*h*w (up to the multiple of 8) are not written.  */
 int rdvc_corr_lookup_ex(const void* pyramid, int vol_dtype, int layout, const float* coords, int B, int h,
                         int w, int num_levels, int radius, void* out, int out_dtype, int out_form, void* stream);
-/* elements per K-major feature row: num_levels * PL rounded up to 16 (352 for 4 levels x radius 4); 0 if unsupported */
+/* K elements per query pixel: num_levels * PL rounded up to 16 (352 for 4 levels x radius 4); 0 if unsupported */
 size_t rdvc_corr_feat_pitch(int num_levels, int radius);
+/* rows of every chunk plane: B*h*w rounded up to 8; and the byte size of the whole K-major feature buffer */
+size_t rdvc_corr_feat_rows(int B, int h, int w);
+size_t rdvc_corr_feat_bytes(int B, int h, int w, int num_levels, int radius);
 
 /* ---- next row f-1: lookup fused with MotionEncoder.convcorr1 ------------- *
  * Replaces index_pyramid (TV:raft.py:394-422) + convcorr1 = Conv2d(L*S*S -> cout, kernel 1) + ReLU (TV:raft.py:185
@@ -146,9 +152,9 @@ size_t rdvc_corr_feat_pitch(int num_levels, int radius);
  * rdvc_conv1x1_pack_weights (HOST, no GPU needed): conv weight (cout, L*S*S) fp32 in torchvision's channel order ->
  *   [cout][K padded to 64] 16-bit rows in the lookup's column order, zero padded; copy them to the device.
  *   cout: multiple of 32, <= 256.  feat_dtype: BF16 or F16 (must match the lookup's).
- * rdvc_conv1x1: out[b, n, y, x] = act(sum_k feat[b*h*w + y*w + x][k] * Wp[n][k] + bias[n]);  bias: cout DEVICE floats
- *   or NULL; out: (B, cout, h, w) F32 | F16 | BF16.
- * rdvc_corr_lookup_conv1x1: both steps (2 launches); feat_ws: DEVICE scratch of B*h*w*rdvc_corr_feat_pitch*2 bytes. */
+ * rdvc_conv1x1: out[b, n, y, x] = act(sum_k feat(k, b*h*w + y*w + x) * Wp[n][k] + bias[n]);  feat: the K-major buffer
+ *   described at rdvc_corr_lookup_ex; bias: cout DEVICE floats or NULL; out: (B, cout, h, w) F32 | F16 | BF16.
+ * rdvc_corr_lookup_conv1x1: both steps (2 launches); feat_ws: DEVICE scratch of rdvc_corr_feat_bytes(...) bytes.     */
 size_t rdvc_conv1x1_packed_weight_bytes(int cout, int num_levels, int radius);
 int rdvc_conv1x1_pack_weights(const float* weight, int cout, int num_levels, int radius, int feat_dtype,
                               void* packed_host);

@@ -39,6 +39,8 @@ SYMBOLS = {
     "rdvc_corr_lookup_ex": (_c.c_int, [_c.c_void_p, _c.c_int, _c.c_int, _c.c_void_p, _c.c_int, _c.c_int,
                                        _c.c_int, _c.c_int, _c.c_int, _c.c_void_p, _c.c_int, _c.c_int, _c.c_void_p]),
     "rdvc_corr_feat_pitch": (_c.c_size_t, [_c.c_int, _c.c_int]),
+    "rdvc_corr_feat_rows": (_c.c_size_t, [_c.c_int] * 3),
+    "rdvc_corr_feat_bytes": (_c.c_size_t, [_c.c_int] * 5),
     "rdvc_conv1x1_packed_weight_bytes": (_c.c_size_t, [_c.c_int] * 3),
     "rdvc_conv1x1_pack_weights": (_c.c_int, [_c.c_void_p, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_void_p]),
     "rdvc_conv1x1": (_c.c_int, [_c.c_void_p, _c.c_int, _c.c_void_p, _c.c_void_p] + [_c.c_int] * 7 +

@@ -210,11 +210,17 @@ def feat_pitch(num_levels: int = 4, radius: int = 4) -> int:
     return int(_cabi.load().rdvc_corr_feat_pitch(num_levels, radius))
 
 
+def feat_shape(B: int, h: int, w: int, num_levels: int = 4, radius: int = 4):
+    """Shape of the K-major feature buffer: (K / 8 chunks, rows = B*h*w rounded up to 8, 8)."""
+    lib = _cabi.load()
+    return (int(lib.rdvc_corr_feat_pitch(num_levels, radius)) // 8, int(lib.rdvc_corr_feat_rows(B, h, w)), 8)
+
+
 def index_pyramid_kmajor(pyr: CorrPyramid, coords: Tensor, radius: int = 4, feat_dtype: torch.dtype = torch.bfloat16,
                          out: Optional[Tensor] = None) -> Tensor:
-    """The lookup as K-major 16-bit feature rows (B*h*w, feat_pitch): column l*PL + j*S + i holds torchvision
-    channel l*S*S + i*S + j (PL = S*S rounded up to 8), padding columns hold 0 -- the A operand of the 1x1
-    convolution (``conv1x1``)."""
+    """The lookup as the K-major 16-bit A operand of the 1x1 convolution (``conv1x1``), chunk-major
+    (K/8, rows, 8): ``out[k // 8, m, k % 8]`` is feature k = l*PL + j*S + i (torchvision channel l*S*S + i*S + j,
+    PL = S*S rounded up to 8, padding features 0) of query pixel m; rows m >= B*h*w are not written."""
     lib = _cabi.load()
     c = _check_coords(pyr, coords)
     B, _, h, w = coords.shape
@@ -222,10 +228,11 @@ def index_pyramid_kmajor(pyr: CorrPyramid, coords: Tensor, radius: int = 4, feat
     kp = feat_pitch(pyr.num_levels, radius)
     if kp == 0 or feat_dtype not in _FEAT_DTYPES:
         raise ValueError(f"unsupported (levels, radius, feat_dtype) = ({pyr.num_levels}, {radius}, {feat_dtype})")
+    shape = feat_shape(B, h, w, pyr.num_levels, radius)
     if out is None:
-        out = torch.empty((B * h * w, kp), dtype=feat_dtype, device=dev)
-    elif tuple(out.shape) != (B * h * w, kp) or out.dtype != feat_dtype or not out.is_contiguous():
-        raise ValueError(f"out must be a contiguous {feat_dtype} tensor of shape (B*h*w, {kp})")
+        out = torch.empty(shape, dtype=feat_dtype, device=dev)
+    elif tuple(out.shape) != shape or out.dtype != feat_dtype or not out.is_contiguous():
+        raise ValueError(f"out must be a contiguous {feat_dtype} tensor of shape {shape}")
     with torch.cuda.device(dev):
         rc = lib.rdvc_corr_lookup_ex(pyr.buffer.data_ptr(), _VOL_DTYPES[pyr.volume_dtype], pyr.layout, c.data_ptr(),
                                      B, h, w, pyr.num_levels, radius, out.data_ptr(), _FEAT_DTYPES[feat_dtype],
@@ -270,7 +277,8 @@ def _param_key(weight, bias, feat_dtype, device):
 
 def conv1x1(feat: Tensor, packed: PackedConv1x1, B: int, h: int, w: int, num_levels: int = 4, radius: int = 4,
             relu: bool = True, out_dtype: torch.dtype = torch.float32, out: Optional[Tensor] = None) -> Tensor:
-    """(B*h*w, feat_pitch) K-major feature rows -> (B, cout, h, w) = act(W . feat + bias) through ``rdvc_conv1x1``."""
+    """(K/8, rows, 8) K-major features (``index_pyramid_kmajor``) -> (B, cout, h, w) = act(W . feat + bias) through
+    ``rdvc_conv1x1``."""
     lib = _cabi.load()
     dev = feat.device
     if out is None:
@@ -355,9 +363,9 @@ class TVCorrBlock(nn.Module):
         key = _param_key(weight, bias, feat_dtype, dev)
         if self._packed is None or self._packed.key != key:
             self._packed = PackedConv1x1(weight, bias, self.num_levels, self.radius, feat_dtype, dev)
-        kp = feat_pitch(self.num_levels, self.radius)
-        if self._feat is None or self._feat.shape != (B * h * w, kp) or self._feat.dtype != feat_dtype or self._feat.device != dev:
-            self._feat = torch.empty((B * h * w, kp), dtype=feat_dtype, device=dev)
+        shape = feat_shape(B, h, w, self.num_levels, self.radius)
+        if self._feat is None or tuple(self._feat.shape) != shape or self._feat.dtype != feat_dtype or self._feat.device != dev:
+            self._feat = torch.zeros(shape, dtype=feat_dtype, device=dev)
         out = torch.empty((B, self._packed.cout, h, w), dtype=out_dtype, device=dev)
         lib = _cabi.load()
         with torch.cuda.device(dev):

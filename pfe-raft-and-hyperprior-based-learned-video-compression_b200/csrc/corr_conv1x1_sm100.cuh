@@ -4,10 +4,17 @@
 //
 //   out[b, n, y, x] = act( sum_k feat[b*N + y*w + x][k] * Wp[n][k] + bias[n] ),   n < cout <= 256
 //
-// feat: [B*N][kp] bf16 / fp16 (kp = rdvc_corr_feat_pitch, 352 for 4 levels x radius 4), Wp: the convolution's
-// weight permuted to the lookup's column order and zero-padded (rdvc_conv1x1_pack_weights), fp32 accumulation
-// in TMEM, bias + ReLU in the epilogue, result written ONCE as the (B, cout, h, w) tensor convcorr2 reads --
-// the (B, 324, h, w) fp32 lookup tensor (42 MB per iteration at 1080p) and its re-read by cuDNN are gone.
+// feat: bf16 / fp16, chunk-major [kp / 8][rows][8] (kp = rdvc_corr_feat_pitch, 352 for 4 levels x radius 4; see
+// corr_lookup.cuh), Wp: the convolution's weight permuted to the lookup's feature order and zero-padded
+// (rdvc_conv1x1_pack_weights), fp32 accumulation in TMEM, bias + ReLU in the epilogue, result written ONCE as
+// the (B, cout, h, w) tensor convcorr2 reads -- the (B, 324, h, w) fp32 lookup tensor (42 MB per iteration at
+// 1080p) and its re-read by cuDNN are gone.
+//
+// Operand layouts in shared memory.  A (features): a TMA box of 8 chunks x 128 rows x 16 bytes lands as
+// [chunk][row][16 B], i.e. core matrices of 8 rows x 16 bytes stored contiguously -- the UN-SWIZZLED K-major
+// canonical layout of tcgen05 (descriptor layout type 0, stride byte offset = 128 between 8-row groups, leading
+// byte offset = 2048 between the two 8-element chunks of a K = 16 step).  B (weights): [cout / 2][64] rows with
+// the 128-byte swizzle, as in the build kernel.
 //
 // Shape of the computation at 1080p: M = 32640 pixels, N = 256, K = 352: 5.9 GFLOP (3.5 us at the bf16 peak),
 // 23 MB of features in (L2-resident: the lookup wrote them a moment ago), 33 MB fp32 out (5.1 us at the HBM
@@ -68,7 +75,8 @@ template <> __device__ __forceinline__ __half c1_cvt<__half>(float x) { return _
 template <> __device__ __forceinline__ __nv_bfloat16 c1_cvt<__nv_bfloat16>(float x) { return __float2bfloat16_rn(x); }
 
 // grid: an even number of CTAs (clusters of 2); block: C1_THREADS; dynamic smem: C1_SMEM_LAUNCH.
-// tm_a: features as a {kp, m_total, 1} tensor, box {64, 128, 1}; tm_w: packed weights {kpw, cout, 1}, box {64, cout / 2, 1}.
+// tm_a: features as a {64 (8 rows x 8 elements), rows / 8, kp / 8} tensor, box {64, 16, 8}, no swizzle;
+// tm_w: packed weights {kpw, cout, 1}, box {64, cout / 2, 1}, 128-byte swizzle.
 template <typename OutT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(C1_THREADS, 1)
 corr_conv1x1_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_w,
@@ -135,13 +143,14 @@ corr_conv1x1_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
             uint32_t a_it = 0;
             for (int t = 0; t < n_tiles; ++t) {
                 long long m0 = row_base + static_cast<long long>(t) * C1_BLOCK_M;
-                if (m0 > p.m_total - 1) m0 = p.m_total - 1;      // a range past the end: rows are masked in the epilogue
+                if (m0 > p.m_total - 1) m0 = (p.m_total - 1) & ~7LL;   // a range past the end: rows are masked in the epilogue
                 for (int kb = 0; kb < n_kb; ++kb, ++a_it) {
                     const uint32_t st = a_it % C1_A_STAGES, ph = (a_it / C1_A_STAGES) & 1;
                     ptx::mbar_wait(bar(A_EMPTY + st), ph ^ 1);
                     if (leader) ptx::mbar_arrive_expect_tx(bar(A_FULL + st), 2 * C1_A_STAGE_BYTES);
-                    ptx::tma_load_3d_2sm(s_a + st * C1_A_STAGE_BYTES, &tm_a, bar(A_FULL + st), kb * C1_BLOCK_K,
-                                         static_cast<int>(m0), 0);
+                    // rows m0 .. m0 + 127 (m0 is a multiple of 8: ranges are multiples of 32), chunks 8 kb .. 8 kb + 7
+                    ptx::tma_load_3d_2sm(s_a + st * C1_A_STAGE_BYTES, &tm_a, bar(A_FULL + st), 0,
+                                         static_cast<int>(m0 >> 3), kb * (C1_BLOCK_K / 8));
                 }
             }
         }
@@ -163,18 +172,18 @@ corr_conv1x1_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
                     const uint32_t st = a_it % C1_A_STAGES, ph = (a_it / C1_A_STAGES) & 1;
                     ptx::mbar_wait(bar(A_FULL + st), ph);
                     ptx::tc_fence_after();
-                    const uint64_t a_desc0 = ptx::umma_desc_k_sw128(s_a + st * C1_A_STAGE_BYTES);
+                    const uint64_t a_desc0 = ptx::umma_desc_k_nosw(s_a + st * C1_A_STAGE_BYTES, 2048, 128);
                     const int ks = n_ksteps - kb * 4;            // k-steps left: 4 for a full block
                     if (ptx::elect_one()) {
                         const uint64_t b_desc = b_desc0 + ((kb * C1_W_SLAB_BYTES) >> 4);
                         if (ks >= 4) {                            // a full k-block: four MMAs back to back
 #pragma unroll
                             for (int k = 0; k < 4; ++k)
-                                ptx::umma_bf16_2sm(d_tmem, a_desc0 + ((k * 32) >> 4), b_desc + ((k * 32) >> 4), idesc,
-                                                   (kb | k) != 0 ? 1u : 0u);
+                                ptx::umma_bf16_2sm(d_tmem, a_desc0 + ((k * 4096) >> 4), b_desc + ((k * 32) >> 4), idesc,
+                                                   (kb | k) != 0 ? 1u : 0u);          // A: two 2 KB chunk planes per k-step
                         } else {                                  // the partial last block (K = 352: two k-steps)
                             for (int k = 0; k < ks; ++k)
-                                ptx::umma_bf16_2sm(d_tmem, a_desc0 + ((k * 32) >> 4), b_desc + ((k * 32) >> 4), idesc,
+                                ptx::umma_bf16_2sm(d_tmem, a_desc0 + ((k * 4096) >> 4), b_desc + ((k * 32) >> 4), idesc,
                                                    (kb | k) != 0 ? 1u : 0u);
                         }
                         ptx::umma_commit_2sm(bar(A_EMPTY + st), 3);                   // ring slot free in both CTAs

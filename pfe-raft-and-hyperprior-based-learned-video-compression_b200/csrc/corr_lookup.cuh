@@ -39,8 +39,9 @@ struct LookupParams {
     int tiles_w[LKP_MAX_LEVELS];     // RDVC_LAYOUT_TILED: tiles per image row
     int twl, thl;                    // RDVC_LAYOUT_TILED: log2 tile width / height
     const float* coords;  // (B, 2, N)
-    void* out;            // LKP_OUT_NCHW_*: (B, L*S*S, N);  LKP_OUT_KM_*: (B*N, feat_pitch) 16-bit rows
-    int feat_pitch;       // LKP_OUT_KM_*: elements per feature row (rdvc_corr_feat_pitch)
+    void* out;            // LKP_OUT_NCHW_*: (B, L*S*S, N);  LKP_OUT_KM_*: [feat_pitch / 8][feat_rows][8] 16-bit chunks
+    int feat_pitch;       // LKP_OUT_KM_*: K elements per query pixel (rdvc_corr_feat_pitch)
+    long long feat_rows;  // LKP_OUT_KM_*: B*N rounded up to a multiple of 8 (rows of every chunk plane)
     int B, N;
     int num_levels;
     long long total;      // B * N
@@ -194,11 +195,15 @@ struct LookupSite {
 // ---- output forms of the tiled kernel ---------------------------------------------------------
 // NCHW: the (B, L*S*S, h, w) tensor torchvision's index_pyramid returns, fp32 (what RAFT.forward consumes) or
 //       fp16 (what the consumer casts it to under the reference's default autocast, R:codec_processing.py:1436).
-// KM  : "K-major" 16-bit feature rows [B*N][feat_pitch] -- the A operand of the 1x1 convolution that follows the
-//       lookup in MotionEncoder (TV:raft.py:185,202; corr_conv1x1_sm100.cuh).  A thread's S*S taps of one level
-//       are written in the order it produces them (window row j outer, x index i inner) at columns
-//       l * PL + j * S + i, PL = S*S rounded up to 8 (one 16-byte store per 8 taps; padding columns hold 0);
-//       the convolution's weight matrix is permuted to match on the host (rdvc_conv1x1_pack_weights).
+// KM  : 16-bit features as the K-major A operand of the 1x1 convolution that follows the lookup in MotionEncoder
+//       (TV:raft.py:185,202; corr_conv1x1_sm100.cuh).  Feature k of query pixel m -- k = l * PL + j * S + i, PL = S*S
+//       rounded up to 8, the order a thread produces its taps in (window row j outer, x index i inner); padding
+//       features hold 0; the convolution's weight matrix is permuted to match on the host
+//       (rdvc_conv1x1_pack_weights) -- lives at element ((k / 8) * feat_rows + m) * 8 + k % 8: CHUNK-major,
+//       [K/8][rows][8].  A warp (32 consecutive pixels) then stores 8 taps of all its pixels as ONE contiguous
+//       512-byte run (row-major rows, 704 bytes apart, cost 32 separate 16-byte segments per store instruction:
+//       45 us per launch instead of 29), and a TMA box of 8 chunks x 128 rows lands in shared memory as exactly the
+//       un-swizzled K-major core-matrix layout of tcgen05 (8 rows x 16 bytes contiguous).
 constexpr int LKP_OUT_NCHW_F32 = 0, LKP_OUT_NCHW_F16 = 1, LKP_OUT_KM_BF16 = 2, LKP_OUT_KM_F16 = 3;
 
 __host__ __device__ constexpr int lkp_level_pitch(int radius) {
@@ -290,9 +295,11 @@ corr_lookup_tiled_kernel(const __grid_constant__ LookupParams p) {
     const size_t C_out = static_cast<size_t>(p.num_levels) * S * S;
     OutT* outp = static_cast<OutT*>(p.out) + (static_cast<size_t>(site.b) * C_out + static_cast<size_t>(l) * S * S) * p.N + site.q;
     const size_t chan_i = static_cast<size_t>(S) * p.N;   // stride of the window's x index
-    // K-major form: this thread's S*S taps go to columns [l * PL, l * PL + PL) of feature row `pix`
+    // K-major form: this thread's S*S taps are chunks l * PL/8 .. of row `pix`; a chunk plane is feat_rows * 16 bytes
     constexpr int PL = lkp_level_pitch(R);
-    uint16_t* featp = static_cast<uint16_t*>(p.out) + static_cast<size_t>(pix) * p.feat_pitch + l * PL;
+    const size_t chunk_stride = static_cast<size_t>(p.feat_rows) * 8;                       // elements
+    uint16_t* featp = static_cast<uint16_t*>(p.out) + static_cast<size_t>(l) * (PL / 8) * chunk_stride +
+                      static_cast<size_t>(pix) * 8;
     float stash[8];
 
     TRow buf[2];
@@ -319,7 +326,7 @@ corr_lookup_tiled_kernel(const __grid_constant__ LookupParams p) {
 #pragma unroll
                         for (int z = (idx & 7) + 1; z < 8; ++z) stash[z] = 0.f;    // padding columns of the level
                         const uint4 wv = lkp_pack8<OUT == LKP_OUT_KM_F16>(stash);
-                        if (DBG != 2 || v == 12345.678f) *reinterpret_cast<uint4*>(featp + (idx >> 3) * 8) = wv;
+                        if (DBG != 2 || v == 12345.678f) *reinterpret_cast<uint4*>(featp + (idx >> 3) * chunk_stride) = wv;
                     }
                 } else if constexpr (OUT == LKP_OUT_NCHW_F16) {
                     if (DBG != 2 || v == 12345.678f) *o = __float2half_rn(v);
@@ -334,9 +341,9 @@ corr_lookup_tiled_kernel(const __grid_constant__ LookupParams p) {
         for (int i = 0; i < S; ++i) prev[i] = hrow[i];
     }
     if constexpr (KM) {
-        if (l == p.num_levels - 1)
+        if (l == p.num_levels - 1)                       // feature-row tail: whole zero chunks up to feat_pitch
             for (int c = PL; l * PL + c < p.feat_pitch; c += 8)
-                *reinterpret_cast<uint4*>(featp + c) = make_uint4(0u, 0u, 0u, 0u);
+                *reinterpret_cast<uint4*>(featp + (c >> 3) * chunk_stride) = make_uint4(0u, 0u, 0u, 0u);
     }
 }
 

@@ -209,6 +209,17 @@ __device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr) {
     d |= static_cast<uint64_t>(2) << 61;
     return d;
 }
+// K-major operand WITHOUT swizzle (descriptor layout type 0): core matrices of 8 rows x 16 bytes stored contiguously
+// (128 B); `sbo_bytes` between core matrices of successive 8-row groups, `lbo_bytes` between the two core matrices
+// (8 elements each) that make up the K = 16 of one MMA.
+__device__ __forceinline__ uint64_t umma_desc_k_nosw(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+    d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16;
+    d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFFu) << 32;
+    d |= static_cast<uint64_t>(1) << 46;
+    return d;
+}
 // kind::f16 instruction descriptor: fp32 accumulate, A/B = bf16 (1) or f16 (0), both K-major.
 __host__ __device__ constexpr uint32_t umma_idesc(int m, int n, int ab_format) {
     return (1u << 4) | (static_cast<uint32_t>(ab_format) << 7) |

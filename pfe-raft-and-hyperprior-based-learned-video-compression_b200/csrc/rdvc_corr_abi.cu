@@ -157,12 +157,13 @@ EncodeTiledFn encode_tiled_fn() {
 
 // Tiled TMA descriptor, 128-byte swizzle, zero OOB fill (loads) / clipped (stores).
 int make_tmap(CUtensorMap* m, CUtensorMapDataType dt, void* base, int rank, const cuuint64_t* dims,
-              const cuuint64_t* strides_bytes, const cuuint32_t* box) {
+              const cuuint64_t* strides_bytes, const cuuint32_t* box,
+              CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
     EncodeTiledFn fn = encode_tiled_fn();
     if (!fn) return fail(RDVC_E_DRIVER, "cuTensorMapEncodeTiled not available from the driver");
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
     CUresult r = fn(m, dt, rank, base, dims, strides_bytes, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle,
                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(RDVC_E_DRIVER, "cuTensorMapEncodeTiled failed: CUresult %d", (int)r);
     return RDVC_OK;
@@ -781,6 +782,15 @@ size_t rdvc_corr_feat_pitch(int num_levels, int radius) {
     return static_cast<size_t>(rdvc::lkp_feat_pitch(num_levels, radius));
 }
 
+size_t rdvc_corr_feat_rows(int B, int h, int w) {
+    if (B <= 0 || h <= 0 || w <= 0) return 0;
+    return align_up(static_cast<size_t>(B) * h * w, 8);
+}
+
+size_t rdvc_corr_feat_bytes(int B, int h, int w, int num_levels, int radius) {
+    return rdvc_corr_feat_pitch(num_levels, radius) * rdvc_corr_feat_rows(B, h, w) * 2;
+}
+
 int rdvc_corr_lookup_ex(const void* pyramid, int vol_dtype, int layout, const float* coords, int B, int h,
                         int w, int num_levels, int radius, void* out, int out_dtype, int out_form, void* stream) {
     if (!pyramid || !coords || !out) return fail(RDVC_E_NULL, "null pointer argument");
@@ -823,6 +833,7 @@ int rdvc_corr_lookup_ex(const void* pyramid, int vol_dtype, int layout, const fl
     p.coords = coords;
     p.out = out;
     p.feat_pitch = rdvc::lkp_feat_pitch(num_levels, radius);
+    p.feat_rows = static_cast<long long>(rdvc_corr_feat_rows(B, h, w));
     p.B = B;
     p.N = h * w;
     p.num_levels = num_levels;
@@ -902,10 +913,14 @@ int rdvc_conv1x1(const void* feat, int feat_dtype, const void* packed_w, const f
     const CUtensorMapDataType op_dt = (feat_dtype == RDVC_DT_F16) ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
     CUtensorMap tm_a, tm_w;
     {
-        cuuint64_t dims[3] = {(cuuint64_t)kp, (cuuint64_t)m_total, 1};
-        cuuint64_t str[2] = {(cuuint64_t)kp * 2, (cuuint64_t)m_total * kp * 2};
-        cuuint32_t box[3] = {rdvc::C1_BLOCK_K, rdvc::C1_BLOCK_M, 1};
-        if (int rc = make_tmap(&tm_a, op_dt, const_cast<void*>(feat), 3, dims, str, box)) return rc;
+        // chunk-major features [kp / 8][rows][8]: 8 consecutive rows of one chunk are 128 contiguous bytes, so the map
+        // is {64 elements, rows / 8, chunks}; a box of {64, 16, 8} = 8 chunks x 128 rows lands in shared memory as
+        // [chunk][row][16 B], the un-swizzled K-major core-matrix layout (corr_conv1x1_sm100.cuh)
+        const cuuint64_t rows = (cuuint64_t)rdvc_corr_feat_rows(B, h, w);
+        cuuint64_t dims[3] = {64, rows / 8, (cuuint64_t)kp / 8};
+        cuuint64_t str[2] = {128, rows * 16};
+        cuuint32_t box[3] = {64, rdvc::C1_BLOCK_M / 8, rdvc::C1_BLOCK_K / 8};
+        if (int rc = make_tmap(&tm_a, op_dt, const_cast<void*>(feat), 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_NONE)) return rc;
     }
     {
         cuuint64_t dims[3] = {(cuuint64_t)kpw, (cuuint64_t)cout, 1};
@@ -943,7 +958,7 @@ int rdvc_corr_lookup_conv1x1(const void* pyramid, int vol_dtype, int layout, con
     const size_t kp = rdvc_corr_feat_pitch(num_levels, radius);
     if (kp == 0) return fail(RDVC_E_UNSUPPORTED, "num_levels=%d / radius=%d not supported", num_levels, radius);
     if (B <= 0 || h <= 0 || w <= 0) return fail(RDVC_E_SHAPE, "non-positive dimension B=%d h=%d w=%d", B, h, w);
-    const size_t need = static_cast<size_t>(B) * h * w * kp * 2;
+    const size_t need = rdvc_corr_feat_bytes(B, h, w, num_levels, radius);
     if (feat_ws_bytes < need) return fail(RDVC_E_WORKSPACE, "feature workspace %zu < required %zu", feat_ws_bytes, need);
     int rc = rdvc_corr_lookup_ex(pyramid, vol_dtype, layout, coords, B, h, w, num_levels, radius, feat_ws, feat_dtype,
                                  RDVC_OUT_KMAJOR, stream);

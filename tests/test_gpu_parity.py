@@ -570,12 +570,17 @@ def test_lookup_output_forms(lib, radius, levels, vol):
     # torchvision channel (l, i, j) -> column l*PL + j*S + i
     l_, i_, j_ = torch.meshgrid(torch.arange(levels), torch.arange(S), torch.arange(S), indexing="ij")
     col = (l_ * PL + j_ * S + i_).reshape(-1).cuda()
+    M = B * h * w
+    shape = rc.corr_block.feat_shape(B, h, w, levels, radius)
+    assert shape == (kp // 8, (M + 7) // 8 * 8, 8)
     for fd in (torch.bfloat16, torch.float16):
-        km = torch.full((B * h * w, kp), float("nan"), dtype=fd, device="cuda")
+        km = torch.full(shape, float("nan"), dtype=fd, device="cuda")
         rc.corr_block.index_pyramid_kmajor(pyr, co, radius, fd, out=km)
-        want = torch.zeros((B * h * w, kp), dtype=fd, device="cuda")
-        want[:, col] = ref.permute(0, 2, 3, 1).reshape(B * h * w, levels * S * S).to(fd)
-        assert torch.equal(km, want), (fd, radius, levels)
+        want = torch.zeros((M, kp), dtype=fd, device="cuda")
+        want[:, col] = ref.permute(0, 2, 3, 1).reshape(M, levels * S * S).to(fd)
+        got = km[:, :M].permute(1, 0, 2).reshape(M, kp)                   # (chunk, row, 8) -> (row, K)
+        assert torch.equal(got, want), (fd, radius, levels)
+        assert torch.isnan(km[:, M:].float()).all()                       # rows past B*h*w are left alone
     with pytest.raises(ValueError, match="RDVC_LAYOUT_TILED"):
         rc.index_pyramid(pyramid_from_levels(rc, cc.split_levels(flat, B, h, w, levels), B, h, w, vol, layout=ROW),
                          co, radius, out_dtype=torch.float16)
@@ -598,8 +603,11 @@ def test_conv1x1_matches_fp64(lib, shape, cout, fd, od):
     bias = torch.randn(cout, device="cuda", generator=g)
     l_, i_, j_ = torch.meshgrid(torch.arange(4), torch.arange(9), torch.arange(9), indexing="ij")
     col = (l_ * 88 + j_ * 9 + i_).reshape(-1).cuda()
-    km = torch.zeros(B * h * w, kp, dtype=fd, device="cuda")
-    km[:, col] = feats_tv.to(fd)
+    M = B * h * w
+    rows = torch.zeros(M, kp, dtype=fd, device="cuda")
+    rows[:, col] = feats_tv.to(fd)
+    km = torch.full(rc.corr_block.feat_shape(B, h, w), float("nan"), dtype=fd, device="cuda")   # garbage rows past M
+    km[:, :M] = rows.view(M, kp // 8, 8).permute(1, 0, 2)
     packed = rc.corr_block.PackedConv1x1(weight, bias, 4, 4, fd, "cuda")
     for relu in (True, False):
         got = rc.corr_block.conv1x1(km, packed, B, h, w, relu=relu, out_dtype=od)

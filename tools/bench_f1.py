@@ -44,7 +44,7 @@ for vol in (torch.float32, torch.bfloat16):
     name = "fp32_volume" if vol == torch.float32 else "bf16_volume"
     r = {}
     buf = torch.empty(B, 324, h, w, device=dev)
-    feat = torch.empty(B * h * w, rc.corr_block.feat_pitch(4, 4), dtype=torch.bfloat16, device=dev)
+    feat = torch.zeros(rc.corr_block.feat_shape(B, h, w), dtype=torch.bfloat16, device=dev)
     packed = rc.corr_block.PackedConv1x1(conv[0].weight, conv[0].bias, 4, 4, torch.bfloat16, dev)
     with torch.no_grad():
         r["lookup_nchw_fp32"] = timed(lambda c: rc.index_pyramid(blk._pyr, c, 4, out=buf))
