@@ -67,7 +67,21 @@ struct Conv1x1Params {
     int tiles_per_cta;      // ceil(rows_per_cta / 128)
     int relu;
     int ab_format;          // tcgen05 kind::f16 operand format: 1 = bf16, 0 = fp16
+    unsigned long long* dbg_timeline;   // RDVC_EXPERIMENTS builds only: 16 globaltimer stamps per CTA (nullptr = off)
 };
+
+#ifdef RDVC_EXPERIMENTS
+__device__ __forceinline__ void c1_stamp(const Conv1x1Params& p, int slot) {
+    if (p.dbg_timeline) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        p.dbg_timeline[blockIdx.x * 16 + slot] = t;
+    }
+}
+#define C1_STAMP(slot) c1_stamp(p, slot)
+#else
+#define C1_STAMP(slot) ((void)0)
+#endif
 
 template <typename OutT> __device__ __forceinline__ OutT c1_cvt(float x);
 template <> __device__ __forceinline__ float c1_cvt<float>(float x) { return x; }
@@ -99,6 +113,7 @@ corr_conv1x1_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
     const bool leader = (rank == 0);
 
     if (warp == 0 && lane == 0) {
+        C1_STAMP(0);                                   // kernel entry
         ptx::prefetch_tensormap(&tm_a);
         ptx::prefetch_tensormap(&tm_w);
     }
@@ -126,6 +141,7 @@ corr_conv1x1_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
     ptx::cluster_sync_all();          // the peer's barriers are initialised before anyone signals them
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (warp == 0 && lane == 0) C1_STAMP(1);           // set-up done (barriers, TMEM, cluster sync)
 
     const int n_kb = (p.kp + C1_BLOCK_K - 1) / C1_BLOCK_K;      // k-blocks (the last may be partial)
     const int n_ksteps = p.kp / 16;                              // UMMA k-steps over the whole K
@@ -161,6 +177,7 @@ corr_conv1x1_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
             const uint32_t idesc = ptx::umma_idesc(2 * C1_BLOCK_M, p.cout, p.ab_format);
             ptx::mbar_wait(bar(W_FULL), 0);
             ptx::tc_fence_after();
+            if (lane == 0) C1_STAMP(2);                // weights landed
             const uint64_t b_desc0 = ptx::umma_desc_k_sw128(s_w);
             uint32_t a_it = 0;
             for (int t = 0; t < n_tiles; ++t) {
@@ -172,6 +189,8 @@ corr_conv1x1_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
                     const uint32_t st = a_it % C1_A_STAGES, ph = (a_it / C1_A_STAGES) & 1;
                     ptx::mbar_wait(bar(A_FULL + st), ph);
                     ptx::tc_fence_after();
+                    if (lane == 0 && kb == 0) C1_STAMP(3 + t);          // first feature block of tile t landed (slots 3, 4)
+                    if (lane == 0 && kb == n_kb - 1) C1_STAMP(5 + t);   // last one (slots 5, 6)
                     const uint64_t a_desc0 = ptx::umma_desc_k_nosw(s_a + st * C1_A_STAGE_BYTES, 2048, 128);
                     const int ks = n_ksteps - kb * 4;            // k-steps left: 4 for a full block
                     if (ptx::elect_one()) {
@@ -213,6 +232,7 @@ corr_conv1x1_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
             const uint32_t acc = t & 1, acc_ph = (t >> 1) & 1;
             ptx::mbar_wait(bar(T_FULL + acc), acc_ph);
             ptx::tc_fence_after();
+            if (e == 0 && lane == 0) C1_STAMP(7 + t);                   // accumulator of tile t ready (slots 7, 8)
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * C1_MAX_COUT + ch0;
             for (int c = 0; c < half; c += 32) {
                 float v[32];
@@ -236,12 +256,15 @@ corr_conv1x1_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
                     }
                 }
             }
+            if (e == 0 && lane == 0) C1_STAMP(9 + t);                   // this warp's stores of tile t issued (slots 9, 10)
         }
     }
 
     ptx::tc_fence_before();
     __syncthreads();
+    if (warp == 0 && lane == 0) C1_STAMP(11);          // every warp of this CTA is done
     ptx::cluster_sync_all();          // the leader's MMAs read the peer's shared memory until the very end
+    if (warp == 0 && lane == 0) C1_STAMP(12);
     if (warp == 2) ptx::tmem_dealloc_2sm(tmem_base, 512);
 }
 
