@@ -347,8 +347,11 @@ class TVCorrBlock(nn.Module):
         """``relu(conv1x1(index_pyramid(coords), weight, bias))`` -- the lookup fused with
         ``MotionEncoder.convcorr1`` (TV:raft.py:185,202) through ``rdvc_corr_lookup_conv1x1``: the (B, 324, h, w)
         fp32 lookup tensor is never written.  ``weight``: (cout, L*S*S[, 1, 1]) in torchvision's channel order.
-        16-bit operands (bf16; fp16 under fp16 autocast, where the stock convolution runs in fp16 too), fp32
-        accumulation; the result is fp32, or the autocast dtype when autocast is on."""
+        16-bit operands, fp32 accumulation: fp16 by default (11-bit mantissa: within 2e-3 of the stock fp32
+        convolution, and exactly what the stock path multiplies under the reference's default fp16 autocast; the
+        conversion saturates at +-65504, three orders above any correlation value RAFT's features produce),
+        ``feat_dtype=torch.bfloat16`` trades mantissa for range (within 1e-2).  The result is fp32, or the autocast
+        dtype when autocast is on."""
         if self._pyr is None:
             raise RuntimeError("index_pyramid_convcorr1 called before build_pyramid")
         pyr = self._pyr
@@ -359,7 +362,7 @@ class TVCorrBlock(nn.Module):
         if out_dtype is None:
             out_dtype = torch.get_autocast_dtype("cuda") if amp else torch.float32
         if feat_dtype is None:
-            feat_dtype = torch.float16 if (amp and torch.get_autocast_dtype("cuda") == torch.float16) else torch.bfloat16
+            feat_dtype = torch.bfloat16 if (amp and torch.get_autocast_dtype("cuda") == torch.bfloat16) else torch.float16
         key = _param_key(weight, bias, feat_dtype, dev)
         if self._packed is None or self._packed.key != key:
             self._packed = PackedConv1x1(weight, bias, self.num_levels, self.radius, feat_dtype, dev)

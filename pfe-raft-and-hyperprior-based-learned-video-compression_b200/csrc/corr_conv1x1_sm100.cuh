@@ -47,7 +47,7 @@ constexpr int C1_MAX_COUT = 256;
 constexpr int C1_A_STAGES = 6;
 constexpr int C1_A_STAGE_BYTES = C1_BLOCK_M * C1_BLOCK_K * 2;            // 16 KB
 constexpr int C1_W_SLAB_BYTES = (C1_MAX_COUT / 2) * C1_BLOCK_K * 2;      // 16 KB: half the channels x one k-block
-constexpr int C1_EPI_WARPS = 8;
+constexpr int C1_EPI_WARPS = 16;               // four per TMEM lane quarter, a quarter of the channels each
 constexpr int C1_THREADS = 128 + C1_EPI_WARPS * 32;
 constexpr int C1_SMEM_W = 0;
 constexpr int C1_SMEM_A = C1_SMEM_W + C1_MAX_KB * C1_W_SLAB_BYTES;       // 98304
@@ -215,12 +215,17 @@ corr_conv1x1_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
         __syncwarp();
     } else if (warp >= 4) {
         // ===================== epilogue (both CTAs) =====================
-        // warp 4 + e: TMEM lane quarter q = e % 4 (pixel rows 32 q .. 32 q + 31 of the tile), channel half e / 4.
-        // A thread is one pixel: for a fixed channel the 32 lanes are 32 consecutive pixels, so every store is a
-        // coalesced line of the (B, cout, h, w) tensor straight from registers -- no staging.
+        // warp 4 + e: TMEM lane quarter q = e % 4 (pixel rows 32 q .. 32 q + 31 of the tile), channel group e / 4
+        // (a quarter of the channels, rounded up to 16).  A thread is one pixel: for a fixed channel the 32 lanes are
+        // 32 consecutive pixels, so every store is a coalesced line of the (B, cout, h, w) tensor straight from
+        // registers -- no staging.  SIXTEEN warps: the kernel's critical path is this store stream (time stamps,
+        // tools/exp_conv1x1_timeline.py: with 8 warps a 128 x 256 fp32 tile took 5.5 us to leave the SM, 23 GB/s,
+        // while the MMAs of both tiles were done after 7 us) and a warp keeps only so many stores in flight.
         const int e = warp - 4;
         const int q = e & 3;
-        const int ch0 = (e >> 2) * half;
+        const int cpg = ((p.cout + 3) / 4 + 15) / 16 * 16;          // channels per warp group
+        const int ch0 = (e >> 2) * cpg;
+        const int nch_w = max(0, min(cpg, p.cout - ch0));            // this warp's channels (a multiple of 16; 0 = none)
         const uint32_t t_empty_leader0 = ptx::mapa(bar(T_EMPTY), 0);
         for (int t = 0; t < n_tiles; ++t) {
             const int row = t * C1_BLOCK_M + q * 32 + lane;                 // row inside this CTA's range
@@ -234,13 +239,17 @@ corr_conv1x1_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
             ptx::tc_fence_after();
             if (e == 0 && lane == 0) C1_STAMP(7 + t);                   // accumulator of tile t ready (slots 7, 8)
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * C1_MAX_COUT + ch0;
-            for (int c = 0; c < half; c += 32) {
+            if (nch_w == 0) {                                        // nothing to read: hand the accumulator straight back
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive_cluster(t_empty_leader0 + 8u * acc);
+            }
+            for (int c = 0; c < nch_w; c += 32) {
                 float v[32];
-                const bool two = (c + 16 < half);
+                const bool two = (c + 16 < nch_w);
                 ptx::tmem_ld_x16(taddr + c, v);
                 if (two) ptx::tmem_ld_x16(taddr + c + 16, v + 16);
                 ptx::tmem_ld_wait();
-                if (c + 32 >= half) {
+                if (c + 32 >= nch_w) {
                     // every TMEM read of this tile is done: hand the accumulator back (to the leader)
                     ptx::tc_fence_before();
                     __syncwarp();

@@ -217,8 +217,11 @@ template <bool F16>
 __device__ __forceinline__ uint4 lkp_pack8(const float* v) {
     uint4 w;
     if constexpr (F16) {
-        const __half2 a = __floats2half2_rn(v[0], v[1]), b = __floats2half2_rn(v[2], v[3]);
-        const __half2 c = __floats2half2_rn(v[4], v[5]), d = __floats2half2_rn(v[6], v[7]);
+        // saturating: a correlation value beyond +-65504 (three orders above anything RAFT's features produce) must
+        // not turn into an infinity that poisons the whole GEMM row
+        auto sat = [](float x) { return fminf(fmaxf(x, -65504.f), 65504.f); };
+        const __half2 a = __floats2half2_rn(sat(v[0]), sat(v[1])), b = __floats2half2_rn(sat(v[2]), sat(v[3]));
+        const __half2 c = __floats2half2_rn(sat(v[4]), sat(v[5])), d = __floats2half2_rn(sat(v[6]), sat(v[7]));
         w.x = *reinterpret_cast<const uint32_t*>(&a); w.y = *reinterpret_cast<const uint32_t*>(&b);
         w.z = *reinterpret_cast<const uint32_t*>(&c); w.w = *reinterpret_cast<const uint32_t*>(&d);
     } else {

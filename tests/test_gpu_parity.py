@@ -624,8 +624,8 @@ def test_conv1x1_matches_fp64(lib, shape, cout, fd, od):
 @pytest.mark.parametrize("hw,vol", [((46, 80), torch.float32), ((46, 80), torch.bfloat16), ((136, 240), torch.float32)])
 def test_lookup_convcorr1_vs_stock_modules(lib, hw, vol):
     """Row f-1: TVCorrBlock.index_pyramid_convcorr1 == MotionEncoder.convcorr1(index_pyramid(coords)) (TV:raft.py:185,
-    202) of a seed-0 raft_large, at RDVC's default RAFT size and at 1080p: <= 1e-2 max-norm relative (bf16 operands)
-    in fp32 mode, and under fp16 autocast (fp16 operands, like the stock fp16 convolution)."""
+    202) of a seed-0 raft_large, at RDVC's default RAFT size and at 1080p: <= 2e-3 max-norm relative with the default
+    fp16 operands, <= 1e-2 with bf16 operands, and <= 5e-3 under fp16 autocast against the stock fp16 convolution."""
     h, w = hw
     B, D = 1, 256
     model = _seeded_raft(rc.TVCorrBlock(volume_dtype=vol))
@@ -641,12 +641,15 @@ def test_lookup_convcorr1_vs_stock_modules(lib, hw, vol):
         ref = conv(blk.index_pyramid(centroids_coords=co))
         torch.backends.cudnn.allow_tf32 = True
         n0 = lib.rdvc_corr_launch_count()
-        got = blk.index_pyramid_convcorr1(co, conv[0].weight, conv[0].bias)
-        assert lib.rdvc_corr_launch_count() - n0 == 2                   # lookup (K-major rows) + GEMM
+        got = blk.index_pyramid_convcorr1(co, conv[0].weight, conv[0].bias)       # default: fp16 operands
+        assert lib.rdvc_corr_launch_count() - n0 == 2                   # lookup (K-major features) + GEMM
         assert got.shape == ref.shape == (B, 256, h, w) and got.dtype == torch.float32
         err = ((got - ref).abs().max() / ref.abs().max()).item()
-        assert err < TOL_CONV1X1, err
+        assert err < 2e-3, err
         assert (got >= 0).all()
+        got_bf = blk.index_pyramid_convcorr1(co, conv[0].weight, conv[0].bias, feat_dtype=torch.bfloat16)
+        err_bf = ((got_bf - ref).abs().max() / ref.abs().max()).item()
+        assert err_bf < TOL_CONV1X1, err_bf
         with torch.autocast("cuda", dtype=torch.float16):
             ref16 = conv(blk.index_pyramid(centroids_coords=co))
             got16 = blk.index_pyramid_convcorr1(co, conv[0].weight, conv[0].bias)
