@@ -66,6 +66,7 @@ struct Conv1x1Params {
     int rows_per_cta;       // pixel rows owned by one CTA (multiple of 32)
     int tiles_per_cta;      // ceil(rows_per_cta / 128)
     int relu;
+    int vec4;               // n_pix % 4 == 0 and `out` 16-byte aligned: quads of lanes transpose 4 x 4 and store 4 pixels at once
     int ab_format;          // tcgen05 kind::f16 operand format: 1 = bf16, 0 = fp16
     unsigned long long* dbg_timeline;   // RDVC_EXPERIMENTS builds only: 16 globaltimer stamps per CTA (nullptr = off)
 };
@@ -82,6 +83,19 @@ __device__ __forceinline__ void c1_stamp(const Conv1x1Params& p, int slot) {
 #else
 #define C1_STAMP(slot) ((void)0)
 #endif
+
+// four consecutive pixels of one channel -> one 16-byte (fp32) / 8-byte (16-bit) store
+__device__ __forceinline__ void c1_store4(float* dst, float a, float b, float c, float d) {
+    *reinterpret_cast<float4*>(dst) = make_float4(a, b, c, d);
+}
+__device__ __forceinline__ void c1_store4(__half* dst, float a, float b, float c, float d) {
+    const __half2 lo = __floats2half2_rn(a, b), hi = __floats2half2_rn(c, d);
+    *reinterpret_cast<uint2*>(dst) = make_uint2(*reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
+}
+__device__ __forceinline__ void c1_store4(__nv_bfloat16* dst, float a, float b, float c, float d) {
+    const __nv_bfloat162 lo = __floats2bfloat162_rn(a, b), hi = __floats2bfloat162_rn(c, d);
+    *reinterpret_cast<uint2*>(dst) = make_uint2(*reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
+}
 
 template <typename OutT> __device__ __forceinline__ OutT c1_cvt(float x);
 template <> __device__ __forceinline__ float c1_cvt<float>(float x) { return x; }
@@ -234,6 +248,11 @@ corr_conv1x1_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
             const long long b = ok ? pix / p.n_pix : 0;
             const long long qp = ok ? pix - b * p.n_pix : 0;
             OutT* o = static_cast<OutT*>(p.out) + (b * p.cout + ch0) * p.n_pix + qp;
+            // vector path: lane j of a quad ends up with channel (i + j) of the quad's four pixels
+            const int j = lane & 3;
+            const long long pixq = pix - j;
+            const long long bq = ok ? pixq / p.n_pix : 0;
+            OutT* oq = static_cast<OutT*>(p.out) + (bq * p.cout + ch0 + j) * p.n_pix + (ok ? pixq - bq * p.n_pix : 0);
             const uint32_t acc = t & 1, acc_ph = (t >> 1) & 1;
             ptx::mbar_wait(bar(T_FULL + acc), acc_ph);
             ptx::tc_fence_after();
@@ -259,10 +278,30 @@ corr_conv1x1_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
 #pragma unroll
                 for (int i = 0; i < 32; ++i) {
                     if (i < nch) {
-                        float x = v[i] + bias_s[ch0 + c + i];
-                        if (p.relu) x = fmaxf(x, 0.f);
-                        if (ok) o[static_cast<long long>(c + i) * p.n_pix] = c1_cvt<OutT>(x);
+                        v[i] += bias_s[ch0 + c + i];
+                        if (p.relu) v[i] = fmaxf(v[i], 0.f);
                     }
+                }
+                if (p.vec4) {
+                    // A 128-byte store per instruction (32 lanes x 4 bytes) left the SM at only ~26 GB/s (time stamps: a
+                    // 128 KB tile took 4.5-5 us with 8 or with 16 warps -- the L1 store path handles about one request per
+                    // 10 cycles, whatever its size).  So quads of lanes transpose 4 channels x 4 pixels with shuffles and
+                    // every lane stores FOUR consecutive pixels of one channel: 512 bytes (four whole lines) per request.
+#pragma unroll
+                    for (int i = 0; i < 32; i += 4) {
+                        if (i < nch) {
+                            float a0 = v[i], a1 = v[i + 1], a2 = v[i + 2], a3 = v[i + 3], tx;
+                            tx = (j & 1) ? a0 : a1; tx = __shfl_xor_sync(0xffffffffu, tx, 1); if (j & 1) a0 = tx; else a1 = tx;
+                            tx = (j & 1) ? a2 : a3; tx = __shfl_xor_sync(0xffffffffu, tx, 1); if (j & 1) a2 = tx; else a3 = tx;
+                            tx = (j & 2) ? a0 : a2; tx = __shfl_xor_sync(0xffffffffu, tx, 2); if (j & 2) a0 = tx; else a2 = tx;
+                            tx = (j & 2) ? a1 : a3; tx = __shfl_xor_sync(0xffffffffu, tx, 2); if (j & 2) a1 = tx; else a3 = tx;
+                            if (ok) c1_store4(oq + static_cast<long long>(c + i) * p.n_pix, a0, a1, a2, a3);
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i)
+                        if (i < nch && ok) o[static_cast<long long>(c + i) * p.n_pix] = c1_cvt<OutT>(v[i]);
                 }
             }
             if (e == 0 && lane == 0) C1_STAMP(9 + t);                   // this warp's stores of tile t issued (slots 9, 10)

@@ -939,6 +939,7 @@ int rdvc_conv1x1(const void* feat, int feat_dtype, const void* packed_w, const f
     p.out = out; p.bias = bias; p.m_total = m_total; p.n_pix = h * w; p.cout = cout; p.kp = static_cast<int>(kp);
     p.relu = (act == RDVC_ACT_RELU); p.ab_format = (feat_dtype == RDVC_DT_F16) ? 0 : 1;
     p.dbg_timeline = RDVC_HAS_EXPERIMENTS ? g_dbg_timeline.load() : nullptr;
+    p.vec4 = ((h * w) % 4 == 0) && !(reinterpret_cast<uintptr_t>(out) & 15);
     // every CTA owns a contiguous range of pixel rows (a multiple of 32, one warp's rows), as equal as possible
     const int G = sm_count() & ~1;
     if (G < 2) return fail(RDVC_E_UNSUPPORTED, "the 1x1 convolution runs on CTA pairs: needs at least 2 SMs");
