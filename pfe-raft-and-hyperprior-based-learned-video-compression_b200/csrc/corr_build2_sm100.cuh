@@ -216,7 +216,7 @@ corr_build2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
                         // every TMEM read of this tile is done: hand the accumulator back (to the leader)
                         ptx::tc_fence_before();
                         __syncwarp();
-                        if (lane == 0) ptx::mbar_arrive_cluster(t_empty_leader0 + 8u * acc);
+                        if (lane == 0) ptx::mbar_arrive_cluster_relaxed(t_empty_leader0 + 8u * acc);   // relaxed: see ptx_sm100.cuh
                     }
                     if (!wr) continue;
                     const int r = lane & 15;

@@ -69,19 +69,22 @@ struct Conv1x1Params {
     int vec4;               // n_pix % 4 == 0 and `out` 16-byte aligned: quads of lanes transpose 4 x 4 and store 4 pixels at once
     int ab_format;          // tcgen05 kind::f16 operand format: 1 = bf16, 0 = fp16
     unsigned long long* dbg_timeline;   // RDVC_EXPERIMENTS builds only: 16 globaltimer stamps per CTA (nullptr = off)
+    int dbg_flags;                      // RDVC_EXPERIMENTS builds only: 1 = no output stores, 2 = no TMEM reads (timing)
 };
 
 #ifdef RDVC_EXPERIMENTS
 __device__ __forceinline__ void c1_stamp(const Conv1x1Params& p, int slot) {
     if (p.dbg_timeline) {
         unsigned long long t;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t) :: "memory");
         p.dbg_timeline[blockIdx.x * 16 + slot] = t;
     }
 }
 #define C1_STAMP(slot) c1_stamp(p, slot)
+#define C1_DBG(bit) ((p.dbg_flags & (bit)) != 0)
 #else
 #define C1_STAMP(slot) ((void)0)
+#define C1_DBG(bit) false
 #endif
 
 // four consecutive pixels of one channel -> one 16-byte (fp32) / 8-byte (16-bit) store
@@ -152,7 +155,7 @@ corr_conv1x1_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
     }
     ptx::tc_fence_before();
     __syncthreads();
-    ptx::cluster_sync_all();          // the peer's barriers are initialised before anyone signals them
+    ptx::cluster_sync_relaxed_arrive();   // the peer's barriers are initialised (and fenced) before anyone signals them
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     if (warp == 0 && lane == 0) C1_STAMP(1);           // set-up done (barriers, TMEM, cluster sync)
@@ -245,13 +248,14 @@ corr_conv1x1_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
             const int row = t * C1_BLOCK_M + q * 32 + lane;                 // row inside this CTA's range
             const long long pix = row_base + row;
             const bool ok = (row < p.rows_per_cta) && (pix < p.m_total);
-            const long long b = ok ? pix / p.n_pix : 0;
+            // (32-bit: the ABI guarantees m_total < 2^31; a 64-bit division is a ~100-instruction subroutine)
+            const long long b = ok ? static_cast<unsigned>(pix) / static_cast<unsigned>(p.n_pix) : 0;
             const long long qp = ok ? pix - b * p.n_pix : 0;
             OutT* o = static_cast<OutT*>(p.out) + (b * p.cout + ch0) * p.n_pix + qp;
             // vector path: lane j of a quad ends up with channel (i + j) of the quad's four pixels
             const int j = lane & 3;
             const long long pixq = pix - j;
-            const long long bq = ok ? pixq / p.n_pix : 0;
+            const long long bq = ok ? static_cast<unsigned>(pixq) / static_cast<unsigned>(p.n_pix) : 0;
             OutT* oq = static_cast<OutT*>(p.out) + (bq * p.cout + ch0 + j) * p.n_pix + (ok ? pixq - bq * p.n_pix : 0);
             const uint32_t acc = t & 1, acc_ph = (t >> 1) & 1;
             ptx::mbar_wait(bar(T_FULL + acc), acc_ph);
@@ -260,19 +264,25 @@ corr_conv1x1_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * C1_MAX_COUT + ch0;
             if (nch_w == 0) {                                        // nothing to read: hand the accumulator straight back
                 __syncwarp();
-                if (lane == 0) ptx::mbar_arrive_cluster(t_empty_leader0 + 8u * acc);
+                if (lane == 0) ptx::mbar_arrive_cluster_relaxed(t_empty_leader0 + 8u * acc);
             }
             for (int c = 0; c < nch_w; c += 32) {
                 float v[32];
                 const bool two = (c + 16 < nch_w);
-                ptx::tmem_ld_x16(taddr + c, v);
-                if (two) ptx::tmem_ld_x16(taddr + c + 16, v + 16);
-                ptx::tmem_ld_wait();
+                if (!C1_DBG(2)) {
+                    ptx::tmem_ld_x16(taddr + c, v);
+                    if (two) ptx::tmem_ld_x16(taddr + c + 16, v + 16);
+                    ptx::tmem_ld_wait();
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] = static_cast<float>(i + c);
+                }
+                if (e == 0 && lane == 0 && c == 0) C1_STAMP(13 + t);        // first chunk out of TMEM (slots 13, 14)
                 if (c + 32 >= nch_w) {
                     // every TMEM read of this tile is done: hand the accumulator back (to the leader)
                     ptx::tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) ptx::mbar_arrive_cluster(t_empty_leader0 + 8u * acc);
+                    if (lane == 0) ptx::mbar_arrive_cluster_relaxed(t_empty_leader0 + 8u * acc);
                 }
                 const int nch = two ? 32 : 16;
 #pragma unroll
@@ -295,7 +305,7 @@ corr_conv1x1_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
                             tx = (j & 1) ? a2 : a3; tx = __shfl_xor_sync(0xffffffffu, tx, 1); if (j & 1) a2 = tx; else a3 = tx;
                             tx = (j & 2) ? a0 : a2; tx = __shfl_xor_sync(0xffffffffu, tx, 2); if (j & 2) a0 = tx; else a2 = tx;
                             tx = (j & 2) ? a1 : a3; tx = __shfl_xor_sync(0xffffffffu, tx, 2); if (j & 2) a1 = tx; else a3 = tx;
-                            if (ok) c1_store4(oq + static_cast<long long>(c + i) * p.n_pix, a0, a1, a2, a3);
+                            if (ok && !C1_DBG(1)) c1_store4(oq + static_cast<long long>(c + i) * p.n_pix, a0, a1, a2, a3);
                         }
                     }
                 } else {

@@ -237,6 +237,12 @@ __device__ __forceinline__ void cluster_sync_all() {   // every thread of every 
     asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
     asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+// The set-up barrier of a CTA pair: mbarrier.init is published by fence.mbarrier_init.release.cluster, so the arrive
+// itself can be relaxed (a releasing arrive compiles to MEMBAR.ALL.GPU, ~0.5 us at kernel start).
+__device__ __forceinline__ void cluster_sync_relaxed_arrive() {
+    asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 // shared::cluster address of `addr` (a shared::cta address of this CTA) inside CTA `rank`
 __device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {
     uint32_t r;
@@ -245,6 +251,14 @@ __device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// The same arrive WITHOUT release semantics.  `.release.cluster` compiles to MEMBAR.ALL.GPU + ERRBAR in front of the
+// arrive: the warp then waits until every global store it has issued so far is visible GPU-wide (microseconds when
+// an epilogue has a tile's worth of stores in flight).  Handing a TMEM accumulator back needs no memory ordering at
+// all -- the tcgen05.ld results are in registers once tcgen05.wait::ld returns, and tcgen05.fence::before_thread_sync
+// orders the tensor-memory reads before the arrive.
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // TMA load issued by either CTA of a pair; the bytes are counted on the LEADER's mbarrier (the peer
 // bit of the barrier address is cleared), the data lands in the issuing CTA's shared memory.

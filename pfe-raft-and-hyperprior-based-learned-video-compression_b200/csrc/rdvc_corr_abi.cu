@@ -62,6 +62,7 @@ std::atomic<int> g_opt_thl{0};
 std::atomic<int> g_opt_epi_warps{0};
 std::atomic<int> g_opt_pair{0};
 std::atomic<int> g_opt_mcn_prefetch{0};
+std::atomic<int> g_dbg_c1_flags{0};
 std::atomic<unsigned long long*> g_dbg_timeline{nullptr};   // RDVC_EXPERIMENTS: device buffer for conv1x1 time stamps
 std::atomic<int> g_opt_mcn_kernel{0};     // 0 = auto, 1 = three boxes per tile, 2 = one box per tile (x halo)   // measured: no effect at 1-4 tiles ahead, slower beyond
 
@@ -657,6 +658,7 @@ unsigned long long rdvc_corr_plan_cache_hits(void) { return g_plan_hits.load(); 
 #ifdef RDVC_EXPERIMENTS
 // experiments library only (not in the header): 16 globaltimer stamps per CTA of the next rdvc_conv1x1 launches
 void rdvc_exp_conv1x1_timeline(void* device_buffer) { g_dbg_timeline = static_cast<unsigned long long*>(device_buffer); }
+void rdvc_exp_conv1x1_flags(int flags) { g_dbg_c1_flags = flags; }     // 1 = no output stores, 2 = no TMEM reads
 #endif
 
 size_t rdvc_corr_level_image_elems(int h, int w, int level, int vol_dtype, int layout) {
@@ -939,6 +941,7 @@ int rdvc_conv1x1(const void* feat, int feat_dtype, const void* packed_w, const f
     p.out = out; p.bias = bias; p.m_total = m_total; p.n_pix = h * w; p.cout = cout; p.kp = static_cast<int>(kp);
     p.relu = (act == RDVC_ACT_RELU); p.ab_format = (feat_dtype == RDVC_DT_F16) ? 0 : 1;
     p.dbg_timeline = RDVC_HAS_EXPERIMENTS ? g_dbg_timeline.load() : nullptr;
+    p.dbg_flags = RDVC_HAS_EXPERIMENTS ? g_dbg_c1_flags.load() : 0;
     p.vec4 = ((h * w) % 4 == 0) && !(reinterpret_cast<uintptr_t>(out) & 15);
     // every CTA owns a contiguous range of pixel rows (a multiple of 32, one warp's rows), as equal as possible
     const int G = sm_count() & ~1;

@@ -21,8 +21,10 @@ blk = rc.TVCorrBlock(); blk.build_pyramid(f1, f2)
 co = torch.stack([xs, ys], 0).float()[None] + torch.randn(1, 2, h, w, device=dev, generator=g)
 stamps = torch.zeros(148 * 16, dtype=torch.int64, device=dev)
 names = ["entry", "setup done", "W landed", "A first t0", "A first t1", "A last t0", "A last t1", "acc t0", "acc t1",
-         "stores t0", "stores t1", "cta done", "cluster done"]
-for rep in range(3):
+         "stores t0", "stores t1", "cta done", "cluster done", "tmem 1st t0", "tmem 1st t1"]
+lib.rdvc_exp_conv1x1_flags.argtypes = [ctypes.c_int]
+for rep, flags in enumerate([0, 0, 1, 2, 3]):
+    lib.rdvc_exp_conv1x1_flags(flags)
     stamps.zero_()
     lib.rdvc_exp_conv1x1_timeline.argtypes = [ctypes.c_void_p]
     lib.rdvc_exp_conv1x1_timeline(stamps.data_ptr())
@@ -31,7 +33,7 @@ for rep in range(3):
     lib.rdvc_exp_conv1x1_timeline(None)
     t = stamps.view(148, 16).cpu()
     t0 = t[:146, 0].min().item()
-    print(f"--- rep {rep}: ns after the first CTA's entry: CTA 0 (leader) | CTA 1 (peer) | median over CTAs | max")
+    print(f"--- rep {rep} flags {flags} (1 = no stores, 2 = no TMEM reads): ns after the first CTA's entry: CTA 0 (leader) | CTA 1 (peer) | median over CTAs | max")
     for i, n in enumerate(names):
         col = t[:146, i]
         ok = col > 0
