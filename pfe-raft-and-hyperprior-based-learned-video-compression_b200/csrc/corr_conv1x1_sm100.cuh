@@ -293,10 +293,12 @@ corr_conv1x1_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
                     }
                 }
                 if (p.vec4) {
-                    // A 128-byte store per instruction (32 lanes x 4 bytes) left the SM at only ~26 GB/s (time stamps: a
-                    // 128 KB tile took 4.5-5 us with 8 or with 16 warps -- the L1 store path handles about one request per
-                    // 10 cycles, whatever its size).  So quads of lanes transpose 4 channels x 4 pixels with shuffles and
-                    // every lane stores FOUR consecutive pixels of one channel: 512 bytes (four whole lines) per request.
+                    // A 128-byte store per instruction (32 lanes x 4 bytes) left the SM at only ~26 GB/s.  So quads of
+                    // lanes transpose 4 channels x 4 pixels with shuffles and every lane stores FOUR consecutive pixels
+                    // of one channel: 512 bytes (four whole lines) per request.  One running pointer per thread (the
+                    // 64-bit channel-stride multiply per store was a third of the loop's instructions).
+                    OutT* dq = oq + static_cast<long long>(c) * p.n_pix;
+                    const long long step4 = 4LL * p.n_pix;
 #pragma unroll
                     for (int i = 0; i < 32; i += 4) {
                         if (i < nch) {
@@ -305,13 +307,19 @@ corr_conv1x1_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
                             tx = (j & 1) ? a2 : a3; tx = __shfl_xor_sync(0xffffffffu, tx, 1); if (j & 1) a2 = tx; else a3 = tx;
                             tx = (j & 2) ? a0 : a2; tx = __shfl_xor_sync(0xffffffffu, tx, 2); if (j & 2) a0 = tx; else a2 = tx;
                             tx = (j & 2) ? a1 : a3; tx = __shfl_xor_sync(0xffffffffu, tx, 2); if (j & 2) a1 = tx; else a3 = tx;
-                            if (ok && !C1_DBG(1)) c1_store4(oq + static_cast<long long>(c + i) * p.n_pix, a0, a1, a2, a3);
+                            if (ok && !C1_DBG(1)) c1_store4(dq, a0, a1, a2, a3);
+                            dq += step4;
                         }
                     }
                 } else {
+                    OutT* ds = o + static_cast<long long>(c) * p.n_pix;
 #pragma unroll
-                    for (int i = 0; i < 32; ++i)
-                        if (i < nch && ok) o[static_cast<long long>(c + i) * p.n_pix] = c1_cvt<OutT>(v[i]);
+                    for (int i = 0; i < 32; ++i) {
+                        if (i < nch) {
+                            if (ok) *ds = c1_cvt<OutT>(v[i]);
+                            ds += p.n_pix;
+                        }
+                    }
                 }
             }
             if (e == 0 && lane == 0) C1_STAMP(9 + t);                   // this warp's stores of tile t issued (slots 9, 10)
