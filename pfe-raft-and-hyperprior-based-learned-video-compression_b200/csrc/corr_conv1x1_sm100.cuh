@@ -21,8 +21,17 @@
 // peak).  What has to be avoided is re-streaming the 176 KB weight matrix per 128-pixel tile through L2 -> SM
 // (the feed ceiling measured on the MCN layers, ~7 TB/s): so CTA PAIRS (tcgen05 cta_group::2, M = 256): each
 // CTA keeps only its HALF of the output channels' weights (6 k-blocks x 16 KB = 96 KB) stationary for the
-// whole kernel and streams its own 128 pixel rows through a 6-stage ring (a whole tile in flight).  Every CTA
-// owns a contiguous pixel range (total / grid, rounded to 32), so the output bytes per SM are equal.
+// whole kernel and streams its own 128 pixel rows through a 4-stage ring.  Every CTA owns a contiguous pixel
+// range (total / grid, rounded to 32), so the output bytes per SM are equal.
+//
+// The epilogue is the critical path (time stamps, tools/exp_conv1x1_timeline.py: both tiles' MMAs are done ~7 us
+// into the kernel; the rest is getting 2 x 128 KB of results out of each SM), and it went through four forms:
+// one 4-byte store per lane and channel (128-byte requests: ~26 GB/s per SM whatever the warp count), a
+// release-ordered remote arrive per tile that compiled to MEMBAR.ALL.GPU (waited for every store in flight),
+// quads of lanes transposing 4 x 4 with shuffles (512-byte requests, but ~300 instructions per 32 channels), and
+// now a per-warp 4 KB shared-memory transpose: 32 conflict-free st.shared, then every lane reads FOUR consecutive
+// pixels of one channel (ld.shared.v4), adds the bias, applies ReLU and writes 16 bytes -- a warp-wide store
+// covers four whole 128-byte lines of the (B, cout, h, w) tensor.
 //
 // Protocol as in corr_build2_sm100.cuh ("leader" = cluster rank 0; barriers at the same offset in both CTAs):
 //   W_FULL, A_FULL[s]   leader only; armed by the leader's producer for BOTH CTAs' bytes, completed by each
@@ -44,14 +53,16 @@ constexpr int C1_BLOCK_M = 128;                 // pixel rows per CTA and tile
 constexpr int C1_BLOCK_K = 64;                  // 16-bit elements per 128-byte swizzle row
 constexpr int C1_MAX_KB = 6;                    // K <= 384
 constexpr int C1_MAX_COUT = 256;
-constexpr int C1_A_STAGES = 6;
+constexpr int C1_A_STAGES = 4;                  // 16 KB each (a tile is 6 k-blocks; the MMAs are far off the critical path)
 constexpr int C1_A_STAGE_BYTES = C1_BLOCK_M * C1_BLOCK_K * 2;            // 16 KB
 constexpr int C1_W_SLAB_BYTES = (C1_MAX_COUT / 2) * C1_BLOCK_K * 2;      // 16 KB: half the channels x one k-block
 constexpr int C1_EPI_WARPS = 16;               // four per TMEM lane quarter, a quarter of the channels each
 constexpr int C1_THREADS = 128 + C1_EPI_WARPS * 32;
 constexpr int C1_SMEM_W = 0;
 constexpr int C1_SMEM_A = C1_SMEM_W + C1_MAX_KB * C1_W_SLAB_BYTES;       // 98304
-constexpr int C1_SMEM_BIAS = C1_SMEM_A + C1_A_STAGES * C1_A_STAGE_BYTES; // 196608
+constexpr int C1_STG_BYTES = 32 * 32 * 4;       // per epilogue warp: 32 channels x 32 pixels fp32, the transpose buffer
+constexpr int C1_SMEM_STG = C1_SMEM_A + C1_A_STAGES * C1_A_STAGE_BYTES;  // 163840
+constexpr int C1_SMEM_BIAS = C1_SMEM_STG + C1_EPI_WARPS * C1_STG_BYTES;  // 229376
 constexpr int C1_SMEM_BAR = C1_SMEM_BIAS + C1_MAX_COUT * 4;
 constexpr int C1_SMEM_TOTAL = C1_SMEM_BAR + 256;
 constexpr int C1_SMEM_LAUNCH = C1_SMEM_TOTAL + 1024;                     // slack for 1024-byte alignment
@@ -100,6 +111,15 @@ __device__ __forceinline__ void c1_store4(__nv_bfloat16* dst, float a, float b, 
     *reinterpret_cast<uint2*>(dst) = make_uint2(*reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
 }
 
+__device__ __forceinline__ void sts_f32(uint32_t addr, float v) {
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ float4 lds_f32x4(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+
 template <typename OutT> __device__ __forceinline__ OutT c1_cvt(float x);
 template <> __device__ __forceinline__ float c1_cvt<float>(float x) { return x; }
 template <> __device__ __forceinline__ __half c1_cvt<__half>(float x) { return __float2half_rn(x); }
@@ -118,6 +138,7 @@ corr_conv1x1_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
     const uint32_t s_w = ptx::smem_u32(smem + C1_SMEM_W);
     const uint32_t s_a = ptx::smem_u32(smem + C1_SMEM_A);
     float* bias_s = reinterpret_cast<float*>(smem + C1_SMEM_BIAS);
+    const uint32_t s_stg = ptx::smem_u32(smem + C1_SMEM_STG);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C1_SMEM_BAR);
     const uint32_t bar0 = ptx::smem_u32(bars);
     constexpr int A_FULL = 0, A_EMPTY = C1_A_STAGES, W_FULL = 2 * C1_A_STAGES, T_FULL = W_FULL + 1, T_EMPTY = T_FULL + 2;
@@ -233,11 +254,9 @@ corr_conv1x1_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
     } else if (warp >= 4) {
         // ===================== epilogue (both CTAs) =====================
         // warp 4 + e: TMEM lane quarter q = e % 4 (pixel rows 32 q .. 32 q + 31 of the tile), channel group e / 4
-        // (a quarter of the channels, rounded up to 16).  A thread is one pixel: for a fixed channel the 32 lanes are
-        // 32 consecutive pixels, so every store is a coalesced line of the (B, cout, h, w) tensor straight from
-        // registers -- no staging.  SIXTEEN warps: the kernel's critical path is this store stream (time stamps,
-        // tools/exp_conv1x1_timeline.py: with 8 warps a 128 x 256 fp32 tile took 5.5 us to leave the SM, 23 GB/s,
-        // while the MMAs of both tiles were done after 7 us) and a warp keeps only so many stores in flight.
+        // (a quarter of the channels, rounded up to 16).  Out of TMEM a thread is one pixel with 32 channels in
+        // registers; the warp's 4 KB buffer turns that into "four consecutive pixels of one channel" per lane (see
+        // the file header).  Shapes whose pixel count is not a multiple of 4 store one value per lane instead.
         const int e = warp - 4;
         const int q = e & 3;
         const int cpg = ((p.cout + 3) / 4 + 15) / 16 * 16;          // channels per warp group
@@ -252,11 +271,15 @@ corr_conv1x1_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
             const long long b = ok ? static_cast<unsigned>(pix) / static_cast<unsigned>(p.n_pix) : 0;
             const long long qp = ok ? pix - b * p.n_pix : 0;
             OutT* o = static_cast<OutT*>(p.out) + (b * p.cout + ch0) * p.n_pix + qp;
-            // vector path: lane j of a quad ends up with channel (i + j) of the quad's four pixels
-            const int j = lane & 3;
-            const long long pixq = pix - j;
-            const long long bq = ok ? static_cast<unsigned>(pixq) / static_cast<unsigned>(p.n_pix) : 0;
-            OutT* oq = static_cast<OutT*>(p.out) + (bq * p.cout + ch0 + j) * p.n_pix + (ok ? pixq - bq * p.n_pix : 0);
+            // vector path: after the shared-memory transpose lane l owns pixels 4 (l % 8) .. + 3 of channel row l / 8 (+ 4 k)
+            const int px4 = (lane & 7) * 4, rsub = lane >> 3;
+            const int row4 = t * C1_BLOCK_M + q * 32 + px4;
+            const long long pix4 = row_base + row4;
+            const bool ok4 = (row4 < p.rows_per_cta) && (pix4 < p.m_total);
+            const long long b4 = ok4 ? static_cast<unsigned>(pix4) / static_cast<unsigned>(p.n_pix) : 0;
+            OutT* o4 = static_cast<OutT*>(p.out) + (b4 * p.cout + ch0 + rsub) * p.n_pix + (ok4 ? pix4 - b4 * p.n_pix : 0);
+            const long long step4 = 4LL * p.n_pix;
+            const uint32_t stg = s_stg + e * C1_STG_BYTES;
             const uint32_t acc = t & 1, acc_ph = (t >> 1) & 1;
             ptx::mbar_wait(bar(T_FULL + acc), acc_ph);
             ptx::tc_fence_after();
@@ -285,38 +308,35 @@ corr_conv1x1_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
                     if (lane == 0) ptx::mbar_arrive_cluster_relaxed(t_empty_leader0 + 8u * acc);
                 }
                 const int nch = two ? 32 : 16;
-#pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    if (i < nch) {
-                        v[i] += bias_s[ch0 + c + i];
-                        if (p.relu) v[i] = fmaxf(v[i], 0.f);
-                    }
-                }
                 if (p.vec4) {
-                    // A 128-byte store per instruction (32 lanes x 4 bytes) left the SM at only ~26 GB/s.  So quads of
-                    // lanes transpose 4 channels x 4 pixels with shuffles and every lane stores FOUR consecutive pixels
-                    // of one channel: 512 bytes (four whole lines) per request.  One running pointer per thread (the
-                    // 64-bit channel-stride multiply per store was a third of the loop's instructions).
-                    OutT* dq = oq + static_cast<long long>(c) * p.n_pix;
-                    const long long step4 = 4LL * p.n_pix;
+                    // transpose through this warp's 4 KB buffer: [channel][pixel] fp32, a row is one conflict-free
+                    // 128-byte st.shared; a quarter-warp then reads one row back as eight 16-byte pieces
 #pragma unroll
-                    for (int i = 0; i < 32; i += 4) {
-                        if (i < nch) {
-                            float a0 = v[i], a1 = v[i + 1], a2 = v[i + 2], a3 = v[i + 3], tx;
-                            tx = (j & 1) ? a0 : a1; tx = __shfl_xor_sync(0xffffffffu, tx, 1); if (j & 1) a0 = tx; else a1 = tx;
-                            tx = (j & 1) ? a2 : a3; tx = __shfl_xor_sync(0xffffffffu, tx, 1); if (j & 1) a2 = tx; else a3 = tx;
-                            tx = (j & 2) ? a0 : a2; tx = __shfl_xor_sync(0xffffffffu, tx, 2); if (j & 2) a0 = tx; else a2 = tx;
-                            tx = (j & 2) ? a1 : a3; tx = __shfl_xor_sync(0xffffffffu, tx, 2); if (j & 2) a1 = tx; else a3 = tx;
-                            if (ok && !C1_DBG(1)) c1_store4(dq, a0, a1, a2, a3);
-                            dq += step4;
+                    for (int i = 0; i < 32; ++i)
+                        if (i < nch) sts_f32(stg + (i * 32 + lane) * 4, v[i]);
+                    __syncwarp();
+                    OutT* d4 = o4 + static_cast<long long>(c) * p.n_pix;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        if (4 * k < nch) {
+                            const int r = 4 * k + rsub;
+                            const float4 x = lds_f32x4(stg + (r * 32 + px4) * 4);
+                            const float bb = bias_s[ch0 + c + r];
+                            float a0 = x.x + bb, a1 = x.y + bb, a2 = x.z + bb, a3 = x.w + bb;
+                            if (p.relu) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); a2 = fmaxf(a2, 0.f); a3 = fmaxf(a3, 0.f); }
+                            if (ok4 && !C1_DBG(1)) c1_store4(d4, a0, a1, a2, a3);
+                            d4 += step4;
                         }
                     }
+                    __syncwarp();                                    // the buffer is reused by the next chunk
                 } else {
                     OutT* ds = o + static_cast<long long>(c) * p.n_pix;
 #pragma unroll
                     for (int i = 0; i < 32; ++i) {
                         if (i < nch) {
-                            if (ok) *ds = c1_cvt<OutT>(v[i]);
+                            float x = v[i] + bias_s[ch0 + c + i];
+                            if (p.relu) x = fmaxf(x, 0.f);
+                            if (ok) *ds = c1_cvt<OutT>(x);
                             ds += p.n_pix;
                         }
                     }
