@@ -114,6 +114,11 @@ __device__ __forceinline__ void c1_store4(__nv_bfloat16* dst, float a, float b, 
 __device__ __forceinline__ void sts_f32(uint32_t addr, float v) {
     asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
 }
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+    return v;
+}
 __device__ __forceinline__ float4 lds_f32x4(uint32_t addr) {
     float4 v;
     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
@@ -139,6 +144,9 @@ corr_conv1x1_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
     const uint32_t s_a = ptx::smem_u32(smem + C1_SMEM_A);
     float* bias_s = reinterpret_cast<float*>(smem + C1_SMEM_BIAS);
     const uint32_t s_stg = ptx::smem_u32(smem + C1_SMEM_STG);
+    // the bias is read with explicit ld.shared: through the generic pointer the compiler emitted LD.E (generic loads, a
+    // long-scoreboard wait in front of every FADD of the epilogue -- half of its samples in the profile)
+    const uint32_t s_bias = ptx::smem_u32(smem + C1_SMEM_BIAS);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C1_SMEM_BAR);
     const uint32_t bar0 = ptx::smem_u32(bars);
     constexpr int A_FULL = 0, A_EMPTY = C1_A_STAGES, W_FULL = 2 * C1_A_STAGES, T_FULL = W_FULL + 1, T_EMPTY = T_FULL + 2;
@@ -321,7 +329,7 @@ corr_conv1x1_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
                         if (4 * k < nch) {
                             const int r = 4 * k + rsub;
                             const float4 x = lds_f32x4(stg + (r * 32 + px4) * 4);
-                            const float bb = bias_s[ch0 + c + r];
+                            const float bb = lds_f32(s_bias + (ch0 + c + r) * 4);
                             float a0 = x.x + bb, a1 = x.y + bb, a2 = x.z + bb, a3 = x.w + bb;
                             if (p.relu) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); a2 = fmaxf(a2, 0.f); a3 = fmaxf(a3, 0.f); }
                             if (ok4 && !C1_DBG(1)) c1_store4(d4, a0, a1, a2, a3);
@@ -334,7 +342,7 @@ corr_conv1x1_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
 #pragma unroll
                     for (int i = 0; i < 32; ++i) {
                         if (i < nch) {
-                            float x = v[i] + bias_s[ch0 + c + i];
+                            float x = v[i] + lds_f32(s_bias + (ch0 + c + i) * 4);
                             if (p.relu) x = fmaxf(x, 0.f);
                             if (ok) *ds = c1_cvt<OutT>(x);
                             ds += p.n_pix;
