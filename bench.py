@@ -395,7 +395,9 @@ def run_ours(args):
     gop_line = None
     if not args.no_gop:
         import bench_gop
-        gop_line = bench_gop.run_sharded(bench_gop.sharded_args(frames=args.gop_frames), own_process_group=False)
+        # fp16 autocast like the reference's GPU default (R:codec_processing.py:1436, "AMP on" in R:jockey.txt:9)
+        gop_line = bench_gop.run_sharded(bench_gop.sharded_args(frames=args.gop_frames, amp=not args.gop_fp32),
+                                         own_process_group=False)
         torch.cuda.empty_cache()
 
     line = None
@@ -485,6 +487,7 @@ def main():
     ap.add_argument("--no-gpu-baseline", action="store_true", help="skip the stock-torchvision-on-this-GPU comparator")
     ap.add_argument("--no-gop", action="store_true", help="skip the GOP-sharded motion-branch run (configs 3 / 4)")
     ap.add_argument("--gop-frames", type=int, default=600, help="frames of the GOP-sharded run (config 4: 600)")
+    ap.add_argument("--gop-fp32", action="store_true", help="run the GOP-sharded RAFT in fp32 / TF32 instead of fp16 autocast")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3   # timing rule: at least 3 warm-up steps
