@@ -165,6 +165,30 @@ int rdvc_corr_lookup_conv1x1(const void* pyramid, int vol_dtype, int layout, con
                              int act, int feat_dtype, void* feat_ws, size_t feat_ws_bytes, void* out, int out_dtype,
                              void* stream);
 
+/* ---- next row f-2 (last sub-item): the feature encoder's final 1x1 convolution, fused into the operand repack ---- *
+ * torchvision's FeatureEncoder ends in conv = Conv2d(128, 256, kernel_size=1) (TV:raft.py:139, called at :150); the
+ * stock path writes its (2B, 256, h, w) fp32 result (67 MB at 1080p) and rdvc_corr_build re-reads it to repack.  A
+ * 1x1 convolution commutes with the transpose and (being linear, bias included) with the pyramid's mean pooling, so:
+ *   rdvc_corr_pack          the repack step of rdvc_corr_build ALONE, on any (B, D, h, w) maps with D % 64 == 0,
+ *                           D <= 256: K-major 16-bit rows of x1 and of x2 at every pyramid level (pyramid row order,
+ *                           padding rows zero) into a workspace of rdvc_corr_workspace_bytes(B, D, h, w);
+ *   rdvc_corr_encoder_tail  every packed 128-channel row -> the 256-channel operand row of the build:
+ *                           out[r][n] = round16(sum_k in[r][k] W[n][k] + bias[n]), layout-padding rows stay 0
+ *                           (tcgen05 GEMM, fp32 accumulation; ws_out = a workspace for D = 256);
+ *   rdvc_corr_build_packed  the GEMM step of rdvc_corr_build ALONE, on a workspace that already holds the rows.
+ * Together: pyramid = build(conv(x1), conv(x2)) without the fp32 feature maps ever existing.  packed_w: the weight
+ * (256, 128) as 16-bit rows (rdvc_linear_pack_weights, HOST) on the device; bias: 256 DEVICE floats or NULL;
+ * op_dtype: BF16, or F16 when the activations are fp16 (the pack keeps fp16 inputs as fp16).                        */
+int rdvc_corr_pack(const void* x1, const void* x2, int B, int D, int h, int w, int in_dtype, int vol_dtype,
+                   int layout, int num_levels, void* workspace, size_t workspace_bytes, void* stream);
+size_t rdvc_linear_packed_weight_bytes(int cout, int cin);
+int rdvc_linear_pack_weights(const float* weight, int cout, int cin, int dtype, void* packed_host);
+int rdvc_corr_encoder_tail(const void* ws_in, size_t ws_in_bytes, int D_in, const void* packed_w, const float* bias,
+                           int D_out, int B, int h, int w, int op_dtype, int vol_dtype, int layout, int num_levels,
+                           void* ws_out, size_t ws_out_bytes, void* stream);
+int rdvc_corr_build_packed(int B, int D, int h, int w, int op_dtype, void* pyramid, int vol_dtype, int layout,
+                           int num_levels, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- one frame pair from host memory (blocking) ------------------------ *
  * fmap1_host, fmap2_host : host fp32 (B, D, h, w)
  * coords_host            : host fp32 (iters, B, 2, h, w)

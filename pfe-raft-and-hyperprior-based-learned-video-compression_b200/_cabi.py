@@ -51,6 +51,13 @@ SYMBOLS = {
     "rdvc_corr_pair_host_submit_ex": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p] +
                                       [_c.c_int] * 10),
     "rdvc_corr_plan_cache_hits": (_c.c_ulonglong, []),
+    "rdvc_corr_pack": (_c.c_int, [_c.c_void_p, _c.c_void_p] + [_c.c_int] * 8 + [_c.c_void_p, _c.c_size_t, _c.c_void_p]),
+    "rdvc_linear_packed_weight_bytes": (_c.c_size_t, [_c.c_int, _c.c_int]),
+    "rdvc_linear_pack_weights": (_c.c_int, [_c.c_void_p, _c.c_int, _c.c_int, _c.c_int, _c.c_void_p]),
+    "rdvc_corr_encoder_tail": (_c.c_int, [_c.c_void_p, _c.c_size_t, _c.c_int, _c.c_void_p, _c.c_void_p] + [_c.c_int] * 8 +
+                               [_c.c_void_p, _c.c_size_t, _c.c_void_p]),
+    "rdvc_corr_build_packed": (_c.c_int, [_c.c_int] * 5 + [_c.c_void_p, _c.c_int, _c.c_int, _c.c_int, _c.c_void_p,
+                                          _c.c_size_t, _c.c_void_p]),
     "rdvc_ec_max_encoded_bytes": (_c.c_size_t, [_c.c_size_t]),
     "rdvc_ec_encode_with_indexes": (_c.c_size_t, [_c.c_void_p, _c.c_void_p, _c.c_size_t, _c.c_void_p, _c.c_void_p,
                                                   _c.c_void_p, _c.c_int, _c.c_int, _c.c_void_p, _c.c_size_t]),

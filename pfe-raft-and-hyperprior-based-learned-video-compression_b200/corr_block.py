@@ -270,6 +270,26 @@ class PackedConv1x1:
         self.key = _param_key(weight, bias, feat_dtype, device)
 
 
+class PackedLinear:
+    """A 1x1 convolution's weight (cout, cin[, 1, 1]) as plain 16-bit rows on the device (``rdvc_linear_pack_weights``,
+    host) + its fp32 bias: the encoder tail's operands.  Rebuilt when the parameters change version or device."""
+
+    def __init__(self, weight: Tensor, bias: Optional[Tensor], op_dtype: torch.dtype, device):
+        import ctypes
+        import numpy as np
+        lib = _cabi.load()
+        cout = weight.shape[0]
+        w2 = weight.detach().to(torch.float32).reshape(cout, -1).cpu().contiguous().numpy()
+        packed = np.zeros(w2.size, np.uint16)
+        _cabi.check(lib.rdvc_linear_pack_weights(w2.ctypes.data_as(ctypes.c_void_p), cout, w2.shape[1],
+                                                 _FEAT_DTYPES[op_dtype], packed.ctypes.data_as(ctypes.c_void_p)),
+                    "rdvc_linear_pack_weights")
+        self.cout, self.cin = cout, w2.shape[1]
+        self.weight = torch.from_numpy(packed.view(np.int16)).to(device)
+        self.bias = None if bias is None else bias.detach().to(torch.float32).to(device).contiguous()
+        self.key = _param_key(weight, bias, op_dtype, device)
+
+
 def _param_key(weight, bias, feat_dtype, device):
     return (weight.data_ptr(), weight._version, None if bias is None else (bias.data_ptr(), bias._version),
             feat_dtype, torch.device(device))
@@ -311,6 +331,8 @@ class TVCorrBlock(nn.Module):
         self._workspace: Optional[Tensor] = None
         self._levels: Optional[List[Tensor]] = None
         self._packed: Optional[PackedConv1x1] = None     # convcorr1 weights packed for rdvc_conv1x1
+        self._packed_tail: Optional[PackedLinear] = None # the feature encoder's final 1x1 convolution, 16-bit rows
+        self._workspace_in: Optional[Tensor] = None      # K-major rows of the encoder's 128-channel activations
         self._feat: Optional[Tensor] = None              # K-major feature rows between the two launches
 
     @property
@@ -340,6 +362,55 @@ class TVCorrBlock(nn.Module):
                 f"Output shape of index pyramid is incorrect. Should be {expected_output_shape}, got {corr_features.shape}"
             )
         return corr_features
+
+    def build_pyramid_from_encoder(self, x1: Tensor, x2: Tensor, weight: Tensor, bias: Optional[Tensor] = None) -> None:
+        """``build_pyramid(conv(x1), conv(x2))`` for the feature encoder's final 1x1 convolution ``conv`` (TV:raft.py:139,
+        150; ``weight``: (256, 128[, 1, 1])) WITHOUT materialising the fp32 feature maps: the 128-channel activations are
+        repacked K-major (``rdvc_corr_pack``), a tcgen05 GEMM turns every packed row into the build's 256-channel operand
+        row (``rdvc_corr_encoder_tail``; a 1x1 convolution commutes with the transpose and the mean pooling), and the
+        build multiplies those rows (``rdvc_corr_build_packed``).  16-bit operands (bf16; fp16 for fp16 activations),
+        fp32 accumulation, 16-bit operand rows: feature rows within one 16-bit ulp of the rounded stock feature maps."""
+        _check_fmaps(x1, x2, self.num_levels)
+        lib = _cabi.load()
+        B, Din, h, w = x1.shape
+        Dout = weight.shape[0]
+        dev = x1.device
+        op_dtype = torch.float16 if x1.dtype == torch.float16 else torch.bfloat16
+        key = _param_key(weight, bias, op_dtype, dev)
+        if self._packed_tail is None or self._packed_tail.key != key:
+            self._packed_tail = PackedLinear(weight, bias, op_dtype, dev)
+        if self._packed_tail.cin != Din:
+            raise ValueError(f"weight expects {self._packed_tail.cin} input channels, the activations have {Din}")
+        vd = _VOL_DTYPES[self.volume_dtype]
+        pyr_bytes = lib.rdvc_corr_pyramid_bytes(B, h, w, self.num_levels, vd, self.layout)
+        ws_in_bytes = lib.rdvc_corr_workspace_bytes(B, Din, h, w)
+        ws_out_bytes = lib.rdvc_corr_workspace_bytes(B, Dout, h, w)
+        a, b = x1.contiguous(), x2.contiguous()
+        with torch.cuda.device(dev):
+            if self._pyr is not None and self._pyr.buffer.numel() >= pyr_bytes and self._pyr.buffer.device == dev:
+                buf = self._pyr.buffer
+            else:
+                buf = torch.empty(pyr_bytes, dtype=torch.uint8, device=dev)
+            if self._workspace is None or self._workspace.numel() < ws_out_bytes or self._workspace.device != dev:
+                self._workspace = torch.empty(ws_out_bytes, dtype=torch.uint8, device=dev)
+            if self._workspace_in is None or self._workspace_in.numel() < ws_in_bytes or self._workspace_in.device != dev:
+                self._workspace_in = torch.empty(ws_in_bytes, dtype=torch.uint8, device=dev)
+            st = _stream_ptr(dev)
+            _cabi.check(lib.rdvc_corr_pack(a.data_ptr(), b.data_ptr(), B, Din, h, w, _IN_DTYPES[a.dtype], vd, self.layout,
+                                           self.num_levels, self._workspace_in.data_ptr(), self._workspace_in.numel(), st),
+                        "rdvc_corr_pack")
+            pt = self._packed_tail
+            _cabi.check(lib.rdvc_corr_encoder_tail(self._workspace_in.data_ptr(), self._workspace_in.numel(), Din,
+                                                   pt.weight.data_ptr(), 0 if pt.bias is None else pt.bias.data_ptr(), Dout,
+                                                   B, h, w, _FEAT_DTYPES[op_dtype], vd, self.layout, self.num_levels,
+                                                   self._workspace.data_ptr(), self._workspace.numel(), st),
+                        "rdvc_corr_encoder_tail")
+            _cabi.check(lib.rdvc_corr_build_packed(B, Dout, h, w, _FEAT_DTYPES[op_dtype], buf.data_ptr(), vd, self.layout,
+                                                   self.num_levels, self._workspace.data_ptr(), self._workspace.numel(), st),
+                        "rdvc_corr_build_packed")
+        self._pyr = CorrPyramid(B, h, w, self.num_levels, self.volume_dtype, buf, self.layout)
+        self._pyr._workspace = self._workspace
+        self._levels = None
 
     def index_pyramid_convcorr1(self, centroids_coords: Tensor, weight: Tensor, bias: Optional[Tensor] = None,
                                 relu: bool = True, out_dtype: Optional[torch.dtype] = None,
@@ -386,6 +457,7 @@ class TVCorrBlock(nn.Module):
         self._workspace = None
         self._levels = None
         self._feat = None
+        self._workspace_in = None
 
 
 class CorrBlock:

@@ -19,6 +19,7 @@
 #include "corr_build2_sm100.cuh"
 #endif
 #include "corr_conv1x1_sm100.cuh"
+#include "corr_encoder_tail_sm100.cuh"
 #include "corr_lookup.cuh"
 #include "corr_pack.cuh"
 #include "entropy_coder.h"
@@ -430,21 +431,51 @@ int choose_msplit(long long units, int m_blks, int G, int forced) {
     return (forced > 0) ? (forced < m_blks ? forced : m_blks) : best;
 }
 
+// Where the K-major operand rows live inside a workspace of rdvc_corr_workspace_bytes(B, D, h, w): fmap1 rows first,
+// then fmap2's rows per level (each block 256-byte aligned and sized for the largest layout), their row counts in this
+// layout, and the byte range that must be zeroed before a pack (levels with layout padding).
+struct WorkspaceLayout {
+    void* a_km;
+    void* b_km[rdvc::BLD_MAX_LEVELS];
+    size_t nl_of[rdvc::BLD_MAX_LEVELS];
+    int twl, thl;
+    void* memset_ptr;
+    size_t memset_bytes;
+};
+
+void workspace_layout(void* workspace, int B, int D, int h, int w, int vol_dtype, int layout, int num_levels,
+                      WorkspaceLayout* out) {
+    WorkspaceLayout& wl = *out;
+    memset(&wl, 0, sizeof(wl));
+    const int N = h * w;
+    uint8_t* ws = static_cast<uint8_t*>(workspace);
+    wl.a_km = ws;
+    size_t off = align_up(static_cast<size_t>(B) * N * D * 2, 256);
+    for (int l = 0; l < rdvc::BLD_MAX_LEVELS; ++l) {
+        wl.b_km[l] = ws + off;
+        off += align_up(static_cast<size_t>(B) * operand_rows_max(h, w, l) * D * 2, 256);
+    }
+    for (int l = 0; l < rdvc::BLD_MAX_LEVELS; ++l) wl.nl_of[l] = level_image_elems(h, w, l, vol_dtype, layout);
+    if (layout == RDVC_LAYOUT_TILED) {
+        tile_log2(vol_dtype, &wl.twl, &wl.thl);
+        int first = -1;
+        for (int l = 0; l < num_levels && first < 0; ++l)
+            if (wl.nl_of[l] != static_cast<size_t>(h >> l) * (w >> l)) first = l;
+        if (first >= 0) {
+            uint8_t* lo = static_cast<uint8_t*>(wl.b_km[first]);
+            uint8_t* hi = static_cast<uint8_t*>(wl.b_km[num_levels - 1]) + static_cast<size_t>(B) * wl.nl_of[num_levels - 1] * D * 2;
+            wl.memset_ptr = lo;
+            wl.memset_bytes = static_cast<size_t>(hi - lo);
+        }
+    }
+}
+
 int make_build_plan(const BuildKey& k, BuildPlan* plan) {
     BuildPlan& pl = *plan;
     memset(&pl, 0, sizeof(pl));
     pl.key = k;
     const int B = k.B, D = k.D, h = k.h, w = k.w, num_levels = k.num_levels, vol_dtype = k.vol_dtype, layout = k.layout;
     const int N = h * w;
-    uint8_t* ws = static_cast<uint8_t*>(k.workspace);
-    pl.a_km = ws;
-    {
-        size_t off = align_up(static_cast<size_t>(B) * N * D * 2, 256);
-        for (int l = 0; l < rdvc::BLD_MAX_LEVELS; ++l) {
-            pl.b_km[l] = ws + off;
-            off += align_up(static_cast<size_t>(B) * operand_rows_max(h, w, l) * D * 2, 256);
-        }
-    }
     int mode = k.opt_mode;
     if (mode == 0) mode = 2;  // default: linear (pooled fmap2 rows), see corr_build_sm100.cuh
     pl.linear = (mode == 2);
@@ -452,18 +483,13 @@ int make_build_plan(const BuildKey& k, BuildPlan* plan) {
         return fail(RDVC_E_UNSUPPORTED, "the fused-epilogue build mode exists in RDVC_EXPERIMENTS builds only");
     if (!pl.linear && layout != RDVC_LAYOUT_ROWMAJOR)
         return fail(RDVC_E_UNSUPPORTED, "the fused-epilogue build mode writes RDVC_LAYOUT_ROWMAJOR only");
-    for (int l = 0; l < rdvc::BLD_MAX_LEVELS; ++l) pl.nl_of[l] = level_image_elems(h, w, l, vol_dtype, layout);
-    if (layout == RDVC_LAYOUT_TILED) {
-        tile_log2(vol_dtype, &pl.twl, &pl.thl);
-        int first = -1;
-        for (int l = 0; l < num_levels && first < 0; ++l)
-            if (pl.nl_of[l] != static_cast<size_t>(h >> l) * (w >> l)) first = l;
-        if (first >= 0) {
-            uint8_t* lo = static_cast<uint8_t*>(pl.b_km[first]);
-            uint8_t* hi = static_cast<uint8_t*>(pl.b_km[num_levels - 1]) + static_cast<size_t>(B) * pl.nl_of[num_levels - 1] * D * 2;
-            pl.memset_ptr = lo;
-            pl.memset_bytes = static_cast<size_t>(hi - lo);
-        }
+    {
+        WorkspaceLayout wl;
+        workspace_layout(k.workspace, B, D, h, w, vol_dtype, layout, num_levels, &wl);
+        pl.a_km = wl.a_km;
+        for (int l = 0; l < rdvc::BLD_MAX_LEVELS; ++l) { pl.b_km[l] = wl.b_km[l]; pl.nl_of[l] = wl.nl_of[l]; }
+        pl.twl = wl.twl; pl.thl = wl.thl;
+        pl.memset_ptr = wl.memset_ptr; pl.memset_bytes = wl.memset_bytes;
     }
     // operand format: fp16 inputs (the reference's default autocast, R:codec_processing.py:1436) stay fp16
     // -- same tensor-core rate, 11 instead of 8 mantissa bits; everything else is multiplied as bf16
@@ -698,10 +724,15 @@ size_t rdvc_corr_workspace_bytes(int B, int D, int h, int w) {
     return total;
 }
 
-int rdvc_corr_build(const void* fmap1, const void* fmap2, int B, int D, int h, int w, int in_dtype,
-                    void* pyramid, int vol_dtype, int layout, int num_levels, void* workspace,
-                    size_t workspace_bytes, void* stream) {
-    if (!fmap1 || !fmap2 || !pyramid || !workspace) return fail(RDVC_E_NULL, "null pointer argument");
+}  // extern "C"
+
+namespace {
+// fmap1 == nullptr: the workspace already holds the K-major operand rows (rdvc_corr_build_packed)
+int build_impl(const void* fmap1, const void* fmap2, int B, int D, int h, int w, int in_dtype,
+               void* pyramid, int vol_dtype, int layout, int num_levels, void* workspace,
+               size_t workspace_bytes, void* stream) {
+    const bool packed = (fmap1 == nullptr);
+    if ((!packed && !fmap2) || !pyramid || !workspace) return fail(RDVC_E_NULL, "null pointer argument");
     int rc = check_geometry(B, h, w, num_levels);
     if (rc) return rc;
     if (D <= 0) return fail(RDVC_E_SHAPE, "non-positive channel count D=%d", D);
@@ -743,7 +774,7 @@ int rdvc_corr_build(const void* fmap1, const void* fmap2, int B, int D, int h, i
         plan_cache_put(plan);
     }
 
-    if (plan.memset_bytes) {
+    if (plan.memset_bytes && !packed) {
         // padding pixels of a level must come out of the GEMM as exact zeros: clear the operand rows of
         // the levels that have any (the pack kernel writes only real pixels) -- ONE memset from the first
         // padded level to the end of the last level (the per-level buffers are contiguous)
@@ -751,7 +782,8 @@ int rdvc_corr_build(const void* fmap1, const void* fmap2, int B, int D, int h, i
         if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(padded operand rows)");
     }
     // 1. repack to K-major 16-bit rows; the linear mode also needs the pooled fmap2 levels
-    {
+    if (packed && !plan.linear) return fail(RDVC_E_UNSUPPORTED, "pre-packed operands need the linear build mode");
+    if (!packed) {
         const int levels2 = plan.linear ? num_levels : 1;
         if (in_dtype == RDVC_DT_F32) rc = launch_pack<float>(fmap1, fmap2, plan.a_km, plan.b_km, B, D, h, w, levels2, layout, plan.twl, plan.thl, plan.nl_of, key.f16_ops, st);
         else if (in_dtype == RDVC_DT_BF16) rc = launch_pack<__nv_bfloat16>(fmap1, fmap2, plan.a_km, plan.b_km, B, D, h, w, levels2, layout, plan.twl, plan.thl, plan.nl_of, key.f16_ops, st);
@@ -783,6 +815,148 @@ int rdvc_corr_build(const void* fmap1, const void* fmap2, int B, int D, int h, i
                             : launch_build<MODE_LINEAR, 16, 16, float, 4>(ta, tb, to, p, st);
     return plan.ew == 8 ? launch_build<MODE_LINEAR, 16, 16, __nv_bfloat16, 8>(ta, tb, to, p, st)
                         : launch_build<MODE_LINEAR, 16, 16, __nv_bfloat16, 4>(ta, tb, to, p, st);
+}
+}  // namespace
+
+extern "C" {
+
+int rdvc_corr_build(const void* fmap1, const void* fmap2, int B, int D, int h, int w, int in_dtype,
+                    void* pyramid, int vol_dtype, int layout, int num_levels, void* workspace,
+                    size_t workspace_bytes, void* stream) {
+    if (!fmap1 || !fmap2) return fail(RDVC_E_NULL, "null pointer argument");
+    return build_impl(fmap1, fmap2, B, D, h, w, in_dtype, pyramid, vol_dtype, layout, num_levels, workspace,
+                      workspace_bytes, stream);
+}
+
+int rdvc_corr_build_packed(int B, int D, int h, int w, int op_dtype, void* pyramid, int vol_dtype, int layout,
+                           int num_levels, void* workspace, size_t workspace_bytes, void* stream) {
+    if (op_dtype != RDVC_DT_BF16 && op_dtype != RDVC_DT_F16)
+        return fail(RDVC_E_DTYPE, "packed operands are BF16 or F16, got op_dtype=%d", op_dtype);
+    return build_impl(nullptr, nullptr, B, D, h, w, op_dtype, pyramid, vol_dtype, layout, num_levels, workspace,
+                      workspace_bytes, stream);
+}
+
+int rdvc_corr_pack(const void* x1, const void* x2, int B, int D, int h, int w, int in_dtype, int vol_dtype,
+                   int layout, int num_levels, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!x1 || !x2 || !workspace) return fail(RDVC_E_NULL, "null pointer argument");
+    int rc = check_geometry(B, h, w, num_levels);
+    if (rc) return rc;
+    if (D <= 0 || D % 64 != 0 || D > 64 * rdvc::BLD_MAX_KC)
+        return fail(RDVC_E_UNSUPPORTED, "D=%d must be a multiple of 64 and <= %d", D, 64 * rdvc::BLD_MAX_KC);
+    if (in_dtype != RDVC_DT_F32 && in_dtype != RDVC_DT_BF16 && in_dtype != RDVC_DT_F16)
+        return fail(RDVC_E_DTYPE, "unsupported in_dtype=%d", in_dtype);
+    if (vol_dtype != RDVC_DT_F32 && vol_dtype != RDVC_DT_BF16)
+        return fail(RDVC_E_DTYPE, "unsupported vol_dtype=%d", vol_dtype);
+    if (layout != RDVC_LAYOUT_ROWMAJOR && layout != RDVC_LAYOUT_TILED)
+        return fail(RDVC_E_UNSUPPORTED, "unknown pyramid layout %d", layout);
+    if (workspace_bytes < rdvc_corr_workspace_bytes(B, D, h, w))
+        return fail(RDVC_E_WORKSPACE, "workspace %zu < required %zu", workspace_bytes, rdvc_corr_workspace_bytes(B, D, h, w));
+    if (reinterpret_cast<uintptr_t>(workspace) & 255) return fail(RDVC_E_ALIGN, "workspace must be 256-byte aligned");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    WorkspaceLayout wl;
+    workspace_layout(workspace, B, D, h, w, vol_dtype, layout, num_levels, &wl);
+    if (wl.memset_bytes) {
+        cudaError_t e = cudaMemsetAsync(wl.memset_ptr, 0, wl.memset_bytes, st);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(padded operand rows)");
+    }
+    const int f16 = (in_dtype == RDVC_DT_F16) ? 1 : 0;
+    if (in_dtype == RDVC_DT_F32) return launch_pack<float>(x1, x2, wl.a_km, wl.b_km, B, D, h, w, num_levels, layout, wl.twl, wl.thl, wl.nl_of, f16, st);
+    if (in_dtype == RDVC_DT_BF16) return launch_pack<__nv_bfloat16>(x1, x2, wl.a_km, wl.b_km, B, D, h, w, num_levels, layout, wl.twl, wl.thl, wl.nl_of, f16, st);
+    return launch_pack<__half>(x1, x2, wl.a_km, wl.b_km, B, D, h, w, num_levels, layout, wl.twl, wl.thl, wl.nl_of, f16, st);
+}
+
+size_t rdvc_linear_packed_weight_bytes(int cout, int cin) {
+    if (cout <= 0 || cin <= 0) return 0;
+    return static_cast<size_t>(cout) * cin * 2;
+}
+
+int rdvc_linear_pack_weights(const float* weight, int cout, int cin, int dtype, void* packed_host) {
+    if (!weight || !packed_host) return fail(RDVC_E_NULL, "null pointer argument");
+    if (dtype != RDVC_DT_BF16 && dtype != RDVC_DT_F16) return fail(RDVC_E_DTYPE, "dtype must be BF16 or F16, got %d", dtype);
+    if (cout <= 0 || cin <= 0) return fail(RDVC_E_SHAPE, "non-positive dimension cout=%d cin=%d", cout, cin);
+    uint16_t* out = static_cast<uint16_t*>(packed_host);
+    for (size_t i = 0; i < static_cast<size_t>(cout) * cin; ++i) {
+        if (dtype == RDVC_DT_F16) { const __half hv = __float2half_rn(weight[i]); memcpy(out + i, &hv, 2); }
+        else { const __nv_bfloat16 bv = __float2bfloat16_rn(weight[i]); memcpy(out + i, &bv, 2); }
+    }
+    return RDVC_OK;
+}
+
+int rdvc_corr_encoder_tail(const void* ws_in, size_t ws_in_bytes, int D_in, const void* packed_w, const float* bias,
+                           int D_out, int B, int h, int w, int op_dtype, int vol_dtype, int layout, int num_levels,
+                           void* ws_out, size_t ws_out_bytes, void* stream) {
+    if (!ws_in || !packed_w || !ws_out) return fail(RDVC_E_NULL, "null pointer argument");
+    int rc = check_geometry(B, h, w, num_levels);
+    if (rc) return rc;
+    if (D_in != rdvc::ET_K || D_out != rdvc::ET_N)
+        return fail(RDVC_E_UNSUPPORTED, "the encoder tail is a %d -> %d convolution, got %d -> %d", rdvc::ET_K, rdvc::ET_N, D_in, D_out);
+    if (op_dtype != RDVC_DT_BF16 && op_dtype != RDVC_DT_F16)
+        return fail(RDVC_E_DTYPE, "operands are BF16 or F16, got op_dtype=%d", op_dtype);
+    if (vol_dtype != RDVC_DT_F32 && vol_dtype != RDVC_DT_BF16)
+        return fail(RDVC_E_DTYPE, "unsupported vol_dtype=%d", vol_dtype);
+    if (layout != RDVC_LAYOUT_ROWMAJOR && layout != RDVC_LAYOUT_TILED)
+        return fail(RDVC_E_UNSUPPORTED, "unknown pyramid layout %d", layout);
+    if (ws_in_bytes < rdvc_corr_workspace_bytes(B, D_in, h, w) || ws_out_bytes < rdvc_corr_workspace_bytes(B, D_out, h, w))
+        return fail(RDVC_E_WORKSPACE, "workspaces must hold rdvc_corr_workspace_bytes for D = %d (in) and D = %d (out)", D_in, D_out);
+    if ((reinterpret_cast<uintptr_t>(ws_in) & 255) || (reinterpret_cast<uintptr_t>(ws_out) & 255) ||
+        (reinterpret_cast<uintptr_t>(packed_w) & 15))
+        return fail(RDVC_E_ALIGN, "workspaces must be 256-byte aligned, packed weights 16-byte aligned");
+    WorkspaceLayout li, lo;
+    workspace_layout(const_cast<void*>(ws_in), B, D_in, h, w, vol_dtype, layout, num_levels, &li);
+    workspace_layout(ws_out, B, D_out, h, w, vol_dtype, layout, num_levels, &lo);
+    rdvc::EncoderTailParams p;
+    memset(&p, 0, sizeof(p));
+    const uint8_t* in0 = static_cast<const uint8_t*>(ws_in);
+    const uint8_t* out0 = static_cast<const uint8_t*>(ws_out);
+    const size_t in_row = static_cast<size_t>(D_in) * 2, out_row = static_cast<size_t>(D_out) * 2;
+    int tiles = 0;
+    auto add_seg = [&](const void* src, const void* dst, long long rows, int img, int hl, int wl_, int tiles_w) {
+        const int s = p.n_segs++;
+        p.in_row0[s] = static_cast<long long>((static_cast<const uint8_t*>(src) - in0) / in_row);
+        p.out_row0[s] = static_cast<long long>((static_cast<const uint8_t*>(dst) - out0) / out_row);
+        p.rows[s] = rows;
+        p.tile0[s] = tiles;
+        p.img[s] = img; p.hl[s] = hl; p.wl[s] = wl_; p.tiles_w[s] = tiles_w;
+        tiles += static_cast<int>((rows + rdvc::ET_BLOCK_M - 1) / rdvc::ET_BLOCK_M);
+    };
+    add_seg(li.a_km, lo.a_km, static_cast<long long>(B) * h * w, h * w, h, w, 0);                 // image 1: every row real
+    for (int l = 0; l < num_levels; ++l) {
+        const int hl = h >> l, wl_ = w >> l;
+        const bool padded = li.nl_of[l] != static_cast<size_t>(hl) * wl_;
+        const int tiles_w = (layout == RDVC_LAYOUT_TILED && padded) ? ((wl_ + (1 << li.twl) - 1) >> li.twl) : 0;
+        add_seg(li.b_km[l], lo.b_km[l], static_cast<long long>(B) * static_cast<long long>(li.nl_of[l]),
+                static_cast<int>(li.nl_of[l]), hl, wl_, tiles_w);
+    }
+    p.tile0[p.n_segs] = tiles;
+    p.n_tiles = tiles;
+    p.twl = li.twl; p.thl = li.thl;
+    p.out = ws_out; p.bias = bias; p.ab_format = (op_dtype == RDVC_DT_F16) ? 0 : 1;
+    const CUtensorMapDataType op_dt = (op_dtype == RDVC_DT_F16) ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+    CUtensorMap tm_a, tm_w;
+    {
+        const cuuint64_t total_rows = ws_in_bytes / in_row;
+        if (total_rows >= (1ull << 31)) return fail(RDVC_E_UNSUPPORTED, "too many rows for 32-bit TMA coordinates");
+        cuuint64_t dims[3] = {(cuuint64_t)D_in, total_rows, 1};
+        cuuint64_t str[2] = {(cuuint64_t)in_row, total_rows * in_row};
+        cuuint32_t box[3] = {64, rdvc::ET_BLOCK_M, 1};
+        if ((rc = make_tmap(&tm_a, op_dt, const_cast<void*>(ws_in), 3, dims, str, box))) return rc;
+    }
+    {
+        cuuint64_t dims[3] = {(cuuint64_t)D_in, (cuuint64_t)D_out, 1};
+        cuuint64_t str[2] = {(cuuint64_t)in_row, (cuuint64_t)D_out * in_row};
+        cuuint32_t box[3] = {64, (cuuint32_t)D_out, 1};
+        if ((rc = make_tmap(&tm_w, op_dt, const_cast<void*>(packed_w), 3, dims, str, box))) return rc;
+    }
+    auto kern = rdvc::corr_encoder_tail_kernel;
+    static std::atomic<unsigned long long> attr_done{0};
+    if ((rc = ensure_dynamic_smem(kern, rdvc::ET_SMEM_LAUNCH, attr_done, "cudaFuncSetAttribute(encoder tail, max dynamic smem)"))) return rc;
+    int grid = sm_count();
+    if (grid > tiles) grid = tiles;
+    kern<<<grid, rdvc::ET_THREADS, rdvc::ET_SMEM_LAUNCH, static_cast<cudaStream_t>(stream)>>>(tm_a, tm_w, p);
+    ++g_launches;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "corr_encoder_tail_kernel launch");
+    return RDVC_OK;
 }
 
 size_t rdvc_corr_feat_pitch(int num_levels, int radius) {

@@ -15,7 +15,12 @@ is restated module by module.  The 1x1 convolution then multiplies 16-bit operan
 (the stock fp32 path multiplies in TF32 / fp32): flows differ by ~1e-3 px, far inside the 0.05 px budget;
 ``fuse_convcorr1=False`` keeps the stock modules and is bit-identical to ``RAFT.forward``.
 
-All other convolutions stay stock PyTorch/cuDNN; only the correlation block (and that 1x1) is this library's.
+With ``fuse_encoder_tail=True`` (default) the feature encoder's LAST layer -- ``FeatureEncoder.conv`` = 1x1
+convolution 128 -> 256, TV:raft.py:139,150 -- is not run by cuDNN either: the 128-channel activations go to
+``TVCorrBlock.build_pyramid_from_encoder`` (row f-2, last sub-item), which produces the build's K-major 16-bit operand
+rows directly; the (2B, 256, h, w) fp32 feature maps (67 MB at 1080p) are never written or re-read.
+
+All other convolutions stay stock PyTorch/cuDNN; only the correlation block (and those two 1x1s) is this library's.
 
 :class:`GraphedRaftFlow` replays the whole call as ONE CUDA graph per input shape.  At the reference's
 default RAFT size (368x640, R:codec_processing.py:649-650) a P-frame's ~700 kernel launches cost more
@@ -57,6 +62,15 @@ def _update_block_fused(model, blk: TVCorrBlock, hidden_state: Tensor, context: 
     return hidden_state, ub.flow_head(hidden_state)
 
 
+def _can_fuse_encoder_tail(model) -> bool:
+    """The feature encoder must be torchvision's: convnormrelu, layer1..3, then Conv2d(128 -> 256, k = 1)."""
+    fe = model.feature_encoder
+    conv = getattr(fe, "conv", None)
+    return (all(hasattr(fe, n) for n in ("convnormrelu", "layer1", "layer2", "layer3")) and isinstance(conv, torch.nn.Conv2d)
+            and conv.kernel_size == (1, 1) and conv.stride == (1, 1) and conv.padding == (0, 0) and conv.groups == 1
+            and conv.in_channels == 128 and conv.out_channels == 256)
+
+
 def _can_fuse_convcorr1(model) -> bool:
     """convcorr1 must be exactly Conv2d(k=1, stride 1, no padding, groups 1) + ReLU with cout a multiple of 32 <= 256."""
     try:
@@ -72,7 +86,7 @@ def _can_fuse_convcorr1(model) -> bool:
 @torch.no_grad()
 def raft_flow(model, image1: Tensor, image2: Tensor, num_flow_updates: int = 12,
               corr_block: Optional[TVCorrBlock] = None, all_predictions: bool = False,
-              fuse_convcorr1: bool = True):
+              fuse_convcorr1: bool = True, fuse_encoder_tail: bool = True):
     """Final optical flow (B, 2, H, W) of a torchvision RAFT ``model`` for one frame pair.
 
     ``corr_block`` defaults to ``model.corr_block``, which must be a :class:`TVCorrBlock`
@@ -90,11 +104,19 @@ def raft_flow(model, image1: Tensor, image2: Tensor, num_flow_updates: int = 12,
     if not ((h % 8 == 0) and (w % 8 == 0)):
         raise ValueError(f"input image H and W should be divisible by 8, instead got {h} (h) and {w} (w)")
 
-    fmaps = model.feature_encoder(torch.cat([image1, image2], dim=0))
-    fmap1, fmap2 = torch.chunk(fmaps, chunks=2, dim=0)
-    if fmap1.shape[-2:] != (h // 8, w // 8):            # TV:raft.py:494-495
-        raise ValueError("The feature encoder should downsample H and W by 8")
-    blk.build_pyramid(fmap1, fmap2)
+    fe = model.feature_encoder
+    if fuse_encoder_tail and _can_fuse_encoder_tail(model):
+        x = fe.layer3(fe.layer2(fe.layer1(fe.convnormrelu(torch.cat([image1, image2], dim=0)))))   # TV:raft.py:145-149
+        fmap1, fmap2 = torch.chunk(x, chunks=2, dim=0)            # 128-channel activations; fe.conv runs inside the block
+        if fmap1.shape[-2:] != (h // 8, w // 8):                  # TV:raft.py:494-495
+            raise ValueError("The feature encoder should downsample H and W by 8")
+        blk.build_pyramid_from_encoder(fmap1, fmap2, fe.conv.weight, fe.conv.bias)
+    else:
+        fmaps = fe(torch.cat([image1, image2], dim=0))
+        fmap1, fmap2 = torch.chunk(fmaps, chunks=2, dim=0)
+        if fmap1.shape[-2:] != (h // 8, w // 8):            # TV:raft.py:494-495
+            raise ValueError("The feature encoder should downsample H and W by 8")
+        blk.build_pyramid(fmap1, fmap2)
     fuse = fuse_convcorr1 and blk.layout == 1 and _can_fuse_convcorr1(model)      # 1 = RDVC_LAYOUT_TILED
 
     context_out = model.context_encoder(image1)
@@ -133,7 +155,8 @@ class GraphedRaftFlow:
     """
 
     def __init__(self, model, num_flow_updates: int = 12, amp_dtype: Optional[torch.dtype] = None,
-                 volume_dtype: torch.dtype = torch.float32, fuse_convcorr1: bool = True, max_entries: int = 4):
+                 volume_dtype: torch.dtype = torch.float32, fuse_convcorr1: bool = True, max_entries: int = 4,
+                 fuse_encoder_tail: bool = True):
         if not isinstance(model.corr_block, TVCorrBlock):
             raise TypeError("GraphedRaftFlow needs a model built with corr_block=rdvc_corr_b200.TVCorrBlock()")
         if model.training:
@@ -144,12 +167,14 @@ class GraphedRaftFlow:
         self.amp_dtype = amp_dtype
         self.volume_dtype = volume_dtype
         self.fuse_convcorr1 = fuse_convcorr1
+        self.fuse_encoder_tail = fuse_encoder_tail
         self.max_entries = max_entries        # every captured shape pins a pyramid (5.7 GB at 1080p fp32)
         self._entries = {}                    # insertion-ordered: least recently used first
 
     def _run(self, blk, a, b):
         with torch.autocast("cuda", dtype=self.amp_dtype or torch.float16, enabled=self.amp_dtype is not None):
-            return raft_flow(self.model, a, b, self.num_flow_updates, corr_block=blk, fuse_convcorr1=self.fuse_convcorr1)
+            return raft_flow(self.model, a, b, self.num_flow_updates, corr_block=blk, fuse_convcorr1=self.fuse_convcorr1,
+                             fuse_encoder_tail=self.fuse_encoder_tail)
 
     def release(self, key=None) -> None:
         """Drop the captured graph(s) and the pyramids they pin (all shapes, or one ``(shape, dtype, device)`` key)."""

@@ -26,14 +26,14 @@ def lib():
 def header_functions():
     src = open(HEADER).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    return sorted(set(re.findall(r"\b(rdvc_(?:corr|motion|preprocess|mcn|conv1x1|ec)\w*)\s*\(", src)))
+    return sorted(set(re.findall(r"\b(rdvc_(?:corr|motion|preprocess|mcn|conv1x1|ec|linear)\w*)\s*\(", src)))
 
 
 def test_header_symbols_exported(lib):
     declared = header_functions()
     assert len(declared) >= 10
     out = subprocess.check_output(["nm", "-D", "--defined-only", rc._cabi.lib_path()], text=True)
-    exported = set(re.findall(r"\bT (rdvc_(?:corr|motion|preprocess|mcn|conv1x1|ec)\w*)", out))
+    exported = set(re.findall(r"\bT (rdvc_(?:corr|motion|preprocess|mcn|conv1x1|ec|linear)\w*)", out))
     missing = [f for f in declared if f not in exported]
     assert not missing, f"header declares symbols the library does not export: {missing}"
     # and the ctypes table binds exactly the header's functions

@@ -500,11 +500,12 @@ def test_raft_flow_runner_matches_forward(lib, golden_dir):
     model = _seeded_raft(rc.TVCorrBlock())
     with torch.no_grad():
         ref = model(a, b, num_flow_updates=12)
-        got = rc.raft_flow(model, a, b, num_flow_updates=12, fuse_convcorr1=False)
-        every = rc.raft_flow(model, a, b, num_flow_updates=12, all_predictions=True, fuse_convcorr1=False)
+        got = rc.raft_flow(model, a, b, num_flow_updates=12, fuse_convcorr1=False, fuse_encoder_tail=False)
+        every = rc.raft_flow(model, a, b, num_flow_updates=12, all_predictions=True, fuse_convcorr1=False,
+                             fuse_encoder_tail=False)
     assert torch.allclose(got, ref[-1], rtol=0, atol=1e-5)
     assert len(every) == 12 and all(torch.allclose(x, y, rtol=0, atol=1e-5) for x, y in zip(every, ref))
-    fused = rc.raft_flow(model, a, b, num_flow_updates=12)      # default: lookup fused with convcorr1 (16-bit operands)
+    fused = rc.raft_flow(model, a, b, num_flow_updates=12)      # default: both 1x1 convolutions fused (16-bit operands)
     assert (fused - ref[-1]).pow(2).sum(dim=1).sqrt().mean().item() < TOL_EPE
     with pytest.raises(TypeError):
         rc.raft_flow(_seeded_raft(), a, b)
@@ -663,7 +664,7 @@ def test_lookup_convcorr1_vs_stock_modules(lib, hw, vol):
 def test_raft_flow_fused_convcorr1_epe(lib, golden_dir, size):
     """rc.raft_flow with the lookup fused into convcorr1 (its default) vs STOCK torchvision RAFT.forward: mean EPE
     < 0.05 px at RDVC's default RAFT size and at 1920x1088 (BASELINE.json config 3's frame size), 12 updates;
-    2 + 2 x 12 launches of this library per pair."""
+    3 + 2 x 12 launches of this library per pair (pack, encoder tail, build; lookup + 1x1 GEMM per update)."""
     g = np.load(os.path.join(golden_dir, "frames_im1_im2.npz"))
     a = _preprocess(g["im1"], size).cuda()
     b = _preprocess(g["im2"], size).cuda()
@@ -672,13 +673,66 @@ def test_raft_flow_fused_convcorr1_epe(lib, golden_dir, size):
         model = _seeded_raft(rc.TVCorrBlock())
         n0 = lib.rdvc_corr_launch_count()
         got = rc.raft_flow(model, a, b, 12)
-        assert lib.rdvc_corr_launch_count() - n0 == 2 + 2 * 12
-        unfused = rc.raft_flow(model, a, b, 12, fuse_convcorr1=False)
+        assert lib.rdvc_corr_launch_count() - n0 == 3 + 2 * 12
+        unfused = rc.raft_flow(model, a, b, 12, fuse_convcorr1=False, fuse_encoder_tail=False)
+        only_tail = rc.raft_flow(model, a, b, 12, fuse_convcorr1=False)
+        assert (only_tail - ref).pow(2).sum(dim=1).sqrt().mean().item() < TOL_EPE
     assert torch.isfinite(got).all()
     epe = (got - ref).pow(2).sum(dim=1).sqrt().mean().item()
     epe_u = (unfused - ref).pow(2).sum(dim=1).sqrt().mean().item()
     assert epe < TOL_EPE and epe_u < TOL_EPE, (epe, epe_u)
     model.corr_block.release()
+
+
+@pytest.mark.parametrize("vol", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("shape", [(1, 46, 80), (2, 18, 22), (1, 17, 19), (1, 33, 47)])
+def test_build_from_encoder_tail(lib, shape, vol):
+    """Row f-2, last sub-item: TVCorrBlock.build_pyramid_from_encoder(x1, x2, W, b) == build_pyramid(conv(x1), conv(x2))
+    for the feature encoder's final 1x1 convolution (TV:raft.py:139,150), without the fp32 feature maps: vs an fp64
+    evaluation with the SAME rounding points (pooled activations, weights and operand rows rounded to bf16 once
+    each), vs the stock order of work through rdvc_corr_build, and the layout's padding pixels stay exact zeros
+    (the bias must not leak into them)."""
+    B, h, w = shape
+    Din, Dout, L = 128, 256, 4
+    g = torch.Generator(device="cuda").manual_seed(h * w + B)
+    x1 = torch.randn(B, Din, h, w, device="cuda", generator=g).relu()          # post-ReLU activations like the encoder's
+    x2 = torch.randn(B, Din, h, w, device="cuda", generator=g).relu()
+    W = torch.randn(Dout, Din, 1, 1, device="cuda", generator=g) * 0.09
+    bias = torch.randn(Dout, device="cuda", generator=g) * 0.5
+    blk = rc.TVCorrBlock(volume_dtype=vol)
+    n0 = lib.rdvc_corr_launch_count()
+    blk.build_pyramid_from_encoder(x1, x2, W, bias)
+    assert lib.rdvc_corr_launch_count() - n0 == 3                              # pack, encoder tail, build
+    bf = lambda t: t.to(torch.bfloat16).double()
+    Wd = bf(W.view(Dout, Din))
+    rows1 = bf((bf(x1).view(B, Din, h * w).transpose(1, 2) @ Wd.t() + bias.double()).float())      # (B, N, 256)
+    tol = TOL_SAME_OPERANDS_BF16 if vol == torch.bfloat16 else TOL_SAME_OPERANDS_POOLED
+    # the stock order of work: fp32 convolution, then the library's own build
+    torch.backends.cudnn.allow_tf32 = False
+    f1 = torch.nn.functional.conv2d(x1, W, bias)
+    f2 = torch.nn.functional.conv2d(x2, W, bias)
+    torch.backends.cudnn.allow_tf32 = True
+    stock = rc.build_pyramid(f1, f2, L, vol)
+    for l in range(L):
+        xp = torch.nn.functional.avg_pool2d(x2, 2 ** l) if l else x2
+        rows2 = bf((bf(xp).flatten(2).transpose(1, 2) @ Wd.t() + bias.double()).float())          # (B, n_l, 256)
+        ref = (rows1 @ rows2.transpose(1, 2) / 16.0).reshape(B * h * w, h >> l, w >> l)
+        got = blk._pyr.level(l)[:, 0].double()
+        err = ((got - ref).abs().max() / ref.abs().max()).item()
+        assert err < tol, (shape, l, err)
+        err_stock = ((got - stock.level(l)[:, 0].double()).abs().max() / ref.abs().max()).item()
+        assert err_stock < TOL_VOLUME, (shape, l, err_stock)
+        hl, wl, tw, th, hp, wp = blk._pyr._tiles(l)                            # padding pixels: exact zeros
+        raw = blk._pyr.storage(l)
+        st = raw[:, : hp * wp].reshape(-1, hp // th, wp // tw, th, tw).permute(0, 1, 3, 2, 4).reshape(-1, hp, wp)
+        assert not st[:, hl:, :].any() and not st[:, :, wl:].any() and not raw[:, hp * wp:].any()
+    # fp16 activations keep fp16 operands (what the stock path multiplies under the reference's autocast)
+    blk.build_pyramid_from_encoder(x1.half(), x2.half(), W, bias)
+    err16 = ((blk._pyr.level(0)[:, 0].double() - stock.level(0)[:, 0].double()).abs().max() / stock.level(0).abs().max()).item()
+    assert err16 < TOL_VOLUME, err16
+    with pytest.raises(ValueError, match="input channels"):
+        blk.build_pyramid_from_encoder(x1[:, :64], x2[:, :64], W, bias)
+    blk.release()
 
 
 def test_build_plan_cache(lib):
