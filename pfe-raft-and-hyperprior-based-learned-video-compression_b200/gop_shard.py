@@ -274,26 +274,32 @@ def gather_spans(local: bytes, tail_failed: bool, spans: Sequence[range], metada
             return None
     else:
         gathered = [(local, bool(tail_failed))]
-    import io
     chunks: List[bytes] = []
     prev_failed = False
+    n_records, p_bytes, expect = 0, 0, 0
+    want = [t for sp in spans for t in sp]
     for r, (data, failed) in enumerate(gathered):
-        if prev_failed and len(spans[r]) > 0:
-            recs = list(fmt.iter_frames(io.BytesIO(data)))
-            if recs and recs[0].kind == "P":
-                if reencode_iframe is None:
-                    raise RuntimeError(f"frame {recs[0].index} must become an I-frame (the frame before it failed) "
-                                       "but no reencode_iframe callback was given")
-                recs[0] = fmt.FrameRecord(recs[0].index, "I", reencode_iframe(recs[0].index))
-                data = b"".join(x.pack() for x in recs)
+        recs = fmt.scan_frames(data)                      # headers only: payloads are not copied
+        if prev_failed and len(spans[r]) > 0 and recs and recs[0][1] == "P":
+            if reencode_iframe is None:
+                raise RuntimeError(f"frame {recs[0][0]} must become an I-frame (the frame before it failed) "
+                                   "but no reencode_iframe callback was given")
+            first = fmt.FrameRecord(recs[0][0], "I", reencode_iframe(recs[0][0])).pack()
+            data = first + bytes(data[recs[0][2] + recs[0][3]:])
+            recs = fmt.scan_frames(data)
         if len(spans[r]) > 0:
             prev_failed = failed
+        for (idx, kind, off, _plen) in recs:
+            if expect >= len(want) or idx != want[expect]:
+                raise RuntimeError("frame records missing or out of order in the gather")
+            expect += 1
+            if kind == "P":
+                p_bytes += fmt.pframe_bitstream_bytes(data, off)
+        n_records += len(recs)
         chunks.append(data)
-    records = [x for b in chunks for x in fmt.iter_frames(io.BytesIO(b))]
-    want = [t for sp in spans for t in sp]
-    if [x.index for x in records] != want:
+    if expect != len(want):
         raise RuntimeError("frame records missing or out of order in the gather")
     meta = dict(metadata)
-    meta["total_frames_processed"] = len(records)
-    meta["total_pframe_payload_bytes"] = fmt.pframe_payload_bytes(records)
+    meta["total_frames_processed"] = n_records
+    meta["total_pframe_payload_bytes"] = p_bytes
     return fmt.write_stream(meta, chunks)

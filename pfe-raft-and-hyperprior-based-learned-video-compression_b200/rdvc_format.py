@@ -117,3 +117,36 @@ def pframe_payload_bytes(records: Iterable[FrameRecord]) -> int:
             _, m, _, res = parse_pframe_payload(r.payload)
             total += len(m) + len(res)
     return total
+
+
+def scan_frames(data) -> List[Tuple[int, str, int, int]]:
+    """(frame index, kind, payload offset, payload length) of every record in a byte string of packed frame records,
+    WITHOUT copying the payloads (the gather on rank 0 only needs to check order and add up lengths: at 44 KB per
+    P-frame the copying reader cost more than the gather itself)."""
+    mv = memoryview(data)
+    out = []
+    pos, n = 0, len(mv)
+    head = len(FRAME_MARKER) + 4 + 1 + 8
+    while pos < n:
+        marker = bytes(mv[pos:pos + len(FRAME_MARKER)])
+        if marker == EOF_MARKER:
+            break
+        if marker != FRAME_MARKER:
+            raise ValueError(f"Invalid RDVC file: Missing or incorrect FRAME marker. Found: {marker!r}")
+        if pos + head > n:
+            raise EOFError("truncated frame record header")
+        idx = struct.unpack_from(_U32, mv, pos + 8)[0]
+        kind = chr(mv[pos + 12])
+        plen = struct.unpack_from(_U64, mv, pos + 13)[0]
+        if pos + head + plen > n:
+            raise EOFError(f"Could not read full frame content for frame {idx}.")
+        out.append((idx, kind, pos + head, plen))
+        pos += head + plen
+    return out
+
+
+def pframe_bitstream_bytes(data, payload_offset: int) -> int:
+    """Motion + residual bitstream lengths of the P payload starting at `payload_offset` (no copies)."""
+    m_len = struct.unpack_from(_U32, data, payload_offset + 8)[0]
+    r_len = struct.unpack_from(_U32, data, payload_offset + 12 + m_len + 8)[0]
+    return m_len + r_len

@@ -288,3 +288,19 @@ def test_encode_gop_logs_and_reraises_fatal_errors(caplog):
         raise RuntimeError("CUDA error: an illegal memory access was encountered")
     with pytest.raises(RuntimeError, match="CUDA error"):
         gs.encode_gop(gs.Gop(0, 0, 3), frames, enc_i, fatal)
+
+
+def test_scan_frames_matches_the_copying_reader():
+    recs = [fmt.FrameRecord(0, "I", fmt.iframe_payload(b"abc")),
+            fmt.FrameRecord(1, "P", fmt.pframe_payload((2, 3), b"m" * 5, (4, 6), b"r" * 9)),
+            fmt.FrameRecord(2, "P", fmt.pframe_payload((2, 3), b"", (4, 6), b""))]
+    data = b"".join(r.pack() for r in recs)
+    scanned = fmt.scan_frames(data)
+    assert [(i, k) for i, k, _, _ in scanned] == [(0, "I"), (1, "P"), (2, "P")]
+    assert [data[o:o + n] for _, _, o, n in scanned] == [r.payload for r in recs]
+    assert sum(fmt.pframe_bitstream_bytes(data, o) for _, k, o, _ in scanned if k == "P") == fmt.pframe_payload_bytes(recs) == 14
+    assert fmt.scan_frames(data + fmt.EOF_MARKER) == scanned and fmt.scan_frames(b"") == []
+    with pytest.raises(EOFError):
+        fmt.scan_frames(data[:-3])
+    with pytest.raises(ValueError, match="FRAME marker"):
+        fmt.scan_frames(b"BADMARK_" + b"\0" * 20)
