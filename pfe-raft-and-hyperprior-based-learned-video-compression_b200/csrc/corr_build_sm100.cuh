@@ -217,7 +217,17 @@ __device__ __forceinline__ void staged_store(uint32_t stg, const float* v, int l
 constexpr int MODE_FUSED = 0;
 constexpr int MODE_LINEAR = 1;
 
-template <int MODE, int TILE_Y, int TILE_X, typename OutT, int EW>
+// CL = 2 (MODE_LINEAR only; launched as clusters of two CTAs): the two CTAs of a cluster hold fmap2 tiles 2j and 2j + 1
+// of the SAME batch item and m-slice, so they stream the same fmap1 tiles in the same order -- each loads HALF of
+// every 16 KB ring stage (64 of the 128 query rows) and TMA-multicasts it into both CTAs' shared memory: one L2 read
+// feeds two SMs.  Why: at full MMA rate the fmap1 stream alone is 61 GB/s per SM = 9.1 TB/s chip-wide, above the
+// ~7 TB/s L2 -> SM feed this part sustains, while the volume's writes cross the same L2.
+// Protocol: A_FULL[s] stays per CTA (armed by the CTA's own producer for the full 16 KB; the peer's half arrives on
+// it through the multicast's mbarrier signal); A_EMPTY[s] takes TWO arrivals per phase -- each CTA's tcgen05.commit is
+// multicast to both CTAs -- because a stage may be overwritten by the peer's next multicast only when BOTH consumers
+// are done with it.  A CTA whose tile index falls off the end (odd tile count) still loads, multiplies and commits
+// (its partner depends on it) but stores nothing.
+template <int MODE, int TILE_Y, int TILE_X, typename OutT, int EW, int CL = 1>
 __global__ void __launch_bounds__(BuildCfg<EW>::THREADS, 1)
 corr_build_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b0,
                   const __grid_constant__ CUtensorMap tm_b1, const __grid_constant__ CUtensorMap tm_b2,
@@ -228,6 +238,7 @@ corr_build_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
     constexpr int BLD_EPI_WARPS = Cfg::EPI_WARPS, BLD_SUBS = Cfg::SUBS, BLD_STG_BUFS = Cfg::STG_BUFS;
     constexpr int BLD_SMEM_BAR = Cfg::SMEM_BAR, BLD_SMEM_STG = Cfg::SMEM_STG, BLD_A_STAGES = Cfg::A_STAGES;
     static_assert(TILE_Y * TILE_X == BLD_BLOCK_N, "tile must hold 256 fmap2 pixels");
+    static_assert(CL == 1 || (CL == 2 && MODE == MODE_LINEAR), "clusters: linear mode, pairs");
     static_assert(TILE_Y % 8 == 0 && TILE_X % 16 == 0, "sub-tiles are 8 x 16");
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>(
@@ -252,7 +263,7 @@ corr_build_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < BLD_A_STAGES; ++i) {
             ptx::mbar_init(bar(A_FULL + i), 1);
-            ptx::mbar_init(bar(A_EMPTY + i), 1);
+            ptx::mbar_init(bar(A_EMPTY + i), CL);      // CL = 2: this CTA's commit and the peer's
         }
         ptx::mbar_init(bar(B_FULL), 1);
         ptx::mbar_init(bar(B_EMPTY), 1);
@@ -268,6 +279,7 @@ corr_build_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
     }
     ptx::tc_fence_before();
     __syncthreads();
+    if constexpr (CL == 2) ptx::cluster_sync_relaxed_arrive();   // the peer's barriers exist before anything signals them
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -277,9 +289,30 @@ corr_build_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
     // moving window of the volume (a few 2 MB pages) instead of 148 scattered ones
     // (measured 2x), and they share the streamed fmap1 tiles in L2.
     const int ntiles = p.ntiles;       // N-tiles per batch item
-    const int units = p.B * ntiles;
-    const int n_items = units * p.msplit;
     const int kc_n = p.kc;
+    // CL = 1: items = (fmap2 tile of any batch item) x slice, dealt over the CTAs.  CL = 2: items = (PAIR of tiles
+    // 2j, 2j + 1 of one batch item) x slice, dealt over the clusters; rank r of the cluster takes tile 2j + r.
+    const uint32_t crank = (CL == 2) ? ptx::cluster_ctarank() : 0u;
+    const int pairs_per_b = (ntiles + 1) / 2;
+    const int units = (CL == 2) ? p.B * pairs_per_b : p.B * ntiles;
+    const int n_items = units * p.msplit;
+    const int item0 = (CL == 2) ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+    const int item_step = (CL == 2) ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+    // item -> (batch item, tile, slice, does this CTA own a real tile)
+    auto decode = [&](int item, int& b, int& nt, int& sl) -> bool {
+        const int u = item % units;
+        sl = item / units;
+        if constexpr (CL == 2) {
+            b = u / pairs_per_b;
+            nt = 2 * (u % pairs_per_b) + static_cast<int>(crank);
+            if (nt >= ntiles) { nt = ntiles - 1; return false; }
+            return true;
+        } else {
+            b = u / ntiles;
+            nt = u % ntiles;
+            return true;
+        }
+    };
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -287,9 +320,9 @@ corr_build_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
         // barrier addresses stay in uniform registers); only the arrive / TMA instructions sit under elect_one().
         {
             uint32_t a_it = 0, b_it = 0;
-            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-                const int u = item % units, sl = item / units;
-                const int b = u / ntiles, nt = u % ntiles;
+            for (int item = item0; item < n_items; item += item_step) {
+                int b, nt, sl;
+                decode(item, b, nt, sl);
                 const int mb0 = static_cast<int>(static_cast<long long>(sl) * p.m_blks / p.msplit);
                 const int mb1 = static_cast<int>(static_cast<long long>(sl + 1) * p.m_blks / p.msplit);
                 if (mb0 == mb1) continue;
@@ -329,8 +362,13 @@ corr_build_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
 #endif
                             {
                                 ptx::mbar_arrive_expect_tx(bar(A_FULL + st), BLD_A_STAGE_BYTES);
-                                ptx::tma_load_3d(s_a + st * BLD_A_STAGE_BYTES, &tm_a, bar(A_FULL + st),
-                                                 kc * BLD_BLOCK_K, mb * BLD_BLOCK_M, b);
+                                if constexpr (CL == 2)      // my half of the stage (64 query rows), into BOTH CTAs
+                                    ptx::tma_load_3d_multicast(s_a + st * BLD_A_STAGE_BYTES + crank * (BLD_A_STAGE_BYTES / 2), &tm_a,
+                                                               bar(A_FULL + st), kc * BLD_BLOCK_K,
+                                                               mb * BLD_BLOCK_M + static_cast<int>(crank) * (BLD_BLOCK_M / 2), b, 3);
+                                else
+                                    ptx::tma_load_3d(s_a + st * BLD_A_STAGE_BYTES, &tm_a, bar(A_FULL + st),
+                                                     kc * BLD_BLOCK_K, mb * BLD_BLOCK_M, b);
                             }
                         }
                         __syncwarp();
@@ -349,7 +387,7 @@ corr_build_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
         {
             const uint32_t idesc = ptx::umma_idesc(BLD_BLOCK_M, BLD_BLOCK_N, p.ab_format);   // 1 = bf16, 0 = fp16 operands
             uint32_t a_it = 0, b_it = 0, tile_it = 0;
-            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+            for (int item = item0; item < n_items; item += item_step) {
                 const int sl = item / units;
                 const int mb0 = static_cast<int>(static_cast<long long>(sl) * p.m_blks / p.msplit);
                 const int mb1 = static_cast<int>(static_cast<long long>(sl + 1) * p.m_blks / p.msplit);
@@ -372,7 +410,9 @@ corr_build_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
                             for (int k = 0; k < BLD_BLOCK_K / BLD_UMMA_K; ++k)
                                 ptx::umma_bf16(d_tmem, a_desc0 + ((k * BLD_UMMA_K * 2) >> 4),
                                                b_desc0 + ((k * BLD_UMMA_K * 2) >> 4), idesc, (kc | k) != 0 ? 1u : 0u);
-                            ptx::umma_commit(bar(A_EMPTY + st));  // frees the ring slot when the MMAs retire
+                            // frees the ring slot when the MMAs retire (CL = 2: in both CTAs -- the peer's multicast writes here too)
+                            if constexpr (CL == 2) ptx::umma_commit_multicast(bar(A_EMPTY + st), 3);
+                            else ptx::umma_commit(bar(A_EMPTY + st));
                             if (kc == kc_n - 1) {
                                 ptx::umma_commit(bar(T_FULL + acc));      // accumulator ready for the epilogue
                                 // every MMA that reads this fmap2 tile has been issued
@@ -405,9 +445,9 @@ corr_build_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
         uint32_t tile_it = 0;
 
         if constexpr (MODE == MODE_LINEAR) {
-            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-                const int u = item % units, sl = item / units;
-                const int b = u / ntiles, nt = u % ntiles;
+            for (int item = item0; item < n_items; item += item_step) {
+                int b, nt, sl;
+                const bool active = decode(item, b, nt, sl);
                 const int mb0 = static_cast<int>(static_cast<long long>(sl) * p.m_blks / p.msplit);
                 const int mb1 = static_cast<int>(static_cast<long long>(sl + 1) * p.m_blks / p.msplit);
                 int l = 0;
@@ -416,7 +456,7 @@ corr_build_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
                 const int tile_col0 = (nt - p.tile_start[l]) * BLD_BLOCK_N;
                 OutT* const lv = static_cast<OutT*>(p.lvl[l]);
                 const bool vec = (n_l % TR::EPC) == 0;
-                const bool wr = (smask >> l) & 1;
+                const bool wr = ((smask >> l) & 1) && active;
                 const int omode = (p.tma_out >> (2 * l)) & 3;
                 const CUtensorMap* tmo = (l == 0) ? &tm_o0 : (l == 1) ? &tm_o1 : (l == 2) ? &tm_o2 : &tm_o3;
                 for (int mb = mb0; mb < mb1; ++mb, ++tile_it) {
@@ -586,9 +626,9 @@ corr_build_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
         const size_t img2 = static_cast<size_t>(p.hl[2]) * p.wl[2];
         const size_t img3 = static_cast<size_t>(p.hl[3]) * p.wl[3];
 
-        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-          const int u = item % units, sl = item / units;
-          const int b = u / ntiles, nt = u % ntiles;
+        for (int item = item0; item < n_items; item += item_step) {
+          int b, nt, sl;
+          decode(item, b, nt, sl);
           const int mb0 = static_cast<int>(static_cast<long long>(sl) * p.m_blks / p.msplit);
           const int mb1 = static_cast<int>(static_cast<long long>(sl + 1) * p.m_blks / p.msplit);
           for (int mb = mb0; mb < mb1; ++mb, ++tile_it) {
@@ -696,6 +736,7 @@ corr_build_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
 
     ptx::tc_fence_before();
     __syncthreads();
+    if constexpr (CL == 2) ptx::cluster_sync_all();    // the peer's commits still arrive on this CTA's barriers until it is done
     if (warp == 2) ptx::tmem_dealloc(tmem_base, 512);
 }
 

@@ -89,6 +89,17 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* m, 
         : "memory");
 }
 
+// the same load delivered to the same shared-memory offset of every CTA in `cta_mask` of this cluster; each destination
+// CTA's mbarrier (same offset) gets the complete_tx for the bytes it received
+__device__ __forceinline__ void tma_load_3d_multicast(uint32_t dst, const CUtensorMap* m, uint32_t bar,
+                                                      int c0, int c1, int c2, uint16_t cta_mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster "
+        "[%0], [%1, {%3, %4, %5}], [%2], %6;"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "h"(cta_mask)
+        : "memory");
+}
+
 // global -> L2 only: warms the cache for a box that a later tma_load_4d will fetch (no shared memory, no barrier)
 __device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap* m, int c0, int c1, int c2, int c3) {
     asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global [%0, {%1, %2, %3, %4}];"
@@ -182,6 +193,13 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
                  ::"r"(bar)
                  : "memory");
+}
+// the same arrive delivered to the barrier at this offset in every CTA of `cta_mask` (single-CTA MMAs, clustered launch)
+__device__ __forceinline__ void umma_commit_multicast(uint32_t bar, uint16_t cta_mask) {
+    asm volatile(
+        "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+        ::"r"(bar), "h"(cta_mask)
+        : "memory");
 }
 // 32 lanes x 16 consecutive fp32 columns: thread i <- lane (base_lane + i), v[j] <- column j.
 __device__ __forceinline__ void tmem_ld_x16(uint32_t taddr, float* v) {

@@ -40,6 +40,10 @@
 #else
 #define RDVC_HAS_EXPERIMENTS 0
 #endif
+// which volume types build with fmap1 multicast across CTA pairs when option key 12 is 0 (auto); set from measurements
+#ifndef RDVC_CLUSTER_DEFAULT
+#define RDVC_CLUSTER_DEFAULT(vol_dtype) false
+#endif
 #ifndef RDVC_SRC_HASH
 #define RDVC_SRC_HASH "unknown"
 #endif
@@ -205,23 +209,45 @@ int ensure_dynamic_smem(K kern, int bytes, std::atomic<unsigned long long>& done
     return RDVC_OK;
 }
 
-template <int MODE, int TY, int TX, typename OutT, int EW>
+template <int MODE, int TY, int TX, typename OutT, int EW, int CL = 1>
 int launch_build(const CUtensorMap& ta, const CUtensorMap* tb, const CUtensorMap* to, const rdvc::BuildParams& p,
                  cudaStream_t st) {
-    auto kern = rdvc::corr_build_kernel<MODE, TY, TX, OutT, EW>;
+    auto kern = rdvc::corr_build_kernel<MODE, TY, TX, OutT, EW, CL>;
     using Cfg = rdvc::BuildCfg<EW>;
     static std::atomic<unsigned long long> attr_done{0};  // per instantiation, one bit per device
     if (int rc = ensure_dynamic_smem(kern, Cfg::SMEM_LAUNCH, attr_done, "cudaFuncSetAttribute(build, max dynamic smem)"))
         return rc;
-    long long grid = sm_count();
-    const long long n_items = static_cast<long long>(p.B) * p.ntiles * p.msplit;
-    if (grid > n_items) grid = n_items;
-    if (g_prof_start) cudaEventRecord(g_prof_start, st);
-    kern<<<static_cast<unsigned>(grid), Cfg::THREADS, Cfg::SMEM_LAUNCH, st>>>(
-        ta, tb[0], tb[1], tb[2], tb[3], to[0], to[1], to[2], to[3], p);
-    if (g_prof_stop) cudaEventRecord(g_prof_stop, st);
+    cudaError_t e;
+    if constexpr (CL == 2) {
+        // clusters of two CTAs that share the fmap1 stream (TMA multicast): items are PAIRS of fmap2 tiles
+        long long grid = sm_count() & ~1;
+        const long long n_items = static_cast<long long>(p.B) * ((p.ntiles + 1) / 2) * p.msplit;
+        if (grid > 2 * n_items) grid = 2 * n_items;
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3(static_cast<unsigned>(grid));
+        cfg.blockDim = dim3(Cfg::THREADS);
+        cfg.dynamicSmemBytes = Cfg::SMEM_LAUNCH;
+        cfg.stream = st;
+        cudaLaunchAttribute attr;
+        attr.id = cudaLaunchAttributeClusterDimension;
+        attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+        cfg.attrs = &attr;
+        cfg.numAttrs = 1;
+        if (g_prof_start) cudaEventRecord(g_prof_start, st);
+        e = cudaLaunchKernelEx(&cfg, kern, ta, tb[0], tb[1], tb[2], tb[3], to[0], to[1], to[2], to[3], p);
+        if (g_prof_stop) cudaEventRecord(g_prof_stop, st);
+    } else {
+        long long grid = sm_count();
+        const long long n_items = static_cast<long long>(p.B) * p.ntiles * p.msplit;
+        if (grid > n_items) grid = n_items;
+        if (g_prof_start) cudaEventRecord(g_prof_start, st);
+        kern<<<static_cast<unsigned>(grid), Cfg::THREADS, Cfg::SMEM_LAUNCH, st>>>(
+            ta, tb[0], tb[1], tb[2], tb[3], to[0], to[1], to[2], to[3], p);
+        if (g_prof_stop) cudaEventRecord(g_prof_stop, st);
+        e = cudaGetLastError();
+    }
     ++g_launches;
-    cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "corr_build_kernel launch");
     return RDVC_OK;
 }
@@ -387,6 +413,7 @@ struct BuildPlan {
     void* memset_ptr;
     size_t memset_bytes;
     bool linear, pair;
+    bool cluster;                            // clusters of two CTAs sharing the fmap1 stream (TMA multicast)
     int tile, ew;
     CUtensorMap ta, tb[rdvc::BLD_MAX_LEVELS], to[rdvc::BLD_MAX_LEVELS], tb2[rdvc::BLD_MAX_LEVELS];
     rdvc::BuildParams p, p2;
@@ -504,12 +531,17 @@ int make_build_plan(const BuildKey& k, BuildPlan* plan) {
     pl.tile = tile;
     const int TY = (tile == 1) ? 16 : 8, TX = (tile == 1) ? 16 : 32;
 
+    // fmap1 multicast across CTA pairs (option key 12: 0 = auto, 1 = one CTA per tile, 3 = clusters of two): linear
+    // mode on a part with an even number of SMs; auto = for the bf16 volume, whose build is bound by the L2 -> SM
+    // operand feed rather than by DRAM writes
+    pl.cluster = pl.linear && sm_count() >= 2 &&
+                 (k.opt_pair == 3 || (k.opt_pair == 0 && RDVC_CLUSTER_DEFAULT(vol_dtype)));
     // TMA descriptors over the repacked maps
     int rc;
     {
         cuuint64_t dims[3] = {(cuuint64_t)D, (cuuint64_t)N, (cuuint64_t)B};
         cuuint64_t str[2] = {(cuuint64_t)D * 2, (cuuint64_t)N * D * 2};
-        cuuint32_t box[3] = {rdvc::BLD_BLOCK_K, rdvc::BLD_BLOCK_M, 1};
+        cuuint32_t box[3] = {rdvc::BLD_BLOCK_K, static_cast<cuuint32_t>(pl.cluster ? rdvc::BLD_BLOCK_M / 2 : rdvc::BLD_BLOCK_M), 1};
         rc = make_tmap(&pl.ta, op_dt, pl.a_km, 3, dims, str, box);
         if (rc) return rc;
     }
@@ -559,14 +591,15 @@ int make_build_plan(const BuildKey& k, BuildPlan* plan) {
     p.ab_format = k.f16_ops ? 0 : 1;
     p.dbg_store_mask = RDVC_HAS_EXPERIMENTS ? k.opt_store_mask : 15;
     p.dbg_policy = RDVC_HAS_EXPERIMENTS ? k.opt_policy : 0;
-    p.msplit = choose_msplit(static_cast<long long>(B) * p.ntiles, p.m_blks, sm_count(), k.opt_msplit);
+    p.msplit = pl.cluster ? choose_msplit(static_cast<long long>(B) * ((p.ntiles + 1) / 2), p.m_blks, sm_count() / 2, k.opt_msplit)
+                          : choose_msplit(static_cast<long long>(B) * p.ntiles, p.m_blks, sm_count(), k.opt_msplit);
 
     // output descriptors (linear mode).  Row pitch a multiple of 128 bytes (always, in the tiled
     // layout): level l as a {128 B, pitch/128, N, B} tensor written in boxes of 16 query rows x 256
     // contiguous bytes.  Row pitch only 16-byte aligned: a {n_l, N, B} tensor, boxes of 32 rows x 128
     // bytes.  Anything else takes the staged-store path.  (option key 5: 0 = staged only, 1 = auto,
     // 2 = never the wide boxes)
-    for (int l = 0; l < rdvc::BLD_MAX_LEVELS; ++l) pl.to[l] = pl.ta;
+    for (int l = 0; l < rdvc::BLD_MAX_LEVELS; ++l) pl.to[l] = pl.tb[0];     // placeholders for levels without a store map
     const int tma_opt = k.opt_tma_out;
     if (pl.linear && tma_opt) {
         const bool f32 = (vol_dtype == RDVC_DT_F32);
@@ -667,7 +700,7 @@ int rdvc_corr_set_option(int key, int value) {
     if (key == 7 && value >= 0 && value <= 4) { g_opt_twl = value; return RDVC_OK; }
     if (key == 8 && value >= 0 && value <= 4) { g_opt_thl = value; return RDVC_OK; }
     if (key == 9 && (value == 0 || value == 4 || value == 8)) { g_opt_epi_warps = value; return RDVC_OK; }
-    if (key == 12 && value >= 0 && value <= 2 && (exp || value != 2)) { g_opt_pair = value; return RDVC_OK; }
+    if (key == 12 && value >= 0 && value <= 3 && (exp || value != 2)) { g_opt_pair = value; return RDVC_OK; }
     if (key == 13 && value >= 0 && value <= 16) { g_opt_mcn_prefetch = value; return RDVC_OK; }
     if (key == 14 && value >= 0 && value <= 2) { g_opt_mcn_kernel = value; return RDVC_OK; }
     return fail(RDVC_E_UNSUPPORTED, "unknown option key=%d value=%d%s", key, value,
@@ -810,6 +843,13 @@ int build_impl(const void* fmap1, const void* fmap2, int B, int D, int h, int w,
     }
 #endif
     // epilogue shape per storage type: see BuildCfg (option key 9: 0 = auto, 4 / 8 = force)
+    if (plan.cluster) {
+        if (vol_dtype == RDVC_DT_F32)
+            return plan.ew == 8 ? launch_build<MODE_LINEAR, 16, 16, float, 8, 2>(ta, tb, to, p, st)
+                                : launch_build<MODE_LINEAR, 16, 16, float, 4, 2>(ta, tb, to, p, st);
+        return plan.ew == 8 ? launch_build<MODE_LINEAR, 16, 16, __nv_bfloat16, 8, 2>(ta, tb, to, p, st)
+                            : launch_build<MODE_LINEAR, 16, 16, __nv_bfloat16, 4, 2>(ta, tb, to, p, st);
+    }
     if (vol_dtype == RDVC_DT_F32)
         return plan.ew == 8 ? launch_build<MODE_LINEAR, 16, 16, float, 8>(ta, tb, to, p, st)
                             : launch_build<MODE_LINEAR, 16, 16, float, 4>(ta, tb, to, p, st);

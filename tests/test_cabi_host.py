@@ -347,3 +347,36 @@ def test_conv1x1_weight_packing(lib):
     assert lib.rdvc_conv1x1_pack_weights(w.ctypes.data_as(ctypes.c_void_p), 48, 4, 4, rc.RDVC_DT_BF16,
                                          w.ctypes.data_as(ctypes.c_void_p)) == -5          # cout % 32 != 0
     assert lib.rdvc_conv1x1_packed_weight_bytes(48, 4, 4) == 0
+
+
+def test_encoder_tail_host_side(lib):
+    """rdvc_linear_pack_weights (host) and the argument validation of the row f-2 entry points (no GPU needed)."""
+    rng = np.random.default_rng(5)
+    wgt = rng.standard_normal((256, 128)).astype(np.float32)
+    for dt, tdt in ((rc.RDVC_DT_BF16, torch.bfloat16), (rc.RDVC_DT_F16, torch.float16)):
+        assert lib.rdvc_linear_packed_weight_bytes(256, 128) == 256 * 128 * 2
+        packed = np.zeros(256 * 128, np.uint16)
+        rc._cabi.check(lib.rdvc_linear_pack_weights(wgt.ctypes.data_as(ctypes.c_void_p), 256, 128, dt,
+                                                    packed.ctypes.data_as(ctypes.c_void_p)), "pack")
+        got = torch.from_numpy(packed.view(np.int16)).view(tdt).float().numpy().reshape(256, 128)
+        assert np.array_equal(got, torch.from_numpy(wgt).to(tdt).float().numpy())
+    assert lib.rdvc_linear_pack_weights(wgt.ctypes.data_as(ctypes.c_void_p), 256, 128, rc.RDVC_DT_F32,
+                                        wgt.ctypes.data_as(ctypes.c_void_p)) == -4
+    one = ctypes.c_void_p(256)          # a non-null, 256-byte aligned dummy: validation runs before any CUDA call
+    big = 1 << 40
+    assert lib.rdvc_corr_pack(None, one, 1, 128, 46, 80, rc.RDVC_DT_F32, rc.RDVC_DT_F32, rc.RDVC_LAYOUT_TILED, 4, one, big, None) == -1
+    assert lib.rdvc_corr_pack(one, one, 1, 96, 46, 80, rc.RDVC_DT_F32, rc.RDVC_DT_F32, rc.RDVC_LAYOUT_TILED, 4, one, big, None) == -5
+    assert lib.rdvc_corr_pack(one, one, 1, 128, 46, 80, rc.RDVC_DT_F32, rc.RDVC_DT_F32, rc.RDVC_LAYOUT_TILED, 4, one, 16, None) == -6
+    assert lib.rdvc_corr_encoder_tail(one, big, 64, one, None, 256, 1, 46, 80, rc.RDVC_DT_BF16, rc.RDVC_DT_F32,
+                                      rc.RDVC_LAYOUT_TILED, 4, one, big, None) == -5          # only 128 -> 256
+    assert lib.rdvc_corr_encoder_tail(one, big, 128, one, None, 256, 1, 46, 80, rc.RDVC_DT_F32, rc.RDVC_DT_F32,
+                                      rc.RDVC_LAYOUT_TILED, 4, one, big, None) == -4          # operands are 16-bit
+    assert lib.rdvc_corr_encoder_tail(one, 16, 128, one, None, 256, 1, 46, 80, rc.RDVC_DT_BF16, rc.RDVC_DT_F32,
+                                      rc.RDVC_LAYOUT_TILED, 4, one, big, None) == -6
+    assert lib.rdvc_corr_build_packed(1, 256, 46, 80, rc.RDVC_DT_F32, one, rc.RDVC_DT_F32, rc.RDVC_LAYOUT_TILED, 4, one, big, None) == -4
+    assert lib.rdvc_corr_build_packed(1, 256, 8, 80, rc.RDVC_DT_BF16, one, rc.RDVC_DT_F32, rc.RDVC_LAYOUT_TILED, 4, one, big, None) == -3
+    assert lib.rdvc_conv1x1(one, rc.RDVC_DT_F32, one, None, 1, 46, 80, 4, 4, 256, 1, one, rc.RDVC_DT_F32, None) == -4
+    assert lib.rdvc_conv1x1(one, rc.RDVC_DT_BF16, one, None, 1, 46, 80, 4, 4, 48, 1, one, rc.RDVC_DT_F32, None) == -5
+    assert lib.rdvc_corr_lookup_ex(one, rc.RDVC_DT_F32, rc.RDVC_LAYOUT_ROWMAJOR, one, 1, 46, 80, 4, 4, one, rc.RDVC_DT_F16, 0, None) == -5
+    assert lib.rdvc_corr_lookup_ex(one, rc.RDVC_DT_F32, rc.RDVC_LAYOUT_TILED, one, 1, 46, 80, 4, 4, one, rc.RDVC_DT_BF16, 0, None) == -4
+    assert lib.rdvc_corr_feat_rows(1, 17, 19) == 328 and lib.rdvc_corr_feat_bytes(1, 17, 19, 4, 4) == 352 * 328 * 2
