@@ -324,9 +324,9 @@ unsigned long long rdvc_corr_plan_cache_hits(void);
  *   key 6: [EXP] L2 policy of the TMA stores (0 default, 1 evict_last, 2 evict_first)
  *   key 7 / 8: experiment: log2 tile width / height of RDVC_LAYOUT_TILED (0 = default)
  *   key 9: build epilogue warps (0 = auto: 8 for an fp32 volume, 4 for bf16; 4; 8)
- *   key 12: build kernel (0 = auto, 1 = one CTA per tile, 3 = clusters of two CTAs that hold neighbouring fmap2 tiles
- *           and share ONE fmap1 stream through TMA multicast (bit-identical results), [EXP] 2 = CTA pairs /
- *           tcgen05 cta_group::2: bit-identical results, measured slower at 1080p)
+ *   key 12: build kernel (0 = auto, 1 = one CTA per tile; [EXP] 2 = CTA pairs / tcgen05 cta_group::2, [EXP] 3 = clusters
+ *           of two CTAs that hold neighbouring fmap2 tiles and share ONE fmap1 stream through TMA multicast: both
+ *           bit-identical, neither faster at 1080p)
  *   key 13: experiment: MCN convolutions pull their boxes into L2 this many tiles ahead with TMA prefetches
  *           (default 0 = off: no effect measured at 1-4, slower beyond)
  *   key 14: MCN convolution kernel (0 = auto, 1 = three activation boxes per tile, 2 = one box per tile

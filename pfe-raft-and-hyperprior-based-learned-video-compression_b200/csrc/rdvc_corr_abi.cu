@@ -40,10 +40,6 @@
 #else
 #define RDVC_HAS_EXPERIMENTS 0
 #endif
-// which volume types build with fmap1 multicast across CTA pairs when option key 12 is 0 (auto); set from measurements
-#ifndef RDVC_CLUSTER_DEFAULT
-#define RDVC_CLUSTER_DEFAULT(vol_dtype) false
-#endif
 #ifndef RDVC_SRC_HASH
 #define RDVC_SRC_HASH "unknown"
 #endif
@@ -531,11 +527,10 @@ int make_build_plan(const BuildKey& k, BuildPlan* plan) {
     pl.tile = tile;
     const int TY = (tile == 1) ? 16 : 8, TX = (tile == 1) ? 16 : 32;
 
-    // fmap1 multicast across CTA pairs (option key 12: 0 = auto, 1 = one CTA per tile, 3 = clusters of two): linear
-    // mode on a part with an even number of SMs; auto = for the bf16 volume, whose build is bound by the L2 -> SM
-    // operand feed rather than by DRAM writes
-    pl.cluster = pl.linear && sm_count() >= 2 &&
-                 (k.opt_pair == 3 || (k.opt_pair == 0 && RDVC_CLUSTER_DEFAULT(vol_dtype)));
+    // fmap1 multicast across CTA pairs (experiments library, option key 12 = 3): bit-identical, measured no faster
+    // (1080p bf16 0.654 -> 0.646 ms, fp32 unchanged, 1440p 9 % slower: DESIGN.md 3.2) -- the L2 -> SM operand feed is
+    // not what bounds the build
+    pl.cluster = RDVC_HAS_EXPERIMENTS && pl.linear && sm_count() >= 2 && k.opt_pair == 3;
     // TMA descriptors over the repacked maps
     int rc;
     {
@@ -700,7 +695,7 @@ int rdvc_corr_set_option(int key, int value) {
     if (key == 7 && value >= 0 && value <= 4) { g_opt_twl = value; return RDVC_OK; }
     if (key == 8 && value >= 0 && value <= 4) { g_opt_thl = value; return RDVC_OK; }
     if (key == 9 && (value == 0 || value == 4 || value == 8)) { g_opt_epi_warps = value; return RDVC_OK; }
-    if (key == 12 && value >= 0 && value <= 3 && (exp || value != 2)) { g_opt_pair = value; return RDVC_OK; }
+    if (key == 12 && value >= 0 && value <= 3 && (exp || value <= 1)) { g_opt_pair = value; return RDVC_OK; }
     if (key == 13 && value >= 0 && value <= 16) { g_opt_mcn_prefetch = value; return RDVC_OK; }
     if (key == 14 && value >= 0 && value <= 2) { g_opt_mcn_kernel = value; return RDVC_OK; }
     return fail(RDVC_E_UNSUPPORTED, "unknown option key=%d value=%d%s", key, value,
@@ -843,6 +838,7 @@ int build_impl(const void* fmap1, const void* fmap2, int B, int D, int h, int w,
     }
 #endif
     // epilogue shape per storage type: see BuildCfg (option key 9: 0 = auto, 4 / 8 = force)
+#ifdef RDVC_EXPERIMENTS
     if (plan.cluster) {
         if (vol_dtype == RDVC_DT_F32)
             return plan.ew == 8 ? launch_build<MODE_LINEAR, 16, 16, float, 8, 2>(ta, tb, to, p, st)
@@ -850,6 +846,7 @@ int build_impl(const void* fmap1, const void* fmap2, int B, int D, int h, int w,
         return plan.ew == 8 ? launch_build<MODE_LINEAR, 16, 16, __nv_bfloat16, 8, 2>(ta, tb, to, p, st)
                             : launch_build<MODE_LINEAR, 16, 16, __nv_bfloat16, 4, 2>(ta, tb, to, p, st);
     }
+#endif
     if (vol_dtype == RDVC_DT_F32)
         return plan.ew == 8 ? launch_build<MODE_LINEAR, 16, 16, float, 8>(ta, tb, to, p, st)
                             : launch_build<MODE_LINEAR, 16, 16, float, 4>(ta, tb, to, p, st);

@@ -308,7 +308,7 @@ def test_stale_library_is_refused(tmp_path, monkeypatch):
 def test_product_build_has_no_work_skipping_knobs(lib):
     if rc._cabi.has_experiments():
         pytest.skip("experiments build")
-    for key, value in [(0, 3), (0, 4), (3, 7), (4, 1), (6, 1), (12, 2)]:
+    for key, value in [(0, 3), (0, 4), (3, 7), (4, 1), (6, 1), (12, 2), (12, 3)]:
         assert lib.rdvc_corr_set_option(key, value) == -5, (key, value)
     for key, value in [(0, 0), (3, 15), (4, 2), (4, 0), (6, 0), (12, 0), (12, 1)]:
         assert lib.rdvc_corr_set_option(key, value) == 0, (key, value)

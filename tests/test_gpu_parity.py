@@ -238,6 +238,7 @@ def test_build_cluster_multicast_is_bit_identical(lib, vol):
     """fmap1 TMA-multicast across CTA pairs (option key 12 = 3): two CTAs holding neighbouring fmap2 tiles share one
     fmap1 stream.  Same MMAs, same K order: the pyramid must be bit-identical to the one-CTA-per-tile build, incl. an
     odd number of tiles (the last cluster's second CTA owns no tile), partial m-blocks, B > 1 and forced m-splits."""
+    need_experiments()
     for (B, D, h, w) in [(1, 64, 16, 16), (2, 64, 18, 22), (1, 128, 33, 47), (1, 256, 46, 80), (3, 64, 24, 40)]:
         f1, f2 = cn.synth_fmaps(B, D, h, w, seed=19)
         for msplit in (0, 3):

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """fmap1 multicast across CTA pairs (option key 12 = 3) vs one CTA per tile (= 1): equality on small shapes, timing of the
-build kernel alone (the library's profile events) at 720p / 1080p / 1440p for both volume types.  Product library."""
+build kernel alone (the library's profile events) at 720p / 1080p / 1440p for both volume types.  Experiments library (RDVC_CORR_LIB=.../librdvc_corr_exp.so)."""
 import os, sys
 ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
 sys.path.insert(0, ROOT)
