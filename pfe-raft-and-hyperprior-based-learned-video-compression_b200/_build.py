@@ -51,6 +51,7 @@ def sources():
 def source_hash() -> str:
     """SHA-256 over (relative name, content) of every source of the library."""
     h = hashlib.sha256()
+    h.update(" ".join(NVCC_FLAGS).encode())          # a change of compiler flags is a change of the binary
     for path in sources():
         h.update(os.path.relpath(path, os.path.join(PKG_DIR, "..")).encode())
         h.update(b"\0")
