@@ -210,8 +210,7 @@ def _span_stream(num_frames, interval, world, enc_p_factory=None, batch=4, batch
     # emulate the multi-rank gather in one process: rank 0 receives every rank's (bytes, tail_failed)
     import unittest.mock as um
     fake = list(zip(out, failed))
-    with um.patch("torch.distributed.gather_object",
-                  lambda obj, lst, dst=0, group=None: lst.__setitem__(slice(None), fake)):
+    with um.patch.object(gs, "_gather_bytes", lambda local, flag, rank, world, group=None: fake):
         return gs.gather_spans(out[0], failed[0], spans, {"rdvc_version": "1.0"}, 0, world,
                                reencode_iframe=lambda t: enc_i(frames(t)))
 
