@@ -244,9 +244,13 @@ def test_span_sharding_failure_rule_across_a_cut():
             assert _span_stream(n, I, world, factory) == serial, (bad, world)
 
 
-def _span_worker(rank, world, port, num_frames, interval, out_path):
+def _span_worker(rank, world, port, num_frames, interval, out_path, shm=False):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
+    if shm:
+        os.environ["LOCAL_WORLD_SIZE"] = str(world)     # what torchrun sets on a single node
+    else:
+        os.environ.pop("LOCAL_WORLD_SIZE", None)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     frames, enc_i, enc_p = _fake_encoders()
     spans = gs.assign_frames(num_frames, interval, world)
@@ -264,11 +268,18 @@ def _span_worker(rank, world, port, num_frames, interval, out_path):
 
 
 @pytest.mark.timeout(180)
-def test_two_rank_span_gather_equals_serial(tmp_path):
+@pytest.mark.parametrize("shm", [False, True], ids=["tensor-gather", "dev-shm"])
+def test_two_rank_span_gather_equals_serial(tmp_path, shm):
+    """Both host-side routes of the byte gather (gloo tensors; /dev/shm files on a single node) over real processes."""
+    if shm and not os.access("/dev/shm", os.W_OK):
+        pytest.skip("/dev/shm not writable")
     out = str(tmp_path / "two_rank_spans.rdvc")
-    mp.spawn(_span_worker, args=(2, _free_port(), 47, 5, out), nprocs=2, join=True)
+    port = _free_port()
+    mp.spawn(_span_worker, args=(2, port, 47, 5, out, shm), nprocs=2, join=True)
     with open(out, "rb") as f:
         assert f.read() == _serial_stream(47, 5, {"rdvc_version": "1.0"})
+    import glob
+    assert not glob.glob(f"/dev/shm/rdvc_gather_{port}_*")          # rank 0 removed what it read
 
 
 def test_encode_gop_logs_and_reraises_fatal_errors(caplog):
