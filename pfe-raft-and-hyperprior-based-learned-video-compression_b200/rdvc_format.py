@@ -83,6 +83,30 @@ def write_stream(metadata: dict, frame_bytes: Iterable[bytes]) -> bytes:
     return b"".join((META_MARKER, struct.pack(_U32, len(meta)), meta, *frame_bytes, EOF_MARKER))
 
 
+class StreamParts:
+    """A complete `.rdvc` stream as the pieces its writer emits in order -- header, packed frame records (any
+    bytes-like objects, e.g. memory-mapped per-rank buffers), end marker -- without concatenating them: the reference
+    itself writes metadata, frame buffer and end marker with three `f.write` calls (R:codec_processing.py:1556-1568)."""
+
+    def __init__(self, metadata: dict, frame_bytes: Iterable):
+        meta = json.dumps(metadata, indent=4).encode("utf-8")
+        self.header = b"".join((META_MARKER, struct.pack(_U32, len(meta)), meta))
+        self.chunks = list(frame_bytes)
+
+    def __len__(self) -> int:
+        return len(self.header) + sum(len(c) for c in self.chunks) + len(EOF_MARKER)
+
+    def write_to(self, f) -> int:
+        f.write(self.header)
+        for c in self.chunks:
+            f.write(c)
+        f.write(EOF_MARKER)
+        return len(self)
+
+    def tobytes(self) -> bytes:
+        return b"".join((self.header, *self.chunks, EOF_MARKER))
+
+
 def read_stream(data: bytes) -> Tuple[dict, List[FrameRecord]]:
     s = io.BytesIO(data)
     if s.read(len(META_MARKER)) != META_MARKER:

@@ -314,3 +314,17 @@ def test_scan_frames_matches_the_copying_reader():
         fmt.scan_frames(data[:-3])
     with pytest.raises(ValueError, match="FRAME marker"):
         fmt.scan_frames(b"BADMARK_" + b"\0" * 20)
+
+
+def test_stream_parts_equal_write_stream():
+    recs = [fmt.FrameRecord(0, "I", fmt.iframe_payload(b"abc")).pack(), fmt.FrameRecord(1, "P", fmt.pframe_payload((2, 3), b"mm", (4, 6), b"r")).pack()]
+    want = fmt.write_stream({"rdvc_version": "1.0", "n": 2}, recs)
+    parts = fmt.StreamParts({"rdvc_version": "1.0", "n": 2}, [memoryview(recs[0]), bytearray(recs[1])])
+    assert parts.tobytes() == want and len(parts) == len(want)
+    buf = io.BytesIO()
+    assert parts.write_to(buf) == len(want) and buf.getvalue() == want
+    frames, enc_i, enc_p = _fake_encoders()
+    spans = gs.assign_frames(12, 4, 1)
+    data, tail = gs.encode_span(spans[0], 4, frames, enc_i, enc_p)
+    p = gs.gather_spans(data, tail, spans, {"rdvc_version": "1.0"}, as_parts=True)
+    assert isinstance(p, fmt.StreamParts) and p.tobytes() == _serial_stream(12, 4, {"rdvc_version": "1.0"})
