@@ -454,6 +454,7 @@ def run_ours(args):
         if gop_line is not None:
             line["gop_sharded"] = {k: gop_line[k] for k in ("metric", "value", "unit", "n_gpus", "scaling", "p_frames",
                                                              "seconds_total_max_over_ranks", "seconds_encode_max_over_ranks",
+                                                             "rank0_p_frames_per_s", "epe_vs_stock_px",
                                                              "stream_bytes", "total_pframe_payload_bytes", "config")}
         if world == 1 and not args.no_gpu_baseline:
             line["gpu_library_baseline"] = gpu_library_pair_ms(dev)

@@ -254,10 +254,27 @@ def run_sharded(args, own_process_group=True):
                        "payload": ("motion: 1/8-resolution quantised flow through the factorised-prior range coder stand-in "
                                    "(bitstream parity unpinned: compressai absent); codec networks out of scope" if args.entropy
                                    else "placeholder int8 dump (codec networks out of scope)"),
-                       "collective": "none on the data path; host-side gather_object of per-rank byte strings (gloo)"},
+                       "feature_encoder_tail_fused": True,
+                       "collective": "none on the data path; host-side gather of per-rank byte strings into the writer "
+                                     "(/dev/shm files on one node, gloo tensors otherwise)"},
             "seconds_total_max_over_ranks": times[0].item(), "seconds_encode_max_over_ranks": times[1].item(),
             "p_frames": n_p, "stream_bytes": len(stream), "total_frames_processed": meta["total_frames_processed"],
+            # "one rank's rate": rank 0's own P-frames over its own encode time, inside this run
+            "rank0_p_frames_per_s": (sum(1 for t in spans[0] if not gs.is_iframe(t, args.gop)) if by_frames
+                                     else sum(g_.num_pframes for g_ in mine)) / max(t_local, 1e-9),
         }
+        # flow end-point error of this configuration against STOCK torchvision RAFT (same weights, same autocast
+        # setting) on one frame pair of the sequence -- outside the timed region
+        a, b = frame_at(big, 3, h, w), frame_at(big, 4, h, w)
+        with torch.no_grad(), ctx():
+            ours_flow = rc.raft_flow(model, a, b, 12, fuse_convcorr1=args.fuse_convcorr1)
+        model.corr_block.release()
+        torch.manual_seed(0)
+        stock = raft_large(weights=None).eval().to(dev)
+        with torch.no_grad(), ctx():
+            stock_flow = stock(a, b, num_flow_updates=12)[-1]
+        line["epe_vs_stock_px"] = (ours_flow.float() - stock_flow.float()).pow(2).sum(1).sqrt().mean().item()
+        del stock, stock_flow, ours_flow
         line["total_pframe_payload_bytes"] = meta["total_pframe_payload_bytes"]
     if runner is not None:
         runner.release()
