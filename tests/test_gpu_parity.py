@@ -749,7 +749,14 @@ def test_build_from_encoder_tail(lib, shape, vol):
     assert err16 < TOL_VOLUME, err16
     with pytest.raises(ValueError, match="input channels"):
         blk.build_pyramid_from_encoder(x1[:, :64], x2[:, :64], W, bias)
+    # the interchange layout (no padding rows): the same numbers, bit for bit
+    blk.build_pyramid_from_encoder(x1, x2, W, bias)
+    row = rc.TVCorrBlock(volume_dtype=vol, layout=ROW)
+    row.build_pyramid_from_encoder(x1, x2, W, bias)
+    for l in range(L):
+        assert torch.equal(row._pyr.level(l), blk._pyr.level(l)), l
     blk.release()
+    row.release()
 
 
 def test_build_plan_cache(lib):
