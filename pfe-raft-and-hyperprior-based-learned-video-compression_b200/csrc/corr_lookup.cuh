@@ -115,6 +115,27 @@ __device__ __forceinline__ void select_row_vec_f32(RowWords<R2>& rw, long long r
     }
 }
 
+// 16-byte volume load of the tiled kernel.  RDVC_LKP_LD (experiment, compile-time): 0 = ld.global.nc (default),
+// 1 / 2 = the same with an L2 prefetch-size hint of 128 / 256 bytes (pulls the neighbouring tiles of the same tile
+// row into L2 with the missing one).  Measured at 1080p (tools/exp_lookup_ld.py, round 2): 128 B no change (29.7 vs
+// 29.8 us fp32, 20.1 vs 20.1 bf16), 256 B 8 % slower -- bigger DRAM bursts do not buy back the extra bytes.
+#ifndef RDVC_LKP_LD
+#define RDVC_LKP_LD 0
+#endif
+__device__ __forceinline__ uint4 lkp_ld16(const void* p) {
+#if RDVC_LKP_LD == 1
+    uint4 v;
+    asm volatile("ld.global.nc.L2::128B.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+#elif RDVC_LKP_LD == 2
+    uint4 v;
+    asm volatile("ld.global.nc.L2::256B.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+#else
+    return __ldg(reinterpret_cast<const uint4*>(p));
+#endif
+}
+
 // ---- RDVC_LAYOUT_TILED rows -------------------------------------------------
 // Footprint columns [xa, xa + R2) of image row y are covered by NV aligned 16-byte words;
 // word k starts at column x0 = (xa & ~(EPW-1)) + k * EPW, which never straddles a tile
@@ -288,7 +309,7 @@ corr_lookup_tiled_kernel(const __grid_constant__ LookupParams p) {
 #pragma unroll
         for (int k = 0; k < NV; ++k) {
             uint4 v = make_uint4(0u, 0u, 0u, 0u);
-            if (live && okx[k]) v = __ldg(reinterpret_cast<const uint4*>(img + (rowpart + colpart[k])));
+            if (live && okx[k]) v = lkp_ld16(img + (rowpart + colpart[k]));
             tr.wd[k] = v;
         }
     };
