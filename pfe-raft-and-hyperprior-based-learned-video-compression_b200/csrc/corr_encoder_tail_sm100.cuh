@@ -18,8 +18,10 @@
 // output are single buffers of 256- / 512-byte rows, so ONE 2-D tensor map addresses every input tile by its row
 // number.  Persistent CTAs, one per SM: the whole weight matrix (256 x 128 x 2 B = 64 KB, two 128B-swizzled
 // k-blocks) stays in shared memory; 128-row tiles stream through a 4-stage 16 KB ring; tcgen05.mma M128 x N256 x
-// K16, fp32 accumulators double-buffered in TMEM; eight epilogue warps: tcgen05.ld -> + bias -> 16-bit pack ->
-// swizzled 4 KB shared-memory transpose per warp -> 16-byte stores that cover whole 128-byte lines of the rows.
+// K16, fp32 accumulators double-buffered in TMEM; sixteen epilogue warps (the epilogue is a latency chain -- TMEM
+// load, convert, shared-memory transpose, store -- so it wants warps, not instructions: 8 warps x 2 passes measured
+// 20.5 us per launch under ncu): tcgen05.ld -> + bias -> 16-bit pack -> swizzled 4 KB shared-memory transpose per
+// warp -> 16-byte stores that cover whole 128-byte lines of the rows.
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -38,7 +40,7 @@ constexpr int ET_KB = ET_K / 64;                 // 2 k-blocks
 constexpr int ET_A_STAGES = 4;
 constexpr int ET_A_STAGE_BYTES = ET_BLOCK_M * 64 * 2;     // 16 KB
 constexpr int ET_W_SLAB_BYTES = ET_N * 64 * 2;            // 32 KB
-constexpr int ET_EPI_WARPS = 8;
+constexpr int ET_EPI_WARPS = 16;                // four per TMEM lane quarter, 64 output channels each
 constexpr int ET_THREADS = 128 + ET_EPI_WARPS * 32;
 constexpr int ET_STG_BYTES = 32 * 128;                    // per epilogue warp: 32 rows x 64 channels x 2 B
 constexpr int ET_SMEM_W = 0;
@@ -174,14 +176,14 @@ corr_encoder_tail_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
         }
     } else if (warp >= 4) {
         // ===================== epilogue =====================
-        // warp 4 + e: TMEM lane quarter q = e % 4 (rows 32 q .. 32 q + 31 of the tile), channel half e / 4 (128 channels,
-        // two passes of 64).  Out of TMEM a thread is one row; its 64 channels of a pass (128 bytes of 16-bit values) go
+        // warp 4 + e: TMEM lane quarter q = e % 4 (rows 32 q .. 32 q + 31 of the tile), channel quarter e / 4 (64 channels,
+        // one pass).  Out of TMEM a thread is one row; its 64 channels (128 bytes of 16-bit values) go
         // to row `lane` of the warp's buffer with the 16-byte chunk index XORed by (lane & 7) (conflict-free both
         // ways); then lane l re-reads chunk l % 8 of rows 4 k + l / 8 and stores it: a warp-wide store = four whole
         // 128-byte lines of four consecutive output rows.
         const int e = warp - 4;
         const int q = e & 3;
-        const int ch_half = (e >> 2) * (ET_N / 2);
+        const int ch_half = (e >> 2) * (ET_N / 4);        // first channel of this warp's quarter
         const uint32_t stg = s_stg + e * ET_STG_BYTES;
         uint8_t* const out = static_cast<uint8_t*>(p.out);
         uint32_t tile_it = 0;
@@ -203,12 +205,12 @@ corr_encoder_tail_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
             ptx::tc_fence_after();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * ET_N + ch_half;
 #pragma unroll
-            for (int pass = 0; pass < 2; ++pass) {
+            for (int pass = 0; pass < 1; ++pass) {
                 float v[64];
 #pragma unroll
                 for (int k = 0; k < 4; ++k) ptx::tmem_ld_x16(taddr + pass * 64 + k * 16, v + k * 16);
                 ptx::tmem_ld_wait();
-                if (pass == 1) {
+                if (pass == 0) {
                     ptx::tc_fence_before();
                     __syncwarp();
                     if (lane == 0) ptx::mbar_arrive_relaxed(bar(T_EMPTY + acc));   // global stores are in flight: no MEMBAR
