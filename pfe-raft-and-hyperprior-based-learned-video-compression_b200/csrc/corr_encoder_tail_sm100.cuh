@@ -65,7 +65,15 @@ struct EncoderTailParams {
     void* out;              // [rows][256] 16-bit
     const float* bias;      // 256 floats on the device, or nullptr
     int ab_format;          // 1 = bf16, 0 = fp16 (operands and output)
+    unsigned long long* dbg_timeline;   // RDVC_EXPERIMENTS builds only: 16 globaltimer stamps per CTA (nullptr = off)
 };
+
+#ifdef RDVC_EXPERIMENTS
+#define ET_STAMP(slot) do { if (p.dbg_timeline) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_) :: "memory"); \
+                                                   p.dbg_timeline[blockIdx.x * 16 + (slot)] = t_; } } while (0)
+#else
+#define ET_STAMP(slot) ((void)0)
+#endif
 
 // grid: min(SMs, n_tiles) CTAs; block: ET_THREADS; dynamic smem: ET_SMEM_LAUNCH.
 // tm_a: the packed input as a {128, total rows, 1} tensor, box {64, 128, 1}; tm_w: weights {128, 256, 1}, box {64, 256, 1}.
@@ -89,6 +97,7 @@ corr_encoder_tail_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
     const int lane = threadIdx.x & 31;
 
     if (warp == 0 && lane == 0) {
+        ET_STAMP(0);                                     // entry
         ptx::prefetch_tensormap(&tm_a);
         ptx::prefetch_tensormap(&tm_w);
     }
@@ -116,6 +125,7 @@ corr_encoder_tail_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
     ptx::tc_fence_after();
     uint32_t tmem_base;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot_addr) : "memory");
+    if (warp == 0 && lane == 0) ET_STAMP(1);             // set-up done
 
     auto seg_of = [&](int tile) {
         int s = 0;
@@ -150,6 +160,7 @@ corr_encoder_tail_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
         const uint32_t idesc = ptx::umma_idesc(ET_BLOCK_M, ET_N, p.ab_format);
         ptx::mbar_wait(bar(W_FULL), 0);
         ptx::tc_fence_after();
+        if (lane == 0) ET_STAMP(2);                      // weights landed
         const uint64_t b_desc0 = ptx::umma_desc_k_sw128(s_w);
         uint32_t a_it = 0, tile_it = 0;
         for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++tile_it) {
@@ -162,6 +173,7 @@ corr_encoder_tail_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
                 const uint32_t st = a_it % ET_A_STAGES, ph = (a_it / ET_A_STAGES) & 1;
                 ptx::mbar_wait(bar(A_FULL + st), ph);
                 ptx::tc_fence_after();
+                if (lane == 0 && kb == ET_KB - 1 && tile_it < 5) ET_STAMP(3 + tile_it);    // tile's operands landed (3..7)
                 const uint64_t a_desc0 = ptx::umma_desc_k_sw128(s_a + st * ET_A_STAGE_BYTES);
                 const uint64_t b_desc = b_desc0 + ((kb * ET_W_SLAB_BYTES) >> 4);
                 if (ptx::elect_one()) {
@@ -204,6 +216,7 @@ corr_encoder_tail_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
             ptx::mbar_wait(bar(T_FULL + acc), acc_ph);
             ptx::tc_fence_after();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * ET_N + ch_half;
+            if (e == 0 && lane == 0 && tile_it < 4) ET_STAMP(8 + 2 * tile_it);            // accumulator ready (8, 10, 12, 14)
 #pragma unroll
             for (int pass = 0; pass < 1; ++pass) {
                 float v[64];
@@ -247,6 +260,7 @@ corr_encoder_tail_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
                 }
                 __syncwarp();
             }
+            if (e == 0 && lane == 0 && tile_it < 4) ET_STAMP(9 + 2 * tile_it);            // this warp's stores issued (9, 11, 13, 15)
         }
     }
 

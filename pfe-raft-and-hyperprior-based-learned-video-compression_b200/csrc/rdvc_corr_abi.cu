@@ -968,6 +968,7 @@ int rdvc_corr_encoder_tail(const void* ws_in, size_t ws_in_bytes, int D_in, cons
     p.n_tiles = tiles;
     p.twl = li.twl; p.thl = li.thl;
     p.out = ws_out; p.bias = bias; p.ab_format = (op_dtype == RDVC_DT_F16) ? 0 : 1;
+    p.dbg_timeline = RDVC_HAS_EXPERIMENTS ? g_dbg_timeline.load() : nullptr;
     const CUtensorMapDataType op_dt = (op_dtype == RDVC_DT_F16) ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
     CUtensorMap tm_a, tm_w;
     {
