@@ -119,6 +119,19 @@ __device__ __forceinline__ float lds_f32(uint32_t addr) {
     asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
     return v;
 }
+// Loads of shared memory that is READ-ONLY after the kernel's set-up barrier (the bias): not volatile, no memory clobber,
+// so the compiler may hoist and batch them instead of issuing load -> wait -> use one at a time (the encoder tail's
+// epilogue spent 2.2 us per tile on 128 such chains).
+__device__ __forceinline__ float lds_ro_f32(uint32_t addr) {
+    float v;
+    asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ float4 lds_ro_f32x4(uint32_t addr) {
+    float4 v;
+    asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
 __device__ __forceinline__ float4 lds_f32x4(uint32_t addr) {
     float4 v;
     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
@@ -142,7 +155,6 @@ corr_conv1x1_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
         (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
     const uint32_t s_w = ptx::smem_u32(smem + C1_SMEM_W);
     const uint32_t s_a = ptx::smem_u32(smem + C1_SMEM_A);
-    float* bias_s = reinterpret_cast<float*>(smem + C1_SMEM_BIAS);
     const uint32_t s_stg = ptx::smem_u32(smem + C1_SMEM_STG);
     // the bias is read with explicit ld.shared: through the generic pointer the compiler emitted LD.E (generic loads, a
     // long-scoreboard wait in front of every FADD of the epilogue -- half of its samples in the profile)
@@ -179,9 +191,8 @@ corr_conv1x1_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
         ptx::tmem_alloc_2sm(ptx::smem_u32(const_cast<uint32_t*>(tmem_slot)), 512);
         ptx::tmem_relinquish_2sm();
     }
-    if (warp == 3) {
-        for (int i = lane; i < p.cout; i += 32) bias_s[i] = p.bias ? __ldg(p.bias + i) : 0.f;
-    }
+    if (warp >= 4 && static_cast<int>(threadIdx.x) - 128 < p.cout)       // one element per thread: ONE global round trip
+        sts_f32(s_bias + (threadIdx.x - 128) * 4, p.bias ? __ldg(p.bias + (threadIdx.x - 128)) : 0.f);
     ptx::tc_fence_before();
     __syncthreads();
     ptx::cluster_sync_relaxed_arrive();   // the peer's barriers are initialised (and fenced) before anyone signals them
@@ -329,7 +340,7 @@ corr_conv1x1_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
                         if (4 * k < nch) {
                             const int r = 4 * k + rsub;
                             const float4 x = lds_f32x4(stg + (r * 32 + px4) * 4);
-                            const float bb = lds_f32(s_bias + (ch0 + c + r) * 4);
+                            const float bb = lds_ro_f32(s_bias + (ch0 + c + r) * 4);
                             float a0 = x.x + bb, a1 = x.y + bb, a2 = x.z + bb, a3 = x.w + bb;
                             if (p.relu) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); a2 = fmaxf(a2, 0.f); a3 = fmaxf(a3, 0.f); }
                             if (ok4 && !C1_DBG(1)) c1_store4(d4, a0, a1, a2, a3);
@@ -342,7 +353,7 @@ corr_conv1x1_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
 #pragma unroll
                     for (int i = 0; i < 32; ++i) {
                         if (i < nch) {
-                            float x = v[i] + lds_f32(s_bias + (ch0 + c + i) * 4);
+                            float x = v[i] + lds_ro_f32(s_bias + (ch0 + c + i) * 4);
                             if (p.relu) x = fmaxf(x, 0.f);
                             if (ok) *ds = c1_cvt<OutT>(x);
                             ds += p.n_pix;

@@ -117,9 +117,8 @@ corr_encoder_tail_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
         ptx::tmem_alloc(tmem_slot_addr, 512);
         ptx::tmem_relinquish();
     }
-    if (warp == 3) {
-        for (int i = lane; i < ET_N; i += 32) sts_f32(s_bias + i * 4, p.bias ? __ldg(p.bias + i) : 0.f);
-    }
+    if (warp >= 4 && threadIdx.x - 128 < ET_N)          // one element per thread: ONE global round trip (a single warp
+        sts_f32(s_bias + (threadIdx.x - 128) * 4, p.bias ? __ldg(p.bias + (threadIdx.x - 128)) : 0.f);   // looping cost 2 us)
     ptx::tc_fence_before();
     __syncthreads();
     ptx::tc_fence_after();
@@ -230,10 +229,14 @@ corr_encoder_tail_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
                 }
                 uint32_t pk[32];
 #pragma unroll
+                for (int i4 = 0; i4 < 16; ++i4) {               // bias: 16 vector loads the compiler is free to batch
+                    const float4 bb = lds_ro_f32x4(s_bias + (ch_half + pass * 64 + 4 * i4) * 4);
+                    v[4 * i4] += bb.x * bias_on; v[4 * i4 + 1] += bb.y * bias_on;
+                    v[4 * i4 + 2] += bb.z * bias_on; v[4 * i4 + 3] += bb.w * bias_on;
+                }
+#pragma unroll
                 for (int i = 0; i < 32; ++i) {
-                    const float b0 = lds_f32(s_bias + (ch_half + pass * 64 + 2 * i) * 4) * bias_on;
-                    const float b1 = lds_f32(s_bias + (ch_half + pass * 64 + 2 * i + 1) * 4) * bias_on;
-                    const float x0 = v[2 * i] + b0, x1 = v[2 * i + 1] + b1;
+                    const float x0 = v[2 * i], x1 = v[2 * i + 1];
                     if (p.ab_format) {
                         const __nv_bfloat162 t2 = __floats2bfloat162_rn(x0, x1);
                         pk[i] = *reinterpret_cast<const uint32_t*>(&t2);
