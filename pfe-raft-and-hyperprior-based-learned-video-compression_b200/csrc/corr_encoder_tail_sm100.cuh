@@ -205,7 +205,7 @@ corr_encoder_tail_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
             const long long rme = rseg0 + lane;
             float bias_on = 1.f;
             if (p.tiles_w[s] > 0) {
-                const int r_img = static_cast<int>(rme % p.img[s]);
+                const int r_img = static_cast<int>(static_cast<unsigned>(rme) % static_cast<unsigned>(p.img[s]));   // rows < 2^31 (ABI check)
                 const int tl = r_img >> (p.twl + p.thl), in = r_img & ((1 << (p.twl + p.thl)) - 1);
                 const int ty = tl / p.tiles_w[s], tx = tl - ty * p.tiles_w[s];
                 const int y = (ty << p.thl) + (in >> p.twl), x = (tx << p.twl) + (in & ((1 << p.twl) - 1));
@@ -234,14 +234,17 @@ corr_encoder_tail_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
                     v[4 * i4] += bb.x * bias_on; v[4 * i4 + 1] += bb.y * bias_on;
                     v[4 * i4 + 2] += bb.z * bias_on; v[4 * i4 + 3] += bb.w * bias_on;
                 }
+                if (p.ab_format) {                               // one uniform branch, not 64 predicated clamps
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const float x0 = v[2 * i], x1 = v[2 * i + 1];
-                    if (p.ab_format) {
-                        const __nv_bfloat162 t2 = __floats2bfloat162_rn(x0, x1);
+                    for (int i = 0; i < 32; ++i) {
+                        const __nv_bfloat162 t2 = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
                         pk[i] = *reinterpret_cast<const uint32_t*>(&t2);
-                    } else {
-                        const __half2 t2 = __floats2half2_rn(fminf(fmaxf(x0, -65504.f), 65504.f), fminf(fmaxf(x1, -65504.f), 65504.f));
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        const __half2 t2 = __floats2half2_rn(fminf(fmaxf(v[2 * i], -65504.f), 65504.f),
+                                                             fminf(fmaxf(v[2 * i + 1], -65504.f), 65504.f));
                         pk[i] = *reinterpret_cast<const uint32_t*>(&t2);
                     }
                 }
@@ -251,15 +254,17 @@ corr_encoder_tail_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
                                  "r"(pk[4 * c]), "r"(pk[4 * c + 1]), "r"(pk[4 * c + 2]), "r"(pk[4 * c + 3]) : "memory");
                 __syncwarp();
                 const int cch = lane & 7, rsub = lane >> 3;
+                // one 64-bit base per tile; a store is base + r * 512 under a 32-bit row bound
+                uint8_t* const obase = out + (p.out_row0[s] + rseg0) * (ET_N * 2) + (ch_half + pass * 64) * 2 + cch * 16;
+                const long long left = p.rows[s] - rseg0;
+                const int nvalid = left > 32 ? 32 : (left < 0 ? 0 : static_cast<int>(left));
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
                     const int r = 4 * k + rsub;
                     uint4 w;
                     asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w.x), "=r"(w.y), "=r"(w.z), "=r"(w.w)
                                  : "r"(stg + r * 128 + ((cch ^ (r & 7)) << 4)) : "memory");
-                    const long long rr = rseg0 + r;
-                    if (rr < p.rows[s])
-                        *reinterpret_cast<uint4*>(out + (p.out_row0[s] + rr) * (ET_N * 2) + (ch_half + pass * 64) * 2 + cch * 16) = w;
+                    if (r < nvalid) *reinterpret_cast<uint4*>(obase + r * (ET_N * 2)) = w;
                 }
                 __syncwarp();
             }
