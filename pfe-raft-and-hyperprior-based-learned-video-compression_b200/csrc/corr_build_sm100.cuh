@@ -46,6 +46,15 @@ constexpr int BLD_UMMA_K = 16;
 #ifndef RDVC_EW4_STG_BUFS
 #define RDVC_EW4_STG_BUFS 2
 #endif
+// Round 2, 8-warp shape at 1080p (tools/exp_epi_shapes.py): 3 stages + 1 buffer fp32 0.958 / bf16 0.710 ms; 4 + 1:
+// 1.011 / 0.650; 2 + 2: 1.187 / 0.990 (the ring starves) -- against 0.982 / 0.632 for the 4-warp shape (4 + 2).  So:
+// fp32 volume -> 8 warps, 3 + 1; bf16 volume -> 4 warps, 4 + 2, as before.
+#ifndef RDVC_EW8_A_STAGES      // the same knobs for the 8-warp shape (3 stages + 1 buffer by default)
+#define RDVC_EW8_A_STAGES 3
+#endif
+#ifndef RDVC_EW8_STG_BUFS
+#define RDVC_EW8_STG_BUFS 1
+#endif
 constexpr int BLD_MAX_KC = 4;    // D <= 256
 constexpr int BLD_A_STAGE_BYTES = BLD_BLOCK_M * BLD_BLOCK_K * 2;  // 16 KB
 constexpr int BLD_B_SLAB_BYTES = BLD_BLOCK_N * BLD_BLOCK_K * 2;   // 32 KB
@@ -69,13 +78,14 @@ struct BuildCfg {
     static_assert(EW == 4 || EW == 8, "epilogue warps");
     static constexpr int EPI_WARPS = EW;
     static constexpr int SUBS = 8 / EW;                 // 128-column halves of a tile per epilogue warp
-    static constexpr int STG_BUFS = (EW == 4) ? RDVC_EW4_STG_BUFS : 1;   // staging buffers per epilogue warp
-    static constexpr int A_STAGES = (EW == 4) ? RDVC_EW4_A_STAGES : 3;   // fmap1 ring stages (16 KB each)
+    static constexpr int STG_BUFS = (EW == 4) ? RDVC_EW4_STG_BUFS : RDVC_EW8_STG_BUFS;   // staging buffers per epilogue warp
+    static constexpr int A_STAGES = (EW == 4) ? RDVC_EW4_A_STAGES : RDVC_EW8_A_STAGES;   // fmap1 ring stages (16 KB each)
     static constexpr int THREADS = 128 + EW * 32;
     static constexpr int SMEM_STG = BLD_SMEM_A + A_STAGES * BLD_A_STAGE_BYTES;
     static constexpr int SMEM_BAR = SMEM_STG + EW * BLD_STG_BYTES * STG_BUFS;
     static constexpr int SMEM_TOTAL = SMEM_BAR + 128;
     static constexpr int SMEM_LAUNCH = SMEM_TOTAL + 1024;  // slack for 1024-byte alignment
+    static_assert(SMEM_LAUNCH <= 232448, "shared memory: 227 KB per CTA");
 };
 
 struct BuildParams {
