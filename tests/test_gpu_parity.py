@@ -865,6 +865,63 @@ def test_no_out_of_bounds_writes(lib, mode, layout, vol):
     set_opts(lib, mode=0, lookup=0)
 
 
+@pytest.mark.parametrize("fdt", [torch.float16, torch.bfloat16])
+def test_no_out_of_bounds_writes_round2_entry_points(lib, fdt):
+    """The same canary check for the round-2 entry points on odd shapes: K-major lookup (rdvc_corr_lookup_ex), the 1x1
+    GEMM (rdvc_conv1x1, vector and scalar store paths), pack -> encoder tail -> packed build.  Guard bands before and
+    after every buffer the library writes must survive; feature rows beyond B*h*w are documented as not written."""
+    import ctypes
+    CANARY, GUARD = 0xAB, 4096
+    vd, layout = rc.RDVC_DT_F32, TILED
+    fd = rc.RDVC_DT_F16 if fdt == torch.float16 else rc.RDVC_DT_BF16
+    st = torch.cuda.current_stream().cuda_stream
+    g = torch.Generator(device="cuda").manual_seed(5)
+    for (B, Din, h, w, cout) in [(2, 128, 18, 22, 256), (1, 128, 33, 47, 96), (1, 128, 17, 16, 32)]:
+        N, D = h * w, 256
+        x1 = torch.randn(B, Din, h, w, device="cuda", generator=g)
+        x2 = torch.randn(B, Din, h, w, device="cuda", generator=g)
+        wt = torch.randn(D, Din, generator=torch.Generator().manual_seed(1)) / Din ** 0.5
+        wp = np.zeros(D * Din, np.uint16)
+        w32 = wt.numpy().copy()
+        rc._cabi.check(lib.rdvc_linear_pack_weights(w32.ctypes.data_as(ctypes.c_void_p), D, Din, fd,
+                                                    wp.ctypes.data_as(ctypes.c_void_p)), "pack linear")
+        wdev = torch.from_numpy(wp.view(np.int16)).cuda()
+        kp = lib.rdvc_corr_feat_pitch(4, 4)
+        rows = lib.rdvc_corr_feat_rows(B, h, w)
+        sizes = {"pyr": lib.rdvc_corr_pyramid_bytes(B, h, w, 4, vd, layout),
+                 "ws_in": lib.rdvc_corr_workspace_bytes(B, Din, h, w),
+                 "ws": lib.rdvc_corr_workspace_bytes(B, D, h, w),
+                 "feat": lib.rdvc_corr_feat_bytes(B, h, w, 4, 4),
+                 "out32": B * cout * N * 4, "out16": B * cout * N * 2}
+        bufs = {k: torch.full((n + 2 * GUARD,), CANARY, dtype=torch.uint8, device="cuda") for k, n in sizes.items()}
+        ptr = {k: v.data_ptr() + GUARD for k, v in bufs.items()}
+        assert all(p % 256 == 0 for p in ptr.values())
+        rc._cabi.check(lib.rdvc_corr_pack(x1.data_ptr(), x2.data_ptr(), B, Din, h, w, rc.RDVC_DT_F32, vd, layout, 4,
+                                          ptr["ws_in"], sizes["ws_in"], st), "pack")
+        rc._cabi.check(lib.rdvc_corr_encoder_tail(ptr["ws_in"], sizes["ws_in"], Din, wdev.data_ptr(), 0, D, B, h, w, fd,
+                                                  vd, layout, 4, ptr["ws"], sizes["ws"], st), "tail")
+        rc._cabi.check(lib.rdvc_corr_build_packed(B, D, h, w, fd, ptr["pyr"], vd, layout, 4, ptr["ws"], sizes["ws"], st),
+                       "build_packed")
+        co = gpu(cn.synth_coords(B, h, w, 5.0, seed=1))
+        rc._cabi.check(lib.rdvc_corr_lookup_ex(ptr["pyr"], vd, layout, co.data_ptr(), B, h, w, 4, 4, ptr["feat"], fd,
+                                               rc._cabi.RDVC_OUT_KMAJOR, st), "lookup_ex")
+        cw = torch.randn(cout, 324, generator=torch.Generator().manual_seed(2)) / 18
+        packed = rc.corr_block.PackedConv1x1(cw, torch.zeros(cout), 4, 4, fdt, "cuda")
+        for key, od in (("out32", rc.RDVC_DT_F32), ("out16", rc.RDVC_DT_F16)):
+            rc._cabi.check(lib.rdvc_conv1x1(ptr["feat"], fd, packed.weight.data_ptr(), packed.bias.data_ptr(), B, h, w,
+                                            4, 4, cout, rc._cabi.RDVC_ACT_RELU, ptr[key], od, st), "conv1x1")
+        torch.cuda.synchronize()
+        for k, v in bufs.items():
+            assert bool((v[:GUARD] == CANARY).all()) and bool((v[-GUARD:] == CANARY).all()), (k, "guard band", (B, h, w))
+        feat = bufs["feat"][GUARD:-GUARD].view(kp // 8, rows, 16)
+        assert bool((feat[:, B * N:, :] == CANARY).all()), "feature rows beyond B*h*w were written"
+        assert not bool((feat[:, :B * N, :] == CANARY).all(dim=-1).any()), "a feature row chunk was not written"
+        o32 = bufs["out32"][GUARD:-GUARD].view(torch.float32)
+        o16 = bufs["out16"][GUARD:-GUARD].view(torch.float16)
+        assert torch.isfinite(o32).all() and bool((o32 >= 0).all())        # every element written (canary = -1.2e-12 < 0)
+        assert torch.equal(o32.to(torch.float16), o16)
+
+
 def test_runs_on_callers_stream(lib):
     B, D, h, w = 1, 64, 24, 40
     f1, f2 = cn.synth_fmaps(B, D, h, w, seed=41)
