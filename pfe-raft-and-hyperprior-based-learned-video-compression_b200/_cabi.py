@@ -144,3 +144,14 @@ def check(rc: int, what: str):
     if rc < 0:
         raise ValueError(f"{what}: {RDVC_E.get(rc, rc)}: {msg}")
     raise RuntimeError(f"{what}: CUDA error {rc}: {msg}")
+
+
+def forward_only(what: str, *tensors) -> None:
+    """The kernels are forward-only (the reference runs this path under ``torch.no_grad()``,
+    R:codec_processing.py:1436): refuse tensors that would carry a gradient instead of silently cutting the graph."""
+    import torch
+    if torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors):
+        raise RuntimeError(
+            f"{what}: rdvc_corr_b200 is forward-only; an input requires grad and gradients cannot flow through these "
+            "kernels. Call it under torch.no_grad() (as the reference does) or detach the inputs."
+        )

@@ -128,6 +128,7 @@ def _check_fmaps(fmap1: Tensor, fmap2: Tensor, num_levels: int):
         )
     if fmap1.dtype != fmap2.dtype or fmap1.dtype not in _IN_DTYPES:
         raise ValueError(f"unsupported feature-map dtypes {fmap1.dtype} / {fmap2.dtype}")
+    _cabi.forward_only("build_pyramid", fmap1, fmap2)
 
 
 def build_pyramid(fmap1: Tensor, fmap2: Tensor, num_levels: int = 4,
@@ -174,6 +175,7 @@ def _check_coords(pyr: CorrPyramid, coords: Tensor) -> Tensor:
         )
     if not coords.is_cuda:
         raise RuntimeError("rdvc_corr_b200 runs on an sm_100 GPU only; got CPU coords.")
+    _cabi.forward_only("index_pyramid", coords)
     return coords.detach().to(torch.float32).contiguous()
 
 

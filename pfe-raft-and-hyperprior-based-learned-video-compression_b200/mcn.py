@@ -192,6 +192,7 @@ class MotionCompensationNetwork(nn.Module):
         if self.training:
             raise RuntimeError("rdvc_corr_b200.MotionCompensationNetwork is inference only (BatchNorm is folded); call .eval()")
         _need_cuda(warped_ref, flow, ref_frame)
+        _cabi.forward_only("MotionCompensationNetwork", warped_ref, flow, ref_frame)
         lib = _cabi.load()
         dev = warped_ref.device
         _, _, ptrs, masks, biases = self._prepare(dev)

@@ -23,6 +23,7 @@ from . import _cabi
 def _launch(prev: Optional[Tensor], flow: Tensor, H: int, W: int, want_flow: bool):
     if not flow.is_cuda or (prev is not None and not prev.is_cuda):
         raise RuntimeError("rdvc_corr_b200 runs on an sm_100 GPU only; got CPU tensors. There is no CPU fallback.")
+    _cabi.forward_only("motion_warp / WarpingLayer / resize_flow", prev, flow)
     lib = _cabi.load()
     dev = flow.device
     f = flow.detach().to(torch.float32).contiguous()

@@ -380,3 +380,14 @@ def test_encoder_tail_host_side(lib):
     assert lib.rdvc_corr_lookup_ex(one, rc.RDVC_DT_F32, rc.RDVC_LAYOUT_ROWMAJOR, one, 1, 46, 80, 4, 4, one, rc.RDVC_DT_F16, 0, None) == -5
     assert lib.rdvc_corr_lookup_ex(one, rc.RDVC_DT_F32, rc.RDVC_LAYOUT_TILED, one, 1, 46, 80, 4, 4, one, rc.RDVC_DT_BF16, 0, None) == -4
     assert lib.rdvc_corr_feat_rows(1, 17, 19) == 328 and lib.rdvc_corr_feat_bytes(1, 17, 19, 4, 4) == 352 * 328 * 2
+
+
+def test_forward_only_guard():
+    """Gradients cannot flow through the kernels: a tensor that requires grad is refused (unless grad mode is off,
+    as in the reference's call, R:codec_processing.py:1436) instead of silently cutting the graph."""
+    t = torch.zeros(2, requires_grad=True)
+    with pytest.raises(RuntimeError, match="forward-only"):
+        rc._cabi.forward_only("x", None, t)
+    rc._cabi.forward_only("x", None, t.detach())
+    with torch.no_grad():
+        rc._cabi.forward_only("x", t)

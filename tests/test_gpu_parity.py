@@ -922,6 +922,25 @@ def test_no_out_of_bounds_writes_round2_entry_points(lib, fdt):
         assert torch.equal(o32.to(torch.float16), o16)
 
 
+def test_inputs_requiring_grad_are_refused(lib):
+    """Forward-only: with grad mode on, activations that require grad raise (a silent ``detach`` would train nothing)."""
+    f1 = torch.randn(1, 64, 16, 16, device="cuda", requires_grad=True)
+    f2 = torch.randn(1, 64, 16, 16, device="cuda")
+    blk = rc.TVCorrBlock()
+    with pytest.raises(RuntimeError, match="forward-only"):
+        blk.build_pyramid(f1, f2)
+    with torch.no_grad():
+        blk.build_pyramid(f1, f2)
+    co = torch.zeros(1, 2, 16, 16, device="cuda", requires_grad=True)
+    with pytest.raises(RuntimeError, match="forward-only"):
+        blk.index_pyramid(co)
+    assert blk.index_pyramid(co.detach()).shape == (1, 324, 16, 16)
+    x = torch.rand(1, 3, 32, 32, device="cuda", requires_grad=True)
+    with pytest.raises(RuntimeError, match="forward-only"):
+        rc.WarpingLayer()(x, torch.zeros(1, 2, 32, 32, device="cuda"))
+    blk.release()
+
+
 def test_runs_on_callers_stream(lib):
     B, D, h, w = 1, 64, 24, 40
     f1, f2 = cn.synth_fmaps(B, D, h, w, seed=41)
