@@ -64,7 +64,7 @@ def frame_at(big, t, h, w):
 def sharded_args(**kw):
     """The argument namespace of run_sharded with its command-line defaults (for callers such as bench.py)."""
     d = dict(frames=600, height=1088, width=1920, gop=10, amp=False, graph=True, volume="fp32", from_uint8=False,
-             mcn=False, batch_gop=True, shard="frames", fuse_convcorr1=True, entropy=True)
+             mcn=False, batch_gop=True, shard="frames", fuse_convcorr1=True, entropy=True, share_features=True)
     d.update(kw)
     return argparse.Namespace(**d)
 
@@ -106,6 +106,7 @@ def run_sharded(args, own_process_group=True):
     mine = gs.assign_gops(gops, world)[rank]
     spans = gs.assign_frames(args.frames, args.gop, world)
     by_frames = (args.shard == "frames")
+    share = bool(getattr(args, "share_features", True)) and args.batch_gop     # runs of consecutive frames: each frame's features once
     ctx = lambda: torch.autocast("cuda", dtype=torch.float16, enabled=args.amp)
 
     def enc_i(frame):
@@ -170,12 +171,24 @@ def run_sharded(args, own_process_group=True):
         return rc.preprocess_frame_raft(u8, (h, w), dev)      # R:codec_processing.py:1430-1431
 
     def enc_p_batch(prevs, curs):
-        a, b = torch.cat(list(prevs), 0), torch.cat(list(curs), 0)
-        if runner is not None:
-            flow = runner(a, b)
+        prevs, curs = list(prevs), list(curs)
+        if share and all(prevs[i + 1] is curs[i] for i in range(len(curs) - 1)):
+            # a run of consecutive frames (gop_shard hands over the same objects on both sides): the feature encoder
+            # sees each frame once (rc.raft_flow_sequence)
+            frames = torch.cat(prevs + [curs[-1]], 0)
+            a, b = frames[:-1], frames[1:]
+            if runner is not None:
+                flow = runner.sequence(frames)
+            else:
+                with torch.no_grad(), ctx():
+                    flow = rc.raft_flow_sequence(model, frames, 12, fuse_convcorr1=args.fuse_convcorr1)
         else:
-            with torch.no_grad(), ctx():
-                flow = rc.raft_flow(model, a, b, 12, fuse_convcorr1=args.fuse_convcorr1)
+            a, b = torch.cat(prevs, 0), torch.cat(curs, 0)
+            if runner is not None:
+                flow = runner(a, b)
+            else:
+                with torch.no_grad(), ctx():
+                    flow = rc.raft_flow(model, a, b, 12, fuse_convcorr1=args.fuse_convcorr1)
         a_codec = a[:, :, :fh].contiguous()
         warped, flow = rc.motion_warp(a_codec, flow, (fh, w))
         res = predict(warped, flow, a_codec, b[:, :, :fh])
@@ -192,16 +205,15 @@ def run_sharded(args, own_process_group=True):
 
     batch = max(1, min(args.gop, args.frames) - 1)        # P-frames per RAFT batch: a GOP's worth
     if args.batch_gop:                                    # warm-up at the batched shape(s) (and graph capture)
-        shapes = {batch}
-        if by_frames:                                     # a span's last batch may be short
-            n_p = sum(1 for t in spans[rank] if not gs.is_iframe(t, args.gop))
-            if n_p % batch:
-                shapes.add(n_p % batch)
-            if 0 < n_p < batch:
-                shapes = {n_p}
+        if by_frames:                                     # the batch sizes this rank's span will produce
+            ts_p = [t for t in spans[rank] if not gs.is_iframe(t, args.gop)]
+            shapes = {len(c) for c in gs.pframe_batches(ts_p, batch, share)}
+        else:
+            shapes = {batch}
         for npf in sorted(shapes, reverse=True):
             for _ in range(2):
-                enc_p_batch([frame_at(big, t, h, w) for t in range(npf)], [frame_at(big, t + 1, h, w) for t in range(npf)])
+                fr = [frame_at(big, t, h, w) for t in range(npf + 1)]
+                enc_p_batch(fr[:-1], fr[1:])
     if runner is not None:                                # warm-up: capture the graph outside the timed region
         for _ in range(2):
             runner(frame_at(big, 0, h, w), frame_at(big, 1, h, w))
@@ -213,7 +225,8 @@ def run_sharded(args, own_process_group=True):
     meta_in = {"rdvc_version": "b200-bench", "iframe_interval": args.gop}
     if by_frames:
         data, tail_failed = gs.encode_span(spans[rank], args.gop, get_frame, enc_i, enc_p,
-                                           enc_p_batch if args.batch_gop else None, batch=batch)
+                                           enc_p_batch if args.batch_gop else None, batch=batch,
+                                           consecutive_runs=share)
         torch.cuda.synchronize()
         t_local = time.perf_counter() - t0
         stream = gs.gather_spans(data, tail_failed, spans, meta_in, rank, world, host_group,
@@ -255,6 +268,7 @@ def run_sharded(args, own_process_group=True):
                                    "(bitstream parity unpinned: compressai absent); codec networks out of scope" if args.entropy
                                    else "placeholder int8 dump (codec networks out of scope)"),
                        "feature_encoder_tail_fused": True,
+                       "feature_maps_shared_by_consecutive_pairs": share,
                        "collective": "none on the data path; host-side gather of per-rank byte strings into the writer "
                                      "(/dev/shm files on one node, gloo tensors otherwise)"},
             "seconds_total_max_over_ranks": times[0].item(), "seconds_encode_max_over_ranks": times[1].item(),
@@ -267,7 +281,11 @@ def run_sharded(args, own_process_group=True):
         # setting) on one frame pair of the sequence -- outside the timed region
         a, b = frame_at(big, 3, h, w), frame_at(big, 4, h, w)
         with torch.no_grad(), ctx():
-            ours_flow = rc.raft_flow(model, a, b, 12, fuse_convcorr1=args.fuse_convcorr1)
+            if share:       # the pair as the middle of a run, the way the timed region computed it
+                run = torch.cat([frame_at(big, 2, h, w), a, b, frame_at(big, 5, h, w)], 0)
+                ours_flow = rc.raft_flow_sequence(model, run, 12, fuse_convcorr1=args.fuse_convcorr1)[1:2]
+            else:
+                ours_flow = rc.raft_flow(model, a, b, 12, fuse_convcorr1=args.fuse_convcorr1)
         model.corr_block.release()
         torch.manual_seed(0)
         stock = raft_large(weights=None).eval().to(dev)
@@ -326,6 +344,9 @@ def main():
                     help="config 4: partition by whole GOPs or by contiguous frame spans (P-frames balanced to one)")
     ap.add_argument("--no-fuse-convcorr1", dest="fuse_convcorr1", action="store_false",
                     help="keep the stock convcorr1 module after an fp32 lookup instead of the fused lookup + 1x1 GEMM")
+    ap.add_argument("--no-share-features", dest="share_features", action="store_false",
+                    help="run the feature encoder on both frames of every pair (2n images per batch) instead of once per "
+                         "frame of a run of consecutive frames (n + 1 images, rc.raft_flow_sequence)")
     ap.add_argument("--no-entropy", dest="entropy", action="store_false",
                     help="config 4: raw int8 motion payload instead of the range coder stand-in")
     ap.add_argument("--cpu-baseline", action="store_true", help="also time stock RAFT on the host cores for 1 P-frame")

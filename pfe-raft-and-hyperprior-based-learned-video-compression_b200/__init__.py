@@ -26,10 +26,10 @@ from .corr_block import (  # noqa: F401
 from .mcn import MotionCompensationNetwork  # noqa: F401
 from .motion_warp import WarpingLayer, motion_warp, resize_flow  # noqa: F401
 from .preprocess import frame_to_tensor, preprocess_frame_codec, preprocess_frame_raft  # noqa: F401
-from .raft_flow import GraphedRaftFlow, raft_flow  # noqa: F401
+from .raft_flow import GraphedRaftFlow, raft_flow, raft_flow_sequence  # noqa: F401
 
 __all__ = [
-    "CorrBlock", "CorrPyramid", "TVCorrBlock", "build_pyramid", "index_pyramid", "raft_flow", "GraphedRaftFlow",
+    "CorrBlock", "CorrPyramid", "TVCorrBlock", "build_pyramid", "index_pyramid", "raft_flow", "raft_flow_sequence", "GraphedRaftFlow",
     "WarpingLayer", "motion_warp", "resize_flow", "MotionCompensationNetwork",
     "frame_to_tensor", "preprocess_frame_codec", "preprocess_frame_raft",
     "RDVC_DT_BF16", "RDVC_DT_F16", "RDVC_DT_F32", "RDVC_LAYOUT_ROWMAJOR", "RDVC_LAYOUT_TILED",

@@ -198,18 +198,39 @@ def assign_frames(num_frames: int, iframe_interval: int, world_size: int) -> Lis
     return [range(cuts[r], cuts[r + 1]) for r in range(world_size)]
 
 
+def pframe_batches(ts_p: Sequence[int], batch: int, consecutive_runs: bool = False) -> List[List[int]]:
+    """The P-frame indices `ts_p` (ascending) cut into batches of at most `batch`: plain slices, or -- with
+    `consecutive_runs` -- runs of consecutive indices (a batch ends at an I-frame or after `batch` frames)."""
+    if batch <= 0:
+        raise ValueError("batch must be positive")
+    ts_p = list(ts_p)
+    if not consecutive_runs:
+        return [ts_p[k:k + batch] for k in range(0, len(ts_p), batch)]
+    out: List[List[int]] = []
+    for t in ts_p:
+        if out and out[-1][-1] == t - 1 and len(out[-1]) < batch:
+            out[-1].append(t)
+        else:
+            out.append([t])
+    return out
+
+
 def encode_span(span: range, iframe_interval: int, frames: Callable[[int], object],
                 encode_iframe: Callable[[object], bytes],
                 encode_pframe: Optional[Callable[[object, object], bytes]] = None,
                 encode_pframes: Optional[Callable[[Sequence[object], Sequence[object]], Sequence[bytes]]] = None,
                 batch: int = 9, failures: Optional[List[int]] = None,
-                force_first_i: bool = False) -> Tuple[bytes, bool]:
+                force_first_i: bool = False, consecutive_runs: bool = False) -> Tuple[bytes, bool]:
     """Frame records of the frames in `span` and whether the span's LAST frame was a failed P-frame (the next
     span's first frame must then become an I-frame, `gather_spans` does that).  With `encode_pframes` all
     P-frames of the span are encoded `batch` at a time, across GOP boundaries (only the last batch may be
     short); if a batch fails and `encode_pframe` is given, the span is redone frame by frame with the
     reference's failure rule (R:codec_processing.py:1501-1506).  `frames(span.start - 1)` is read when the
-    span starts with a P-frame: the previous ORIGINAL frame, whichever rank encodes it."""
+    span starts with a P-frame: the previous ORIGINAL frame, whichever rank encodes it.
+    With `consecutive_runs` a batch never straddles an I-frame: it is a run of up to `batch` CONSECUTIVE P-frames
+    t0 .. t1, its frames t0 - 1 .. t1 are fetched ONCE and `encode_pframes(fr[:-1], fr[1:])` gets the same objects
+    on both sides (`prevs[i + 1] is curs[i]`), so the callee can run the feature encoder once per frame
+    (`raft_flow_sequence`).  Same records, same order, either way."""
     if encode_pframe is None and encode_pframes is None:
         raise ValueError("need encode_pframe and/or encode_pframes")
     if batch <= 0:
@@ -225,9 +246,12 @@ def encode_span(span: range, iframe_interval: int, frames: Callable[[int], objec
         try:
             ts_p = [t for t in ts if kind(t) == "P"]
             payloads: Dict[int, bytes] = {}
-            for k in range(0, len(ts_p), batch):
-                chunk = ts_p[k:k + batch]
-                out = list(encode_pframes([frames(t - 1) for t in chunk], [frames(t) for t in chunk]))
+            for chunk in pframe_batches(ts_p, batch, consecutive_runs):
+                if consecutive_runs:
+                    fr = [frames(t) for t in range(chunk[0] - 1, chunk[-1] + 1)]
+                    out = list(encode_pframes(fr[:-1], fr[1:]))
+                else:
+                    out = list(encode_pframes([frames(t - 1) for t in chunk], [frames(t) for t in chunk]))
                 if len(out) != len(chunk):
                     raise RuntimeError("encode_pframes returned the wrong number of payloads")
                 payloads.update(zip(chunk, out))

@@ -93,27 +93,54 @@ def raft_flow(model, image1: Tensor, image2: Tensor, num_flow_updates: int = 12,
     (inject it with ``raft_large(corr_block=TVCorrBlock())``).  With ``all_predictions=True`` the
     list of all upsampled flows is returned, exactly like ``RAFT.forward``.
     """
+    if image1.dim() != 4 or image1.shape[-2:] != image2.shape[-2:]:
+        raise ValueError(f"input images should have the same shape, instead got {tuple(image1.shape[-2:])} != {tuple(image2.shape[-2:])}")
+    batch = image1.shape[0]
+    return _raft_flow_impl(model, torch.cat([image1, image2], dim=0), lambda x: (x[:batch], x[batch:]), image1,
+                           num_flow_updates, corr_block, all_predictions, fuse_convcorr1, fuse_encoder_tail)
+
+
+@torch.no_grad()
+def raft_flow_sequence(model, frames: Tensor, num_flow_updates: int = 12, corr_block: Optional[TVCorrBlock] = None,
+                       all_predictions: bool = False, fuse_convcorr1: bool = True, fuse_encoder_tail: bool = True):
+    """Flows (n, 2, H, W) of the n CONSECUTIVE pairs (frames[i], frames[i + 1]) of a run of n + 1 frames -- what the
+    open-loop encoder asks for inside a GOP (R:codec_processing.py:1498-1499: every P-frame's reference is the previous
+    ORIGINAL frame).  Same modules, same order as ``raft_flow(model, frames[:-1], frames[1:])``, but the feature
+    encoder sees each frame ONCE (n + 1 images instead of 2n): its normalisation is per sample (InstanceNorm,
+    TV:raft.py:790), so a frame's feature map does not depend on which pair it is part of; the context encoder still
+    runs on every pair's first frame."""
+    if frames.dim() != 4 or frames.shape[0] < 2:
+        raise ValueError(f"frames should be (n + 1 >= 2, 3, H, W), got {tuple(frames.shape)}")
+    fe_norms = [m for m in model.feature_encoder.modules() if isinstance(m, torch.nn.modules.batchnorm._BatchNorm)]
+    if any(m.training or not m.track_running_stats for m in fe_norms):
+        raise RuntimeError("raft_flow_sequence needs a feature encoder whose normalisation is per sample (InstanceNorm) or "
+                           "frozen (BatchNorm in eval mode); batch statistics would couple the frames")
+    return _raft_flow_impl(model, frames, lambda x: (x[:-1], x[1:]), frames[:-1], num_flow_updates, corr_block,
+                           all_predictions, fuse_convcorr1, fuse_encoder_tail)
+
+
+def _raft_flow_impl(model, enc_in: Tensor, split, image1: Tensor, num_flow_updates, corr_block, all_predictions,
+                    fuse_convcorr1, fuse_encoder_tail):
+    """``enc_in``: every image the feature encoder has to see; ``split``: its output -> (first, second) feature maps of
+    the pairs; ``image1``: the pairs' first frames (context encoder input)."""
     from torchvision.models.optical_flow._utils import upsample_flow
 
     blk = corr_block if corr_block is not None else model.corr_block
     if not isinstance(blk, TVCorrBlock):
         raise TypeError("raft_flow needs a rdvc_corr_b200.TVCorrBlock as the model's corr_block")
     batch, _, h, w = image1.shape
-    if (h, w) != image2.shape[-2:]:
-        raise ValueError(f"input images should have the same shape, instead got ({h}, {w}) != {image2.shape[-2:]}")
     if not ((h % 8 == 0) and (w % 8 == 0)):
         raise ValueError(f"input image H and W should be divisible by 8, instead got {h} (h) and {w} (w)")
 
     fe = model.feature_encoder
     if fuse_encoder_tail and _can_fuse_encoder_tail(model):
-        x = fe.layer3(fe.layer2(fe.layer1(fe.convnormrelu(torch.cat([image1, image2], dim=0)))))   # TV:raft.py:145-149
-        fmap1, fmap2 = torch.chunk(x, chunks=2, dim=0)            # 128-channel activations; fe.conv runs inside the block
+        x = fe.layer3(fe.layer2(fe.layer1(fe.convnormrelu(enc_in))))   # TV:raft.py:145-149
+        fmap1, fmap2 = split(x)                                   # 128-channel activations; fe.conv runs inside the block
         if fmap1.shape[-2:] != (h // 8, w // 8):                  # TV:raft.py:494-495
             raise ValueError("The feature encoder should downsample H and W by 8")
         blk.build_pyramid_from_encoder(fmap1, fmap2, fe.conv.weight, fe.conv.bias)
     else:
-        fmaps = fe(torch.cat([image1, image2], dim=0))
-        fmap1, fmap2 = torch.chunk(fmaps, chunks=2, dim=0)
+        fmap1, fmap2 = split(fe(enc_in))
         if fmap1.shape[-2:] != (h // 8, w // 8):            # TV:raft.py:494-495
             raise ValueError("The feature encoder should downsample H and W by 8")
         blk.build_pyramid(fmap1, fmap2)
@@ -173,6 +200,9 @@ class GraphedRaftFlow:
 
     def _run(self, blk, a, b):
         with torch.autocast("cuda", dtype=self.amp_dtype or torch.float16, enabled=self.amp_dtype is not None):
+            if b is None:      # a = a run of n + 1 frames
+                return raft_flow_sequence(self.model, a, self.num_flow_updates, corr_block=blk,
+                                          fuse_convcorr1=self.fuse_convcorr1, fuse_encoder_tail=self.fuse_encoder_tail)
             return raft_flow(self.model, a, b, self.num_flow_updates, corr_block=blk, fuse_convcorr1=self.fuse_convcorr1,
                              fuse_encoder_tail=self.fuse_encoder_tail)
 
@@ -185,11 +215,11 @@ class GraphedRaftFlow:
                 e["graph"] = None
                 e["blk"].release()
 
-    def _capture(self, image1: Tensor, image2: Tensor):
+    def _capture(self, image1: Tensor, image2: Optional[Tensor]):
         dev = image1.device
         blk = TVCorrBlock(num_levels=self.model.corr_block.num_levels, radius=self.model.corr_block.radius,
                           volume_dtype=self.volume_dtype, layout=self.model.corr_block.layout)
-        in1, in2 = image1.clone(), image2.clone()
+        in1, in2 = image1.clone(), None if image2 is None else image2.clone()
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side), torch.no_grad():
@@ -210,7 +240,21 @@ class GraphedRaftFlow:
             raise ValueError(f"input images should have the same shape and dtype, got {image1.shape} / {image2.shape}")
         if self.model.training:
             raise RuntimeError("GraphedRaftFlow is inference only: the model was switched back to train mode")
-        key = (tuple(image1.shape), image1.dtype, image1.device)
+        return self._replay((tuple(image1.shape), image1.dtype, image1.device), image1, image2)
+
+    @torch.no_grad()
+    def sequence(self, frames: Tensor) -> Tensor:
+        """``raft_flow_sequence(model, frames)`` -- the n flows of a run of n + 1 consecutive frames, the feature
+        encoder seeing each frame once -- as one graph per run length."""
+        if not frames.is_cuda:
+            raise RuntimeError("rdvc_corr_b200 runs on an sm_100 GPU only; got CPU frames.")
+        if frames.dim() != 4 or frames.shape[0] < 2:
+            raise ValueError(f"frames should be (n + 1 >= 2, 3, H, W), got {tuple(frames.shape)}")
+        if self.model.training:
+            raise RuntimeError("GraphedRaftFlow is inference only: the model was switched back to train mode")
+        return self._replay(("sequence", tuple(frames.shape), frames.dtype, frames.device), frames, None)
+
+    def _replay(self, key, image1: Tensor, image2: Optional[Tensor]) -> Tensor:
         e = self._entries.pop(key, None)
         if e is None:
             while len(self._entries) >= self.max_entries:          # evict the least recently used shape
@@ -218,6 +262,7 @@ class GraphedRaftFlow:
             e = self._capture(image1, image2)
         self._entries[key] = e                                      # most recently used last
         e["in1"].copy_(image1)
-        e["in2"].copy_(image2)
+        if image2 is not None:
+            e["in2"].copy_(image2)
         e["graph"].replay()
         return e["out"].clone()

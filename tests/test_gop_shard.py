@@ -195,15 +195,20 @@ def test_assign_frames_is_a_balanced_contiguous_partition(world, frames_interval
         assert max(loads) == 68 and min(loads) == 67                                     # 540 / 8: 7.94x, not 7.5x
 
 
-def _span_stream(num_frames, interval, world, enc_p_factory=None, batch=4, batched=True):
+def _span_stream(num_frames, interval, world, enc_p_factory=None, batch=4, batched=True, runs=False, seen=None):
     frames, enc_i, enc_p = _fake_encoders()
     if enc_p_factory is not None:
         enc_p = enc_p_factory(frames, enc_p)
-    enc_batch = (lambda prevs, curs: [enc_p(a, b) for a, b in zip(prevs, curs)]) if batched else None
+
+    def enc_batch_fn(prevs, curs):
+        if seen is not None:
+            seen.append((list(prevs), list(curs)))
+        return [enc_p(a, b) for a, b in zip(prevs, curs)]
+    enc_batch = enc_batch_fn if batched else None
     spans = gs.assign_frames(num_frames, interval, world)
     out, failed = [], []
     for sp in spans:
-        data, tail = gs.encode_span(sp, interval, frames, enc_i, enc_p, enc_batch, batch=batch)
+        data, tail = gs.encode_span(sp, interval, frames, enc_i, enc_p, enc_batch, batch=batch, consecutive_runs=runs)
         out.append(data); failed.append(tail)
     if world == 1:
         return gs.gather_spans(out[0], failed[0], spans, {"rdvc_version": "1.0"}, 0, 1)
@@ -221,6 +226,49 @@ def test_span_sharding_equals_gop_serial_stream(world):
     for (n, I) in [(47, 5), (25, 10), (12, 4)]:
         assert _span_stream(n, I, world) == _serial_stream(n, I, {"rdvc_version": "1.0"}), (n, I, world)
         assert _span_stream(n, I, world, batched=False) == _serial_stream(n, I, {"rdvc_version": "1.0"})
+
+
+def test_pframe_batches():
+    assert gs.pframe_batches([1, 2, 3, 4, 6, 7], 4) == [[1, 2, 3, 4], [6, 7]]
+    assert gs.pframe_batches([1, 2, 3, 4, 6, 7], 3) == [[1, 2, 3], [4, 6, 7]]
+    assert gs.pframe_batches([1, 2, 3, 4, 6, 7], 3, True) == [[1, 2, 3], [4], [6, 7]]
+    assert gs.pframe_batches([8, 9, 11, 12, 13], 9, True) == [[8, 9], [11, 12, 13]]
+    assert gs.pframe_batches([], 9, True) == []
+    with pytest.raises(ValueError):
+        gs.pframe_batches([1], 0)
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 8])
+def test_consecutive_run_batches_give_the_same_stream(world):
+    """`consecutive_runs`: every batch is a run of consecutive frames whose frames are handed over ONCE (the same
+    object ends one pair and starts the next, so a callee can share per-frame work), batches never straddle an
+    I-frame, and the stream is byte-identical to the serial encode."""
+    for (n, I, batch) in [(47, 5, 4), (25, 10, 9), (12, 4, 2), (30, 10, 4)]:
+        seen = []
+        assert _span_stream(n, I, world, batch=batch, runs=True, seen=seen) == _serial_stream(n, I, {"rdvc_version": "1.0"})
+        p_total = 0
+        for prevs, curs in seen:
+            assert 1 <= len(curs) <= batch and len(prevs) == len(curs)
+            assert all(prevs[i + 1] is curs[i] for i in range(len(curs) - 1))
+            p_total += len(curs)
+        assert p_total == n - len(gs.split_gops(n, I))
+
+
+def test_consecutive_runs_failure_rule_across_a_cut():
+    n, I = 20, 10
+    frames, enc_i, enc_p = _fake_encoders()
+    for bad in (3, 9, 11, 19):
+        def factory(frames_, enc_p_, bad=bad):
+            def flaky(prev, cur):
+                if cur == frames_(bad):
+                    raise RuntimeError("boom")
+                return enc_p_(prev, cur)
+            return flaky
+        gops = gs.split_gops(n, I)
+        serial = gs.gather_stream({g.index: gs.encode_gop(g, frames, enc_i, factory(frames, enc_p)) for g in gops},
+                                  len(gops), {"rdvc_version": "1.0"})
+        for world in (2, 3):
+            assert _span_stream(n, I, world, factory, runs=True) == serial, (bad, world)
 
 
 def test_span_sharding_failure_rule_across_a_cut():

@@ -556,6 +556,41 @@ def test_graphed_raft_flow_is_bit_identical(lib, golden_dir):
     assert not runner._entries
 
 
+def test_raft_flow_sequence_matches_pairs(lib, golden_dir):
+    """rc.raft_flow_sequence(frames) == the flows of the consecutive pairs, the feature encoder having seen each frame
+    once (n + 1 images instead of 2n): InstanceNorm is per sample, so only cuDNN's batch-size-dependent algorithm choice
+    can differ -- and the pairs' flows against STOCK RAFT.forward stay inside the EPE budget."""
+    g = np.load(os.path.join(golden_dir, "frames_im1_im2.npz"))
+    a = _preprocess(g["im1"], (256, 448)).cuda()
+    b = _preprocess(g["im2"], (256, 448)).cuda()
+    frames = torch.cat([a, b, torch.roll(a, (3, -5), (2, 3)), torch.roll(b, (-2, 4), (2, 3))], 0)     # a run of 4 frames
+    model = _seeded_raft(rc.TVCorrBlock())
+    with torch.no_grad():
+        for kw in ({}, {"fuse_convcorr1": False, "fuse_encoder_tail": False}):
+            pairs = rc.raft_flow(model, frames[:-1], frames[1:], 12, **kw)
+            seq = rc.raft_flow_sequence(model, frames, 12, **kw)
+            assert seq.shape == pairs.shape == (3, 2, 256, 448)
+            epe = (seq - pairs).pow(2).sum(dim=1).sqrt().mean().item()
+            assert epe < 2e-3, (kw, epe)
+        stock = _seeded_raft()
+        ref = torch.cat([stock(frames[i:i + 1], frames[i + 1:i + 2], num_flow_updates=12)[-1] for i in range(3)], 0)
+        assert (seq - ref).pow(2).sum(dim=1).sqrt().mean().item() < TOL_EPE
+        every = rc.raft_flow_sequence(model, frames, 12, all_predictions=True)
+        assert len(every) == 12 and every[-1].shape == (3, 2, 256, 448)
+        with pytest.raises(ValueError, match="n \\+ 1"):
+            rc.raft_flow_sequence(model, frames[:1], 12)
+    # graphed: one graph per run length, bit-identical to the eager call, also for new frames
+    runner = rc.GraphedRaftFlow(model, 12)
+    with torch.no_grad():
+        eager = rc.raft_flow_sequence(model, frames, 12)
+        eager_rev = rc.raft_flow_sequence(model, frames.flip(0), 12)
+    assert torch.equal(runner.sequence(frames), eager)
+    assert torch.equal(runner.sequence(frames.flip(0).contiguous()), eager_rev)
+    assert torch.equal(runner(frames[:-1], frames[1:]), rc.raft_flow(model, frames[:-1], frames[1:], 12))   # pair graphs coexist
+    assert len(runner._entries) == 2
+    runner.release()
+
+
 def test_princeton_facade(lib):
     B, D, h, w = 1, 64, 24, 40
     f1, f2 = cn.synth_fmaps(B, D, h, w, seed=21)
