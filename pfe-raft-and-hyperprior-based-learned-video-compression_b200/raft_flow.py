@@ -20,6 +20,9 @@ convolution 128 -> 256, TV:raft.py:139,150 -- is not run by cuDNN either: the 12
 ``TVCorrBlock.build_pyramid_from_encoder`` (row f-2, last sub-item), which produces the build's K-major 16-bit operand
 rows directly; the (2B, 256, h, w) fp32 feature maps (67 MB at 1080p) are never written or re-read.
 
+:func:`raft_flow_sequence` is the same call for a RUN of n + 1 consecutive frames (the n pairs of an open-loop GOP):
+the feature encoder sees each frame once.
+
 All other convolutions stay stock PyTorch/cuDNN; only the correlation block (and those two 1x1s) is this library's.
 
 :class:`GraphedRaftFlow` replays the whole call as ONE CUDA graph per input shape.  At the reference's
