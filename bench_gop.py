@@ -269,6 +269,7 @@ def run_sharded(args, own_process_group=True):
                                    else "placeholder int8 dump (codec networks out of scope)"),
                        "feature_encoder_tail_fused": True,
                        "feature_maps_shared_by_consecutive_pairs": share,
+                       "cudnn_benchmark": bool(torch.backends.cudnn.benchmark),
                        "collective": "none on the data path; host-side gather of per-rank byte strings into the writer "
                                      "(/dev/shm files on one node, gloo tensors otherwise)"},
             "seconds_total_max_over_ranks": times[0].item(), "seconds_encode_max_over_ranks": times[1].item(),
@@ -347,10 +348,14 @@ def main():
     ap.add_argument("--no-share-features", dest="share_features", action="store_false",
                     help="run the feature encoder on both frames of every pair (2n images per batch) instead of once per "
                          "frame of a run of consecutive frames (n + 1 images, rc.raft_flow_sequence)")
+    ap.add_argument("--cudnn-benchmark", action="store_true",
+                    help="torch.backends.cudnn.benchmark = True for the stock convolutions (ours and the stock comparator alike)")
     ap.add_argument("--no-entropy", dest="entropy", action="store_false",
                     help="config 4: raw int8 motion payload instead of the range coder stand-in")
     ap.add_argument("--cpu-baseline", action="store_true", help="also time stock RAFT on the host cores for 1 P-frame")
     args = ap.parse_args()
+    if args.cudnn_benchmark:
+        torch.backends.cudnn.benchmark = True
     if args.frames > 0:
         line = run_sharded(args)
         if line is not None:
