@@ -64,7 +64,7 @@ def frame_at(big, t, h, w):
 def sharded_args(**kw):
     """The argument namespace of run_sharded with its command-line defaults (for callers such as bench.py)."""
     d = dict(frames=600, height=1088, width=1920, gop=10, amp=False, graph=True, volume="fp32", from_uint8=False,
-             mcn=False, batch_gop=True, shard="frames", fuse_convcorr1=True, entropy=True, share_features=True)
+             mcn=False, batch_gop=True, shard="frames", fuse_convcorr1=True, entropy=True, share_features=True, overlap_host=True)
     d.update(kw)
     return argparse.Namespace(**d)
 
@@ -107,6 +107,7 @@ def run_sharded(args, own_process_group=True):
     spans = gs.assign_frames(args.frames, args.gop, world)
     by_frames = (args.shard == "frames")
     share = bool(getattr(args, "share_features", True)) and args.batch_gop     # runs of consecutive frames: each frame's features once
+    overlap = bool(getattr(args, "overlap_host", True)) and args.batch_gop and by_frames   # entropy-code batch k while batch k + 1 runs
     ctx = lambda: torch.autocast("cuda", dtype=torch.float16, enabled=args.amp)
 
     def enc_i(frame):
@@ -193,10 +194,31 @@ def run_sharded(args, own_process_group=True):
         warped, flow = rc.motion_warp(a_codec, flow, (fh, w))
         res = predict(warped, flow, a_codec, b[:, :, :fh])
         small = F.avg_pool2d(flow.float(), 8)
-        q = motion_bytes((small * 4).round().clamp(-127, 127).to(torch.int8).cpu().numpy())
-        rb = None if res is None else res.cpu().numpy().astype("<f4")
-        return [fmt.pframe_payload(tuple(small.shape[-2:]), q[i], (0, 0) if rb is None else (1, 1),
-                                   b"" if rb is None else rb[i].tobytes()) for i in range(len(q))]
+        q_dev = (small * 4).round().clamp(-127, 127).to(torch.int8)
+        shape = tuple(small.shape[-2:])
+        if not overlap:
+            q = motion_bytes(q_dev.cpu().numpy())
+            rb = None if res is None else res.cpu().numpy().astype("<f4")
+            return [fmt.pframe_payload(shape, q[i], (0, 0) if rb is None else (1, 1),
+                                       b"" if rb is None else rb[i].tobytes()) for i in range(len(q))]
+        # device -> pinned host copies on the stream, an event behind them; the entropy coding (host C) happens in the
+        # returned callable, which gop_shard.encode_span calls AFTER it has submitted the next batch
+        q_host = torch.empty(q_dev.shape, dtype=torch.int8, pin_memory=True)
+        q_host.copy_(q_dev, non_blocking=True)
+        r_host = None
+        if res is not None:
+            r_host = torch.empty(res.shape, dtype=torch.float32, pin_memory=True)
+            r_host.copy_(res.float(), non_blocking=True)
+        done = torch.cuda.Event()
+        done.record()
+
+        def finish():
+            done.synchronize()
+            q = motion_bytes(q_host.numpy())
+            rb = None if r_host is None else r_host.numpy().astype("<f4")
+            return [fmt.pframe_payload(shape, q[i], (0, 0) if rb is None else (1, 1),
+                                       b"" if rb is None else rb[i].tobytes()) for i in range(len(q))]
+        return finish
 
     def barrier():
         torch.cuda.synchronize()
@@ -213,7 +235,9 @@ def run_sharded(args, own_process_group=True):
         for npf in sorted(shapes, reverse=True):
             for _ in range(2):
                 fr = [frame_at(big, t, h, w) for t in range(npf + 1)]
-                enc_p_batch(fr[:-1], fr[1:])
+                out = enc_p_batch(fr[:-1], fr[1:])
+                if callable(out):
+                    out()
     if runner is not None:                                # warm-up: capture the graph outside the timed region
         for _ in range(2):
             runner(frame_at(big, 0, h, w), frame_at(big, 1, h, w))
@@ -270,6 +294,7 @@ def run_sharded(args, own_process_group=True):
                        "feature_encoder_tail_fused": True,
                        "feature_maps_shared_by_consecutive_pairs": share,
                        "cudnn_benchmark": bool(torch.backends.cudnn.benchmark),
+                       "host_entropy_coding_overlaps_next_batch": overlap,
                        "collective": "none on the data path; host-side gather of per-rank byte strings into the writer "
                                      "(/dev/shm files on one node, gloo tensors otherwise)"},
             "seconds_total_max_over_ranks": times[0].item(), "seconds_encode_max_over_ranks": times[1].item(),
@@ -348,6 +373,8 @@ def main():
     ap.add_argument("--no-share-features", dest="share_features", action="store_false",
                     help="run the feature encoder on both frames of every pair (2n images per batch) instead of once per "
                          "frame of a run of consecutive frames (n + 1 images, rc.raft_flow_sequence)")
+    ap.add_argument("--no-overlap-host", dest="overlap_host", action="store_false",
+                    help="entropy-code a batch's flows right after its device work instead of while the next batch runs")
     ap.add_argument("--cudnn-benchmark", action="store_true",
                     help="torch.backends.cudnn.benchmark = True for the stock convolutions (ours and the stock comparator alike)")
     ap.add_argument("--no-entropy", dest="entropy", action="store_false",

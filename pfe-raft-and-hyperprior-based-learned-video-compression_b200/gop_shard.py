@@ -227,6 +227,9 @@ def encode_span(span: range, iframe_interval: int, frames: Callable[[int], objec
     short); if a batch fails and `encode_pframe` is given, the span is redone frame by frame with the
     reference's failure rule (R:codec_processing.py:1501-1506).  `frames(span.start - 1)` is read when the
     span starts with a P-frame: the previous ORIGINAL frame, whichever rank encodes it.
+    `encode_pframes` may return the payloads or a zero-argument callable that returns them: the callable is called
+    only after the NEXT batch has been submitted, so host-side work (entropy coding after a device -> host copy) of
+    one batch overlaps the device work of the next.
     With `consecutive_runs` a batch never straddles an I-frame: it is a run of up to `batch` CONSECUTIVE P-frames
     t0 .. t1, its frames t0 - 1 .. t1 are fetched ONCE and `encode_pframes(fr[:-1], fr[1:])` gets the same objects
     on both sides (`prevs[i + 1] is curs[i]`), so the callee can run the feature encoder once per frame
@@ -246,15 +249,28 @@ def encode_span(span: range, iframe_interval: int, frames: Callable[[int], objec
         try:
             ts_p = [t for t in ts if kind(t) == "P"]
             payloads: Dict[int, bytes] = {}
-            for chunk in pframe_batches(ts_p, batch, consecutive_runs):
-                if consecutive_runs:
-                    fr = [frames(t) for t in range(chunk[0] - 1, chunk[-1] + 1)]
-                    out = list(encode_pframes(fr[:-1], fr[1:]))
-                else:
-                    out = list(encode_pframes([frames(t - 1) for t in chunk], [frames(t) for t in chunk]))
+            def settle(chunk, out):
+                out = list(out() if callable(out) else out)
                 if len(out) != len(chunk):
                     raise RuntimeError("encode_pframes returned the wrong number of payloads")
                 payloads.update(zip(chunk, out))
+
+            pending = None      # a batch whose payloads are still being produced (encode_pframes returned a callable)
+            for chunk in pframe_batches(ts_p, batch, consecutive_runs):
+                if consecutive_runs:
+                    fr = [frames(t) for t in range(chunk[0] - 1, chunk[-1] + 1)]
+                    out = encode_pframes(fr[:-1], fr[1:])
+                else:
+                    out = encode_pframes([frames(t - 1) for t in chunk], [frames(t) for t in chunk])
+                if pending is not None:     # ... finish the previous batch while this one runs on the device
+                    settle(*pending)
+                    pending = None
+                if callable(out):
+                    pending = (chunk, out)
+                else:
+                    settle(chunk, out)
+            if pending is not None:
+                settle(*pending)
             recs = [fmt.FrameRecord(t, "I", encode_iframe(frames(t))).pack() if kind(t) == "I"
                     else fmt.FrameRecord(t, "P", payloads[t]).pack() for t in ts]
             return b"".join(recs), False

@@ -254,6 +254,38 @@ def test_consecutive_run_batches_give_the_same_stream(world):
         assert p_total == n - len(gs.split_gops(n, I))
 
 
+def test_deferred_payloads_are_settled_after_the_next_batch_is_submitted():
+    """encode_pframes may return a callable: encode_span calls it only after submitting the next batch (so host work
+    overlaps device work) and the stream is the same; an exception raised by the deferred half takes the usual route."""
+    n, I = 30, 10
+    frames, enc_i, enc_p = _fake_encoders()
+    events = []
+
+    def enc_batch(prevs, curs):
+        k = len([e for e in events if e[0] == "submit"])
+        events.append(("submit", k))
+        prevs, curs = list(prevs), list(curs)
+
+        def finish():
+            events.append(("finish", k))
+            return [enc_p(a, b) for a, b in zip(prevs, curs)]
+        return finish
+    data, tail = gs.encode_span(range(0, n), I, frames, enc_i, enc_p, enc_batch, batch=4, consecutive_runs=True)
+    ref, _ = gs.encode_span(range(0, n), I, frames, enc_i, enc_p, None)
+    assert data == ref and tail is False
+    n_b = len([e for e in events if e[0] == "submit"])
+    assert n_b == 9 and [e for e in events if e[0] == "finish"] == [("finish", k) for k in range(n_b)]
+    for k in range(n_b - 1):
+        assert events.index(("submit", k + 1)) < events.index(("finish", k))       # overlap: next submitted first
+
+    def enc_batch_bad(prevs, curs):
+        def finish():
+            raise RuntimeError("late failure")
+        return finish
+    data2, _ = gs.encode_span(range(0, n), I, frames, enc_i, enc_p, enc_batch_bad, batch=4)
+    assert data2 == ref                               # redone frame by frame through encode_pframe
+
+
 def test_consecutive_runs_failure_rule_across_a_cut():
     n, I = 20, 10
     frames, enc_i, enc_p = _fake_encoders()
