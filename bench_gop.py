@@ -64,7 +64,8 @@ def frame_at(big, t, h, w):
 def sharded_args(**kw):
     """The argument namespace of run_sharded with its command-line defaults (for callers such as bench.py)."""
     d = dict(frames=600, height=1088, width=1920, gop=10, amp=False, graph=True, volume="fp32", from_uint8=False,
-             mcn=False, batch_gop=True, shard="frames", fuse_convcorr1=True, entropy=True, share_features=True, overlap_host=True)
+             mcn=False, batch_gop=True, shard="frames", fuse_convcorr1=True, entropy=True, share_features=True, overlap_host=True,
+             update_channels_last=True)
     d.update(kw)
     return argparse.Namespace(**d)
 
@@ -117,7 +118,7 @@ def run_sharded(args, own_process_group=True):
     fh = args.height - 8 if args.height % 16 == 0 and args.height > 64 else args.height   # 1088 -> 1080 codec frame
 
     runner = (rc.GraphedRaftFlow(model, 12, amp_dtype=torch.float16 if args.amp else None, volume_dtype=vol,
-                                 fuse_convcorr1=args.fuse_convcorr1) if args.graph else None)
+                                 fuse_convcorr1=args.fuse_convcorr1, update_block_channels_last=getattr(args, 'update_channels_last', True)) if args.graph else None)
     coder = rc.entropy_coder.FlowCoder() if args.entropy else None
 
     mcn_net = None
@@ -143,7 +144,7 @@ def run_sharded(args, own_process_group=True):
             flow = runner(prev, cur)
         else:
             with torch.no_grad(), ctx():
-                flow = rc.raft_flow(model, prev, cur, 12, fuse_convcorr1=args.fuse_convcorr1)
+                flow = rc.raft_flow(model, prev, cur, 12, fuse_convcorr1=args.fuse_convcorr1, update_block_channels_last=getattr(args, 'update_channels_last', True))
         # steps 3 + 5a of the reference (R:codec_processing.py:1446,1456): flow to frame resolution and the
         # warped previous frame, one fused launch; the MCN / residual / codecs that consume them are out of scope
         prev_codec = prev[:, :, :fh].contiguous()
@@ -182,14 +183,14 @@ def run_sharded(args, own_process_group=True):
                 flow = runner.sequence(frames)
             else:
                 with torch.no_grad(), ctx():
-                    flow = rc.raft_flow_sequence(model, frames, 12, fuse_convcorr1=args.fuse_convcorr1)
+                    flow = rc.raft_flow_sequence(model, frames, 12, fuse_convcorr1=args.fuse_convcorr1, update_block_channels_last=getattr(args, 'update_channels_last', True))
         else:
             a, b = torch.cat(prevs, 0), torch.cat(curs, 0)
             if runner is not None:
                 flow = runner(a, b)
             else:
                 with torch.no_grad(), ctx():
-                    flow = rc.raft_flow(model, a, b, 12, fuse_convcorr1=args.fuse_convcorr1)
+                    flow = rc.raft_flow(model, a, b, 12, fuse_convcorr1=args.fuse_convcorr1, update_block_channels_last=getattr(args, 'update_channels_last', True))
         a_codec = a[:, :, :fh].contiguous()
         warped, flow = rc.motion_warp(a_codec, flow, (fh, w))
         res = predict(warped, flow, a_codec, b[:, :, :fh])
@@ -243,7 +244,7 @@ def run_sharded(args, own_process_group=True):
             runner(frame_at(big, 0, h, w), frame_at(big, 1, h, w))
     with torch.no_grad(), ctx():                          # warm-up: cuDNN autotune + allocator
         for _ in range(2):
-            rc.raft_flow(model, frame_at(big, 0, h, w), frame_at(big, 1, h, w), 12, fuse_convcorr1=args.fuse_convcorr1)
+            rc.raft_flow(model, frame_at(big, 0, h, w), frame_at(big, 1, h, w), 12, fuse_convcorr1=args.fuse_convcorr1, update_block_channels_last=getattr(args, 'update_channels_last', True))
     barrier()
     t0 = time.perf_counter()
     meta_in = {"rdvc_version": "b200-bench", "iframe_interval": args.gop}
@@ -295,6 +296,7 @@ def run_sharded(args, own_process_group=True):
                        "feature_maps_shared_by_consecutive_pairs": share,
                        "cudnn_benchmark": bool(torch.backends.cudnn.benchmark),
                        "host_entropy_coding_overlaps_next_batch": overlap,
+                       "update_block_channels_last": bool(getattr(args, "update_channels_last", True)) and args.fuse_convcorr1,
                        "collective": "none on the data path; host-side gather of per-rank byte strings into the writer "
                                      "(/dev/shm files on one node, gloo tensors otherwise)"},
             "seconds_total_max_over_ranks": times[0].item(), "seconds_encode_max_over_ranks": times[1].item(),
@@ -309,9 +311,9 @@ def run_sharded(args, own_process_group=True):
         with torch.no_grad(), ctx():
             if share:       # the pair as the middle of a run, the way the timed region computed it
                 run = torch.cat([frame_at(big, 2, h, w), a, b, frame_at(big, 5, h, w)], 0)
-                ours_flow = rc.raft_flow_sequence(model, run, 12, fuse_convcorr1=args.fuse_convcorr1)[1:2]
+                ours_flow = rc.raft_flow_sequence(model, run, 12, fuse_convcorr1=args.fuse_convcorr1, update_block_channels_last=getattr(args, 'update_channels_last', True))[1:2]
             else:
-                ours_flow = rc.raft_flow(model, a, b, 12, fuse_convcorr1=args.fuse_convcorr1)
+                ours_flow = rc.raft_flow(model, a, b, 12, fuse_convcorr1=args.fuse_convcorr1, update_block_channels_last=getattr(args, 'update_channels_last', True))
         model.corr_block.release()
         torch.manual_seed(0)
         stock = raft_large(weights=None).eval().to(dev)
@@ -373,6 +375,8 @@ def main():
     ap.add_argument("--no-share-features", dest="share_features", action="store_false",
                     help="run the feature encoder on both frames of every pair (2n images per batch) instead of once per "
                          "frame of a run of consecutive frames (n + 1 images, rc.raft_flow_sequence)")
+    ap.add_argument("--no-update-channels-last", dest="update_channels_last", action="store_false",
+                    help="feed the stock update block NCHW tensors like RAFT.forward does (cuDNN then transposes around every convolution)")
     ap.add_argument("--no-overlap-host", dest="overlap_host", action="store_false",
                     help="entropy-code a batch's flows right after its device work instead of while the next batch runs")
     ap.add_argument("--cudnn-benchmark", action="store_true",
@@ -405,7 +409,7 @@ def main():
     ctx = lambda: torch.autocast("cuda", dtype=torch.float16, enabled=args.amp)
 
     runner = (rc.GraphedRaftFlow(ours, 12, amp_dtype=torch.float16 if args.amp else None,
-                                 fuse_convcorr1=args.fuse_convcorr1) if args.graph else None)
+                                 fuse_convcorr1=args.fuse_convcorr1, update_block_channels_last=getattr(args, 'update_channels_last', True)) if args.graph else None)
 
     def run_ours():
         if args.batch_gop:
@@ -413,11 +417,11 @@ def main():
             if runner is not None:
                 return list(runner(a_, b_).split(1, 0))
             with torch.no_grad(), ctx():
-                return list(rc.raft_flow(ours, a_, b_, 12, fuse_convcorr1=args.fuse_convcorr1).split(1, 0))
+                return list(rc.raft_flow(ours, a_, b_, 12, fuse_convcorr1=args.fuse_convcorr1, update_block_channels_last=getattr(args, 'update_channels_last', True)).split(1, 0))
         if runner is not None:
             return [runner(a, b) for a, b in pairs]
         with torch.no_grad(), ctx():
-            return [rc.raft_flow(ours, a, b, 12, fuse_convcorr1=args.fuse_convcorr1) for a, b in pairs]
+            return [rc.raft_flow(ours, a, b, 12, fuse_convcorr1=args.fuse_convcorr1, update_block_channels_last=getattr(args, 'update_channels_last', True)) for a, b in pairs]
 
     def run_stock():
         with torch.no_grad(), ctx():

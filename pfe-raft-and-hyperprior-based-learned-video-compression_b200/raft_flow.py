@@ -48,13 +48,18 @@ def _coords_grid(batch: int, h: int, w: int, device) -> Tensor:
 
 
 @torch.no_grad()
-def _update_block_fused(model, blk: TVCorrBlock, hidden_state: Tensor, context: Tensor, coords1: Tensor, flow: Tensor):
+def _update_block_fused(model, blk: TVCorrBlock, hidden_state: Tensor, context: Tensor, coords1: Tensor, flow: Tensor,
+                        channels_last: bool = False):
     """``UpdateBlock.forward`` (TV:raft.py:278-285) with ``MotionEncoder.forward`` (TV:raft.py:200-210) inlined and its
-    first step -- ``convcorr1(index_pyramid(coords1))`` -- replaced by the fused call."""
+    first step -- ``convcorr1(index_pyramid(coords1))`` -- replaced by the fused call.  With ``channels_last`` the
+    tensors entering the stock convolutions are NHWC (see ``raft_flow``)."""
     ub = model.update_block
     me = ub.motion_encoder
     conv = me.convcorr1[0]                              # Conv2dNormActivation(324, 256, norm_layer=None, kernel_size=1): [Conv2d, ReLU]
     corr = blk.index_pyramid_convcorr1(coords1, conv.weight, conv.bias, relu=True)
+    if channels_last:
+        corr = corr.contiguous(memory_format=torch.channels_last)
+        flow = flow.contiguous(memory_format=torch.channels_last)
     corr = me.convcorr2(corr)
     flow_orig = flow
     f = me.convflow2(me.convflow1(flow))
@@ -89,7 +94,7 @@ def _can_fuse_convcorr1(model) -> bool:
 @torch.no_grad()
 def raft_flow(model, image1: Tensor, image2: Tensor, num_flow_updates: int = 12,
               corr_block: Optional[TVCorrBlock] = None, all_predictions: bool = False,
-              fuse_convcorr1: bool = True, fuse_encoder_tail: bool = True):
+              fuse_convcorr1: bool = True, fuse_encoder_tail: bool = True, update_block_channels_last: bool = True):
     """Final optical flow (B, 2, H, W) of a torchvision RAFT ``model`` for one frame pair.
 
     ``corr_block`` defaults to ``model.corr_block``, which must be a :class:`TVCorrBlock`
@@ -100,12 +105,14 @@ def raft_flow(model, image1: Tensor, image2: Tensor, num_flow_updates: int = 12,
         raise ValueError(f"input images should have the same shape, instead got {tuple(image1.shape[-2:])} != {tuple(image2.shape[-2:])}")
     batch = image1.shape[0]
     return _raft_flow_impl(model, torch.cat([image1, image2], dim=0), lambda x: (x[:batch], x[batch:]), image1,
-                           num_flow_updates, corr_block, all_predictions, fuse_convcorr1, fuse_encoder_tail)
+                           num_flow_updates, corr_block, all_predictions, fuse_convcorr1, fuse_encoder_tail,
+                           update_block_channels_last)
 
 
 @torch.no_grad()
 def raft_flow_sequence(model, frames: Tensor, num_flow_updates: int = 12, corr_block: Optional[TVCorrBlock] = None,
-                       all_predictions: bool = False, fuse_convcorr1: bool = True, fuse_encoder_tail: bool = True):
+                       all_predictions: bool = False, fuse_convcorr1: bool = True, fuse_encoder_tail: bool = True,
+                       update_block_channels_last: bool = True):
     """Flows (n, 2, H, W) of the n CONSECUTIVE pairs (frames[i], frames[i + 1]) of a run of n + 1 frames -- what the
     open-loop encoder asks for inside a GOP (R:codec_processing.py:1498-1499: every P-frame's reference is the previous
     ORIGINAL frame).  Same modules, same order as ``raft_flow(model, frames[:-1], frames[1:])``, but the feature
@@ -119,11 +126,19 @@ def raft_flow_sequence(model, frames: Tensor, num_flow_updates: int = 12, corr_b
         raise RuntimeError("raft_flow_sequence needs a feature encoder whose normalisation is per sample (InstanceNorm) or "
                            "frozen (BatchNorm in eval mode); batch statistics would couple the frames")
     return _raft_flow_impl(model, frames, lambda x: (x[:-1], x[1:]), frames[:-1], num_flow_updates, corr_block,
-                           all_predictions, fuse_convcorr1, fuse_encoder_tail)
+                           all_predictions, fuse_convcorr1, fuse_encoder_tail, update_block_channels_last)
+
+
+def _to_channels_last(module) -> None:
+    """Store the module's convolution weights NHWC (values unchanged; a no-op when they already are).  NOTE: this
+    re-allocates the weights once -- CUDA graphs captured before it must be re-captured (GraphedRaftFlow checks)."""
+    if not getattr(module, "_rdvc_channels_last", False):
+        module.to(memory_format=torch.channels_last)
+        module._rdvc_channels_last = True
 
 
 def _raft_flow_impl(model, enc_in: Tensor, split, image1: Tensor, num_flow_updates, corr_block, all_predictions,
-                    fuse_convcorr1, fuse_encoder_tail):
+                    fuse_convcorr1, fuse_encoder_tail, update_block_channels_last=True):
     """``enc_in``: every image the feature encoder has to see; ``split``: its output -> (first, second) feature maps of
     the pairs; ``image1``: the pairs' first frames (context encoder input)."""
     from torchvision.models.optical_flow._utils import upsample_flow
@@ -154,6 +169,18 @@ def _raft_flow_impl(model, enc_in: Tensor, split, image1: Tensor, num_flow_updat
     hidden_state, context = torch.split(context_out, [hidden_size, context_out.shape[1] - hidden_size], dim=1)
     hidden_state = torch.tanh(hidden_state)
     context = F.relu(context)
+    # The update block's twelve stock convolutions per iteration run in NHWC inside cuDNN; fed NCHW tensors (as
+    # RAFT.forward does) every one of them is wrapped in nchw->nhwc / nhwc->nchw transposes -- 24 % of a P-frame's GPU
+    # time at 1080p (profiles/r02raft_launches_summary.csv).  With the fused path the tensors entering the block are
+    # made channels_last once (hidden state, context) or per iteration (the 1x1 GEMM's output, the flow) and the
+    # block's weights are stored NHWC: same kernels, same bits (tools/exp_update_block_layout.py), no transposes.
+    cl = bool(update_block_channels_last) and fuse
+    if cl:
+        _to_channels_last(model.update_block)
+        if model.mask_predictor is not None:
+            _to_channels_last(model.mask_predictor)
+        hidden_state = hidden_state.contiguous(memory_format=torch.channels_last)
+        context = context.contiguous(memory_format=torch.channels_last)
 
     coords0 = _coords_grid(batch, h // 8, w // 8, fmap1.device)
     coords1 = coords0.clone()
@@ -163,14 +190,14 @@ def _raft_flow_impl(model, enc_in: Tensor, split, image1: Tensor, num_flow_updat
     for it in range(num_flow_updates):
         flow = coords1 - coords0
         if fuse:
-            hidden_state, delta_flow = _update_block_fused(model, blk, hidden_state, context, coords1, flow)
+            hidden_state, delta_flow = _update_block_fused(model, blk, hidden_state, context, coords1, flow, cl)
         else:
             corr_features = index_pyramid(blk._pyr, coords1, blk.radius, out=corr_out)
             hidden_state, delta_flow = model.update_block(hidden_state, context, corr_features, flow)
         coords1 = coords1 + delta_flow
         if all_predictions or it == num_flow_updates - 1:
-            up_mask = None if model.mask_predictor is None else model.mask_predictor(hidden_state)
-            preds.append(upsample_flow(flow=(coords1 - coords0), up_mask=up_mask))
+            up_mask = None if model.mask_predictor is None else model.mask_predictor(hidden_state).contiguous()   # upsample_flow views it
+            preds.append(upsample_flow(flow=(coords1 - coords0).contiguous(), up_mask=up_mask))
     return preds if all_predictions else preds[-1]
 
 
@@ -186,7 +213,7 @@ class GraphedRaftFlow:
 
     def __init__(self, model, num_flow_updates: int = 12, amp_dtype: Optional[torch.dtype] = None,
                  volume_dtype: torch.dtype = torch.float32, fuse_convcorr1: bool = True, max_entries: int = 4,
-                 fuse_encoder_tail: bool = True):
+                 fuse_encoder_tail: bool = True, update_block_channels_last: bool = True):
         if not isinstance(model.corr_block, TVCorrBlock):
             raise TypeError("GraphedRaftFlow needs a model built with corr_block=rdvc_corr_b200.TVCorrBlock()")
         if model.training:
@@ -198,16 +225,22 @@ class GraphedRaftFlow:
         self.volume_dtype = volume_dtype
         self.fuse_convcorr1 = fuse_convcorr1
         self.fuse_encoder_tail = fuse_encoder_tail
+        self.update_block_channels_last = update_block_channels_last
         self.max_entries = max_entries        # every captured shape pins a pyramid (5.7 GB at 1080p fp32)
         self._entries = {}                    # insertion-ordered: least recently used first
 
     def _run(self, blk, a, b):
         with torch.autocast("cuda", dtype=self.amp_dtype or torch.float16, enabled=self.amp_dtype is not None):
+            kw = dict(corr_block=blk, fuse_convcorr1=self.fuse_convcorr1, fuse_encoder_tail=self.fuse_encoder_tail,
+                      update_block_channels_last=self.update_block_channels_last)
             if b is None:      # a = a run of n + 1 frames
-                return raft_flow_sequence(self.model, a, self.num_flow_updates, corr_block=blk,
-                                          fuse_convcorr1=self.fuse_convcorr1, fuse_encoder_tail=self.fuse_encoder_tail)
-            return raft_flow(self.model, a, b, self.num_flow_updates, corr_block=blk, fuse_convcorr1=self.fuse_convcorr1,
-                             fuse_encoder_tail=self.fuse_encoder_tail)
+                return raft_flow_sequence(self.model, a, self.num_flow_updates, **kw)
+            return raft_flow(self.model, a, b, self.num_flow_updates, **kw)
+
+    def _weights_signature(self):
+        """Where the model's parameters live: a captured graph has these addresses baked in, so a model that was
+        moved / re-typed / re-laid-out since (``.half()``, ``.to(memory_format=...)``, a new device) must be re-captured."""
+        return tuple(p.data_ptr() for p in self.model.parameters())
 
     def release(self, key=None) -> None:
         """Drop the captured graph(s) and the pyramids they pin (all shapes, or one ``(shape, dtype, device)`` key)."""
@@ -233,7 +266,7 @@ class GraphedRaftFlow:
         graph = torch.cuda.CUDAGraph()
         with torch.no_grad(), torch.cuda.graph(graph):
             out = self._run(blk, in1, in2)
-        return {"graph": graph, "in1": in1, "in2": in2, "out": out, "blk": blk}
+        return {"graph": graph, "in1": in1, "in2": in2, "out": out, "blk": blk, "weights": self._weights_signature()}
 
     @torch.no_grad()
     def __call__(self, image1: Tensor, image2: Tensor) -> Tensor:
@@ -259,6 +292,10 @@ class GraphedRaftFlow:
 
     def _replay(self, key, image1: Tensor, image2: Optional[Tensor]) -> Tensor:
         e = self._entries.pop(key, None)
+        if e is not None and e["weights"] != self._weights_signature():
+            e["graph"] = None                                       # the parameters moved since the capture
+            e["blk"].release()
+            e = None
         if e is None:
             while len(self._entries) >= self.max_entries:          # evict the least recently used shape
                 self.release(next(iter(self._entries)))

@@ -591,6 +591,35 @@ def test_raft_flow_sequence_matches_pairs(lib, golden_dir):
     runner.release()
 
 
+def test_update_block_channels_last_and_graph_recapture(lib, golden_dir):
+    """The fused path feeds the stock update block NHWC tensors and stores its weights NHWC (cuDNN then runs the same
+    kernels without nchw<->nhwc transposes): same flow as with NCHW tensors.  Storing the weights NHWC re-allocates
+    them, so a graph captured before must notice and re-capture instead of reading freed memory."""
+    g = np.load(os.path.join(golden_dir, "frames_im1_im2.npz"))
+    a = _preprocess(g["im1"], (256, 448)).cuda()
+    b = _preprocess(g["im2"], (256, 448)).cuda()
+    model = _seeded_raft(rc.TVCorrBlock())
+    w = model.update_block.flow_head.conv1.weight
+    runner = rc.GraphedRaftFlow(model, 12, update_block_channels_last=False)
+    with torch.no_grad():
+        nchw = rc.raft_flow(model, a, b, 12, update_block_channels_last=False)
+        assert torch.equal(runner(a, b), nchw)
+        assert model.update_block.flow_head.conv1.weight.is_contiguous()                     # untouched so far
+        ptr0 = w.data_ptr()
+        nhwc = rc.raft_flow(model, a, b, 12)                                                 # default: channels_last
+        w2 = model.update_block.flow_head.conv1.weight
+        assert w2.is_contiguous(memory_format=torch.channels_last) and w2.data_ptr() != ptr0
+        assert (nhwc - nchw).pow(2).sum(dim=1).sqrt().mean().item() < 2e-3       # fp32 here: cuDNN picks other algorithms for NHWC
+        stock = _seeded_raft()(a, b, num_flow_updates=12)[-1]
+        assert (nhwc - stock).pow(2).sum(dim=1).sqrt().mean().item() < TOL_EPE
+        n_before = len(runner._entries)
+        again = runner(a, b)                                                                 # weights moved -> re-captured
+        assert n_before == len(runner._entries) == 1
+        assert (again - nchw).pow(2).sum(dim=1).sqrt().mean().item() < 2e-3      # NHWC weights now steer cuDNN's choice
+        assert torch.equal(runner(b, a), rc.raft_flow(model, b, a, 12, update_block_channels_last=False))
+    runner.release()
+
+
 def test_princeton_facade(lib):
     B, D, h, w = 1, 64, 24, 40
     f1, f2 = cn.synth_fmaps(B, D, h, w, seed=21)
