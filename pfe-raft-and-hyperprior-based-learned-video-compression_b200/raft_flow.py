@@ -100,6 +100,8 @@ def raft_flow(model, image1: Tensor, image2: Tensor, num_flow_updates: int = 12,
     ``corr_block`` defaults to ``model.corr_block``, which must be a :class:`TVCorrBlock`
     (inject it with ``raft_large(corr_block=TVCorrBlock())``).  With ``all_predictions=True`` the
     list of all upsampled flows is returned, exactly like ``RAFT.forward``.
+    ``update_block_channels_last`` (with the fused path): the stock update block, mask predictor and context encoder
+    get NHWC inputs and have their weights stored NHWC (values unchanged) -- cuDNN then skips its layout transposes.
     """
     if image1.dim() != 4 or image1.shape[-2:] != image2.shape[-2:]:
         raise ValueError(f"input images should have the same shape, instead got {tuple(image1.shape[-2:])} != {tuple(image2.shape[-2:])}")
@@ -164,21 +166,26 @@ def _raft_flow_impl(model, enc_in: Tensor, split, image1: Tensor, num_flow_updat
         blk.build_pyramid(fmap1, fmap2)
     fuse = fuse_convcorr1 and blk.layout == 1 and _can_fuse_convcorr1(model)      # 1 = RDVC_LAYOUT_TILED
 
+    # Stock convolutions in NHWC where it pays: the update block's twelve convolutions per iteration and the context
+    # encoder's run NHWC inside cuDNN; fed NCHW tensors (as RAFT.forward does) every one of them is wrapped in
+    # nchw->nhwc / nhwc->nchw transposes -- 24 % of a P-frame's GPU time at 1080p
+    # (profiles/r02raft_launches_summary.csv).  With the fused path their inputs are made channels_last and their
+    # weights are stored NHWC: the same convolution kernels without the transposes (update block 10.3 -> 7.8 ms,
+    # context encoder 2.6 -> 1.8 ms per P-frame at 1080p, tools/exp_update_block_layout.py, exp_encoder_layout.py).
+    # The feature encoder stays NCHW: its InstanceNorm is slower in NHWC (3.1 -> 4.3 ms).
+    cl = bool(update_block_channels_last) and fuse
+    if cl:
+        _to_channels_last(model.context_encoder)
+        _to_channels_last(model.update_block)
+        if model.mask_predictor is not None:
+            _to_channels_last(model.mask_predictor)
+        image1 = image1.contiguous(memory_format=torch.channels_last)
     context_out = model.context_encoder(image1)
     hidden_size = model.update_block.hidden_state_size
     hidden_state, context = torch.split(context_out, [hidden_size, context_out.shape[1] - hidden_size], dim=1)
     hidden_state = torch.tanh(hidden_state)
     context = F.relu(context)
-    # The update block's twelve stock convolutions per iteration run in NHWC inside cuDNN; fed NCHW tensors (as
-    # RAFT.forward does) every one of them is wrapped in nchw->nhwc / nhwc->nchw transposes -- 24 % of a P-frame's GPU
-    # time at 1080p (profiles/r02raft_launches_summary.csv).  With the fused path the tensors entering the block are
-    # made channels_last once (hidden state, context) or per iteration (the 1x1 GEMM's output, the flow) and the
-    # block's weights are stored NHWC: same kernels, same bits (tools/exp_update_block_layout.py), no transposes.
-    cl = bool(update_block_channels_last) and fuse
-    if cl:
-        _to_channels_last(model.update_block)
-        if model.mask_predictor is not None:
-            _to_channels_last(model.mask_predictor)
+    if cl:      # no-ops when the context encoder already produced NHWC
         hidden_state = hidden_state.contiguous(memory_format=torch.channels_last)
         context = context.contiguous(memory_format=torch.channels_last)
 
