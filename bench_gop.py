@@ -61,6 +61,11 @@ def frame_at(big, t, h, w):
     return big[:, :, 32 - dy:32 - dy + h, 32 - dx:32 - dx + w].contiguous()
 
 
+def raft_kw(args):
+    """The rc.raft_flow / rc.GraphedRaftFlow switches the command line controls."""
+    return dict(fuse_convcorr1=args.fuse_convcorr1, update_block_channels_last=getattr(args, "update_channels_last", True))
+
+
 def sharded_args(**kw):
     """The argument namespace of run_sharded with its command-line defaults (for callers such as bench.py)."""
     d = dict(frames=600, height=1088, width=1920, gop=10, amp=False, graph=True, volume="fp32", from_uint8=False,
@@ -118,7 +123,7 @@ def run_sharded(args, own_process_group=True):
     fh = args.height - 8 if args.height % 16 == 0 and args.height > 64 else args.height   # 1088 -> 1080 codec frame
 
     runner = (rc.GraphedRaftFlow(model, 12, amp_dtype=torch.float16 if args.amp else None, volume_dtype=vol,
-                                 fuse_convcorr1=args.fuse_convcorr1, update_block_channels_last=getattr(args, 'update_channels_last', True)) if args.graph else None)
+                                 **raft_kw(args)) if args.graph else None)
     coder = rc.entropy_coder.FlowCoder() if args.entropy else None
 
     mcn_net = None
@@ -144,7 +149,7 @@ def run_sharded(args, own_process_group=True):
             flow = runner(prev, cur)
         else:
             with torch.no_grad(), ctx():
-                flow = rc.raft_flow(model, prev, cur, 12, fuse_convcorr1=args.fuse_convcorr1, update_block_channels_last=getattr(args, 'update_channels_last', True))
+                flow = rc.raft_flow(model, prev, cur, 12, **raft_kw(args))
         # steps 3 + 5a of the reference (R:codec_processing.py:1446,1456): flow to frame resolution and the
         # warped previous frame, one fused launch; the MCN / residual / codecs that consume them are out of scope
         prev_codec = prev[:, :, :fh].contiguous()
@@ -183,14 +188,14 @@ def run_sharded(args, own_process_group=True):
                 flow = runner.sequence(frames)
             else:
                 with torch.no_grad(), ctx():
-                    flow = rc.raft_flow_sequence(model, frames, 12, fuse_convcorr1=args.fuse_convcorr1, update_block_channels_last=getattr(args, 'update_channels_last', True))
+                    flow = rc.raft_flow_sequence(model, frames, 12, **raft_kw(args))
         else:
             a, b = torch.cat(prevs, 0), torch.cat(curs, 0)
             if runner is not None:
                 flow = runner(a, b)
             else:
                 with torch.no_grad(), ctx():
-                    flow = rc.raft_flow(model, a, b, 12, fuse_convcorr1=args.fuse_convcorr1, update_block_channels_last=getattr(args, 'update_channels_last', True))
+                    flow = rc.raft_flow(model, a, b, 12, **raft_kw(args))
         a_codec = a[:, :, :fh].contiguous()
         warped, flow = rc.motion_warp(a_codec, flow, (fh, w))
         res = predict(warped, flow, a_codec, b[:, :, :fh])
@@ -244,7 +249,7 @@ def run_sharded(args, own_process_group=True):
             runner(frame_at(big, 0, h, w), frame_at(big, 1, h, w))
     with torch.no_grad(), ctx():                          # warm-up: cuDNN autotune + allocator
         for _ in range(2):
-            rc.raft_flow(model, frame_at(big, 0, h, w), frame_at(big, 1, h, w), 12, fuse_convcorr1=args.fuse_convcorr1, update_block_channels_last=getattr(args, 'update_channels_last', True))
+            rc.raft_flow(model, frame_at(big, 0, h, w), frame_at(big, 1, h, w), 12, **raft_kw(args))
     barrier()
     t0 = time.perf_counter()
     meta_in = {"rdvc_version": "b200-bench", "iframe_interval": args.gop}
@@ -311,9 +316,9 @@ def run_sharded(args, own_process_group=True):
         with torch.no_grad(), ctx():
             if share:       # the pair as the middle of a run, the way the timed region computed it
                 run = torch.cat([frame_at(big, 2, h, w), a, b, frame_at(big, 5, h, w)], 0)
-                ours_flow = rc.raft_flow_sequence(model, run, 12, fuse_convcorr1=args.fuse_convcorr1, update_block_channels_last=getattr(args, 'update_channels_last', True))[1:2]
+                ours_flow = rc.raft_flow_sequence(model, run, 12, **raft_kw(args))[1:2]
             else:
-                ours_flow = rc.raft_flow(model, a, b, 12, fuse_convcorr1=args.fuse_convcorr1, update_block_channels_last=getattr(args, 'update_channels_last', True))
+                ours_flow = rc.raft_flow(model, a, b, 12, **raft_kw(args))
         model.corr_block.release()
         torch.manual_seed(0)
         stock = raft_large(weights=None).eval().to(dev)
@@ -409,7 +414,7 @@ def main():
     ctx = lambda: torch.autocast("cuda", dtype=torch.float16, enabled=args.amp)
 
     runner = (rc.GraphedRaftFlow(ours, 12, amp_dtype=torch.float16 if args.amp else None,
-                                 fuse_convcorr1=args.fuse_convcorr1, update_block_channels_last=getattr(args, 'update_channels_last', True)) if args.graph else None)
+                                 **raft_kw(args)) if args.graph else None)
 
     def run_ours():
         if args.batch_gop:
@@ -417,11 +422,11 @@ def main():
             if runner is not None:
                 return list(runner(a_, b_).split(1, 0))
             with torch.no_grad(), ctx():
-                return list(rc.raft_flow(ours, a_, b_, 12, fuse_convcorr1=args.fuse_convcorr1, update_block_channels_last=getattr(args, 'update_channels_last', True)).split(1, 0))
+                return list(rc.raft_flow(ours, a_, b_, 12, **raft_kw(args)).split(1, 0))
         if runner is not None:
             return [runner(a, b) for a, b in pairs]
         with torch.no_grad(), ctx():
-            return [rc.raft_flow(ours, a, b, 12, fuse_convcorr1=args.fuse_convcorr1, update_block_channels_last=getattr(args, 'update_channels_last', True)) for a, b in pairs]
+            return [rc.raft_flow(ours, a, b, 12, **raft_kw(args)) for a, b in pairs]
 
     def run_stock():
         with torch.no_grad(), ctx():
