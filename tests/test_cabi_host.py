@@ -391,3 +391,21 @@ def test_forward_only_guard():
     rc._cabi.forward_only("x", None, t.detach())
     with torch.no_grad():
         rc._cabi.forward_only("x", t)
+
+
+def test_to_channels_last_keeps_values_and_is_idempotent():
+    """raft_flow stores the stock update block / context encoder weights NHWC: values unchanged, done once (a second
+    call must not re-allocate -- CUDA graphs captured in between hold the addresses)."""
+    from rdvc_corr_b200.raft_flow import _to_channels_last
+    m = torch.nn.Sequential(torch.nn.Conv2d(8, 16, 3), torch.nn.BatchNorm2d(16), torch.nn.Conv2d(16, 4, 1))
+    before = {k: v.clone() for k, v in m.state_dict().items()}
+    _to_channels_last(m)
+    assert m[0].weight.is_contiguous(memory_format=torch.channels_last)
+    assert all(torch.equal(v, before[k]) for k, v in m.state_dict().items())
+    ptrs = [p.data_ptr() for p in m.parameters()]
+    _to_channels_last(m)
+    assert ptrs == [p.data_ptr() for p in m.parameters()]
+    x = torch.randn(2, 8, 12, 12)
+    ref = torch.nn.Sequential(torch.nn.Conv2d(8, 16, 3), torch.nn.BatchNorm2d(16), torch.nn.Conv2d(16, 4, 1))
+    ref.load_state_dict(before)
+    assert torch.allclose(m.eval()(x), ref.eval()(x), atol=1e-5)
